@@ -1,0 +1,37 @@
+"""Load the committed golden vectors (made by tests/golden/make_golden.py from the
+reference itself) together with the regenerated seeded inputs."""
+from __future__ import annotations
+
+import os
+import warnings
+from functools import lru_cache
+
+import numpy as np
+
+from tests import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def dense(idx, val, shape, dtype=np.float32):
+    a = np.zeros(int(np.prod(shape)), dtype)
+    a[idx] = val
+    return a.reshape(shape)
+
+
+@lru_cache(maxsize=None)
+def load(name: str):
+    cfg = synth.CONFIGS[name]
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"{name}.npz")))
+    batch = synth.make_batch(cfg, seed=0)
+    if synth.digest(batch) != str(g["digest"]):
+        # numpy's SIMD exp may differ in the last bit between hosts; tolerances absorb that.
+        warnings.warn(f"{name}: regenerated inputs differ bitwise from the ones the goldens were made with")
+    assert np.array_equal(batch["kps"], g["kps"]) and np.array_equal(batch["vis"], g["vis"]), \
+        "seeded keypoints drifted: the generator changed, regenerate tests/golden"
+    B, K, H, W = cfg.B, cfg.K, cfg.H, cfg.W
+    g["target"] = dense(g["enc_nz_idx"], g["enc_nz_val"], (B, K, H, W))
+    eb = g["edge_kps"].shape[0]
+    g["edge_target"] = dense(g["edge_nz_idx"], g["edge_nz_val"], (eb, K, H, W))
+    g["grad_off"] = dense(g["grad_off_idx"], g["grad_off_val"], (B, K, 2, H, W))
+    return cfg, batch, g
