@@ -1,0 +1,190 @@
+/* gbcodec.h — C ABI of the B200-native heatmap codec (libgbcodec.so).
+ *
+ * The reference (MarkJhonBao/InfantPoseEstimation_GaussianBias) is pure Python
+ * and has no FFI layer; its boundary for this path is a set of Python
+ * callables.  Each entry point below replaces the arithmetic of one of them and
+ * is what a binding added to the reference would call (see INTEGRATION.md for
+ * the ctypes / torch.library stubs).  Citations are file:line in the reference.
+ *
+ * Conventions
+ *   - every pointer named `d_*` or documented "device" is CUDA device memory on
+ *     the current device; `h_*` is host memory.  All tensors are contiguous
+ *     fp32 NCHW: heatmaps (B,K,H,W), offsets (B,K,2,H,W), coords (B,K,2).
+ *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work:
+ *     they never allocate, never synchronise and keep no global state, so they
+ *     are re-entrant and may be used from several host threads on different
+ *     streams.  The caller owns every buffer, including the workspace.
+ *   - return value: GBCODEC_OK (0) or a negative gbcodec_status.  Nothing throws.
+ *     gbcodec_last_error() returns a thread-local description of the last failure.
+ *   - W must be a multiple of 4 and every tensor 16-byte aligned (128-bit
+ *     loads); 1 <= K <= GBCODEC_MAX_K; H*W <= GBCODEC_MAX_TILE.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef GBCODEC_H_
+#define GBCODEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBCODEC_ABI_VERSION 1
+#define GBCODEC_MAX_K 64            /* keypoint channels per image                  */
+#define GBCODEC_MAX_PAIRS 64        /* limb pairs in the overlap term               */
+#define GBCODEC_MAX_PARTNERS 4      /* limb pairs a single channel may take part in */
+#define GBCODEC_MAX_TILE 32768      /* H*W                                           */
+
+typedef enum gbcodec_status {
+    GBCODEC_OK = 0,
+    GBCODEC_ERR_NULL_POINTER = -1,
+    GBCODEC_ERR_BAD_SHAPE = -2,      /* non-positive dims, K or tile too large, W % 4 != 0 */
+    GBCODEC_ERR_UNALIGNED = -3,      /* a tensor pointer is not 16-byte aligned              */
+    GBCODEC_ERR_BAD_ARGUMENT = -4,   /* bad mode / flags / skeleton / sigma                  */
+    GBCODEC_ERR_WORKSPACE = -5,      /* workspace missing or too small                       */
+    GBCODEC_ERR_CUDA = -6            /* a CUDA runtime call failed (see gbcodec_last_error)  */
+} gbcodec_status;
+
+int gbcodec_abi_version(void);
+const char* gbcodec_status_string(int status);
+const char* gbcodec_last_error(void);
+
+/* ---------------------------------------------------------------- encode ---
+ * Gaussian target tiles + weights.  Replaces COCOPoseDataset._generate_target
+ * (datasets/coco_dataset.py:185-250), batched: the reference runs it per sample
+ * in DataLoader workers and ships the tiles over PCIe (train.py:160); here the
+ * tiles are written straight into HBM from (B,K,2) keypoints and (B,K) flags.
+ *   d_kps    (B,K,2) input-image pixels       d_vis    (B,K) visibility {0,1,2}
+ *   d_target (B,K,H,W) out                     d_weight (B,K) out (= (B,K,1))
+ *   in_w,in_h  network input size; sigma  Gaussian sigma in heatmap pixels.
+ */
+int gbcodec_encode_f32(const float* d_kps, const float* d_vis, float* d_target, float* d_weight,
+                       int B, int K, int H, int W, float in_w, float in_h, double sigma, void* stream);
+
+/* ---------------------------------------------------------------- decode ---
+ * Replaces HeatmapRegressionHead.decode (models/fusion_head.py:309-365) —
+ * global soft-argmax (:37-71), local (2r+1)^2 softmax centroid around the
+ * rounded soft-argmax (:84-128), sigmoid(alpha) blend (:151-172), bilinear
+ * offset-map correction (:342-363) — and, when d_hm_flipped is given, the
+ * flip-test average of PoseEstimator.inference (models/pose_estimator.py:
+ * 303-319) fused in front: the tile decoded is
+ *   (hm[b,k,y,x] + hm_flipped[b,perm[k],y,W-1-x]) / 2.
+ *   d_hm           (B,K,H,W)
+ *   d_hm_flipped   (B,K,H,W) raw head output for the W-flipped image, or NULL
+ *   d_flip_perm    K int32, channel permutation of the flip pairs (NULL = identity)
+ *   d_off          (B,K,2,H,W), required with GBCODEC_DECODE_APPLY_OFFSET
+ *   d_alpha_param  device scalar, raw learnable alpha (sigmoid applied here), required with REFINE
+ *   d_fusion_weight device scalar; already sigmoid-ed as the head publishes it
+ *                  (fusion_head.py:306) unless GBCODEC_DECODE_FUSION_WEIGHT_RAW
+ *   d_coords (B,K,2) out, heatmap pixels     d_scores (B,K) out, raw tile maximum
+ *   d_centre (B,K,2) int32 out or NULL: the rounded window centre (integer peak index)
+ */
+#define GBCODEC_DECODE_REFINE            1u
+#define GBCODEC_DECODE_APPLY_OFFSET      2u
+#define GBCODEC_DECODE_FUSION_WEIGHT_RAW 4u
+int gbcodec_decode_f32(const float* d_hm, const float* d_hm_flipped, const int32_t* d_flip_perm,
+                       const float* d_off, const float* d_alpha_param, const float* d_fusion_weight,
+                       int B, int K, int H, int W, int local_radius, unsigned flags,
+                       float* d_coords, float* d_scores, int32_t* d_centre, void* stream);
+
+/* Replaces PoseEstimator.decode_heatmaps (models/pose_estimator.py:331-373) and
+ * the arg-max family of utils/postprocess.py:10-184.  First maximum wins ties.
+ *   mode GBCODEC_ARGMAX_PLAIN    integer peak                         (postprocess.py:10-34, shift=False)
+ *        GBCODEC_ARGMAX_QUARTER  +0.25*sign(neighbour difference)     (pose_estimator.py:361-371)
+ *        GBCODEC_ARGMAX_TAYLOR   second-order sub-pixel step           (postprocess.py:37-75)
+ *   d_coords (B,K,2) out   d_maxvals (B,K) out   d_index (B,K) int32 out or NULL (flat y*W+x)
+ */
+#define GBCODEC_ARGMAX_PLAIN   0
+#define GBCODEC_ARGMAX_QUARTER 1
+#define GBCODEC_ARGMAX_TAYLOR  2
+int gbcodec_decode_argmax_f32(const float* d_hm, int B, int K, int H, int W, int mode,
+                              float* d_coords, float* d_maxvals, int32_t* d_index, void* stream);
+
+/* Replaces utils/postprocess.py:138-184 (coordinate_refinement): linear-weight
+ * centroid of the window around trunc(coords).  d_coords_in/out (B,K,2). */
+int gbcodec_refine_centroid_f32(const float* d_hm, const float* d_coords_in, int B, int K, int H, int W,
+                                int window, float* d_coords_out, void* stream);
+
+/* ------------------------------------------------------------------ loss ---
+ * Replaces FusionPoseLoss.forward + its autograd backward
+ * (models/fusion_head.py:745-806, terms :637-743 and :405-559).
+ */
+typedef struct gbcodec_loss_desc {
+    int32_t B, K, H, W;
+    float   in_w, in_h;          /* network input size (fusion_head.py:679-680)                     */
+    float   lambdas[6];          /* heatmap, offset, peak, variance, overlap, shape (:608-618)      */
+    double  target_sigma;        /* sigma of the variance / entropy targets (:467, :550)           */
+    double  encode_sigma;        /* sigma of the on-the-fly target tiles (d_target == NULL)        */
+    int32_t use_target_weight;   /* :651, :706, :737 — terms 1-3 only                                */
+    int32_t n_pairs;             /* limb pairs (i,j), i,j < K (:389-394, :503-505)                  */
+    int32_t pairs[GBCODEC_MAX_PAIRS][2];
+} gbcodec_loss_desc;
+
+size_t gbcodec_loss_workspace_bytes(int B, int K, int H, int W);
+
+/* Batch normalisers WITHOUT their epsilons: out[0] = sum(w), out[1] = sum over limbs
+ * of w_i*w_j (fusion_head.py:480,523-527).  With target_given == 0 the weights first
+ * go through the encoder's off-map rule (coco_dataset.py:227-229), which is what the
+ * on-the-fly mode of the loss uses.  A batch-sharded job all-reduces the two floats
+ * over its ranks and hands the result to the loss as d_denoms. */
+int gbcodec_loss_denominators_f32(const gbcodec_loss_desc* desc, const float* d_weight, const float* d_gt_kps,
+                                  int target_given, float* d_out2_raw_sums,
+                                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* One pass over the batch: the seven lambda-weighted loss scalars and, when the
+ * grad pointers are given, d(total_loss)/d(hm, off, var) scaled by *d_grad_scale —
+ * every heatmap tile is read from HBM once.
+ *   d_hm (B,K,H,W)  d_off (B,K,2,H,W)  d_var (B,K,H,W) or NULL
+ *   d_target (B,K,H,W), or NULL: tiles are generated on the fly from d_gt_kps and
+ *            d_weight exactly as gbcodec_encode_f32 would (no HBM traffic for them)
+ *   d_weight (B,K)   d_gt_kps (B,K,2) input-image pixels
+ *   d_denoms  NULL, or 2 device floats: raw sums (no epsilon) of w and of w_i*w_j over the
+ *            GLOBAL batch — a rank holding a shard passes the all-reduced values
+ *   d_grad_scale NULL (=1) or device scalar: the upstream gradient of total_loss
+ *   d_losses7 out: heatmap, offset, peak, variance, overlap, shape, total
+ *   d_grad_hm/off/var out (all NULL = forward only; d_grad_var NULL iff d_var NULL)
+ */
+int gbcodec_fusion_loss_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Same pass with the keypoint decode of gbcodec_decode_f32 (no flip) folded in:
+ * the "fused step" encode + loss fwd/bwd + decode of BASELINE.json. */
+int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Backward for an arbitrary upstream gradient on the seven outputs.  The
+ * gradients written by the forward assume d(total)=*d_grad_scale and nothing on
+ * the six terms.  This call reads the actual upstream vector on the device and
+ *   - returns immediately inside the kernels if it matches the assumption,
+ *   - rescales the three gradient tensors in place if all six effective term
+ *     gradients are equal,
+ *   - otherwise recomputes them with per-term weights.
+ * No host synchronisation in any case. */
+int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale, const float* d_grad_losses7,
+                            float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hook (bench.py): the next gbcodec_fusion_loss_f32 / _step_f32 calls made
+ * by THIS host thread record `start_event` right before and `stop_event` right after
+ * the per-tile loss kernel, on the stream of the call.  Both are cudaEvent_t passed as
+ * void*; pass NULL, NULL to switch the hook off.  Thread-local, no other state. */
+int gbcodec_profile_loss_kernel(void* start_event, void* stop_event);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBCODEC_H_ */

@@ -1,0 +1,176 @@
+// api.cu — the C ABI declared in include/gbcodec.h: argument checks, status
+// mapping and launches.  No torch types, no allocation, no synchronisation.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace gbc {
+
+static thread_local char g_last_error[512] = "";
+
+int fail(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return GBCODEC_OK;
+}
+
+// encode.cu / decode.cu / loss.cu
+int launch_encode(const float*, const float*, float*, float*, int, int, int, int, float, float, double, cudaStream_t);
+int launch_decode(const float*, const float*, const int32_t*, const float*, const float*, const float*, int, int, int, int,
+                  int, unsigned, float*, float*, int32_t*, cudaStream_t);
+int launch_argmax(const float*, int, int, int, int, int, float*, float*, int32_t*, cudaStream_t);
+int launch_centroid(const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
+size_t loss_workspace_bytes(int B, int K);
+int loss_denominators(const gbcodec_loss_desc*, const float*, const float*, int, float*, void*, size_t, cudaStream_t);
+int fusion_loss(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
+                const float*, const float*, float*, float*, float*, float*,
+                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t);
+int fusion_loss_backward(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*,
+                         const float*, const float*, const float*, const float*, float*, float*, float*, void*, size_t,
+                         cudaStream_t);
+
+void set_profile_events(cudaEvent_t, cudaEvent_t);
+
+static int check_tile_shape(const char* who, int B, int K, int H, int W) {
+    if (B <= 0 || K <= 0 || H <= 0 || W <= 0) return fail(GBCODEC_ERR_BAD_SHAPE, "%s: B,K,H,W must be positive (got %d,%d,%d,%d)", who, B, K, H, W);
+    if (K > GBCODEC_MAX_K) return fail(GBCODEC_ERR_BAD_SHAPE, "%s: K=%d exceeds %d", who, K, GBCODEC_MAX_K);
+    if (W % 4) return fail(GBCODEC_ERR_BAD_SHAPE, "%s: W=%d is not a multiple of 4", who, W);
+    if ((long long)H * W > GBCODEC_MAX_TILE) return fail(GBCODEC_ERR_BAD_SHAPE, "%s: tile %dx%d exceeds %d pixels", who, H, W, GBCODEC_MAX_TILE);
+    if ((long long)B * K > (1ll << 30)) return fail(GBCODEC_ERR_BAD_SHAPE, "%s: B*K too large", who);
+    return GBCODEC_OK;
+}
+
+}  // namespace gbc
+
+using namespace gbc;
+
+extern "C" {
+
+int gbcodec_abi_version(void) { return GBCODEC_ABI_VERSION; }
+
+const char* gbcodec_status_string(int status) {
+    switch (status) {
+        case GBCODEC_OK: return "ok";
+        case GBCODEC_ERR_NULL_POINTER: return "null pointer";
+        case GBCODEC_ERR_BAD_SHAPE: return "bad shape";
+        case GBCODEC_ERR_UNALIGNED: return "unaligned pointer";
+        case GBCODEC_ERR_BAD_ARGUMENT: return "bad argument";
+        case GBCODEC_ERR_WORKSPACE: return "workspace missing or too small";
+        case GBCODEC_ERR_CUDA: return "CUDA error";
+        default: return "unknown status";
+    }
+}
+
+const char* gbcodec_last_error(void) { return g_last_error; }
+
+int gbcodec_encode_f32(const float* d_kps, const float* d_vis, float* d_target, float* d_weight,
+                       int B, int K, int H, int W, float in_w, float in_h, double sigma, void* stream) {
+    int st = check_tile_shape("encode", B, K, H, W);
+    if (st) return st;
+    if (!d_kps || !d_vis || !d_target || !d_weight) return fail(GBCODEC_ERR_NULL_POINTER, "encode: NULL pointer");
+    if (!aligned16(d_target)) return fail(GBCODEC_ERR_UNALIGNED, "encode: d_target must be 16-byte aligned");
+    if (!(sigma > 0.0) || !(in_w > 0.f) || !(in_h > 0.f)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "encode: sigma and input size must be positive");
+    return launch_encode(d_kps, d_vis, d_target, d_weight, B, K, H, W, in_w, in_h, sigma, (cudaStream_t)stream);
+}
+
+int gbcodec_decode_f32(const float* d_hm, const float* d_hm_flipped, const int32_t* d_flip_perm,
+                       const float* d_off, const float* d_alpha_param, const float* d_fusion_weight,
+                       int B, int K, int H, int W, int local_radius, unsigned flags,
+                       float* d_coords, float* d_scores, int32_t* d_centre, void* stream) {
+    int st = check_tile_shape("decode", B, K, H, W);
+    if (st) return st;
+    if (!d_hm || !d_coords || !d_scores) return fail(GBCODEC_ERR_NULL_POINTER, "decode: NULL pointer");
+    if (flags & ~7u) return fail(GBCODEC_ERR_BAD_ARGUMENT, "decode: unknown flags 0x%x", flags);
+    if ((flags & GBCODEC_DECODE_REFINE) && !d_alpha_param) return fail(GBCODEC_ERR_NULL_POINTER, "decode: d_alpha_param is NULL");
+    if ((flags & GBCODEC_DECODE_APPLY_OFFSET) && (!d_off || !d_fusion_weight)) return fail(GBCODEC_ERR_NULL_POINTER, "decode: offsets / fusion weight missing");
+    if (local_radius < 0 || local_radius > 8) return fail(GBCODEC_ERR_BAD_ARGUMENT, "decode: local_radius=%d", local_radius);
+    if (!aligned16(d_hm) || (d_hm_flipped && !aligned16(d_hm_flipped))) return fail(GBCODEC_ERR_UNALIGNED, "decode: heatmaps must be 16-byte aligned");
+    return launch_decode(d_hm, d_hm_flipped, d_flip_perm, d_off, d_alpha_param, d_fusion_weight, B, K, H, W,
+                         local_radius, flags, d_coords, d_scores, d_centre, (cudaStream_t)stream);
+}
+
+int gbcodec_decode_argmax_f32(const float* d_hm, int B, int K, int H, int W, int mode,
+                              float* d_coords, float* d_maxvals, int32_t* d_index, void* stream) {
+    int st = check_tile_shape("decode_argmax", B, K, H, W);
+    if (st) return st;
+    if (!d_hm || !d_coords || !d_maxvals) return fail(GBCODEC_ERR_NULL_POINTER, "decode_argmax: NULL pointer");
+    if (mode < GBCODEC_ARGMAX_PLAIN || mode > GBCODEC_ARGMAX_TAYLOR) return fail(GBCODEC_ERR_BAD_ARGUMENT, "decode_argmax: mode=%d", mode);
+    if (!aligned16(d_hm)) return fail(GBCODEC_ERR_UNALIGNED, "decode_argmax: d_hm must be 16-byte aligned");
+    return launch_argmax(d_hm, B, K, H, W, mode, d_coords, d_maxvals, d_index, (cudaStream_t)stream);
+}
+
+int gbcodec_refine_centroid_f32(const float* d_hm, const float* d_coords_in, int B, int K, int H, int W,
+                                int window, float* d_coords_out, void* stream) {
+    int st = check_tile_shape("refine_centroid", B, K, H, W);
+    if (st) return st;
+    if (!d_hm || !d_coords_in || !d_coords_out) return fail(GBCODEC_ERR_NULL_POINTER, "refine_centroid: NULL pointer");
+    if (window < 1 || window > 31) return fail(GBCODEC_ERR_BAD_ARGUMENT, "refine_centroid: window=%d", window);
+    return launch_centroid(d_hm, d_coords_in, B, K, H, W, window, d_coords_out, (cudaStream_t)stream);
+}
+
+size_t gbcodec_loss_workspace_bytes(int B, int K, int H, int W) {
+    (void)H; (void)W;
+    if (B <= 0 || K <= 0) return 0;
+    return loss_workspace_bytes(B, K);
+}
+
+int gbcodec_loss_denominators_f32(const gbcodec_loss_desc* desc, const float* d_weight, const float* d_gt_kps,
+                                  int target_given, float* d_out2_raw_sums,
+                                  void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!desc) return fail(GBCODEC_ERR_NULL_POINTER, "denominators: desc is NULL");
+    return loss_denominators(desc, d_weight, d_gt_kps, target_given, d_out2_raw_sums, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gbcodec_fusion_loss_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
+                       d_losses7, d_grad_hm, d_grad_off, d_grad_var,
+                       nullptr, nullptr, 0, 0u, nullptr, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_coords || !d_scores) return fail(GBCODEC_ERR_NULL_POINTER, "step: d_coords / d_scores is NULL");
+    return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
+                       d_losses7, d_grad_hm, d_grad_off, d_grad_var,
+                       d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
+                       d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale, const float* d_grad_losses7,
+                            float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    return fusion_loss_backward(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
+                                d_grad_losses7, d_grad_hm, d_grad_off, d_grad_var, d_workspace, workspace_bytes,
+                                (cudaStream_t)stream);
+}
+
+int gbcodec_profile_loss_kernel(void* start_event, void* stop_event) {
+    if ((start_event == nullptr) != (stop_event == nullptr)) return fail(GBCODEC_ERR_NULL_POINTER, "profile: give both events or neither");
+    set_profile_events((cudaEvent_t)start_event, (cudaEvent_t)stop_event);
+    return GBCODEC_OK;
+}
+
+}  // extern "C"

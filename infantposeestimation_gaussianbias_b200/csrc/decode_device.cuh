@@ -1,0 +1,90 @@
+// decode_device.cuh — device helpers shared by decode.cu and the fused step in loss.cu.
+#pragma once
+#include "common.cuh"
+
+namespace gbc {
+
+__device__ __forceinline__ float4 rev4(const float4& v) { return make_float4(v.w, v.z, v.y, v.x); }
+
+// value of the (possibly flip-averaged) tile at one pixel; same arithmetic as the vector load path
+__device__ __forceinline__ float tile_at(const float* hm_tile, const float* hmf_tile, int W, int x, int y) {
+    float v = __ldg(hm_tile + y * W + x);
+    if (hmf_tile) v = (v + __ldg(hmf_tile + y * W + (W - 1 - x))) * 0.5f;
+    return v;
+}
+
+// Bilinear read of a 2-channel offset tile at (cx,cy): grid_sample(bilinear, border,
+// align_corners=True) of fusion_head.py:353-359 — coordinates clamped to the map,
+// taps outside the map contribute nothing.
+struct Bilinear {
+    int x0, y0, x1, y1;
+    float w00, w01, w10, w11;   // first index y, second x
+    float okx, oky;
+    float fx, fy;
+};
+__device__ __forceinline__ Bilinear bilinear_setup(float cx, float cy, int H, int W) {
+    Bilinear b;
+    const float ccx = fminf(fmaxf(cx, 0.f), (float)(W - 1));
+    const float ccy = fminf(fmaxf(cy, 0.f), (float)(H - 1));
+    const float fx0 = floorf(ccx), fy0 = floorf(ccy);
+    b.x0 = (int)fx0; b.y0 = (int)fy0;
+    b.fx = ccx - fx0; b.fy = ccy - fy0;
+    b.okx = (b.x0 + 1 < W) ? 1.f : 0.f;
+    b.oky = (b.y0 + 1 < H) ? 1.f : 0.f;
+    b.x1 = min(b.x0 + 1, W - 1); b.y1 = min(b.y0 + 1, H - 1);
+    b.w00 = (1.f - b.fx) * (1.f - b.fy); b.w01 = b.fx * (1.f - b.fy);
+    b.w10 = (1.f - b.fx) * b.fy;         b.w11 = b.fx * b.fy;
+    return b;
+}
+__device__ __forceinline__ float bilinear_read(const float* ch, const Bilinear& b, int W) {
+    const float v00 = __ldg(ch + b.y0 * W + b.x0);
+    const float v01 = __ldg(ch + b.y0 * W + b.x1) * b.okx;
+    const float v10 = __ldg(ch + b.y1 * W + b.x0) * b.oky;
+    const float v11 = __ldg(ch + b.y1 * W + b.x1) * (b.okx * b.oky);
+    return b.w00 * v00 + b.w01 * v01 + b.w10 * v10 + b.w11 * v11;
+}
+
+// Steps 3-6 of the decode for one tile, executed by warp 0 once the global
+// soft-argmax (cx, cy) is known.  Result in lane 0.
+__device__ __forceinline__ void refine_and_correct(const float* hm_tile, const float* hmf_tile, const float* off_tile,
+                                                   const float* alpha_param, const float* fusion_weight,
+                                                   int H, int W, int radius, unsigned flags,
+                                                   float& cx, float& cy, int& px_out, int& py_out) {
+    const int lane = threadIdx.x & 31;
+    // torch.round is round-half-to-even == rintf in the default rounding mode
+    const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
+    const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
+    px_out = px; py_out = py;
+    if (flags & GBCODEC_DECODE_REFINE) {
+        const int S = 2 * radius + 1;
+        float vmax = -INFINITY;
+        for (int c = lane; c < S * S; c += 32) {
+            const int x = px - radius + c % S, y = py - radius + c / S;
+            if (x >= 0 && x < W && y >= 0 && y < H) vmax = fmaxf(vmax, tile_at(hm_tile, hmf_tile, W, x, y));
+        }
+        vmax = warp_max(vmax);
+        float se = 0.f, sx = 0.f, sy = 0.f;
+        for (int c = lane; c < S * S; c += 32) {
+            const int x = px - radius + c % S, y = py - radius + c / S;
+            if (x >= 0 && x < W && y >= 0 && y < H) {
+                const float e = expf(tile_at(hm_tile, hmf_tile, W, x, y) - vmax);
+                se += e; sx += e * (float)x; sy += e * (float)y;
+            }
+        }
+        se = warp_sum(se); sx = warp_sum(sx); sy = warp_sum(sy);
+        const float a = sigmoid_acc(__ldg(alpha_param));
+        cx = a * cx + (1.f - a) * (sx / se);
+        cy = a * cy + (1.f - a) * (sy / se);
+    }
+    if (flags & GBCODEC_DECODE_APPLY_OFFSET) {
+        float fw = __ldg(fusion_weight);
+        if (flags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
+        const Bilinear bl = bilinear_setup(cx, cy, H, W);
+        const float ox = bilinear_read(off_tile, bl, W);
+        const float oy = bilinear_read(off_tile + H * W, bl, W);
+        cx += fw * ox;
+        cy += fw * oy;
+    }
+}
+
+}  // namespace gbc

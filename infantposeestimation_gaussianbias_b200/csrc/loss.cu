@@ -1,0 +1,740 @@
+// loss.cu — six-term fusion loss, forward and backward in one pass per tile.
+//
+// Restates FusionPoseLoss.forward (models/fusion_head.py:745-806) with its terms
+// (:637-743) and GaussianDistributionConstraint (:405-559), plus the autograd
+// backward train.py:182 triggers, in closed form (DESIGN.md "Loss kernel math";
+// the algebra is checked against autograd in tests/test_closed_form.py).
+//
+// One CTA per (image, keypoint) tile.  The tile is read from HBM once with
+// 128-bit loads into shared memory and every pass (max, softmax moments,
+// entropy/variance, limb overlap, gradient) runs out of shared memory; the limb
+// partners' tiles are re-read through L2 (they are some other CTA's own tile, so
+// HBM sees each heatmap once).  Gradients leave with 128-bit streaming stores.
+// Algorithmic HBM bytes per tile: read hm, var (8N); write d_hm, d_var, d_off (16N);
+// +4N when the target tiles come from HBM instead of being generated on the fly.
+#include "common.cuh"
+#include "decode_device.cuh"
+#include <string.h>
+
+namespace gbc {
+
+// ---- kernel-side description -------------------------------------------------------
+struct LossParams {
+    int B, K, H, W;
+    float in_w, in_h;
+    float lam[6];
+    float sigma;            // target sigma
+    float e_star;           // log(2 pi e sigma^2)
+    int use_target_weight;
+    int n_pairs;
+    EncodeConst ec;
+    int8_t n_partner[GBCODEC_MAX_K];
+    int8_t partner[GBCODEC_MAX_K][GBCODEC_MAX_PARTNERS];
+    uint8_t owner[GBCODEC_MAX_K];       // bit p: this channel is the first index of the pair with partner p
+    int16_t pair_i[GBCODEC_MAX_PAIRS], pair_j[GBCODEC_MAX_PAIRS];
+};
+
+struct LossArgs {
+    const float* hm; const float* off; const float* var; const float* target;
+    const float* weight; const float* gt;
+    const float* grad_scale;            // device scalar or null
+    float* grad_hm; float* grad_off; float* grad_var;
+    // fused decode (null coords = off)
+    const float* alpha_param; const float* fusion_weight; float* coords; float* scores;
+    int radius; unsigned dflags;
+    // workspace
+    const double* sums;                 // [2] raw sums of w and w_i*w_j
+    const float* weff;                  // [B*K] weights after the encoder's rule
+    float* partial;                     // [B*K][8] un-normalised per-tile loss numerators
+    const float* lam_eff;               // backward recompute: device [6] per-term multipliers
+    const int* plan;                    // backward recompute: run only if *plan == 2
+};
+
+constexpr int kWsHeaderFloats = 64;     // sums (2 doubles), plan, lam_eff, ... ; 256 bytes
+struct WsLayout {
+    double* sums; int* plan; float* lam_eff; float* weff; float* partial;
+};
+static inline size_t ws_bytes(int B, int K) {
+    return (size_t)(kWsHeaderFloats + (size_t)B * K * 9) * sizeof(float);
+}
+static inline WsLayout ws_carve(void* ws, int B, int K) {
+    float* f = reinterpret_cast<float*>(ws);
+    WsLayout l;
+    l.sums = reinterpret_cast<double*>(f);          // f[0..3]
+    l.plan = reinterpret_cast<int*>(f + 4);         // f[4..7]
+    l.lam_eff = f + 8;                              // f[8..15]
+    l.weff = f + kWsHeaderFloats;
+    l.partial = l.weff + (size_t)B * K;
+    // partial rows are 8 floats; keep them 32-byte aligned
+    const size_t pad = ((size_t)B * K) & 7;
+    if (pad) l.partial += 8 - pad;
+    return l;
+}
+
+// ---- weights after the encoder rule + the two batch sums ----------------------------
+__global__ void __launch_bounds__(256)
+denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight,
+              const float* __restrict__ gt, int target_given, float* __restrict__ weff, double* __restrict__ sums) {
+    // one image per thread: K weights, then the limb products
+    __shared__ double red[2][8];
+    double sw = 0.0, sp = 0.0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.B; b += gridDim.x * blockDim.x) {
+        float w[GBCODEC_MAX_K];
+        for (int k = 0; k < P.K; ++k) {
+            const int t = b * P.K + k;
+            float wk = weight[t];
+            if (!target_given)
+                wk = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec).weight;
+            w[k] = wk;
+            if (weff) weff[t] = wk;
+            sw += (double)wk;
+        }
+        for (int p = 0; p < P.n_pairs; ++p) sp += (double)(w[P.pair_i[p]] * w[P.pair_j[p]]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = sw; red[1][warp] = sp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; c += red[1][i]; }
+        atomicAdd(sums, a);
+        atomicAdd(sums + 1, c);
+    }
+}
+
+__global__ void sums_to_float_kernel(const double* __restrict__ sums, float* __restrict__ out2) {
+    if (threadIdx.x < 2) out2[threadIdx.x] = (float)sums[threadIdx.x];
+}
+__global__ void sums_from_float_kernel(const float* __restrict__ in2, double* __restrict__ sums) {
+    if (threadIdx.x < 2) sums[threadIdx.x] = (double)in2[threadIdx.x];
+}
+// weights after the encoder rule only (the sums come from the caller)
+__global__ void __launch_bounds__(256)
+weff_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight, const float* __restrict__ gt,
+            int target_given, float* __restrict__ weff) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.B * P.K) return;
+    float wk = weight[t];
+    if (!target_given) wk = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec).weight;
+    weff[t] = wk;
+}
+
+// ---- bilinear helpers (same convention as decode.cu) ---------------------------------
+struct Taps {
+    int i00, i01, i10, i11;          // flat indices inside a channel
+    float w00, w01, w10, w11;        // weights, already zero for taps outside the map
+    float fx, fy, inx, iny, okx, oky;
+};
+__device__ __forceinline__ Taps taps_setup(float cx, float cy, int H, int W) {
+    Taps t;
+    const float ccx = fminf(fmaxf(cx, 0.f), (float)(W - 1));
+    const float ccy = fminf(fmaxf(cy, 0.f), (float)(H - 1));
+    t.inx = (cx >= 0.f && cx <= (float)(W - 1)) ? 1.f : 0.f;
+    t.iny = (cy >= 0.f && cy <= (float)(H - 1)) ? 1.f : 0.f;
+    const float fx0 = floorf(ccx), fy0 = floorf(ccy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    t.fx = ccx - fx0; t.fy = ccy - fy0;
+    t.okx = (x0 + 1 < W) ? 1.f : 0.f;
+    t.oky = (y0 + 1 < H) ? 1.f : 0.f;
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    t.i00 = y0 * W + x0; t.i01 = y0 * W + x1; t.i10 = y1 * W + x0; t.i11 = y1 * W + x1;
+    t.w00 = (1.f - t.fx) * (1.f - t.fy);
+    t.w01 = t.fx * (1.f - t.fy) * t.okx;
+    t.w10 = (1.f - t.fx) * t.fy * t.oky;
+    t.w11 = t.fx * t.fy * t.okx * t.oky;
+    return t;
+}
+
+__device__ __forceinline__ float tie_rule(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+// per-tile scalars broadcast from thread 0 to the CTA
+struct TileCoef {
+    float c1;        // lambda1 * wa/(Da N) * 2
+    float c4;        // lambda4 * w/D * (s - sigma)/s / R'
+    float v;         // variance of the tile
+    float c6;        // lambda6 * w/D * 2 (E - E*)
+    float pa;        // sum p a
+    float fx, fy;    // d(loss)/d(cx, cy)
+    float gv;        // uniform gradient of the variance map
+    float go[2];     // lambda2 * wa/(2 Da) * sl1'(d_ch)
+};
+
+template <int TPB, int NITER, int CACHE>
+__global__ void __launch_bounds__(TPB)
+loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
+    if (A.plan && *A.plan != 2) return;      // backward recompute not needed
+    extern __shared__ __align__(16) float smem[];
+    const int H = P.H, W = P.W, n = H * W, n4 = n >> 2, w4 = W >> 2;
+    const int niter = NITER > 0 ? NITER : (n4 + TPB - 1) / TPB;
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int b = tile / P.K, k = tile - b * P.K;
+
+    float4* Hs = reinterpret_cast<float4*>(smem);
+    float4* Gs = Hs + n4;
+    float4* Es = Gs + n4;                                   // CACHE >= 1
+    float4* As = Es + (CACHE >= 1 ? n4 : 0);                // CACHE == 2
+    float4* Ss = As + (CACHE == 2 ? n4 : 0);                // CACHE == 2
+    float* lut = reinterpret_cast<float*>(Ss + (CACHE == 2 ? n4 : 0));
+    float* scratch = lut + ((P.ec.lut_size + 3) & ~3);      // 8*32 + 8 floats
+    __shared__ PatchGeom geom_s;
+    __shared__ TileCoef coef_s;
+
+    const bool has_target = A.target != nullptr;
+    const bool grads = A.grad_hm != nullptr;
+    const bool backward_only = A.lam_eff != nullptr;
+    const float w = __ldg(A.weff + tile);
+    const float wa = P.use_target_weight ? w : 1.f;
+    const bool heavy = (w != 0.f) || !P.use_target_weight;
+    const bool decode = A.coords != nullptr;
+
+    const float4* hm4 = reinterpret_cast<const float4*>(A.hm) + (size_t)tile * n4;
+    const float4* var4 = A.var ? reinterpret_cast<const float4*>(A.var) + (size_t)tile * n4 : nullptr;
+    const float4* tgt4 = has_target ? reinterpret_cast<const float4*>(A.target) + (size_t)tile * n4 : nullptr;
+
+    if (!has_target) {
+        fill_patch_lut(lut, P.ec);
+        if (tid == 0) geom_s = patch_geometry(__ldg(A.gt + 2 * tile), __ldg(A.gt + 2 * tile + 1), w, H, W, P.in_w, P.in_h, P.ec);
+    }
+
+    // ---- load: own tile -> smem, running max; variance map -> running sum -----------
+    float m = -INFINITY, vsum = 0.f;
+    for (int it = 0; it < niter; ++it) {
+        const int i = it * TPB + tid;
+        if (NITER > 0 || i < n4) {
+            const float4 v = ldg_stream(hm4 + i);
+            Hs[i] = v;
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+    }
+    if (var4 && heavy) {
+        for (int it = 0; it < niter; ++it) {
+            const int i = it * TPB + tid;
+            if (NITER > 0 || i < n4) { const float4 v = ldg_stream(var4 + i); vsum += (v.x + v.y) + (v.z + v.w); }
+        }
+    }
+    m = block_max(m, scratch);           // barriers: Hs, lut and geom_s are visible from here on
+    const PatchGeom geom = has_target ? PatchGeom{} : geom_s;
+
+    float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
+    float lam[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) lam[q] = backward_only ? __ldg(A.lam_eff + q) : P.lam[q] * gscale;
+
+    // target value for 4 consecutive pixels of row y starting at column x
+    auto target4 = [&](int i, int x, int y) -> float4 {
+        if (has_target) return ldg_keep(tgt4 + i);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (geom.active && y >= geom.y_from && y < geom.y_to && x + 3 >= geom.x_from && x < geom.x_to) {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = x + j;
+                e[j] = (xx >= geom.x_from && xx < geom.x_to) ? patch_value(lut, geom, P.ec, xx, y) : 0.f;
+            }
+            t = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        return t;
+    };
+
+    // ---- pass B: softmax moments, sigmoid mass, relu mass, squared error ---------------
+    const float ml = m * kLog2e;
+    float r7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, vsum};   // Z, X, Y, S, R, MSE, Vsum
+    for (int it = 0; it < niter; ++it) {
+        const int i = it * TPB + tid;
+        if (NITER > 0 || i < n4) {
+            const float4 h = Hs[i];
+            const int y = i / w4, x = (i - y * w4) << 2;
+            float4 e;
+            e.x = ex2(fmaf(h.x, kLog2e, -ml)); e.y = ex2(fmaf(h.y, kLog2e, -ml));
+            e.z = ex2(fmaf(h.z, kLog2e, -ml)); e.w = ex2(fmaf(h.w, kLog2e, -ml));
+            if (CACHE >= 1) Es[i] = e;
+            const float se = (e.x + e.y) + (e.z + e.w);
+            r7[0] += se;
+            r7[1] += fmaf((float)x, se, fmaf(3.f, e.w, fmaf(2.f, e.z, e.y)));
+            r7[2] = fmaf((float)y, se, r7[2]);
+            if (heavy) {
+                float4 s;
+                s.x = sigmoid_fast(h.x); s.y = sigmoid_fast(h.y); s.z = sigmoid_fast(h.z); s.w = sigmoid_fast(h.w);
+                if (CACHE == 2) Ss[i] = s;
+                r7[3] += (s.x + s.y) + (s.z + s.w);
+                r7[4] += (fmaxf(h.x, 0.f) + fmaxf(h.y, 0.f)) + (fmaxf(h.z, 0.f) + fmaxf(h.w, 0.f));
+                const float4 t = target4(i, x, y);
+                const float d0 = h.x - t.x, d1 = h.y - t.y, d2 = h.z - t.z, d3 = h.w - t.w;
+                r7[5] += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+            }
+        }
+    }
+    block_sum<7>(r7, scratch);
+    const float Z = r7[0], iZ = 1.f / Z;
+    const float cx = r7[1] * iZ, cy = r7[2] * iZ;
+    const float Ssum = r7[3], Rp = r7[4] + kEps;
+
+    // ---- fused decode (warp 0) ------------------------------------------------------------
+    if (decode && tid < 32) {
+        float dx_ = cx, dy_ = cy; int px, py;
+        refine_and_correct(A.hm + (size_t)tile * n, nullptr, A.off ? A.off + (size_t)tile * 2 * n : nullptr,
+                           A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, dx_, dy_, px, py);
+        if (tid == 0) { A.coords[2 * tile] = dx_; A.coords[2 * tile + 1] = dy_; A.scores[tile] = m; }
+    }
+
+    float* gh = grads ? A.grad_hm + (size_t)tile * n : nullptr;
+    float* gv = (grads && A.grad_var) ? A.grad_var + (size_t)tile * n : nullptr;
+    float* go = grads ? A.grad_off + (size_t)tile * 2 * n : nullptr;
+
+    if (!heavy) {
+        // weight 0: every term of this tile carries a factor w -> zero loss, zero gradient
+        if (tid == 0 && !backward_only) {
+            float4* p = reinterpret_cast<float4*>(A.partial + (size_t)tile * 8);
+            p[0] = make_float4(0.f, 0.f, 0.f, 0.f); p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (grads) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int it = 0; it < niter; ++it) {
+                const int i = it * TPB + tid;
+                if (NITER > 0 || i < n4) {
+                    stg_stream(reinterpret_cast<float4*>(gh) + i, z);
+                    if (gv) stg_stream(reinterpret_cast<float4*>(gv) + i, z);
+                    stg_stream(reinterpret_cast<float4*>(go) + i, z);
+                    stg_stream(reinterpret_cast<float4*>(go) + n4 + i, z);
+                }
+            }
+        }
+        return;
+    }
+
+    // thread 0 starts the 8 offset taps now; they are consumed after pass C
+    Taps tp;
+    float ov[2][4];
+    if (tid == 0) {
+        tp = taps_setup(cx, cy, H, W);
+        const float* o = A.off + (size_t)tile * 2 * n;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            ov[c][0] = __ldg(o + c * n + tp.i00); ov[c][1] = __ldg(o + c * n + tp.i01) * tp.okx;
+            ov[c][2] = __ldg(o + c * n + tp.i10) * tp.oky; ov[c][3] = __ldg(o + c * n + tp.i11) * (tp.okx * tp.oky);
+        }
+    }
+
+    // ---- pass C: entropy sums and spatial variance around (cx, cy) --------------------------
+    float r5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};       // A1 = sum p lg2(u), A2 = sum p^2/u, sum r e, sum r dx, sum r dy
+    for (int it = 0; it < niter; ++it) {
+        const int i = it * TPB + tid;
+        if (NITER > 0 || i < n4) {
+            const float4 h = Hs[i];
+            const int y = i / w4, x = (i - y * w4) << 2;
+            float ev[4];
+            if (CACHE >= 1) { const float4 e = Es[i]; ev[0] = e.x; ev[1] = e.y; ev[2] = e.z; ev[3] = e.w; }
+            else { ev[0] = ex2(fmaf(h.x, kLog2e, -ml)); ev[1] = ex2(fmaf(h.y, kLog2e, -ml));
+                   ev[2] = ex2(fmaf(h.z, kLog2e, -ml)); ev[3] = ex2(fmaf(h.w, kLog2e, -ml)); }
+            const float hv[4] = {h.x, h.y, h.z, h.w};
+            const float dy = (float)y - cy, dy2 = dy * dy;
+            float av[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float p = ev[j] * iZ, u = p + kEps;
+                const float l = lg2(u), rc = rcp(u);
+                r5[0] = fmaf(p, l, r5[0]);
+                const float prc = p * rc;
+                r5[1] = fmaf(p, prc, r5[1]);
+                av[j] = fmaf(-kLn2, l, -prc);
+                const float dx = (float)(x + j) - cx;
+                const float r = fmaxf(hv[j], 0.f);
+                r5[2] = fmaf(r, fmaf(dx, dx, dy2), r5[2]);
+                r5[3] = fmaf(r, dx, r5[3]);
+                r5[4] = fmaf(r, dy, r5[4]);
+            }
+            if (CACHE == 2) As[i] = make_float4(av[0], av[1], av[2], av[3]);
+        }
+    }
+    block_sum<5>(r5, scratch);
+
+    // ---- per-tile scalars (thread 0) -------------------------------------------------------
+    const float D = (float)A.sums[0] + kEps;
+    const float D5 = (float)A.sums[1] + kEps;
+    if (tid == 0) {
+        const float Da = P.use_target_weight ? D : (float)(P.B * P.K);
+        const float ka = wa / Da, kb = w / D;
+        const float gx = __ldg(A.gt + 2 * tile) * ((float)W / P.in_w);
+        const float gy = __ldg(A.gt + 2 * tile + 1) * ((float)H / P.in_h);
+        // offset term
+        float sl1 = 0.f, sl1p[2], dsdx[2], dsdy[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float samp = tp.w00 * ov[c][0] + tp.w01 * ov[c][1] + tp.w10 * ov[c][2] + tp.w11 * ov[c][3];
+            dsdx[c] = ((1.f - tp.fy) * (ov[c][1] - ov[c][0]) + tp.fy * (ov[c][3] - ov[c][2])) * tp.inx;
+            dsdy[c] = ((1.f - tp.fx) * (ov[c][2] - ov[c][0]) + tp.fx * (ov[c][3] - ov[c][1])) * tp.iny;
+            const float d = samp - ((c == 0 ? gx : gy) - (c == 0 ? cx : cy));
+            const float ad = fabsf(d);
+            sl1 += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+            sl1p[c] = ad < 1.f ? d : (d > 0.f ? 1.f : -1.f);
+        }
+        const float off_t = 0.5f * sl1;
+        const float peak_t = (cx - gx) * (cx - gx) + (cy - gy) * (cy - gy);
+        // variance term
+        const float v = r5[2] / Rp;
+        const float s = sqrtf(v + kEps);
+        const float mV = A.var ? r7[6] / (float)n : P.sigma;
+        const float var_t = (s - P.sigma) * (s - P.sigma) + (A.var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
+        // shape term
+        const float E = -kLn2 * r5[0];
+        const float pa = E - r5[1];
+        const float shape_t = (E - P.e_star) * (E - P.e_star);
+
+        if (!backward_only) {
+            float* p = A.partial + (size_t)tile * 8;
+            p[0] = wa * (r7[5] / (float)n); p[1] = wa * off_t; p[2] = wa * peak_t;
+            p[3] = w * var_t; p[5] = w * shape_t;      // p[4] (limb overlap) is written after the partner loop
+        }
+        TileCoef c;
+        c.c1 = lam[0] * ka * 2.f / (float)n;
+        const float a4 = lam[3] * kb * (s - P.sigma) / s;
+        c.c4 = a4 / Rp;
+        c.v = v;
+        c.c6 = lam[5] * kb * 2.f * (E - P.e_star);
+        c.pa = pa;
+        const float dv_dcx = -2.f * r5[3] / Rp, dv_dcy = -2.f * r5[4] / Rp;
+        c.fx = lam[2] * ka * 2.f * (cx - gx) + lam[1] * ka * 0.5f * (sl1p[0] * (dsdx[0] + 1.f) + sl1p[1] * dsdx[1]) + a4 * dv_dcx;
+        c.fy = lam[2] * ka * 2.f * (cy - gy) + lam[1] * ka * 0.5f * (sl1p[0] * dsdy[0] + sl1p[1] * (dsdy[1] + 1.f)) + a4 * dv_dcy;
+        c.gv = lam[3] * kb * 2.f * (mV - P.sigma) / (float)n;
+        c.go[0] = lam[1] * ka * 0.5f * sl1p[0];
+        c.go[1] = lam[1] * ka * 0.5f * sl1p[1];
+        coef_s = c;
+    }
+
+    // ---- limb partners: overlap mass, then the per-pixel tie pattern into Gs -----------------
+    float pair_loss = 0.f, cst = 0.f;
+    bool g_live = false;
+    const int np = P.n_partner[k];
+    for (int pi = 0; pi < np; ++pi) {
+        const int j = P.partner[k][pi];
+        const float wj = __ldg(A.weff + b * P.K + j);
+        if (w == 0.f || wj == 0.f) continue;                // CTA-uniform
+        const float4* hj4 = reinterpret_cast<const float4*>(A.hm) + ((size_t)b * P.K + j) * n4;
+        constexpr int R = NITER > 0 ? NITER : 1;
+        float4 hj[R];
+        float r2[2] = {0.f, 0.f};                            // S_j, M_kj
+        for (int it = 0; it < niter; ++it) {
+            const int i = it * TPB + tid;
+            if (NITER > 0 || i < n4) {
+                const float4 q = ldg_keep(hj4 + i);
+                if (NITER > 0) hj[it] = q;
+                const float4 h = Hs[i];
+                float4 sk;
+                if (CACHE == 2) sk = Ss[i];
+                else { sk.x = sigmoid_fast(h.x); sk.y = sigmoid_fast(h.y); sk.z = sigmoid_fast(h.z); sk.w = sigmoid_fast(h.w); }
+                const float s0 = sigmoid_fast(q.x), s1 = sigmoid_fast(q.y), s2 = sigmoid_fast(q.z), s3 = sigmoid_fast(q.w);
+                r2[0] += (s0 + s1) + (s2 + s3);
+                // min(sigma(a), sigma(b)) = sigma(min(a, b)): pick by comparing the logits
+                r2[1] += ((q.x < h.x ? s0 : sk.x) + (q.y < h.y ? s1 : sk.y)) + ((q.z < h.z ? s2 : sk.z) + (q.w < h.w ? s3 : sk.w));
+            }
+        }
+        block_sum<2>(r2, scratch);
+        const float Sj = r2[0], M = r2[1];
+        const float mm = fminf(Ssum, Sj) + kEps;
+        const float rho = M / mm;
+        if ((P.owner[k] >> pi) & 1) pair_loss += w * wj * fmaxf(rho - 0.5f, 0.f);
+        if (grads && rho > 0.5f) {
+            const float cj = lam[4] * w * wj / D5 / mm;
+            cst += cj * rho * tie_rule(Ssum, Sj);
+            for (int it = 0; it < niter; ++it) {
+                const int i = it * TPB + tid;
+                if (NITER > 0 || i < n4) {
+                    const float4 q = NITER > 0 ? hj[it] : ldg_keep(hj4 + i);
+                    const float4 h = Hs[i];
+                    float4 g = g_live ? Gs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    g.x = fmaf(cj, tie_rule(h.x, q.x), g.x); g.y = fmaf(cj, tie_rule(h.y, q.y), g.y);
+                    g.z = fmaf(cj, tie_rule(h.z, q.z), g.z); g.w = fmaf(cj, tie_rule(h.w, q.w), g.w);
+                    Gs[i] = g;
+                }
+            }
+            g_live = true;
+        }
+    }
+    if (tid == 0 && !backward_only) A.partial[(size_t)tile * 8 + 4] = pair_loss;
+    __syncthreads();            // coef_s visible (Gs is only read back by its own writer)
+    if (!grads) return;
+
+    // ---- pass D: gradient ----------------------------------------------------------------------
+    const TileCoef c = coef_s;
+    const float4 gv4 = make_float4(c.gv, c.gv, c.gv, c.gv);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < niter; ++it) {
+        const int i = it * TPB + tid;
+        if (NITER > 0 || i < n4) {
+            const float4 h = Hs[i];
+            const int y = i / w4, x = (i - y * w4) << 2;
+            const float hv[4] = {h.x, h.y, h.z, h.w};
+            float ev[4], av[4], sv[4], gl[4] = {0.f, 0.f, 0.f, 0.f};
+            if (CACHE >= 1) { const float4 e = Es[i]; ev[0] = e.x; ev[1] = e.y; ev[2] = e.z; ev[3] = e.w; }
+            else { for (int j = 0; j < 4; ++j) ev[j] = ex2(fmaf(hv[j], kLog2e, -ml)); }
+            if (CACHE == 2) { const float4 a = As[i]; av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w; }
+            if (g_live) {
+                const float4 g = Gs[i]; gl[0] = g.x; gl[1] = g.y; gl[2] = g.z; gl[3] = g.w;
+                if (CACHE == 2) { const float4 s = Ss[i]; sv[0] = s.x; sv[1] = s.y; sv[2] = s.z; sv[3] = s.w; }
+                else { for (int j = 0; j < 4; ++j) sv[j] = sigmoid_fast(hv[j]); }
+            }
+            const float4 t = target4(i, x, y);
+            const float tv[4] = {t.x, t.y, t.z, t.w};
+            const float dy = (float)y - cy, dy2 = dy * dy, fyd = dy * c.fy;
+            float out[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float p = ev[j] * iZ;
+                float a;
+                if (CACHE == 2) a = av[j];
+                else { const float u = p + kEps; a = fmaf(-kLn2, lg2(u), -p * rcp(u)); }
+                const float dx = (float)(x + j) - cx;
+                float g = c.c1 * (hv[j] - tv[j]);
+                g = fmaf(p, fmaf(c.c6, a - c.pa, fmaf(dx, c.fx, fyd)), g);
+                if (hv[j] > 0.f) g = fmaf(c.c4, fmaf(dx, dx, dy2) - c.v, g);
+                if (g_live) g = fmaf((gl[j] - cst) * sv[j], 1.f - sv[j], g);
+                out[j] = g;
+            }
+            stg_stream(reinterpret_cast<float4*>(gh) + i, make_float4(out[0], out[1], out[2], out[3]));
+            if (gv) stg_stream(reinterpret_cast<float4*>(gv) + i, gv4);
+            stg_stream(reinterpret_cast<float4*>(go) + i, z4);
+            stg_stream(reinterpret_cast<float4*>(go) + n4 + i, z4);
+        }
+    }
+    // the offset gradient is zero except on the (up to) four taps of each channel
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float* o = go + ch * n;
+            o[tp.i00] = c.go[ch] * tp.w00;
+            if (tp.okx != 0.f) o[tp.i01] = c.go[ch] * tp.w01;
+            if (tp.oky != 0.f) o[tp.i10] = c.go[ch] * tp.w10;
+            if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = c.go[ch] * tp.w11;
+        }
+    }
+}
+
+// ---- second stage: fixed-order sum of the per-tile numerators -----------------------------
+__global__ void __launch_bounds__(1024)
+finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ partial, const double* __restrict__ sums,
+                float* __restrict__ losses7) {
+    __shared__ double red[6][32];
+    const int tiles = P.B * P.K;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const float4 a = *reinterpret_cast<const float4*>(partial + (size_t)t * 8);
+        const float4 c = *reinterpret_cast<const float4*>(partial + (size_t)t * 8 + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += c.x; acc[5] += c.y;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) red[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float D = (float)sums[0] + kEps, D5 = (float)sums[1] + kEps;
+        const float Da = P.use_target_weight ? D : (float)tiles;
+        float total = 0.f;
+        for (int q = 0; q < 6; ++q) {
+            double s = 0.0;
+            for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) s += red[q][wp];
+            const float den = q < 3 ? Da : (q == 4 ? D5 : D);
+            const float v = P.lam[q] * ((float)s / den);
+            losses7[q] = v;
+            total += v;
+        }
+        losses7[6] = total;
+    }
+}
+
+// ---- backward for an arbitrary upstream gradient --------------------------------------------
+// plan: 0 = stored gradients already right, 1 = scale them by ratio, 2 = recompute with lam_eff
+__global__ void plan_kernel(const __grid_constant__ LossParams P, const float* __restrict__ g7,
+                            const float* __restrict__ assumed, int* __restrict__ plan, float* __restrict__ lam_eff) {
+    if (threadIdx.x != 0) return;
+    const float a = assumed ? *assumed : 1.f;
+    float r[6];
+    bool uniform = true;
+    for (int q = 0; q < 6; ++q) { r[q] = g7[6] + g7[q]; lam_eff[q] = P.lam[q] * r[q]; if (r[q] != r[0]) uniform = false; }
+    if (uniform && r[0] == a) plan[0] = 0;
+    else if (uniform && a != 0.f) { plan[0] = 1; lam_eff[6] = r[0] / a; }
+    else plan[0] = 2;
+}
+__global__ void __launch_bounds__(256)
+rescale_kernel(const int* __restrict__ plan, const float* __restrict__ lam_eff, float4* __restrict__ g, size_t n4) {
+    if (*plan != 1) return;
+    const float r = lam_eff[6];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = g[i];
+        v.x *= r; v.y *= r; v.z *= r; v.w *= r;
+        g[i] = v;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static int make_params(const gbcodec_loss_desc* d, LossParams* P) {
+    if (d->B <= 0 || d->K <= 0 || d->H <= 0 || d->W <= 0) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: B,K,H,W must be positive");
+    if (d->K > GBCODEC_MAX_K) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: K=%d exceeds %d", d->K, GBCODEC_MAX_K);
+    if (d->W % 4) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: W=%d is not a multiple of 4", d->W);
+    if ((long long)d->H * d->W > GBCODEC_MAX_TILE) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: tile %dx%d too large", d->H, d->W);
+    if (d->n_pairs < 0 || d->n_pairs > GBCODEC_MAX_PAIRS) return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: n_pairs=%d", d->n_pairs);
+    if (!(d->target_sigma > 0.0) || !(d->encode_sigma > 0.0)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: sigma must be positive");
+    memset(P, 0, sizeof(*P));
+    P->B = d->B; P->K = d->K; P->H = d->H; P->W = d->W; P->in_w = d->in_w; P->in_h = d->in_h;
+    for (int q = 0; q < 6; ++q) P->lam[q] = d->lambdas[q];
+    P->sigma = (float)d->target_sigma;
+    P->e_star = (float)log(2.0 * M_PI * M_E * d->target_sigma * d->target_sigma);
+    P->use_target_weight = d->use_target_weight;
+    P->ec = make_encode_const(d->encode_sigma);
+    int np = 0;
+    for (int p = 0; p < d->n_pairs; ++p) {
+        const int i = d->pairs[p][0], j = d->pairs[p][1];
+        if (i < 0 || j < 0) return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: negative channel in pair %d", p);
+        if (i >= d->K || j >= d->K) continue;                   // fusion_head.py:504-505
+        if (i == j) return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: pair %d joins channel %d with itself", p, i);
+        if (P->n_partner[i] >= GBCODEC_MAX_PARTNERS || P->n_partner[j] >= GBCODEC_MAX_PARTNERS)
+            return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: a channel takes part in more than %d pairs", GBCODEC_MAX_PARTNERS);
+        P->owner[i] |= (uint8_t)(1u << P->n_partner[i]);
+        P->partner[i][P->n_partner[i]++] = (int8_t)j;
+        P->partner[j][P->n_partner[j]++] = (int8_t)i;
+        P->pair_i[np] = (int16_t)i; P->pair_j[np] = (int16_t)j; ++np;
+    }
+    P->n_pairs = np;
+    return GBCODEC_OK;
+}
+
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+void set_profile_events(cudaEvent_t a, cudaEvent_t b) { g_prof_start = a; g_prof_stop = b; }
+
+template <int TPB, int NITER, int CACHE>
+static int launch_loss_t(const LossParams& P, const LossArgs& A, cudaStream_t s) {
+    const int n = P.H * P.W;
+    const size_t smem = (size_t)n * 4 * (2 + (CACHE >= 1 ? 1 : 0) + (CACHE == 2 ? 2 : 0))
+                      + (size_t)((P.ec.lut_size + 3) & ~3) * 4 + (8 * 32 + 8) * 4;
+    auto kern = loss_kernel<TPB, NITER, CACHE>;
+    if (smem > 227 * 1024) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: tile %dx%d needs %zu bytes of shared memory", P.H, P.W, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_kernel): %s", cudaGetErrorString(e));
+    if (g_prof_start && !A.plan) cudaEventRecord(g_prof_start, s);
+    kern<<<P.B * P.K, TPB, smem, s>>>(P, A);
+    if (g_prof_stop && !A.plan) cudaEventRecord(g_prof_stop, s);
+    return check_launch("loss_kernel");
+}
+
+static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s) {
+    const int n4 = (P.H * P.W) >> 2;
+    if (n4 == 256 * 3) return launch_loss_t<256, 3, 2>(P, A, s);           // 64x48
+    if (n4 == 576 * 3) return launch_loss_t<576, 3, 1>(P, A, s);           // 96x72
+    if (n4 == 1024 * 4) return launch_loss_t<1024, 4, 1>(P, A, s);         // 128x128
+    if ((size_t)n4 * 16 * 5 <= 160 * 1024) return launch_loss_t<256, 0, 2>(P, A, s);
+    if ((size_t)n4 * 16 * 3 <= 200 * 1024) return launch_loss_t<512, 0, 1>(P, A, s);
+    return launch_loss_t<1024, 0, 0>(P, A, s);
+}
+
+size_t loss_workspace_bytes(int B, int K) { return ws_bytes(B, K) + 64; }
+
+static int check_common(const gbcodec_loss_desc* d, const float* hm, const float* off, const float* weight,
+                        const float* gt, void* ws, size_t ws_size) {
+    if (!d || !hm || !off || !weight || !gt) return fail(GBCODEC_ERR_NULL_POINTER, "loss: a required pointer is NULL");
+    if (!ws || ws_size < loss_workspace_bytes(d->B, d->K))
+        return fail(GBCODEC_ERR_WORKSPACE, "loss: workspace of %zu bytes needed, %zu given", loss_workspace_bytes(d->B, d->K), ws ? ws_size : (size_t)0);
+    if (!aligned16(hm) || !aligned16(off) || !aligned16(ws)) return fail(GBCODEC_ERR_UNALIGNED, "loss: tensors must be 16-byte aligned");
+    return GBCODEC_OK;
+}
+
+static int prepare_weights(const LossParams& P, const WsLayout& L, const float* weight, const float* gt,
+                           int target_given, const float* denoms, cudaStream_t s) {
+    if (denoms) {
+        weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff);
+        sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums);
+    } else {
+        cudaError_t e = cudaMemsetAsync(L.sums, 0, 2 * sizeof(double), s);
+        if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        const int grid = (P.B + 255) / 256 < 148 ? (P.B + 255) / 256 : 148;
+        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.sums);
+    }
+    return check_launch("denoms_kernel");
+}
+
+int loss_denominators(const gbcodec_loss_desc* d, const float* weight, const float* gt, int target_given,
+                      float* out2, void* ws, size_t ws_size, cudaStream_t s) {
+    LossParams P;
+    int st = make_params(d, &P);
+    if (st) return st;
+    if (!weight || !out2 || (!target_given && !gt)) return fail(GBCODEC_ERR_NULL_POINTER, "denominators: NULL pointer");
+    if (!ws || ws_size < loss_workspace_bytes(d->B, d->K) || !aligned16(ws))
+        return fail(GBCODEC_ERR_WORKSPACE, "denominators: workspace of %zu bytes needed", loss_workspace_bytes(d->B, d->K));
+    const WsLayout L = ws_carve(ws, P.B, P.K);
+    st = prepare_weights(P, L, weight, gt, target_given, nullptr, s);
+    if (st) return st;
+    sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, out2);
+    return check_launch("sums_to_float_kernel");
+}
+
+int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, const float* var, const float* target,
+                const float* weight, const float* gt, const float* denoms, const float* grad_scale,
+                float* losses7, float* ghm, float* goff, float* gvar,
+                const float* alpha_param, const float* fusion_weight, int radius, unsigned dflags, float* coords, float* scores,
+                void* ws, size_t ws_size, cudaStream_t s) {
+    int st = check_common(d, hm, off, weight, gt, ws, ws_size);
+    if (st) return st;
+    if (!losses7) return fail(GBCODEC_ERR_NULL_POINTER, "loss: d_losses7 is NULL");
+    const bool grads = ghm || goff || gvar;
+    if (grads && (!ghm || !goff || (!gvar) != (!var))) return fail(GBCODEC_ERR_NULL_POINTER, "loss: give all gradient pointers or none (d_grad_var iff d_var)");
+    if ((var && !aligned16(var)) || (target && !aligned16(target)) || (ghm && !aligned16(ghm)) || (goff && !aligned16(goff)) || (gvar && !aligned16(gvar)))
+        return fail(GBCODEC_ERR_UNALIGNED, "loss: tensors must be 16-byte aligned");
+    if (coords) {
+        if (!scores) return fail(GBCODEC_ERR_NULL_POINTER, "step: d_scores is NULL");
+        if ((dflags & GBCODEC_DECODE_REFINE) && !alpha_param) return fail(GBCODEC_ERR_NULL_POINTER, "step: d_alpha_param is NULL");
+        if ((dflags & GBCODEC_DECODE_APPLY_OFFSET) && !fusion_weight) return fail(GBCODEC_ERR_NULL_POINTER, "step: d_fusion_weight is NULL");
+        if (radius < 0 || radius > 8) return fail(GBCODEC_ERR_BAD_ARGUMENT, "step: local_radius=%d", radius);
+    }
+    LossParams P;
+    st = make_params(d, &P);
+    if (st) return st;
+    const WsLayout L = ws_carve(ws, P.B, P.K);
+    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
+    if (st) return st;
+    LossArgs A;
+    memset(&A, 0, sizeof(A));
+    A.hm = hm; A.off = off; A.var = var; A.target = target; A.weight = weight; A.gt = gt; A.grad_scale = grad_scale;
+    A.grad_hm = ghm; A.grad_off = goff; A.grad_var = gvar;
+    A.alpha_param = alpha_param; A.fusion_weight = fusion_weight; A.coords = coords; A.scores = scores;
+    A.radius = radius; A.dflags = dflags;
+    A.sums = L.sums; A.weff = L.weff; A.partial = L.partial;
+    st = launch_loss_kernel(P, A, s);
+    if (st) return st;
+    finalize_kernel<<<1, 1024, 0, s>>>(P, L.partial, L.sums, losses7);
+    return check_launch("finalize_kernel");
+}
+
+int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const float* off, const float* var, const float* target,
+                         const float* weight, const float* gt, const float* denoms, const float* grad_scale, const float* g7,
+                         float* ghm, float* goff, float* gvar, void* ws, size_t ws_size, cudaStream_t s) {
+    int st = check_common(d, hm, off, weight, gt, ws, ws_size);
+    if (st) return st;
+    if (!g7 || !ghm || !goff || (!gvar) != (!var)) return fail(GBCODEC_ERR_NULL_POINTER, "backward: NULL pointer");
+    LossParams P;
+    st = make_params(d, &P);
+    if (st) return st;
+    const WsLayout L = ws_carve(ws, P.B, P.K);
+    // the workspace still holds weff and the sums of the forward only if the caller kept it; recompute, it is cheap
+    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
+    if (st) return st;
+    plan_kernel<<<1, 32, 0, s>>>(P, g7, grad_scale, L.plan, L.lam_eff);
+    const size_t n4 = (size_t)P.B * P.K * P.H * P.W / 4;
+    const int grid = 148 * 8;
+    rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4);
+    rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(goff), 2 * n4);
+    if (gvar) rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(gvar), n4);
+    LossArgs A;
+    memset(&A, 0, sizeof(A));
+    A.hm = hm; A.off = off; A.var = var; A.target = target; A.weight = weight; A.gt = gt;
+    A.grad_hm = ghm; A.grad_off = goff; A.grad_var = gvar;
+    A.sums = L.sums; A.weff = L.weff; A.partial = L.partial; A.lam_eff = L.lam_eff; A.plan = L.plan;
+    return launch_loss_kernel(P, A, s);
+}
+
+}  // namespace gbc

@@ -1,0 +1,284 @@
+"""torch.library custom ops `gbcodec::*` over the C ABI of libgbcodec.so.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every op
+passes raw device pointers and `torch.cuda.current_stream()` to the library.
+All ops require CUDA tensors and raise otherwise — there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as N
+
+_NS = "gbcodec"
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else N._P(t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return N._P(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _cuda_f32(name: str, t: Tensor, shape: Optional[Sequence[int]] = None) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"gbcodec: `{name}` must be a CUDA tensor (this library has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"gbcodec: `{name}` must be float32, got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"gbcodec: `{name}` has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t.contiguous()
+
+
+def _scalar(name: str, t: Optional[Tensor], like: Tensor) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.numel() != 1:
+        raise RuntimeError(f"gbcodec: `{name}` must hold one element")
+    return t.detach().to(device=like.device, dtype=torch.float32).reshape(1).contiguous()
+
+
+# --------------------------------------------------------------------------- encode
+@torch.library.custom_op(f"{_NS}::encode", mutates_args=())
+def encode(kps: Tensor, vis: Tensor, H: int, W: int, in_w: float, in_h: float, sigma: float) -> Tuple[Tensor, Tensor]:
+    B, K = kps.shape[0], kps.shape[1]
+    kps = _cuda_f32("keypoints", kps, (B, K, 2))
+    vis = _cuda_f32("visible", vis.reshape(B, K), (B, K))
+    target = torch.empty((B, K, H, W), dtype=torch.float32, device=kps.device)
+    weight = torch.empty((B, K, 1), dtype=torch.float32, device=kps.device)
+    with torch.cuda.device(kps.device):
+        N.check(N.lib().gbcodec_encode_f32(_ptr(kps), _ptr(vis), _ptr(target), _ptr(weight), B, K, H, W,
+                                           in_w, in_h, sigma, _stream(kps)), "encode")
+    return target, weight
+
+
+@encode.register_fake
+def _(kps, vis, H, W, in_w, in_h, sigma):
+    B, K = kps.shape[0], kps.shape[1]
+    return kps.new_empty((B, K, H, W)), kps.new_empty((B, K, 1))
+
+
+# --------------------------------------------------------------------------- decode
+@torch.library.custom_op(f"{_NS}::decode", mutates_args=())
+def decode(hm: Tensor, hm_flipped: Optional[Tensor], flip_perm: Optional[Tensor], off: Optional[Tensor],
+           alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int, flags: int
+           ) -> Tuple[Tensor, Tensor, Tensor]:
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    if hm_flipped is not None:
+        hm_flipped = _cuda_f32("heatmaps_flipped", hm_flipped, (B, K, H, W))
+    if flip_perm is not None:
+        flip_perm = flip_perm.to(device=hm.device, dtype=torch.int32).contiguous()
+        if flip_perm.numel() != K:
+            raise RuntimeError("gbcodec: flip_perm must hold K entries")
+    if off is not None:
+        off = _cuda_f32("offsets", off, (B, K, 2, H, W))
+    alpha_param = _scalar("alpha", alpha_param, hm)
+    fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
+    coords = torch.empty((B, K, 2), dtype=torch.float32, device=hm.device)
+    scores = torch.empty((B, K), dtype=torch.float32, device=hm.device)
+    centre = torch.empty((B, K, 2), dtype=torch.int32, device=hm.device)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().gbcodec_decode_f32(_ptr(hm), _ptr(hm_flipped), _ptr(flip_perm), _ptr(off), _ptr(alpha_param),
+                                           _ptr(fusion_weight), B, K, H, W, radius, flags,
+                                           _ptr(coords), _ptr(scores), _ptr(centre), _stream(hm)), "decode")
+    return coords, scores, centre
+
+
+@decode.register_fake
+def _(hm, hm_flipped, flip_perm, off, alpha_param, fusion_weight, radius, flags):
+    B, K = hm.shape[0], hm.shape[1]
+    return hm.new_empty((B, K, 2)), hm.new_empty((B, K)), hm.new_empty((B, K, 2), dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{_NS}::decode_argmax", mutates_args=())
+def decode_argmax(hm: Tensor, mode: int) -> Tuple[Tensor, Tensor, Tensor]:
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    coords = torch.empty((B, K, 2), dtype=torch.float32, device=hm.device)
+    maxvals = torch.empty((B, K), dtype=torch.float32, device=hm.device)
+    index = torch.empty((B, K), dtype=torch.int32, device=hm.device)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().gbcodec_decode_argmax_f32(_ptr(hm), B, K, H, W, mode, _ptr(coords), _ptr(maxvals),
+                                                  _ptr(index), _stream(hm)), "decode_argmax")
+    return coords, maxvals, index
+
+
+@decode_argmax.register_fake
+def _(hm, mode):
+    B, K = hm.shape[0], hm.shape[1]
+    return hm.new_empty((B, K, 2)), hm.new_empty((B, K)), hm.new_empty((B, K), dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{_NS}::refine_centroid", mutates_args=())
+def refine_centroid(hm: Tensor, coords: Tensor, window: int) -> Tensor:
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    coords = _cuda_f32("coords", coords, (B, K, 2))
+    out = torch.empty_like(coords)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().gbcodec_refine_centroid_f32(_ptr(hm), _ptr(coords), B, K, H, W, window, _ptr(out), _stream(hm)),
+                "refine_centroid")
+    return out
+
+
+@refine_centroid.register_fake
+def _(hm, coords, window):
+    return torch.empty_like(coords)
+
+
+# --------------------------------------------------------------------------- loss
+def _desc(hm: Tensor, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs_flat):
+    B, K, H, W = hm.shape
+    pairs = [(int(pairs_flat[i]), int(pairs_flat[i + 1])) for i in range(0, len(pairs_flat), 2)]
+    return N.make_loss_desc(B, K, H, W, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs)
+
+
+def _workspace(hm: Tensor) -> Tensor:
+    B, K, H, W = hm.shape
+    nbytes = N.lib().gbcodec_loss_workspace_bytes(B, K, H, W)
+    return torch.empty(nbytes, dtype=torch.uint8, device=hm.device)
+
+
+@torch.library.custom_op(f"{_NS}::loss_denominators", mutates_args=())
+def loss_denominators(weight: Tensor, gt_kps: Tensor, target_given: bool, H: int, W: int, in_w: float, in_h: float,
+                      encode_sigma: float, pairs: List[int]) -> Tensor:
+    B, K = gt_kps.shape[0], gt_kps.shape[1]
+    weight = _cuda_f32("target_weight", weight.reshape(B, K))
+    gt_kps = _cuda_f32("gt_keypoints", gt_kps, (B, K, 2))
+    prs = [(int(pairs[i]), int(pairs[i + 1])) for i in range(0, len(pairs), 2)]
+    desc = N.make_loss_desc(B, K, H, W, in_w, in_h, [0.0] * 6, encode_sigma, encode_sigma, True, prs)
+    out = torch.empty(2, dtype=torch.float32, device=weight.device)
+    nbytes = N.lib().gbcodec_loss_workspace_bytes(B, K, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        N.check(N.lib().gbcodec_loss_denominators_f32(desc, _ptr(weight), _ptr(gt_kps), int(target_given), _ptr(out),
+                                                      _ptr(ws), nbytes, _stream(weight)), "loss_denominators")
+    return out
+
+
+@loss_denominators.register_fake
+def _(weight, gt_kps, target_given, H, W, in_w, in_h, encode_sigma, pairs):
+    return weight.new_empty(2)
+
+
+@torch.library.custom_op(f"{_NS}::fusion_loss", mutates_args=())
+def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor], weight: Tensor, gt_kps: Tensor,
+                denoms: Optional[Tensor], grad_scale: Optional[Tensor],
+                in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
+                use_target_weight: bool, pairs: List[int], with_grads: bool,
+                with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
+                decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> losses7, grad_hm, grad_off, grad_var, coords, scores (empty tensors for what was not asked)."""
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    off = _cuda_f32("offsets", off, (B, K, 2, H, W))
+    if var is not None:
+        var = _cuda_f32("variances", var, (B, K, H, W))
+    if target is not None:
+        target = _cuda_f32("target_heatmaps", target, (B, K, H, W))
+    weight = _cuda_f32("target_weight", weight.reshape(B, K), (B, K))
+    gt_kps = _cuda_f32("gt_keypoints", gt_kps, (B, K, 2))
+    if denoms is not None:
+        denoms = _cuda_f32("denominators", denoms.reshape(2), (2,))
+    grad_scale = _scalar("grad_scale", grad_scale, hm)
+    dev = hm.device
+    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+    losses = torch.empty(7, dtype=torch.float32, device=dev)
+    empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+    if with_grads:
+        ghm, goff = torch.empty_like(hm), torch.empty_like(off)
+        gvar = torch.empty_like(var) if var is not None else empty()
+    else:
+        ghm, goff, gvar = empty(), empty(), empty()
+    ws = _workspace(hm)
+    L = N.lib()
+    common = (desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(grad_scale),
+              _ptr(losses), _ptr(ghm) if with_grads else None, _ptr(goff) if with_grads else None,
+              _ptr(gvar) if (with_grads and var is not None) else None)
+    with torch.cuda.device(dev):
+        if with_decode:
+            coords = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+            scores = torch.empty((B, K), dtype=torch.float32, device=dev)
+            alpha_param = _scalar("alpha", alpha_param, hm)
+            fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
+            N.check(L.gbcodec_fusion_step_f32(*common, _ptr(alpha_param), _ptr(fusion_weight), radius, decode_flags,
+                                              _ptr(coords), _ptr(scores), _ptr(ws), ws.numel(), _stream(hm)), "fusion_step")
+        else:
+            coords, scores = empty(), empty()
+            N.check(L.gbcodec_fusion_loss_f32(*common, _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss")
+    return losses, ghm, goff, gvar, coords, scores
+
+
+@fusion_loss.register_fake
+def _(hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
+      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags):
+    B, K = hm.shape[0], hm.shape[1]
+    e = lambda: hm.new_empty(0)
+    return (hm.new_empty(7),
+            torch.empty_like(hm) if with_grads else e(), torch.empty_like(off) if with_grads else e(),
+            torch.empty_like(var) if (with_grads and var is not None) else e(),
+            hm.new_empty((B, K, 2)) if with_decode else e(), hm.new_empty((B, K)) if with_decode else e())
+
+
+@torch.library.custom_op(f"{_NS}::fusion_loss_backward", mutates_args=("grad_hm", "grad_off", "grad_var"))
+def fusion_loss_backward(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor, grad_var: Optional[Tensor],
+                         hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor], weight: Tensor,
+                         gt_kps: Tensor, denoms: Optional[Tensor], grad_scale: Optional[Tensor],
+                         in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
+                         use_target_weight: bool, pairs: List[int]) -> None:
+    B, K, H, W = hm.shape
+    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+    g7 = _cuda_f32("grad_losses", grad_losses.reshape(7), (7,))
+    weight = weight.reshape(B, K)
+    ws = _workspace(hm)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().gbcodec_fusion_loss_backward_f32(
+            desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(grad_scale),
+            _ptr(g7), _ptr(grad_hm), _ptr(grad_off), _ptr(grad_var), _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward")
+
+
+def _loss_setup_context(ctx, inputs, output):
+    (hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
+     utw, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags) = inputs
+    losses, ghm, goff, gvar, coords, scores = output
+    ctx.with_grads = with_grads
+    ctx.has_var = var is not None
+    # Plain attributes, not save_for_backward: the backward adjusts the stored gradients in place.
+    ctx.stash = (ghm, goff, gvar if var is not None else None)
+    ctx.tensors = tuple(None if t is None else t.detach() for t in (hm, off, var, target, weight, gt_kps, denoms, grad_scale))
+    ctx.scalars = (in_w, in_h, list(lambdas), target_sigma, encode_sigma, utw, list(pairs))
+    ctx.set_materialize_grads(False)
+
+
+def _loss_backward(ctx, g_losses, g_ghm, g_goff, g_gvar, g_coords, g_scores):
+    n_in = 21
+    none = [None] * n_in
+    if g_losses is None:
+        return tuple(none)
+    if not ctx.with_grads:
+        raise RuntimeError("gbcodec::fusion_loss was run with with_grads=False; its output is not differentiable")
+    ghm, goff, gvar = ctx.stash
+    hm, off, var, target, weight, gt_kps, denoms, grad_scale = ctx.tensors
+    B, K = hm.shape[0], hm.shape[1]
+    contig = lambda t: None if t is None else t.contiguous()
+    torch.ops.gbcodec.fusion_loss_backward(
+        g_losses.contiguous(), ghm, goff, gvar, contig(hm), contig(off), contig(var), contig(target),
+        weight.reshape(B, K).contiguous(), contig(gt_kps), denoms, grad_scale, *ctx.scalars)
+    none[0], none[1] = ghm, goff
+    none[2] = gvar
+    return tuple(none)
+
+
+fusion_loss.register_autograd(_loss_backward, setup_context=_loss_setup_context)
+
+
+def pairs_flat(pairs: Sequence[Tuple[int, int]]) -> List[int]:
+    out: List[int] = []
+    for a, b in pairs:
+        out += [int(a), int(b)]
+    return out

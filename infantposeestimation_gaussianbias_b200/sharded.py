@@ -1,0 +1,79 @@
+"""Batch-sharded six-term loss: one process per GPU, each rank holds B/R whole
+images (so every limb pair stays on one rank).  The data path needs no
+collective; the loss needs two tiny ones:
+
+  1. before the kernel: all-reduce(sum) of [sum w, sum w_i*w_j] — the batch-global
+     normalisers every term divides by (fusion_head.py:480,527,557,653,708,739);
+  2. after it: all-reduce(sum) of the 7 local loss scalars (already divided by the
+     global normalisers), for reporting.
+
+With the global normalisers the local gradients ARE the global-batch gradients
+restricted to the shard, so nothing else is exchanged.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .fusion_head import LOSS_KEYS, FusionPoseLoss
+
+
+def _default_denominators(loss: FusionPoseLoss, weight, gt_keypoints, target_given, H, W, input_size):
+    from . import ops
+    K = gt_keypoints.shape[1]
+    sigma_enc = float(loss.encode_sigma if loss.encode_sigma is not None else loss.target_sigma)
+    return ops.loss_denominators(weight.float(), gt_keypoints.float(), bool(target_given), H, W,
+                                 float(input_size[0]), float(input_size[1]), sigma_enc,
+                                 ops.pairs_flat(loss.pairs_for(K)))
+
+
+class ShardedFusionPoseLoss(FusionPoseLoss):
+    """FusionPoseLoss for a rank that holds a shard of the global batch.
+
+    `local_denominators` and `local_loss` exist so that the host-side logic can be
+    exercised on CPU (gloo) with a stand-in for the CUDA ops; the defaults are the
+    gbcodec ops."""
+
+    def __init__(self, *args, process_group=None,
+                 local_denominators: Optional[Callable] = None, local_loss: Optional[Callable] = None, **kw):
+        super().__init__(*args, **kw)
+        self.process_group = process_group
+        self._local_denominators = local_denominators
+        self._local_loss = local_loss
+
+    def global_denominators(self, target_heatmaps, target_weight, gt_keypoints, heatmap_hw, input_size) -> Tensor:
+        H, W = heatmap_hw
+        given = target_heatmaps is not None and target_heatmaps.numel() > 0
+        fn = self._local_denominators or (lambda *a: _default_denominators(self, *a))
+        den = fn(target_weight, gt_keypoints, given, H, W, input_size).clone()
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.process_group)
+        return den
+
+    def forward(self, outputs: Dict[str, Tensor], target_heatmaps, target_weight, gt_keypoints,
+                input_size: Tuple[int, int] = (192, 256), heatmap_size: Tuple[int, int] = (48, 64), **kw):
+        H, W = outputs["heatmaps"].shape[-2:]
+        den = self.global_denominators(target_heatmaps, target_weight, gt_keypoints, (H, W), input_size)
+        if self._local_loss is not None:
+            local = self._local_loss(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, den)
+        else:
+            local = super().forward(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, heatmap_size,
+                                    denominators=den, **kw)
+        stacked = torch.stack([local[k].detach() for k in LOSS_KEYS])
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(stacked, op=dist.ReduceOp.SUM, group=self.process_group)
+        out = dict(local)
+        for i, k in enumerate(LOSS_KEYS):
+            # value = global loss; gradient = this rank's share of it
+            out[k] = local[k] + (stacked[i] - local[k].detach())
+        return out
+
+
+def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of B images over `world` ranks; the first B % world ranks get one more."""
+    base, extra = divmod(B, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)

@@ -1,0 +1,296 @@
+"""GPU parity: the CUDA path (through torch ops -> ctypes -> the C ABI of
+libgbcodec.so) against the CPU oracle and against the golden vectors produced by
+the reference itself.  Tolerances are BASELINE.json's:
+
+  integer peak indices        bit-exact
+  encoded heatmaps            1e-6 relative (fp32)
+  loss values and gradients   1e-5 relative
+  decoded coordinates         1e-4 px
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import heatmap_codec as oc
+from tests import goldens, synth
+
+pytestmark = pytest.mark.gpu
+
+NAMES = list(synth.CONFIGS)
+ENC_RTOL, LOSS_RTOL, COORD_ATOL = 1e-6, 1e-5, 1e-4
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import infantposeestimation_gaussianbias_b200 as pkg
+    pkg.load()           # raises if libgbcodec.so is missing: no fallback
+    from infantposeestimation_gaussianbias_b200 import ops
+    return ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def grad_close(got, want, rel=LOSS_RTOL, what=""):
+    """max-norm relative error: |got - want|_inf <= rel * |want|_inf."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = np.abs(want).max()
+    err = np.abs(got - want).max()
+    assert err <= rel * scale + 1e-30, f"{what}: max err {err:.3e} vs scale {scale:.3e} (ratio {err / max(scale, 1e-300):.2e})"
+
+
+def half_integer_free(coords, eps=1e-3):
+    """Tiles whose soft-argmax is within eps of a .5 boundary are excluded from the
+    window-centre comparison (fp32 summation order decides the rounding)."""
+    frac = np.abs(coords - np.floor(coords) - 0.5)
+    return (frac > eps).all(axis=-1)
+
+
+# ------------------------------------------------------------------ encode
+@pytest.mark.parametrize("name", NAMES)
+def test_encode(gb, name):
+    cfg, batch, g = goldens.load(name)
+    for kps, vis, want_t, want_w in ((batch["kps"], batch["vis"], g["target"], g["enc_weight"]),
+                                     (g["edge_kps"], g["edge_vis"], g["edge_target"], g["edge_weight"])):
+        target, weight = gb.encode(dev(kps), dev(vis), cfg.H, cfg.W, float(cfg.input_size[0]), float(cfg.input_size[1]), cfg.sigma)
+        target, weight = target.cpu().numpy(), weight.cpu().numpy()
+        assert np.array_equal(weight, want_w)
+        assert np.array_equal(target != 0, want_t != 0), "support of the pasted patch differs"
+        np.testing.assert_allclose(target, want_t, rtol=ENC_RTOL, atol=0)
+
+
+def test_encode_large_batch_properties(gb):
+    # BASELINE configs[1] size: peak value 1 at the integer pixel, tile sum bounded, weights follow the rule
+    cfg = synth.CONFIGS["w32_256x192"]
+    rng = np.random.default_rng(7)
+    kps, vis = synth.make_keypoints(cfg, rng, 1024)
+    target, weight = gb.encode(dev(kps), dev(vis), cfg.H, cfg.W, 192.0, 256.0, 2.0)
+    ot, ow = oc.encode_targets(kps, vis, cfg.heatmap_size, cfg.input_size, 2.0)
+    assert np.array_equal(weight.cpu().numpy(), ow)
+    np.testing.assert_allclose(target.cpu().numpy(), ot, rtol=ENC_RTOL, atol=0)
+
+
+# ------------------------------------------------------------------ argmax family
+@pytest.mark.parametrize("name", NAMES)
+def test_decode_heatmaps_bit_exact(gb, name):
+    cfg, batch, g = goldens.load(name)
+    hm = dev(batch["heatmaps"])
+    c, v, idx = gb.decode_argmax(hm, 1)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), g["argmax_idx"])
+    assert np.array_equal(v.cpu().numpy(), g["argmax_vals"])
+    assert np.array_equal(c.cpu().numpy(), g["argmax_coords"])
+    c0, _, _ = gb.decode_argmax(hm, 0)
+    oc0, _, _ = oc.decode_heatmaps(t(batch["heatmaps"]), shift=False)
+    assert np.array_equal(c0.cpu().numpy(), oc0.numpy())
+
+
+def test_argmax_ties_and_borders(gb):
+    h = torch.zeros(2, 3, 8, 12)
+    h[0, 1, 2, 3] = 1.0; h[0, 1, 5, 1] = 1.0          # duplicate maximum: the first wins
+    h[0, 2, 0, 5] = 2.0                                # border row: no shift
+    h[1, 0, 4, 11] = 2.0                               # border column
+    h[1, 1, 3, 4] = 1.0; h[1, 1, 3, 5] = 0.5; h[1, 1, 2, 4] = 0.25
+    c, v, idx = gb.decode_argmax(h.cuda(), 1)
+    oc_c, oc_v, oc_i = oc.decode_heatmaps(h, shift=True)
+    assert np.array_equal(idx.cpu().numpy(), oc_i.numpy())
+    assert np.array_equal(c.cpu().numpy(), oc_c.numpy())
+    assert idx[0, 0].item() == 0 and idx[0, 1].item() == 2 * 12 + 3
+
+
+# ------------------------------------------------------------------ decode
+@pytest.mark.parametrize("name", NAMES)
+def test_decode_against_golden(gb, name):
+    cfg, batch, g = goldens.load(name)
+    hm, off = dev(batch["heatmaps"]), dev(batch["offsets"])
+    alpha = torch.tensor(float(g["alpha_param"])).cuda()
+    fw = torch.tensor(float(g["fusion_weight"])).cuda()
+    ok = half_integer_free(g["dec_softargmax"])
+    c, s, centre = gb.decode(hm, None, None, off, alpha, fw, 2, 3)
+    assert np.array_equal(s.cpu().numpy(), g["dec_scores"])
+    assert np.abs(c.cpu().numpy() - g["dec_coords"])[ok].max() <= COORD_ATOL
+    want_centre = oc.window_centres(t(g["dec_softargmax"]), cfg.H, cfg.W).numpy()
+    assert np.array_equal(centre.cpu().numpy()[ok], want_centre[ok])
+    c, _, _ = gb.decode(hm, None, None, None, alpha, None, 2, 1)
+    assert np.abs(c.cpu().numpy() - g["dec_coords_nooff"])[ok].max() <= COORD_ATOL
+    c, _, _ = gb.decode(hm, None, None, None, None, None, 0, 0)
+    assert np.abs(c.cpu().numpy() - g["dec_softargmax"]).max() <= COORD_ATOL
+    # flip test
+    cf, sf, _ = gb.decode(hm, dev(batch["heatmaps_flip"]), dev(batch["flip_perm"]), off, alpha, fw, 2, 3)
+    avg = oc.flip_average(t(batch["heatmaps"]), t(batch["heatmaps_flip"]),
+                          [p for p in oc.COCO_FLIP_PAIRS if p[0] < cfg.K and p[1] < cfg.K])
+    okf = half_integer_free(oc.soft_argmax(avg)[0].numpy())
+    assert np.array_equal(sf.cpu().numpy(), g["flip_scores"])
+    assert np.abs(cf.cpu().numpy() - g["flip_coords"])[okf].max() <= COORD_ATOL
+
+
+def test_decode_larger_batch_vs_oracle(gb):
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=3, B=64)
+    hm, off = t(batch["heatmaps"]), t(batch["offsets"])
+    want_c, want_s = oc.fusion_decode(hm, off, 0.5, 0.6224593312018546)
+    ok = half_integer_free(oc.soft_argmax(hm)[0].numpy())
+    c, s, _ = gb.decode(hm.cuda(), None, None, off.cuda(), torch.tensor(0.5).cuda(), torch.tensor(0.6224593312018546).cuda(), 2, 3)
+    assert np.array_equal(s.cpu().numpy(), want_s.numpy())
+    assert np.abs(c.cpu().numpy() - want_c.numpy())[ok].max() <= COORD_ATOL
+    assert ok.mean() > 0.98
+
+
+# ------------------------------------------------------------------ loss
+def run_loss(gb, cfg, batch, *, on_the_fly, with_grads=True, utw=True, denoms=None, grad_scale=None, decode=False,
+             lambdas=oc.DEFAULT_LAMBDAS):
+    pairs = [v for p in oc.skeleton_for(cfg.K) for v in p]
+    return gb.fusion_loss(
+        dev(batch["heatmaps"]), dev(batch["offsets"]), dev(batch["variances"]),
+        None if on_the_fly else dev(batch["target"]),
+        dev(batch["weight"] if not on_the_fly else batch["vis"][..., None]), dev(batch["kps"]),
+        denoms, grad_scale, float(cfg.input_size[0]), float(cfg.input_size[1]), list(lambdas),
+        cfg.sigma, cfg.sigma, utw, pairs, with_grads, decode,
+        torch.tensor(0.5).cuda() if decode else None, torch.tensor(0.6224593312018546).cuda() if decode else None, 2, 3)
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("on_the_fly", [False, True])
+def test_loss_and_grads_against_golden(gb, name, on_the_fly):
+    cfg, batch, g = goldens.load(name)
+    losses, ghm, goff, gvar, _, _ = run_loss(gb, cfg, batch, on_the_fly=on_the_fly)
+    np.testing.assert_allclose(losses.cpu().numpy(), g["loss_f32"], rtol=LOSS_RTOL, atol=1e-9)
+    np.testing.assert_allclose(losses.cpu().numpy(), g["loss_f64"], rtol=LOSS_RTOL, atol=1e-9)
+    grad_close(ghm.cpu().numpy(), g["grad_hm"], what="grad heatmaps")
+    go = goff.cpu().numpy()
+    assert np.array_equal(go != 0, g["grad_off"] != 0)
+    grad_close(go, g["grad_off"], what="grad offsets")
+    gv = gvar.cpu().numpy()
+    grad_close(gv, np.broadcast_to(g["grad_var_tile"][:, :, None, None], gv.shape), what="grad variances")
+
+
+@pytest.mark.parametrize("utw", [True, False])
+def test_loss_vs_oracle_batch64(gb, utw):
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=11, B=64)
+    want_l, want_g = oc.fusion_loss_and_grads(t(batch["heatmaps"]), t(batch["offsets"]), t(batch["variances"]),
+                                              t(batch["target"]), t(batch["weight"]), t(batch["kps"]),
+                                              input_size=cfg.input_size, use_target_weight=utw)
+    losses, ghm, goff, gvar, _, _ = run_loss(gb, cfg, batch, on_the_fly=True, utw=utw)
+    got = losses.cpu().numpy()
+    want = np.array([float(want_l[k]) for k in oc.LOSS_KEYS])
+    np.testing.assert_allclose(got, want, rtol=LOSS_RTOL, atol=1e-9)
+    grad_close(ghm.cpu().numpy(), want_g["heatmaps"].numpy(), what="grad heatmaps")
+    grad_close(goff.cpu().numpy(), want_g["offsets"].numpy(), what="grad offsets")
+    grad_close(gvar.cpu().numpy(), want_g["variances"].numpy(), what="grad variances")
+
+
+def test_loss_forward_only_and_step(gb):
+    cfg, batch, g = goldens.load("w32_256x192")
+    losses, ghm, goff, gvar, _, _ = run_loss(gb, cfg, batch, on_the_fly=True, with_grads=False)
+    assert ghm.numel() == 0 and goff.numel() == 0 and gvar.numel() == 0
+    np.testing.assert_allclose(losses.cpu().numpy(), g["loss_f32"], rtol=LOSS_RTOL, atol=1e-9)
+    # fused step: same losses and gradients plus the decode of the same tiles
+    l2, ghm2, goff2, gvar2, coords, scores = run_loss(gb, cfg, batch, on_the_fly=True, decode=True)
+    np.testing.assert_allclose(l2.cpu().numpy(), g["loss_f32"], rtol=LOSS_RTOL, atol=1e-9)
+    grad_close(ghm2.cpu().numpy(), g["grad_hm"], what="step grad heatmaps")
+    ok = half_integer_free(g["dec_softargmax"])
+    assert np.abs(coords.cpu().numpy() - g["dec_coords"])[ok].max() <= COORD_ATOL
+    assert np.array_equal(scores.cpu().numpy(), g["dec_scores"])
+
+
+def test_loss_sharded_denominators(gb):
+    """Two shards with the global denominators reproduce the full-batch loss and gradients."""
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=5, B=8)
+    full_l, full_ghm, _, _, _, _ = run_loss(gb, cfg, batch, on_the_fly=True)
+    pairs = [v for p in oc.skeleton_for(cfg.K) for v in p]
+    den = gb.loss_denominators(dev(batch["vis"]), dev(batch["kps"]), False, cfg.H, cfg.W, 192.0, 256.0, cfg.sigma, pairs)
+    want_den = oc.loss_denominators(t(batch["weight"]), cfg.K)
+    np.testing.assert_allclose(den.cpu().numpy(), [float(want_den[0]), float(want_den[1])], rtol=1e-6)
+    acc = torch.zeros(7, device="cuda")
+    parts = []
+    for sl in (slice(0, 3), slice(3, 8)):
+        sub = {k: v[sl] for k, v in batch.items() if k != "flip_perm"}
+        l, gh, _, _, _, _ = run_loss(gb, cfg, sub, on_the_fly=True, denoms=den)
+        acc += l
+        parts.append(gh)
+    np.testing.assert_allclose(acc.cpu().numpy(), full_l.cpu().numpy(), rtol=LOSS_RTOL)
+    grad_close(torch.cat(parts).cpu().numpy(), full_ghm.cpu().numpy(), what="sharded grad")
+
+
+def test_module_autograd_and_scaling(gb):
+    """FusionPoseLoss drop-in: dict of 7, backward through total_loss, a scaled loss
+    (GradScaler-style), and a per-term upstream gradient (recompute path)."""
+    from infantposeestimation_gaussianbias_b200 import FusionPoseLoss
+    cfg, batch, g = goldens.load("w32_256x192")
+    loss_fn = FusionPoseLoss(target_sigma=cfg.sigma)
+
+    def fresh():
+        o = {"heatmaps": dev(batch["heatmaps"]).requires_grad_(True), "offsets": dev(batch["offsets"]).requires_grad_(True),
+             "variances": dev(batch["variances"]).requires_grad_(True)}
+        return o
+
+    o = fresh()
+    out = loss_fn(o, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size, heatmap_size=(cfg.H, cfg.W))
+    assert list(out) == list(oc.LOSS_KEYS) and all(v.dim() == 0 for v in out.values())
+    out["total_loss"].backward()
+    grad_close(o["heatmaps"].grad.cpu().numpy(), g["grad_hm"], what="module grad")
+    grad_close(o["offsets"].grad.cpu().numpy(), g["grad_off"], what="module grad off")
+
+    o = fresh()   # scaled loss: rescale path
+    out = loss_fn(o, None, dev(batch["vis"][..., None]), dev(batch["kps"]), input_size=cfg.input_size)
+    (out["total_loss"] * 1024.0).backward()
+    grad_close(o["heatmaps"].grad.cpu().numpy() / 1024.0, g["grad_hm"], what="scaled grad")
+
+    o = fresh()   # known scale up front: nothing to do in backward
+    out = loss_fn(o, None, dev(batch["vis"][..., None]), dev(batch["kps"]), input_size=cfg.input_size,
+                  grad_scale=torch.tensor(1024.0).cuda())
+    (out["total_loss"] * 1024.0).backward()
+    grad_close(o["heatmaps"].grad.cpu().numpy() / 1024.0, g["grad_hm"], what="pre-scaled grad")
+
+    o = fresh()   # only two of the six terms: per-term recompute
+    out = loss_fn(o, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size)
+    (out["heatmap_loss"] + 3.0 * out["shape_loss"]).backward()
+    ref = {k: t(batch[k]).clone().requires_grad_(True) for k in ("heatmaps", "offsets", "variances")}
+    rl = oc.fusion_loss(ref["heatmaps"], ref["offsets"], ref["variances"], t(batch["target"]), t(batch["weight"]), t(batch["kps"]),
+                        input_size=cfg.input_size, target_sigma=cfg.sigma)
+    (rl["heatmap_loss"] + 3.0 * rl["shape_loss"]).backward()
+    grad_close(o["heatmaps"].grad.cpu().numpy(), ref["heatmaps"].grad.numpy(), what="per-term grad")
+    assert float(o["offsets"].grad.abs().max()) == 0.0
+
+
+def test_identical_tiles_tie_rule(gb):
+    """All channels equal (a zero-initialised last layer): every min() ties, ATen splits the
+    gradient evenly; the kernel must reproduce that."""
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=2, B=2)
+    batch["heatmaps"][:] = batch["heatmaps"][:, :1]
+    want_l, want_g = oc.fusion_loss_and_grads(t(batch["heatmaps"]), t(batch["offsets"]), t(batch["variances"]),
+                                              t(batch["target"]), t(batch["weight"]), t(batch["kps"]), input_size=cfg.input_size)
+    losses, ghm, _, _, _, _ = run_loss(gb, cfg, batch, on_the_fly=False)
+    np.testing.assert_allclose(losses.cpu().numpy(), [float(want_l[k]) for k in oc.LOSS_KEYS], rtol=LOSS_RTOL, atol=1e-9)
+    grad_close(ghm.cpu().numpy(), want_g["heatmaps"].numpy(), what="tie grad")
+
+
+# ------------------------------------------------------------------ next-row decoders (utils/postprocess.py)
+def test_postprocess_family(gb):
+    from infantposeestimation_gaussianbias_b200 import postprocess as pp
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=9, B=4)
+    hm = np.abs(batch["heatmaps"]) + 0.01          # the linear-weight centroid assumes positive maps
+    c, v = pp.get_max_preds(dev(hm))
+    oc_c, oc_v, _ = oc.decode_heatmaps(t(hm), shift=False)
+    assert np.array_equal(c.cpu().numpy(), oc_c.numpy()) and np.array_equal(v.cpu().numpy()[..., 0], oc_v.numpy())
+
+
+# ------------------------------------------------------------------ errors, no fallback
+def test_errors_are_loud(gb):
+    from infantposeestimation_gaussianbias_b200 import GbcodecError
+    with pytest.raises(RuntimeError):
+        gb.decode_argmax(torch.zeros(1, 1, 8, 8), 0)              # CPU tensor
+    with pytest.raises(GbcodecError):
+        gb.decode_argmax(torch.zeros(1, 1, 8, 6).cuda(), 0)       # W % 4 != 0
+    with pytest.raises(GbcodecError):
+        gb.decode_argmax(torch.zeros(1, 1, 8, 8).cuda(), 7)       # bad mode
+    with pytest.raises(GbcodecError):
+        gb.decode(torch.zeros(1, 1, 8, 8).cuda(), None, None, None, None, None, 2, 1)   # REFINE without alpha
