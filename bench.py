@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — heatmaps/s of the fused codec step (encode + six-term loss fwd/bwd + decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N = 1 workload is BASELINE.json configs[1]: HRNet-W32 256x192 (64x48 heatmaps, K=17,
+sigma=2), batch 1024 per GPU; one step = one pass of the hot path over one batch:
+target tiles generated on the fly from the keypoints, the six-term loss forward and
+backward, and the keypoint decode, every heatmap read from HBM once.
+For N > 1 the driver launches one rank per GPU (torch.distributed.run); the batch is
+sharded by image, per-GPU work fixed (weak scaling), the only collectives are the
+2-float normaliser all-reduce before and the 7-float loss all-reduce after the kernel.
+
+`--impl reference` times the reference's CPU implementation of the same step on the
+host cores.  The reference is Python and cannot travel to the GPU box, so this is
+the oracle port (oracle/heatmap_codec.py, pinned to the reference by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "heatmaps/sec (Bx17x64x48, encode+loss+decode)"
+UNIT = "heatmaps/s"
+K, H, W = 17, 64, 48
+IN_W, IN_H = 192, 256
+SIGMA = 2.0
+LAMBDAS = [1.0, 1.0, 0.5, 0.1, 0.05, 0.05]
+SKELETON = ((0, 1), (0, 2), (1, 3), (2, 4), (5, 6), (5, 7), (7, 9), (6, 8), (8, 10),
+            (5, 11), (6, 12), (11, 12), (11, 13), (13, 15), (12, 14), (14, 16))
+BYTES_PER_HM = 24 * H * W          # fused step: read P,V (8N); write dP,dV,dO (16N)  — SURVEY §8d / DESIGN.md
+
+
+def workload_name(B):
+    return (f"BASELINE configs[1]: HRNet-W32 256x192 (64x48 heatmaps, K=17, sigma=2) fused codec step "
+            f"(on-the-fly encode + six-term loss fwd/bwd + decode), batch {B} per GPU")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]          # the loaded half of the samples
+            out.update(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- inputs
+def synth_device_batch(B, device, seed, ops):
+    """Synthetic batch created on the device (SURVEY §8d recipe): peaked heatmaps around
+    jittered keypoints + noise, gaussian offsets, softplus variances."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g, device=device)
+    rn = lambda *s: torch.randn(*s, generator=g, device=device)
+    u = r(B, K)
+    vis = torch.where(u < 0.15, 0.0, torch.where(u < 0.40, 1.0, 2.0))
+    kps = torch.stack(((r(B, K) * 1.2 - 0.1) * IN_W, (r(B, K) * 1.2 - 0.1) * IN_H), dim=-1)
+    jitter = rn(B, K, 2) * 1.5 * 4.0
+    shifted, _ = ops.encode(kps + jitter, torch.full_like(vis, 2.0), H, W, float(IN_W), float(IN_H), SIGMA)
+    amp = r(B, K, 1, 1) * 0.9 + 0.3
+    hm = amp * shifted + 0.05 * rn(B, K, H, W)
+    off = 0.3 * rn(B, K, 2, H, W)
+    var = torch.nn.functional.softplus(rn(B, K, H, W))
+    return dict(kps=kps.contiguous(), vis=vis.contiguous(), hm=hm.contiguous(), off=off.contiguous(), var=var.contiguous())
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_step_rate(sample_B: int, min_seconds: float, max_reps: int):
+    """Oracle port of the reference step (encode -> loss fwd+bwd -> decode) on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import heatmap_codec as oc
+    from tests import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=0, B=sample_B)
+    T = lambda k: torch.from_numpy(batch[k])
+    args = (batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"))
+
+    def one():
+        t0 = time.perf_counter()
+        oc.codec_step(*args, heatmap_size=cfg.heatmap_size, input_size=cfg.input_size, sigma=cfg.sigma, loop_decode=True)
+        return time.perf_counter() - t0
+
+    one()                                   # warm-up
+    times, t_start = [], time.perf_counter()
+    while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
+        times.append(one())
+    return sample_B * K / statistics.median(times), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_B = 64
+    # each step = one bounded sample of the workload (B=64 of the 1024-image batch)
+    import torch
+    from oracle import heatmap_codec as oc
+    from tests import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=0, B=sample_B)
+    T = lambda k: torch.from_numpy(batch[k])
+    call = lambda: oc.codec_step(batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"),
+                                 heatmap_size=cfg.heatmap_size, input_size=cfg.input_size, sigma=cfg.sigma, loop_decode=True)
+    for _ in range(max(1, min(args.warmup, 3))):
+        call()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call()
+    dt = time.perf_counter() - t0
+    value = sample_B * K * args.steps / dt
+    sample = f"{sample_B} images x {K} heatmaps per step (a bounded sample of the {args.batch}-image batch), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import infantposeestimation_gaussianbias_b200 as pkg
+    pkg.load()                                   # raises if libgbcodec.so is missing — no fallback
+    from infantposeestimation_gaussianbias_b200 import _native as N
+    from infantposeestimation_gaussianbias_b200 import ops
+    from infantposeestimation_gaussianbias_b200.host_step import HostCodecStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the codec has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B = args.batch
+    pairs = ops.pairs_flat(SKELETON)
+    data = synth_device_batch(B, device, 1234 + rank, ops)
+    alpha = torch.tensor([0.5], device=device)
+    fw = torch.tensor([0.6224593312018546], device=device)
+    dflags = N.DECODE_REFINE | N.DECODE_APPLY_OFFSET
+    # N=1: weights/normalisers + loss + finalize.  N>1: (normalisers + export) + (weights + import + loss + finalize)
+    launches_per_step = 3 if world == 1 else 6
+
+    def step():
+        den = None
+        if world > 1:
+            den = ops.loss_denominators(data["vis"], data["kps"], False, H, W, float(IN_W), float(IN_H), SIGMA, pairs)
+            dist.all_reduce(den)
+        res = ops.fusion_loss(data["hm"], data["off"], data["var"], None, data["vis"], data["kps"], den, None,
+                              float(IN_W), float(IN_H), LAMBDAS, SIGMA, SIGMA, True, pairs, True, True, alpha, fw, 2, dflags)
+        if world > 1:
+            dist.all_reduce(res[0])
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:                               # materialise the handles
+        a.record(); b.record()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_a.record()
+    for i in range(args.steps):
+        N.check(N.lib().gbcodec_profile_loss_kernel(N._P(ev[i][0].cuda_event), N._P(ev[i][1].cuda_event)), "profile")
+        res = step()
+    t_b.record()
+    barrier()
+    N.lib().gbcodec_profile_loss_kernel(None, None)
+    ms = torch.tensor([t_a.elapsed_time(t_b)], device=device, dtype=torch.float64)
+    kern_ms = torch.tensor([statistics.mean(a.elapsed_time(b) for a, b in ev)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    kern_ms = float(kern_ms.item())
+    # keep the sampler running a little longer under load so that it sees loaded clocks
+    if rank == 0:
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    value = world * B * K * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end on host buffers (pinned -> H2D -> step -> D2H), same metric ---------------
+    e2e = None
+    if not args.no_e2e:
+        host = {k: v.cpu().pin_memory() for k, v in data.items()}
+        hs = HostCodecStep(B, K, H, W, (IN_W, IN_H), SIGMA, LAMBDAS, chunk_images=args.chunk, device=device)
+        for _ in range(2):
+            out = hs(host["hm"], host["off"], host["var"], host["kps"], host["vis"])
+        n_e2e = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = hs(host["hm"], host["off"], host["var"], host["kps"], host["vis"])   # synchronises
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * K * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
+               "d2h_bytes_per_step": hs.d2h_bytes, "steps": n_e2e, "chunk_images": hs.chunk,
+               "total_loss": float(out["losses"][6])}
+        check = float(res[0][6].item())
+        if world == 1 and abs(e2e["total_loss"] - check) > 1e-4 * abs(check):
+            raise SystemExit(f"bench.py: host-buffer step disagrees with the resident step: {e2e['total_loss']} vs {check}")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = B * K * BYTES_PER_HM / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "loss_kernel<256,3,2> (fused step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": B * K * BYTES_PER_HM}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            roofline["traffic"] = json.load(open(traffic_path)).get("loss_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu:
+        v, cores, times = cpu_step_rate(sample_B=32, min_seconds=10.0, max_reps=20)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"32 images x {K} heatmaps of the same workload, median of {len(times)} passes ({sum(times):.1f} s of CPU work)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "total_loss": float(res[0][6].item()),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU")
+    ap.add_argument("--chunk", type=int, default=128, help="images per chunk of the host-buffer pipeline")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

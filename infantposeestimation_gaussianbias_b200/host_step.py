@@ -1,0 +1,104 @@
+"""Fused codec step on HOST buffers: pinned host tensors in, host results out.
+
+The batch is cut into chunks of whole images; while chunk i is in the loss kernel,
+chunk i+1 is on its way over PCIe (copy stream + double-buffered device staging).
+Chunks are shards in the sense of sharded.py: the two batch-global normalisers
+are computed first from the (tiny) keypoint/visibility arrays of the whole
+batch, every chunk is then normalised by them, and the per-chunk loss vectors
+simply add up — so the result equals one pass over the whole batch.
+Gradients stay on the device (their consumer, the backbone backward, is there).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as N
+from . import ops
+from .fusion_head import SKELETON
+
+
+class HostCodecStep:
+    def __init__(self, B: int, K: int, H: int, W: int, input_size: Sequence[int] = (192, 256), sigma: float = 2.0,
+                 lambdas: Sequence[float] = (1.0, 1.0, 0.5, 0.1, 0.05, 0.05), chunk_images: int = 128,
+                 device: Optional[torch.device] = None, with_grads: bool = True,
+                 skeleton: Sequence[Tuple[int, int]] = SKELETON):
+        self.B, self.K, self.H, self.W = B, K, H, W
+        self.in_w, self.in_h = float(input_size[0]), float(input_size[1])
+        self.sigma = float(sigma)
+        self.lambdas = [float(v) for v in lambdas]
+        self.chunk = min(chunk_images, B)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.with_grads = with_grads
+        self.pairs = ops.pairs_flat([(i, j) for (i, j) in skeleton if i < K and j < K])
+        d, f = self.device, torch.float32
+        C = self.chunk
+        self.stage = [dict(hm=torch.empty((C, K, H, W), dtype=f, device=d), off=torch.empty((C, K, 2, H, W), dtype=f, device=d),
+                           var=torch.empty((C, K, H, W), dtype=f, device=d)) for _ in range(2)]
+        self.kps_d = torch.empty((B, K, 2), dtype=f, device=d)
+        self.vis_d = torch.empty((B, K), dtype=f, device=d)
+        self.losses_d = torch.zeros(7, dtype=f, device=d)
+        self.coords_d = torch.empty((B, K, 2), dtype=f, device=d)
+        self.scores_d = torch.empty((B, K), dtype=f, device=d)
+        self.alpha = torch.tensor([0.5], dtype=f, device=d)
+        self.fw = torch.tensor([0.6224593312018546], dtype=f, device=d)
+        self.grads = None      # last chunk's gradient tensors (device)
+        self.copy_stream = torch.cuda.Stream(device=d)
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.out_h = dict(losses=torch.empty(7, dtype=f).pin_memory(), coords=torch.empty((B, K, 2), dtype=f).pin_memory(),
+                          scores=torch.empty((B, K), dtype=f).pin_memory())
+        self.launches = 0
+
+    @property
+    def h2d_bytes(self) -> int:
+        n = self.B * self.K * self.H * self.W * 4
+        return n * 4 + self.B * self.K * 12
+
+    @property
+    def d2h_bytes(self) -> int:
+        return 7 * 4 + self.B * self.K * 12
+
+    def set_decode_params(self, alpha_param: Tensor, fusion_weight: Tensor):
+        self.alpha.copy_(alpha_param.reshape(1)); self.fw.copy_(fusion_weight.reshape(1))
+
+    def __call__(self, hm_h: Tensor, off_h: Tensor, var_h: Tensor, kps_h: Tensor, vis_h: Tensor) -> Dict[str, Tensor]:
+        """All arguments are pinned host tensors.  Returns pinned host tensors
+        {losses (7,), coords (B,K,2), scores (B,K)}; synchronises before returning."""
+        B, K, H, W, C = self.B, self.K, self.H, self.W, self.chunk
+        main = torch.cuda.current_stream(self.device)
+        self.kps_d.copy_(kps_h, non_blocking=True)
+        self.vis_d.copy_(vis_h.reshape(B, K), non_blocking=True)
+        den = ops.loss_denominators(self.vis_d, self.kps_d, False, H, W, self.in_w, self.in_h, self.sigma, self.pairs)
+        self.losses_d.zero_()
+        self.launches = 2
+        self.copy_stream.wait_stream(main)
+        nchunk = (B + C - 1) // C
+        for c in range(nchunk):
+            lo, hi = c * C, min(B, (c + 1) * C)
+            n = hi - lo
+            s = self.stage[c & 1]
+            with torch.cuda.stream(self.copy_stream):
+                if c >= 2:
+                    self.copy_stream.wait_event(self.consumed[c & 1])
+                s["hm"][:n].copy_(hm_h[lo:hi], non_blocking=True)
+                s["off"][:n].copy_(off_h[lo:hi], non_blocking=True)
+                s["var"][:n].copy_(var_h[lo:hi], non_blocking=True)
+                self.staged[c & 1].record(self.copy_stream)
+            main.wait_event(self.staged[c & 1])
+            res = ops.fusion_loss(s["hm"][:n], s["off"][:n], s["var"][:n], None, self.vis_d[lo:hi], self.kps_d[lo:hi],
+                                  den, None, self.in_w, self.in_h, self.lambdas, self.sigma, self.sigma, True, self.pairs,
+                                  self.with_grads, True, self.alpha, self.fw, 2, N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)
+            self.consumed[c & 1].record(main)
+            self.losses_d += res[0]
+            self.coords_d[lo:hi] = res[4]
+            self.scores_d[lo:hi] = res[5]
+            self.grads = res[1:4]
+            self.launches += 3
+        self.out_h["losses"].copy_(self.losses_d, non_blocking=True)
+        self.out_h["coords"].copy_(self.coords_d, non_blocking=True)
+        self.out_h["scores"].copy_(self.scores_d, non_blocking=True)
+        main.synchronize()
+        return self.out_h

@@ -132,6 +132,8 @@ def main():
                 out["grad_hm_f64_absmax"] = np.abs(h.grad.numpy()).max(axis=(2, 3))
                 # store the f64 gradient at a strided subset: an error bar for the f32 reference itself
                 out["grad_hm_f64_sub"] = h.grad.numpy().reshape(-1)[::97].copy()
+                out["grad_off_f64_idx"], out["grad_off_f64_val"] = sparse(o.grad.numpy())
+                out["grad_var_f64_tile"] = v.grad.numpy()[:, :, 0, 0].copy()
 
         # ---- decode ------------------------------------------------------------
         head = fh.HeatmapRegressionHead(in_channels=8, num_keypoints=cfg.K, hidden_dim=8)

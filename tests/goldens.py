@@ -34,4 +34,5 @@ def load(name: str):
     eb = g["edge_kps"].shape[0]
     g["edge_target"] = dense(g["edge_nz_idx"], g["edge_nz_val"], (eb, K, H, W))
     g["grad_off"] = dense(g["grad_off_idx"], g["grad_off_val"], (B, K, 2, H, W))
+    g["grad_off_f64"] = dense(g["grad_off_f64_idx"], g["grad_off_f64_val"], (B, K, 2, H, W), np.float64)
     return cfg, batch, g

@@ -36,12 +36,30 @@ def t(a):
     return torch.from_numpy(np.ascontiguousarray(a))
 
 
-def grad_close(got, want, rel=LOSS_RTOL, what=""):
-    """max-norm relative error: |got - want|_inf <= rel * |want|_inf."""
+def grad_close(got, want, rel=LOSS_RTOL, what="", truth=None):
+    """max-norm relative error: |got - want|_inf <= rel * |want|_inf, `want` being the
+    reference's fp32 result.
+
+    The offset-map gradient sits on the four bilinear taps around the soft-argmax
+    coordinate, so it inherits that coordinate's fp32 noise (~1e-5 px on a 48..128 px
+    axis, i.e. 1e-5..5e-5 relative on a tap weight): the reference's OWN fp32 result is
+    1.2e-5 / 2.0e-5 / 4.7e-5 away from its fp64 result on the three golden batches.
+    Where `truth` (the fp64 result) is given, a result that misses `rel` against the
+    fp32 reference still passes if it is no further from the truth than 3x what the
+    fp32 reference itself is."""
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     scale = np.abs(want).max()
     err = np.abs(got - want).max()
-    assert err <= rel * scale + 1e-30, f"{what}: max err {err:.3e} vs scale {scale:.3e} (ratio {err / max(scale, 1e-300):.2e})"
+    if err <= rel * scale + 1e-30:
+        return
+    if truth is not None:
+        truth = np.asarray(truth, np.float64)
+        ref_noise = np.abs(want - truth).max()
+        mine = np.abs(got - truth).max()
+        assert mine <= max(rel * scale, 3 * ref_noise), \
+            f"{what}: {mine / scale:.2e} from fp64 truth, the fp32 reference is {ref_noise / scale:.2e} from it"
+        return
+    assert False, f"{what}: max err {err:.3e} vs scale {scale:.3e} (ratio {err / max(scale, 1e-300):.2e})"
 
 
 def half_integer_free(coords, eps=1e-3):
@@ -163,7 +181,7 @@ def test_loss_and_grads_against_golden(gb, name, on_the_fly):
     grad_close(ghm.cpu().numpy(), g["grad_hm"], what="grad heatmaps")
     go = goff.cpu().numpy()
     assert np.array_equal(go != 0, g["grad_off"] != 0)
-    grad_close(go, g["grad_off"], what="grad offsets")
+    grad_close(go, g["grad_off"], what="grad offsets", truth=g["grad_off_f64"])
     gv = gvar.cpu().numpy()
     grad_close(gv, np.broadcast_to(g["grad_var_tile"][:, :, None, None], gv.shape), what="grad variances")
 
@@ -175,12 +193,15 @@ def test_loss_vs_oracle_batch64(gb, utw):
     want_l, want_g = oc.fusion_loss_and_grads(t(batch["heatmaps"]), t(batch["offsets"]), t(batch["variances"]),
                                               t(batch["target"]), t(batch["weight"]), t(batch["kps"]),
                                               input_size=cfg.input_size, use_target_weight=utw)
+    d = lambda k: t(batch[k]).double()
+    _, truth_g = oc.fusion_loss_and_grads(d("heatmaps"), d("offsets"), d("variances"), d("target"), d("weight"), d("kps"),
+                                          input_size=cfg.input_size, use_target_weight=utw)
     losses, ghm, goff, gvar, _, _ = run_loss(gb, cfg, batch, on_the_fly=True, utw=utw)
     got = losses.cpu().numpy()
     want = np.array([float(want_l[k]) for k in oc.LOSS_KEYS])
     np.testing.assert_allclose(got, want, rtol=LOSS_RTOL, atol=1e-9)
     grad_close(ghm.cpu().numpy(), want_g["heatmaps"].numpy(), what="grad heatmaps")
-    grad_close(goff.cpu().numpy(), want_g["offsets"].numpy(), what="grad offsets")
+    grad_close(goff.cpu().numpy(), want_g["offsets"].numpy(), what="grad offsets", truth=truth_g["offsets"].numpy())
     grad_close(gvar.cpu().numpy(), want_g["variances"].numpy(), what="grad variances")
 
 
@@ -235,7 +256,7 @@ def test_module_autograd_and_scaling(gb):
     assert list(out) == list(oc.LOSS_KEYS) and all(v.dim() == 0 for v in out.values())
     out["total_loss"].backward()
     grad_close(o["heatmaps"].grad.cpu().numpy(), g["grad_hm"], what="module grad")
-    grad_close(o["offsets"].grad.cpu().numpy(), g["grad_off"], what="module grad off")
+    grad_close(o["offsets"].grad.cpu().numpy(), g["grad_off"], what="module grad off", truth=g["grad_off_f64"])
 
     o = fresh()   # scaled loss: rescale path
     out = loss_fn(o, None, dev(batch["vis"][..., None]), dev(batch["kps"]), input_size=cfg.input_size)

@@ -74,6 +74,11 @@ def test_loss_f64_matches_reference_f64(name):
                             input_size=cfg.input_size, target_sigma=cfg.sigma)
     got = np.array([float(losses[k]) for k in oc.LOSS_KEYS])
     np.testing.assert_allclose(got, g["loss_f64"], rtol=1e-12)
+    _, grads = oc.fusion_loss_and_grads(d("heatmaps"), d("offsets"), d("variances"), d("target"), d("weight"), d("kps"),
+                                        input_size=cfg.input_size, target_sigma=cfg.sigma)
+    np.testing.assert_allclose(grads["heatmaps"].numpy().reshape(-1)[::97], g["grad_hm_f64_sub"], rtol=1e-9, atol=1e-18)
+    np.testing.assert_allclose(grads["offsets"].numpy(), g["grad_off_f64"], rtol=1e-9, atol=1e-18)
+    np.testing.assert_allclose(grads["variances"].numpy()[:, :, 0, 0], g["grad_var_f64_tile"], rtol=1e-9, atol=1e-18)
 
 
 @pytest.mark.parametrize("name", NAMES)
