@@ -164,11 +164,16 @@ def local_refine_loop(heatmaps: torch.Tensor, coarse: torch.Tensor, radius: int 
     return out
 
 
-def local_refine(heatmaps: torch.Tensor, coarse: torch.Tensor, radius: int = 2) -> torch.Tensor:
+def local_refine(heatmaps: torch.Tensor, coarse: torch.Tensor, radius: int = 2,
+                 centre: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Batched form of :func:`local_refine_loop` (same arithmetic per tile, the
-    out-of-map taps carry weight exp(-inf)=0)."""
+    out-of-map taps carry weight exp(-inf)=0).  ``centre`` (B,K,2) int64 replaces
+    the rounded soft-argmax as the window centre: tests use it to check tiles whose
+    soft-argmax lies on a .5 rounding boundary under either rounding."""
     B, K, H, W = heatmaps.shape
-    centre = window_centres(coarse, H, W)
+    if centre is None:
+        centre = window_centres(coarse, H, W)
+    centre = centre.long()
     d = torch.arange(-radius, radius + 1)
     xs = centre[..., 0:1] + d            # (B,K,S)
     ys = centre[..., 1:2] + d
@@ -215,7 +220,7 @@ def fusion_decode(heatmaps: torch.Tensor, offsets: Optional[torch.Tensor],
                   apply_offset: bool = True, refine: bool = True, radius: int = 2,
                   heatmaps_of_flipped_input: Optional[torch.Tensor] = None,
                   flip_pairs: Optional[Sequence[Tuple[int, int]]] = COCO_FLIP_PAIRS,
-                  loop: bool = False):
+                  loop: bool = False, centre: Optional[torch.Tensor] = None):
     """coords (B,K,2) in heatmap pixels and scores (B,K) as
     HeatmapRegressionHead.decode returns them (fusion_head.py:309-365), with the
     optional flip-test average in front (pose_estimator.py:303-327).
@@ -227,7 +232,10 @@ def fusion_decode(heatmaps: torch.Tensor, offsets: Optional[torch.Tensor],
         heatmaps = flip_average(heatmaps, heatmaps_of_flipped_input, flip_pairs)
     coords, scores = soft_argmax(heatmaps)
     if refine:
-        local = (local_refine_loop if loop else local_refine)(heatmaps, coords, radius)
+        if centre is not None:
+            local = local_refine(heatmaps, coords, radius, centre=centre)
+        else:
+            local = (local_refine_loop if loop else local_refine)(heatmaps, coords, radius)
         a = torch.sigmoid(torch.as_tensor(alpha_param, dtype=heatmaps.dtype))
         coords = a * coords + (1 - a) * local
     if apply_offset:

@@ -151,11 +151,18 @@ def test_decode_larger_batch_vs_oracle(gb):
     batch = synth.make_batch(cfg, seed=3, B=64)
     hm, off = t(batch["heatmaps"]), t(batch["offsets"])
     want_c, want_s = oc.fusion_decode(hm, off, 0.5, 0.6224593312018546)
-    ok = half_integer_free(oc.soft_argmax(hm)[0].numpy())
-    c, s, _ = gb.decode(hm.cuda(), None, None, off.cuda(), torch.tensor(0.5).cuda(), torch.tensor(0.6224593312018546).cuda(), 2, 3)
+    soft = oc.soft_argmax(hm)[0]
+    ok = half_integer_free(soft.numpy())
+    c, s, centre = gb.decode(hm.cuda(), None, None, off.cuda(), torch.tensor(0.5).cuda(), torch.tensor(0.6224593312018546).cuda(), 2, 3)
     assert np.array_equal(s.cpu().numpy(), want_s.numpy())
     assert np.abs(c.cpu().numpy() - want_c.numpy())[ok].max() <= COORD_ATOL
-    assert ok.mean() > 0.98
+    assert ok.mean() > 0.9        # flat tiles put the soft-argmax at (W-1)/2 = 23.5: ~5 % sit on the boundary
+    # boundary tiles: the kernel's window centre must be one of the two neighbouring pixels, and with
+    # THAT centre the oracle must reproduce the kernel's coordinates (so only the rounding is in doubt)
+    centre = centre.cpu()
+    assert (np.abs(centre.numpy() - soft.numpy()) <= 0.5 + 1e-3).all()
+    alt_c, _ = oc.fusion_decode(hm, off, 0.5, 0.6224593312018546, centre=centre)
+    assert np.abs(c.cpu().numpy() - alt_c.numpy()).max() <= COORD_ATOL
 
 
 # ------------------------------------------------------------------ loss
