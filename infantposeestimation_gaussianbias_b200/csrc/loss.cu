@@ -12,69 +12,16 @@
 // HBM sees each heatmap once).  Gradients leave with 128-bit streaming stores.
 // Algorithmic HBM bytes per tile: read hm, var (8N); write d_hm, d_var, d_off (16N);
 // +4N when the target tiles come from HBM instead of being generated on the fly.
-#include "common.cuh"
-#include "decode_device.cuh"
-#include <string.h>
+#include "loss_common.cuh"
+#include <stdlib.h>
 
 namespace gbc {
-
-// ---- kernel-side description -------------------------------------------------------
-struct LossParams {
-    int B, K, H, W;
-    float in_w, in_h;
-    float lam[6];
-    float sigma;            // target sigma
-    float e_star;           // log(2 pi e sigma^2)
-    int use_target_weight;
-    int n_pairs;
-    EncodeConst ec;
-    int8_t n_partner[GBCODEC_MAX_K];
-    int8_t partner[GBCODEC_MAX_K][GBCODEC_MAX_PARTNERS];
-    uint8_t owner[GBCODEC_MAX_K];       // bit p: this channel is the first index of the pair with partner p
-    int16_t pair_i[GBCODEC_MAX_PAIRS], pair_j[GBCODEC_MAX_PAIRS];
-};
-
-struct LossArgs {
-    const float* hm; const float* off; const float* var; const float* target;
-    const float* weight; const float* gt;
-    const float* grad_scale;            // device scalar or null
-    float* grad_hm; float* grad_off; float* grad_var;
-    // fused decode (null coords = off)
-    const float* alpha_param; const float* fusion_weight; float* coords; float* scores;
-    int radius; unsigned dflags;
-    // workspace
-    const double* sums;                 // [2] raw sums of w and w_i*w_j
-    const float* weff;                  // [B*K] weights after the encoder's rule
-    float* partial;                     // [B*K][8] un-normalised per-tile loss numerators
-    const float* lam_eff;               // backward recompute: device [6] per-term multipliers
-    const int* plan;                    // backward recompute: run only if *plan == 2
-};
-
-constexpr int kWsHeaderFloats = 64;     // sums (2 doubles), plan, lam_eff, ... ; 256 bytes
-struct WsLayout {
-    double* sums; int* plan; float* lam_eff; float* weff; float* partial;
-};
-static inline size_t ws_bytes(int B, int K) {
-    return (size_t)(kWsHeaderFloats + (size_t)B * K * 9) * sizeof(float);
-}
-static inline WsLayout ws_carve(void* ws, int B, int K) {
-    float* f = reinterpret_cast<float*>(ws);
-    WsLayout l;
-    l.sums = reinterpret_cast<double*>(f);          // f[0..3]
-    l.plan = reinterpret_cast<int*>(f + 4);         // f[4..7]
-    l.lam_eff = f + 8;                              // f[8..15]
-    l.weff = f + kWsHeaderFloats;
-    l.partial = l.weff + (size_t)B * K;
-    // partial rows are 8 floats; keep them 32-byte aligned
-    const size_t pad = ((size_t)B * K) & 7;
-    if (pad) l.partial += 8 - pad;
-    return l;
-}
 
 // ---- weights after the encoder rule + the two batch sums ----------------------------
 __global__ void __launch_bounds__(256)
 denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight,
-              const float* __restrict__ gt, int target_given, float* __restrict__ weff, double* __restrict__ sums) {
+              const float* __restrict__ gt, int target_given, float* __restrict__ weff, int4* __restrict__ geom,
+              double* __restrict__ sums) {
     // one image per thread: K weights, then the limb products
     __shared__ double red[2][8];
     double sw = 0.0, sp = 0.0;
@@ -83,8 +30,11 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
         for (int k = 0; k < P.K; ++k) {
             const int t = b * P.K + k;
             float wk = weight[t];
-            if (!target_given)
-                wk = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec).weight;
+            if (!target_given) {
+                const PatchGeom g = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec);
+                wk = g.weight;
+                if (geom) geom[t] = pack_geom(g);
+            }
             w[k] = wk;
             if (weff) weff[t] = wk;
             sw += (double)wk;
@@ -115,53 +65,17 @@ __global__ void sums_from_float_kernel(const float* __restrict__ in2, double* __
 // weights after the encoder rule only (the sums come from the caller)
 __global__ void __launch_bounds__(256)
 weff_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight, const float* __restrict__ gt,
-            int target_given, float* __restrict__ weff) {
+            int target_given, float* __restrict__ weff, int4* __restrict__ geom) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.B * P.K) return;
     float wk = weight[t];
-    if (!target_given) wk = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec).weight;
+    if (!target_given) {
+        const PatchGeom g = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec);
+        wk = g.weight;
+        geom[t] = pack_geom(g);
+    }
     weff[t] = wk;
 }
-
-// ---- bilinear helpers (same convention as decode.cu) ---------------------------------
-struct Taps {
-    int i00, i01, i10, i11;          // flat indices inside a channel
-    float w00, w01, w10, w11;        // weights, already zero for taps outside the map
-    float fx, fy, inx, iny, okx, oky;
-};
-__device__ __forceinline__ Taps taps_setup(float cx, float cy, int H, int W) {
-    Taps t;
-    const float ccx = fminf(fmaxf(cx, 0.f), (float)(W - 1));
-    const float ccy = fminf(fmaxf(cy, 0.f), (float)(H - 1));
-    t.inx = (cx >= 0.f && cx <= (float)(W - 1)) ? 1.f : 0.f;
-    t.iny = (cy >= 0.f && cy <= (float)(H - 1)) ? 1.f : 0.f;
-    const float fx0 = floorf(ccx), fy0 = floorf(ccy);
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    t.fx = ccx - fx0; t.fy = ccy - fy0;
-    t.okx = (x0 + 1 < W) ? 1.f : 0.f;
-    t.oky = (y0 + 1 < H) ? 1.f : 0.f;
-    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-    t.i00 = y0 * W + x0; t.i01 = y0 * W + x1; t.i10 = y1 * W + x0; t.i11 = y1 * W + x1;
-    t.w00 = (1.f - t.fx) * (1.f - t.fy);
-    t.w01 = t.fx * (1.f - t.fy) * t.okx;
-    t.w10 = (1.f - t.fx) * t.fy * t.oky;
-    t.w11 = t.fx * t.fy * t.okx * t.oky;
-    return t;
-}
-
-__device__ __forceinline__ float tie_rule(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
-
-// per-tile scalars broadcast from thread 0 to the CTA
-struct TileCoef {
-    float c1;        // lambda1 * wa/(Da N) * 2
-    float c4;        // lambda4 * w/D * (s - sigma)/s / R'
-    float v;         // variance of the tile
-    float c6;        // lambda6 * w/D * 2 (E - E*)
-    float pa;        // sum p a
-    float fx, fy;    // d(loss)/d(cx, cy)
-    float gv;        // uniform gradient of the variance map
-    float go[2];     // lambda2 * wa/(2 Da) * sl1'(d_ch)
-};
 
 template <int TPB, int NITER, int CACHE>
 __global__ void __launch_bounds__(TPB)
@@ -623,7 +537,17 @@ static int launch_loss_t(const LossParams& P, const LossArgs& A, cudaStream_t s)
     return check_launch("loss_kernel");
 }
 
+// GBCODEC_LOSS_KERNEL=generic forces the shared-memory kernel below for every shape (A/B measurements).
+static bool force_generic() {
+    static const int v = [] { const char* e = getenv("GBCODEC_LOSS_KERNEL"); return (e && !strcmp(e, "generic")) ? 1 : 0; }();
+    return v != 0;
+}
+
 static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s) {
+    if (!force_generic()) {
+        const int st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
+        if (st != 1) return st;
+    }
     const int n4 = (P.H * P.W) >> 2;
     if (n4 == 256 * 3) return launch_loss_t<256, 3, 2>(P, A, s);           // 64x48
     if (n4 == 576 * 3) return launch_loss_t<576, 3, 1>(P, A, s);           // 96x72
@@ -647,13 +571,13 @@ static int check_common(const gbcodec_loss_desc* d, const float* hm, const float
 static int prepare_weights(const LossParams& P, const WsLayout& L, const float* weight, const float* gt,
                            int target_given, const float* denoms, cudaStream_t s) {
     if (denoms) {
-        weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff);
+        weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom);
         sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums);
     } else {
         cudaError_t e = cudaMemsetAsync(L.sums, 0, 2 * sizeof(double), s);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         const int grid = (P.B + 255) / 256 < 148 ? (P.B + 255) / 256 : 148;
-        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.sums);
+        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums);
     }
     return check_launch("denoms_kernel");
 }
@@ -703,7 +627,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.grad_hm = ghm; A.grad_off = goff; A.grad_var = gvar;
     A.alpha_param = alpha_param; A.fusion_weight = fusion_weight; A.coords = coords; A.scores = scores;
     A.radius = radius; A.dflags = dflags;
-    A.sums = L.sums; A.weff = L.weff; A.partial = L.partial;
+    A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial;
     st = launch_loss_kernel(P, A, s);
     if (st) return st;
     finalize_kernel<<<1, 1024, 0, s>>>(P, L.partial, L.sums, losses7);
@@ -733,7 +657,7 @@ int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const floa
     memset(&A, 0, sizeof(A));
     A.hm = hm; A.off = off; A.var = var; A.target = target; A.weight = weight; A.gt = gt;
     A.grad_hm = ghm; A.grad_off = goff; A.grad_var = gvar;
-    A.sums = L.sums; A.weff = L.weff; A.partial = L.partial; A.lam_eff = L.lam_eff; A.plan = L.plan;
+    A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial; A.lam_eff = L.lam_eff; A.plan = L.plan;
     return launch_loss_kernel(P, A, s);
 }
 

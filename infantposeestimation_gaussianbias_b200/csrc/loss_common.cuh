@@ -1,0 +1,123 @@
+// loss_common.cuh — descriptors shared by the loss kernels (loss.cu: host side, pre/post
+// kernels and the generic tile kernel; loss_tile.cu: the register-resident tile kernel).
+#pragma once
+#include "common.cuh"
+#include "decode_device.cuh"
+#include <string.h>
+
+namespace gbc {
+
+// ---- kernel-side description -------------------------------------------------------
+struct LossParams {
+    int B, K, H, W;
+    float in_w, in_h;
+    float lam[6];
+    float sigma;            // target sigma
+    float e_star;           // log(2 pi e sigma^2)
+    int use_target_weight;
+    int n_pairs;
+    EncodeConst ec;
+    int8_t n_partner[GBCODEC_MAX_K];
+    int8_t partner[GBCODEC_MAX_K][GBCODEC_MAX_PARTNERS];
+    uint8_t owner[GBCODEC_MAX_K];       // bit p: this channel is the first index of the pair with partner p
+    int16_t pair_i[GBCODEC_MAX_PAIRS], pair_j[GBCODEC_MAX_PAIRS];
+};
+
+struct LossArgs {
+    const float* hm; const float* off; const float* var; const float* target;
+    const float* weight; const float* gt;
+    const float* grad_scale;            // device scalar or null
+    float* grad_hm; float* grad_off; float* grad_var;
+    // fused decode (null coords = off)
+    const float* alpha_param; const float* fusion_weight; float* coords; float* scores;
+    int radius; unsigned dflags;
+    // workspace
+    const double* sums;                 // [2] raw sums of w and w_i*w_j
+    const float* weff;                  // [B*K] weights after the encoder's rule
+    const int4* geom;                   // [B*K] packed patch geometry of the on-the-fly target (pack_geom)
+    float* partial;                     // [B*K][8] un-normalised per-tile loss numerators
+    const float* lam_eff;               // backward recompute: device [6] per-term multipliers
+    const int* plan;                    // backward recompute: run only if *plan == 2
+};
+
+constexpr int kWsHeaderFloats = 64;     // sums (2 doubles), plan, lam_eff, ... ; 256 bytes
+struct WsLayout {
+    double* sums; int* plan; float* lam_eff; float* weff; int4* geom; float* partial;
+};
+static inline size_t ws_bytes(int B, int K) {
+    return (size_t)(kWsHeaderFloats + (size_t)B * K * 13 + 8) * sizeof(float);
+}
+static inline WsLayout ws_carve(void* ws, int B, int K) {
+    float* f = reinterpret_cast<float*>(ws);
+    WsLayout l;
+    l.sums = reinterpret_cast<double*>(f);          // f[0..3]
+    l.plan = reinterpret_cast<int*>(f + 4);         // f[4..7]
+    l.lam_eff = f + 8;                              // f[8..15]
+    // geom rows are 16 bytes and partial rows 32 bytes: keep both aligned
+    const size_t tiles = (size_t)B * K, tiles8 = (tiles + 7) & ~(size_t)7;
+    l.geom = reinterpret_cast<int4*>(f + kWsHeaderFloats);
+    l.partial = f + kWsHeaderFloats + 4 * tiles8;
+    l.weff = l.partial + 8 * tiles;
+    return l;
+}
+
+// patch geometry in 16 bytes: origin, then [from, to) ranges packed as from | to << 16
+__device__ __forceinline__ int4 pack_geom(const PatchGeom& g) {
+    return make_int4(g.ulx, g.uly, g.active ? (g.x_from | (g.x_to << 16)) : 0, g.active ? (g.y_from | (g.y_to << 16)) : 0);
+}
+__device__ __forceinline__ PatchGeom unpack_geom(const int4& v, float weight) {
+    PatchGeom g;
+    g.ulx = v.x; g.uly = v.y;
+    g.x_from = v.z & 0xffff; g.x_to = v.z >> 16;
+    g.y_from = v.w & 0xffff; g.y_to = v.w >> 16;
+    g.weight = weight;
+    g.active = (g.x_to > g.x_from) && (g.y_to > g.y_from);
+    return g;
+}
+
+// ---- bilinear helpers (same convention as decode.cu) ---------------------------------
+struct Taps {
+    int i00, i01, i10, i11;          // flat indices inside a channel
+    float w00, w01, w10, w11;        // weights, already zero for taps outside the map
+    float fx, fy, inx, iny, okx, oky;
+};
+__device__ __forceinline__ Taps taps_setup(float cx, float cy, int H, int W) {
+    Taps t;
+    const float ccx = fminf(fmaxf(cx, 0.f), (float)(W - 1));
+    const float ccy = fminf(fmaxf(cy, 0.f), (float)(H - 1));
+    t.inx = (cx >= 0.f && cx <= (float)(W - 1)) ? 1.f : 0.f;
+    t.iny = (cy >= 0.f && cy <= (float)(H - 1)) ? 1.f : 0.f;
+    const float fx0 = floorf(ccx), fy0 = floorf(ccy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    t.fx = ccx - fx0; t.fy = ccy - fy0;
+    t.okx = (x0 + 1 < W) ? 1.f : 0.f;
+    t.oky = (y0 + 1 < H) ? 1.f : 0.f;
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    t.i00 = y0 * W + x0; t.i01 = y0 * W + x1; t.i10 = y1 * W + x0; t.i11 = y1 * W + x1;
+    t.w00 = (1.f - t.fx) * (1.f - t.fy);
+    t.w01 = t.fx * (1.f - t.fy) * t.okx;
+    t.w10 = (1.f - t.fx) * t.fy * t.oky;
+    t.w11 = t.fx * t.fy * t.okx * t.oky;
+    return t;
+}
+
+__device__ __forceinline__ float tie_rule(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+// per-tile scalars broadcast from thread 0 to the CTA
+struct TileCoef {
+    float c1;        // lambda1 * wa/(Da N) * 2
+    float c4;        // lambda4 * w/D * (s - sigma)/s / R'
+    float v;         // variance of the tile
+    float c6;        // lambda6 * w/D * 2 (E - E*)
+    float pa;        // sum p a
+    float fx, fy;    // d(loss)/d(cx, cy)
+    float gv;        // uniform gradient of the variance map
+    float go[2];     // lambda2 * wa/(2 Da) * sl1'(d_ch)
+};
+
+
+// loss_tile.cu: register-resident kernel for tiles whose rows split evenly over the CTA;
+// returns 1 if it has no instantiation for this shape (the caller then uses the generic kernel).
+int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+
+}  // namespace gbc
