@@ -500,6 +500,8 @@ static int make_params(const gbcodec_loss_desc* d, LossParams* P) {
     for (int q = 0; q < 6; ++q) P->lam[q] = d->lambdas[q];
     P->sigma = (float)d->target_sigma;
     P->e_star = (float)log(2.0 * M_PI * M_E * d->target_sigma * d->target_sigma);
+    P->inv_n = 1.0f / (float)(d->H * d->W);
+    P->sx = (float)d->W / d->in_w; P->sy = (float)d->H / d->in_h;
     P->use_target_weight = d->use_target_weight;
     P->ec = make_encode_const(d->encode_sigma);
     int np = 0;

@@ -14,6 +14,8 @@ struct LossParams {
     float lam[6];
     float sigma;            // target sigma
     float e_star;           // log(2 pi e sigma^2)
+    float inv_n;            // 1 / (H*W)
+    float sx, sy;           // W / in_w, H / in_h (fusion_head.py:679-684)
     int use_target_weight;
     int n_pairs;
     EncodeConst ec;

@@ -10,12 +10,14 @@
 //     loads); the per-pixel intermediates a later pass needs (softmax weight, sigmoid, entropy
 //     derivative) are parked in thread-private shared-memory slots — no cross-thread traffic,
 //     conflict-free 128-bit accesses;
-//   * four block reductions per tile, ONE barrier each (halving butterfly inside the warp,
+//   * three block reductions per tile, ONE barrier each (halving butterfly inside the warp,
 //     then every warp finishes the cross-warp sum redundantly); the per-tile scalars are
 //     computed by every thread, so nothing waits for "thread 0";
-//   * all limb partners of the tile are visited once (their tiles are some other CTA's own
-//     tile: L2 hits); the per-pixel tie pattern the gradient needs is kept as one bit per pixel
-//     and partner in a register;
+//   * the limb partners' tiles (some other CTA's own tile: L2 hits) stream through a
+//     thread-private shared-memory slot with cp.async, the next partner's copy in flight while
+//     the current one is consumed; each is visited once, the per-pixel tie pattern the gradient
+//     needs is kept as one bit per pixel and partner, and the gradient pass turns the 4-bit
+//     pattern of a pixel into its overlap coefficient with one table look-up;
 //   * stores are spread over the kernel's lifetime: the (almost all zero) offset-gradient tile
 //     leaves right after the loads are issued, the uniform variance-gradient tile once the
 //     first reduction is known, the heatmap gradient at the end;
@@ -53,9 +55,10 @@ template <> struct Log2<1> { static constexpr int value = 0; };
 
 // Block-wide sums of NV values; `red` holds NW*NV floats and must not be the buffer of the
 // previous reduction (the callers alternate two buffers).  Fixed order: deterministic, and
-// every thread ends with the same bits.
+// every thread ends with the same bits.  Returns the lane-distributed totals: value k sits in
+// lane k << (5 - log2 NV) of every warp (fetch it with __shfl_sync).
 template <int NV, int NW>
-__device__ __forceinline__ void block_sum1(float (&v)[NV], float* red) {
+__device__ __forceinline__ float block_sum1(float (&v)[NV], float* red) {
     constexpr int SH = 5 - Log2<NV>::value, SUB = 32 / NV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     warp_scatter_sum<NV>(v);
@@ -70,9 +73,10 @@ __device__ __forceinline__ void block_sum1(float (&v)[NV], float* red) {
     }
 #pragma unroll
     for (int o = SUB / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = __shfl_sync(0xffffffffu, acc, k << SH);
+    return acc;
 }
+template <int NV>
+__device__ __forceinline__ float lane_value(float acc, int k) { return __shfl_sync(0xffffffffu, acc, k << (5 - Log2<NV>::value)); }
 
 template <int NW>
 __device__ __forceinline__ float block_max1(float m, float* red) {
@@ -83,49 +87,94 @@ __device__ __forceinline__ float block_max1(float m, float* red) {
     return warp_max(lane < NW ? red[lane] : -INFINITY);
 }
 
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+// ---- small helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float fsqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// bit i of the low byte -> bit 4*i
+__device__ __forceinline__ unsigned spread8(unsigned t) {
+    unsigned x = t & 0xFFu;
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x;
+}
+template <typename T>
+__device__ __forceinline__ T pick4(int i, T a, T b, T c, T d) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d)); }
+
+// Out-of-line copy of the un-staged decode tail for the rare paths (weight-0 tiles, radius > 2),
+// so that the hot path's code stays small.
+__device__ __noinline__ void refine_and_correct_cold(const float* hm_tile, const float* off_tile, const float* alpha_param,
+                                                     const float* fusion_weight, int H, int W, int radius, unsigned flags,
+                                                     float* cx, float* cy) {
+    int px, py;
+    refine_and_correct(hm_tile, nullptr, off_tile, alpha_param, fusion_weight, H, W, radius, flags, *cx, *cy, px, py);
+}
+
+// Target modes: where the target tile comes from
+constexpr int kTargetOneHit = 0;   // generated on the fly; the patch is no taller than ROWS, so a thread meets it in at most one row
+constexpr int kTargetGlobal = 1;   // read from HBM (stand-alone loss with d_target)
+constexpr int kTargetLut = 2;      // generated on the fly, any patch height
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int TM, int MINB>
 __global__ void __launch_bounds__(W4* ROWS, MINB)
 loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
     constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
+    constexpr int NWORD = (NIT + 1) / 2;            // tie-pattern words: 8 pixels x 4 partners each
     static_assert(TPB % 32 == 0 && TPB <= 1024, "CTA must be whole warps");
-    static_assert(4 * NIT <= 32, "one tie bit per owned pixel must fit a register");
+    static_assert(GBCODEC_MAX_PARTNERS == 4, "tie patterns are nibbles");
     if (A.plan && *A.plan != 2) return;      // backward recompute not needed
 
     extern __shared__ __align__(16) float smem[];
-    float4* Es = reinterpret_cast<float4*>(smem);                 // exp(h - max), later softmax weight p
+    float4* Qs = reinterpret_cast<float4*>(smem);                 // partner tile, thread-private slots
+    float4* Es = Qs + N4;                                         // exp(h - max), later softmax weight p
     float4* Ss = Es + (CE ? N4 : 0);                              // sigmoid(h)
     float4* As = Ss + (CS ? N4 : 0);                              // a = -log(p + eps) - p / (p + eps)
-    float* lut = reinterpret_cast<float*>(As + (CA ? N4 : 0));
-    float* red = lut + ((P.ec.lut_size + 3) & ~3);                // 2 buffers of NW * 8 floats
-    float* red0 = red, *red1 = red + NW * 8;
+    float* red0 = reinterpret_cast<float*>(As + (CA ? N4 : 0));   // two reduction buffers of NW * 16 floats
+    float* red1 = red0 + NW * 16;
+    float* lutG = red1 + NW * 16;                                 // per warp: 16 overlap coefficients + 4 partner scales
+    float* lut = lutG + NW * 20;                                  // exp table of the target patch
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % W4, ty = tid / W4;
     const int x0 = tx << 2;
     const float fx0 = (float)x0, fty = (float)ty;
     const int tile = blockIdx.x;
     const int b = tile / P.K, k = tile - b * P.K;
 
-    const bool has_target = A.target != nullptr;
     const bool grads = A.grad_hm != nullptr;
     const bool backward_only = A.lam_eff != nullptr;
     const bool decode = A.coords != nullptr;
 
-    const float4* hm4 = reinterpret_cast<const float4*>(A.hm) + (size_t)tile * N4 + tid;
-    const float4* tgt4 = has_target ? reinterpret_cast<const float4*>(A.target) + (size_t)tile * N4 + tid : nullptr;
+    const float4* hmb = reinterpret_cast<const float4*>(A.hm) + tid;
+    const float4* hm4 = hmb + (size_t)tile * N4;
     float4* gh4 = grads ? reinterpret_cast<float4*>(A.grad_hm) + (size_t)tile * N4 + tid : nullptr;
     float4* gv4 = (grads && A.grad_var) ? reinterpret_cast<float4*>(A.grad_var) + (size_t)tile * N4 + tid : nullptr;
-    float4* go4 = grads ? reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid : nullptr;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // ---- loads first: the tile into registers -----------------------------------------------
+    // ---- loads first: the tile into registers, then every scalar the tile will need ------------
     float4 h[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) h[it] = ldg_stream(hm4 + it * TPB);
     const float w = __ldg(A.weff + tile);
+    const int np = P.n_partner[k];
+    const int4 pj4 = make_int4(P.partner[k][0], P.partner[k][1], P.partner[k][2], P.partner[k][3]);
+    float wjv[4];
+#pragma unroll
+    for (int pi = 0; pi < 4; ++pi) wjv[pi] = pi < np ? __ldg(A.weff + b * P.K + pick4(pi, pj4.x, pj4.y, pj4.z, pj4.w)) : 0.f;
+    const float gx = __ldg(A.gt + 2 * tile) * P.sx;
+    const float gy = __ldg(A.gt + 2 * tile + 1) * P.sy;
+    const float D = (float)__ldg(A.sums) + kEps;
+    const float D5 = (float)__ldg(A.sums + 1) + kEps;
+    const float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
+    int4 gq = make_int4(0, 0, 0, 0);
+    if (TM != kTargetGlobal) gq = __ldg(A.geom + tile);
+
     const float wa = P.use_target_weight ? w : 1.f;
     const bool heavy = (w != 0.f) || !P.use_target_weight;
     float vsum = 0.f;
@@ -139,49 +188,60 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
     // the offset gradient is zero except on (up to) four taps per channel, patched at the end
     if (grads) {
+        float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
 #pragma unroll
         for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
     }
-    const float D = (float)__ldg(A.sums) + kEps;
-    const float D5 = (float)__ldg(A.sums + 1) + kEps;
-    const float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
-    float lam[6];
+    // active partners (both weights non-zero), as a 4-bit mask; CTA-uniform
+    unsigned act = 0;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) lam[q] = backward_only ? __ldg(A.lam_eff + q) : P.lam[q] * gscale;
+    for (int pi = 0; pi < 4; ++pi) if (w != 0.f && wjv[pi] != 0.f) act |= 1u << pi;
 
     // on-the-fly target: patch geometry (from the weights pre-kernel) and the exp table
     PatchGeom geom = PatchGeom{};
     bool cols_hit = false;
     int pcx = 0, pcy = 0;
-    if (!has_target && heavy) {
-        geom = unpack_geom(__ldg(A.geom + tile), w);
+    if (TM != kTargetGlobal && heavy) {
+        geom = unpack_geom(gq, w);
         cols_hit = geom.active && x0 + 3 >= geom.x_from && x0 < geom.x_to;
         pcx = geom.ulx + (int)P.ec.centre; pcy = geom.uly + (int)P.ec.centre;
         if (geom.active) fill_patch_lut(lut, P.ec);
     }
-    auto target4 = [&](int it) -> float4 {
-        if (has_target) return ldg_keep(tgt4 + it * TPB);
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int y = it * ROWS + ty;
-        if (cols_hit && y >= geom.y_from && y < geom.y_to) {
-            const int dy2 = (y - pcy) * (y - pcy);
-            float e[4];
+    auto patch_row = [&](int y) -> float4 {
+        const int dy2 = (y - pcy) * (y - pcy);
+        float e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int xx = x0 + j, dx = xx - pcx;
-                e[j] = (xx >= geom.x_from && xx < geom.x_to) ? lut[dx * dx + dy2] : 0.f;
-            }
-            t = make_float4(e[0], e[1], e[2], e[3]);
+        for (int j = 0; j < 4; ++j) {
+            const int xx = x0 + j, dx = xx - pcx;
+            e[j] = (xx >= geom.x_from && xx < geom.x_to) ? lut[dx * dx + dy2] : 0.f;
         }
-        return t;
+        return make_float4(e[0], e[1], e[2], e[3]);
     };
 
     // ---- reduction 1: tile maximum -----------------------------------------------------------
     float m = -INFINITY;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) m = fmaxf(m, fmaxf(fmaxf(h[it].x, h[it].y), fmaxf(h[it].z, h[it].w)));
-    m = block_max1<NW>(m, red0);             // also publishes the exp table
+    m = block_max1<NW>(m, red0);             // the barrier also publishes the exp table
     const float ml = m * kLog2e;
+
+    // kTargetOneHit: the one row (if any) in which this thread meets the patch
+    int hit_it = -1;
+    float4 thit = z4;
+    if (TM == kTargetOneHit && cols_hit) {
+        const int it0 = max(0, (geom.y_from - ty + ROWS - 1) / ROWS);
+        const int y = it0 * ROWS + ty;
+        if (it0 < NIT && y < geom.y_to) { hit_it = it0; thit = patch_row(y); }
+    }
+    auto target4 = [&](int it) -> float4 {
+        if (TM == kTargetGlobal) return ldg_keep(reinterpret_cast<const float4*>(A.target) + (size_t)tile * N4 + tid + it * TPB);
+        if (TM == kTargetOneHit) {
+            const bool on = it == hit_it;
+            return make_float4(on ? thit.x : 0.f, on ? thit.y : 0.f, on ? thit.z : 0.f, on ? thit.w : 0.f);
+        }
+        const int y = it * ROWS + ty;
+        return (cols_hit && y >= geom.y_from && y < geom.y_to) ? patch_row(y) : z4;
+    };
 
     // ---- pass B: softmax moments, sigmoid mass, squared error ------------------------------------
     float r8[8];
@@ -213,20 +273,18 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         r8[2] = fmaf(fty, Zt, Yw);
         r8[3] = Ssum_t; r8[4] = mse; r8[5] = vsum; r8[6] = 0.f; r8[7] = 0.f;
     }
-    block_sum1<8, NW>(r8, red1);
-    const float iZ = 1.f / r8[0];
-    const float cx = r8[1] * iZ, cy = r8[2] * iZ;
-    const float Ssum = r8[3], mse_sum = r8[4], mV = A.var ? r8[5] / (float)N : P.sigma;
+    const float acc8 = block_sum1<8, NW>(r8, red1);
+    const float iZ = rcp(lane_value<8>(acc8, 0));
+    const float cx = lane_value<8>(acc8, 1) * iZ, cy = lane_value<8>(acc8, 2) * iZ;
 
-    float* gh = grads ? A.grad_hm + (size_t)tile * N : nullptr;
     const float* hm_tile = A.hm + (size_t)tile * N;
     const float* off_tile = A.off + (size_t)tile * 2 * N;
 
     // ---- weight 0: every term carries a factor w -> zero loss and gradient; decode only ----------
     if (!heavy) {
         if (decode && tid < 32) {
-            float dx_ = cx, dy_ = cy; int px, py;
-            refine_and_correct(hm_tile, nullptr, off_tile, A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, dx_, dy_, px, py);
+            float dx_ = cx, dy_ = cy;
+            refine_and_correct_cold(hm_tile, off_tile, A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, &dx_, &dy_);
             if (tid == 0) { A.coords[2 * tile] = dx_; A.coords[2 * tile + 1] = dy_; A.scores[tile] = m; }
         }
         if (tid == 0 && !backward_only) {
@@ -242,10 +300,24 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         }
         return;
     }
+    const float Ssum = lane_value<8>(acc8, 3), mse_sum = lane_value<8>(acc8, 4);
+    const float mV = A.var ? lane_value<8>(acc8, 5) * P.inv_n : P.sigma;
+    float lam[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) lam[q] = backward_only ? __ldg(A.lam_eff + q) : P.lam[q] * gscale;
+    const float iD = rcp(D);
+    const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
 
     // ---- things that only need the soft-argmax: start their loads now ----------------------------
-    const float ka = wa / (P.use_target_weight ? D : (float)(P.B * P.K)), kb = w / D;
-    // (1) the 8 offset taps of the offset term (same addresses in every thread: one L1 line per warp)
+    // (1) first active partner's tile -> thread-private smem slots
+    int cur = act ? __ffs(act) - 1 : -1;
+    if (cur >= 0) {
+        const float4* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+        cp_async_commit();
+    }
+    // (2) the 8 offset taps of the offset term (same addresses in every thread: one L1 line per warp)
     const Taps tp = taps_setup(cx, cy, H, W);
     float ov[2][4];
 #pragma unroll
@@ -253,7 +325,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         ov[c][0] = __ldg(off_tile + c * N + tp.i00); ov[c][1] = __ldg(off_tile + c * N + tp.i01) * tp.okx;
         ov[c][2] = __ldg(off_tile + c * N + tp.i10) * tp.oky; ov[c][3] = __ldg(off_tile + c * N + tp.i11) * (tp.okx * tp.oky);
     }
-    // (2) decode stage 1 (warp 0): window taps around the rounded soft-argmax
+    // (3) decode stage 1 (warp 0): window taps around the rounded soft-argmax
     const bool staged_decode = decode && (A.dflags & GBCODEC_DECODE_REFINE) && A.radius <= 2;
     float win = -INFINITY, winx = 0.f, winy = 0.f;
     bool win_ok = false;
@@ -266,9 +338,9 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         winx = (float)x; winy = (float)y;
         if (win_ok) win = __ldg(hm_tile + y * W + x);
     }
-    // (3) the variance-map gradient is uniform over the tile
+    // (4) the variance-map gradient is uniform over the tile
     if (gv4) {
-        const float g = lam[3] * kb * 2.f * (mV - P.sigma) / (float)N;
+        const float g = lam[3] * kb * 2.f * (mV - P.sigma) * P.inv_n;
         const float4 g4 = make_float4(g, g, g, g);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) stg_stream(gv4 + it * TPB, g4);
@@ -279,6 +351,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
     for (int j = 0; j < 4; ++j) { dxj[j] = (fx0 + (float)j) - cx; dx2j[j] = dxj[j] * dxj[j]; }
     const float dy0 = fty - cy;
+    float r16[16];
     {
         float A1 = 0.f, A2 = 0.f, Ry = 0.f, Ry2 = 0.f;
         float Rj[4] = {0.f, 0.f, 0.f, 0.f};
@@ -311,14 +384,62 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             Ry = fmaf(dy, rs, Ry);
             Ry2 = fmaf(dy * dy, rs, Ry2);
         }
-        r8[0] = A1; r8[1] = A2;
-        r8[2] = fmaf(dx2j[0], Rj[0], fmaf(dx2j[1], Rj[1], fmaf(dx2j[2], Rj[2], fmaf(dx2j[3], Rj[3], Ry2))));
-        r8[3] = fmaf(dxj[0], Rj[0], fmaf(dxj[1], Rj[1], fmaf(dxj[2], Rj[2], dxj[3] * Rj[3])));
-        r8[4] = Ry;
-        r8[5] = (Rj[0] + Rj[1]) + (Rj[2] + Rj[3]);
-        r8[6] = 0.f; r8[7] = 0.f;
+        r16[0] = A1; r16[1] = A2;
+        r16[2] = fmaf(dx2j[0], Rj[0], fmaf(dx2j[1], Rj[1], fmaf(dx2j[2], Rj[2], fmaf(dx2j[3], Rj[3], Ry2))));
+        r16[3] = fmaf(dxj[0], Rj[0], fmaf(dxj[1], Rj[1], fmaf(dxj[2], Rj[2], dxj[3] * Rj[3])));
+        r16[4] = Ry;
+        r16[5] = (Rj[0] + Rj[1]) + (Rj[2] + Rj[3]);
+#pragma unroll
+        for (int q = 6; q < 16; ++q) r16[q] = 0.f;
     }
-    block_sum1<8, NW>(r8, red0);
+
+    // ---- limb partners: one visit each; sums for the overlap ratio, one tie bit per pixel -------------
+    unsigned words[NWORD];
+#pragma unroll
+    for (int q = 0; q < NWORD; ++q) words[q] = 0u;
+    bool anyeq = false;
+    while (cur >= 0) {
+        const unsigned rest = act & ~((2u << cur) - 1u);
+        const int nxt = rest ? __ffs(rest) - 1 : -1;
+        const float4* src = hmb + ((size_t)b * P.K + pick4(nxt < 0 ? 0 : nxt, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        cp_async_wait_all();                          // this thread's slots hold partner `cur`
+        float Sj = 0.f, M = 0.f;
+        unsigned tb = 0u;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const float4 q4 = Qs[it * TPB + tid];
+            const float hv[4] = {h[it].x, h[it].y, h[it].z, h[it].w};
+            const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+            float sk[4], sq[4];
+            if (CS) { const float4 s4 = Ss[it * TPB + tid]; sk[0] = s4.x; sk[1] = s4.y; sk[2] = s4.z; sk[3] = s4.w; }
+            else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) sk[jj] = sigmoid_fast(hv[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) sq[jj] = sigmoid_fast(qq[jj]);
+            // the slot has been consumed (its value went through the sigmoid): refill it with the next partner
+            if (nxt >= 0) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                Sj += sq[jj];
+                // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
+                const bool own_smaller = hv[jj] < qq[jj];
+                M += own_smaller ? sk[jj] : sq[jj];
+                if (own_smaller) tb |= 1u << (it * 4 + jj);
+                anyeq |= hv[jj] == qq[jj];
+            }
+        }
+        cp_async_commit();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) if (cur == s) { r16[6 + 2 * s] = Sj; r16[7 + 2 * s] = M; }
+#pragma unroll
+        for (int q = 0; q < NWORD; ++q) words[q] |= spread8(tb >> (8 * q)) << cur;
+        cur = nxt;
+    }
+
+    // ---- reduction 3: entropy / variance sums and the partner sums in one go ------------------------------
+    const float acc16 = block_sum1<16, NW>(r16, red0);
 
     // ---- decode stage 2 (warp 0): window softmax, blend, start the bilinear offset read ---------------
     float dcx = cx, dcy = cy, dtap = 0.f;
@@ -332,8 +453,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             dcx = a * cx + (1.f - a) * (sx / se);
             dcy = a * cy + (1.f - a) * (sy / se);
         } else if (A.dflags & GBCODEC_DECODE_REFINE) {
-            int px, py;
-            refine_and_correct(hm_tile, nullptr, nullptr, A.alpha_param, nullptr, H, W, A.radius, GBCODEC_DECODE_REFINE, dcx, dcy, px, py);
+            refine_and_correct_cold(hm_tile, nullptr, A.alpha_param, nullptr, H, W, A.radius, GBCODEC_DECODE_REFINE, &dcx, &dcy);
         }
         if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
             dbl = bilinear_setup(dcx, dcy, H, W);
@@ -345,10 +465,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
 
     // ---- per-tile scalars (every thread: nobody waits) ---------------------------------------------------
-    const float gx = __ldg(A.gt + 2 * tile) * ((float)W / P.in_w);
-    const float gy = __ldg(A.gt + 2 * tile + 1) * ((float)H / P.in_h);
-    const float Rp = r8[5] + kEps;
-    const float iRp = 1.f / Rp;
+    const float iRp = rcp(lane_value<16>(acc16, 5) + kEps);
     float c1, c4, k4, c6, fxx, fyy, go0, go1, pa_;
     {
         float sl1 = 0.f, sl1p[2], dsdx[2], dsdy[2];
@@ -364,118 +481,77 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         }
         const float off_t = 0.5f * sl1;
         const float peak_t = (cx - gx) * (cx - gx) + (cy - gy) * (cy - gy);
-        const float v = r8[2] * iRp;
-        const float s = sqrtf(v + kEps);
+        const float v = lane_value<16>(acc16, 2) * iRp;
+        const float s = fsqrt_fast(v + kEps);
         const float var_t = (s - P.sigma) * (s - P.sigma) + (A.var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
-        const float E = -kLn2 * r8[0];
-        const float pa = E - r8[1];
+        const float E = -kLn2 * lane_value<16>(acc16, 0);
+        const float pa = E - lane_value<16>(acc16, 1);
         const float shape_t = (E - P.e_star) * (E - P.e_star);
         if (tid == 0 && !backward_only) {
             float* p = A.partial + (size_t)tile * 8;
-            p[0] = wa * (mse_sum / (float)N); p[1] = wa * off_t; p[2] = wa * peak_t;
-            p[3] = w * var_t; p[5] = w * shape_t;      // p[4] (limb overlap) follows the partner pass
+            p[0] = wa * (mse_sum * P.inv_n); p[1] = wa * off_t; p[2] = wa * peak_t;
+            p[3] = w * var_t; p[5] = w * shape_t;      // p[4] (limb overlap) below
         }
-        c1 = lam[0] * ka * 2.f / (float)N;
-        const float a4 = lam[3] * kb * (s - P.sigma) / s;
+        c1 = lam[0] * ka * 2.f * P.inv_n;
+        const float a4 = lam[3] * kb * (s - P.sigma) * rcp(s);
         c4 = a4 * iRp;
         k4 = -c4 * v;
         c6 = lam[5] * kb * 2.f * (E - P.e_star);
         pa_ = pa;
-        const float dv_dcx = -2.f * r8[3] * iRp, dv_dcy = -2.f * r8[4] * iRp;
+        const float dv_dcx = -2.f * lane_value<16>(acc16, 3) * iRp, dv_dcy = -2.f * lane_value<16>(acc16, 4) * iRp;
         fxx = lam[2] * ka * 2.f * (cx - gx) + lam[1] * ka * 0.5f * (sl1p[0] * (dsdx[0] + 1.f) + sl1p[1] * dsdx[1]) + a4 * dv_dcx;
         fyy = lam[2] * ka * 2.f * (cy - gy) + lam[1] * ka * 0.5f * (sl1p[0] * dsdy[0] + sl1p[1] * (dsdy[1] + 1.f)) + a4 * dv_dcy;
         go0 = lam[1] * ka * 0.5f * sl1p[0];
         go1 = lam[1] * ka * 0.5f * sl1p[1];
     }
-
-    // ---- limb partners: one visit each; sums for the overlap ratio, one tie bit per pixel -------------
-    const int np = P.n_partner[k];
-    unsigned bits[GBCODEC_MAX_PARTNERS];
-    float wj_[GBCODEC_MAX_PARTNERS];
-    unsigned eqflags = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) r8[q] = 0.f;
-#pragma unroll
-    for (int pi = 0; pi < GBCODEC_MAX_PARTNERS; ++pi) {
-        bits[pi] = 0u; wj_[pi] = 0.f;
-        if (pi < np) {                                              // CTA-uniform
-            const int j = P.partner[k][pi];
-            const float wj = __ldg(A.weff + b * P.K + j);
-            wj_[pi] = wj;
-            if (w != 0.f && wj != 0.f) {
-                const float4* hj4 = reinterpret_cast<const float4*>(A.hm) + ((size_t)b * P.K + j) * N4 + tid;
-                float4 qv[NIT];
-#pragma unroll
-                for (int it = 0; it < NIT; ++it) qv[it] = ldg_stream(hj4 + it * TPB);
-                float Sj = 0.f, M = 0.f;
-                bool anyeq = false;
-#pragma unroll
-                for (int it = 0; it < NIT; ++it) {
-                    const float hv[4] = {h[it].x, h[it].y, h[it].z, h[it].w};
-                    const float qq[4] = {qv[it].x, qv[it].y, qv[it].z, qv[it].w};
-                    float sk[4];
-                    if (CS) { const float4 s4 = Ss[it * TPB + tid]; sk[0] = s4.x; sk[1] = s4.y; sk[2] = s4.z; sk[3] = s4.w; }
-                    else {
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) sk[jj] = sigmoid_fast(hv[jj]);
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float sq = sigmoid_fast(qq[jj]);
-                        Sj += sq;
-                        // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
-                        const bool own_smaller = hv[jj] < qq[jj];
-                        M += own_smaller ? sk[jj] : sq;
-                        if (own_smaller) bits[pi] |= 1u << (it * 4 + jj);
-                        anyeq |= hv[jj] == qq[jj];
-                    }
-                }
-                r8[2 * pi] = Sj; r8[2 * pi + 1] = M;
-                if (anyeq) eqflags |= 1u << pi;
-            }
-        }
-    }
-    float cj[GBCODEC_MAX_PARTNERS] = {0.f, 0.f, 0.f, 0.f};
-    float cst = 0.f;
+    // overlap ratios -> loss numerator and the per-partner gradient scale
     bool g_live = false;
-    if (np > 0) {
-        block_sum1<8, NW>(r8, red1);
-        float pair_loss = 0.f;
+    float* lutw = lutG + warp * 20;
+    {
+        float cj[4] = {0.f, 0.f, 0.f, 0.f};
+        float cst = 0.f, pair_loss = 0.f;
+        const float iD5 = rcp(D5);
 #pragma unroll
-        for (int pi = 0; pi < GBCODEC_MAX_PARTNERS; ++pi) {
-            if (pi < np && w != 0.f && wj_[pi] != 0.f) {
-                const float Sj = r8[2 * pi], M = r8[2 * pi + 1];
-                const float mm = fminf(Ssum, Sj) + kEps;
-                const float rho = M / mm;
-                if ((P.owner[k] >> pi) & 1) pair_loss += w * wj_[pi] * fmaxf(rho - 0.5f, 0.f);
+        for (int pi = 0; pi < 4; ++pi) {
+            if ((act >> pi) & 1u) {                     // CTA-uniform
+                const float Sj = lane_value<16>(acc16, 6 + 2 * pi), M = lane_value<16>(acc16, 7 + 2 * pi);
+                const float imm = rcp(fminf(Ssum, Sj) + kEps);
+                const float rho = M * imm;
+                if ((P.owner[k] >> pi) & 1) pair_loss += w * wjv[pi] * fmaxf(rho - 0.5f, 0.f);
                 if (grads && rho > 0.5f) {
-                    cj[pi] = lam[4] * w * wj_[pi] / D5 / mm;
+                    cj[pi] = lam[4] * w * wjv[pi] * iD5 * imm;
                     cst += cj[pi] * rho * tie_rule(Ssum, Sj);
                     g_live = true;
                 }
             }
         }
         if (tid == 0 && !backward_only) A.partial[(size_t)tile * 8 + 4] = pair_loss;
-    } else if (tid == 0 && !backward_only) {
-        A.partial[(size_t)tile * 8 + 4] = 0.f;
+        if (g_live) {
+            // per warp: the overlap coefficient of a pixel as a function of its 4-bit tie pattern
+            if (lane < 16) {
+                float g = -cst;
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi) if ((lane >> pi) & 1) g += cj[pi];
+                lutw[lane] = g;
+            } else if (lane < 20) {
+                lutw[lane] = pick4(lane - 16, cj[0], cj[1], cj[2], cj[3]);
+            }
+            __syncwarp();
+        }
     }
-
-    // ---- decode stage 3 (warp 0): finish the bilinear read, publish -----------------------------------
-    if (decode && tid < 32) {
-        if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
+    if (!grads) {
+        if (decode && tid < 32 && (A.dflags & GBCODEC_DECODE_APPLY_OFFSET)) {
             float fw = __ldg(A.fusion_weight);
             if (A.dflags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
             float t[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) t[q] = __shfl_sync(0xffffffffu, dtap, q);
-            const float ox = dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky));
-            const float oy = dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky));
-            dcx += fw * ox;
-            dcy += fw * oy;
+            dcx += fw * (dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky)));
+            dcy += fw * (dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky)));
         }
-        if (tid == 0) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
+        if (decode && tid == 0) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
+        return;
     }
-    if (!grads) return;
 
     // ---- pass D: the heatmap gradient ----------------------------------------------------------------------
     float basej[4];
@@ -509,37 +585,56 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             out[j] = g;
         }
         if (g_live) {
-            float G[4] = {-cst, -cst, -cst, -cst};
-#pragma unroll
-            for (int pi = 0; pi < GBCODEC_MAX_PARTNERS; ++pi) {
-                if (cj[pi] != 0.f) {                                  // CTA-uniform
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if ((bits[pi] >> (it * 4 + j)) & 1u) G[j] += cj[pi];
-                }
-            }
-            if (eqflags) {
-                // rare: some logit of this thread equals its partner's; ATen's minimum splits that gradient evenly
-#pragma unroll
-                for (int pi = 0; pi < GBCODEC_MAX_PARTNERS; ++pi) {
-                    if (((eqflags >> pi) & 1u) && cj[pi] != 0.f) {
-                        const int jp = P.partner[k][pi];
-                        const float4 q = ldg_keep(reinterpret_cast<const float4*>(A.hm) + ((size_t)b * P.K + jp) * N4 + tid + it * TPB);
-                        const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (qq[j] == hv[j]) G[j] += 0.5f * cj[pi];
-                    }
-                }
-            }
             float sv[4];
             if (CS) { const float4 s4 = Ss[it * TPB + tid]; sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w; }
             else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sv[j] = sigmoid_fast(hv[j]);
             }
+            const unsigned wd = words[it >> 1] >> ((it & 1) * 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = fmaf(G[j] * sv[j], 1.f - sv[j], out[j]);
+            for (int j = 0; j < 4; ++j) {
+                const float G = lutw[(wd >> (4 * j)) & 15u];
+                out[j] = fmaf(G, fmaf(-sv[j], sv[j], sv[j]), out[j]);
+            }
         }
         stg_stream(gh4 + it * TPB, make_float4(out[0], out[1], out[2], out[3]));
+    }
+
+    // rare: a logit of this thread equals its partner's — ATen's minimum splits that gradient evenly.
+    // Patch the pixels this thread has just written (same thread, program order).
+    if (g_live && anyeq) {
+        for (int pi = 0; pi < 4; ++pi) {
+            const float cjp = lutw[16 + pi];
+            if (!((act >> pi) & 1u) || cjp == 0.f) continue;
+            const float4* src = hmb + ((size_t)b * P.K + pick4(pi, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+            for (int it = 0; it < NIT; ++it) {
+                const float4 q = ldg_keep(src + it * TPB), o = ldg_keep(hm4 + it * TPB);
+                if (q.x == o.x || q.y == o.y || q.z == o.z || q.w == o.w) {
+                    float4 g = gh4[it * TPB];
+                    float s;
+                    if (q.x == o.x) { s = sigmoid_fast(o.x); g.x = fmaf(0.5f * cjp * s, 1.f - s, g.x); }
+                    if (q.y == o.y) { s = sigmoid_fast(o.y); g.y = fmaf(0.5f * cjp * s, 1.f - s, g.y); }
+                    if (q.z == o.z) { s = sigmoid_fast(o.z); g.z = fmaf(0.5f * cjp * s, 1.f - s, g.z); }
+                    if (q.w == o.w) { s = sigmoid_fast(o.w); g.w = fmaf(0.5f * cjp * s, 1.f - s, g.w); }
+                    gh4[it * TPB] = g;
+                }
+            }
+        }
+    }
+
+    // ---- decode stage 3 (warp 0): finish the bilinear read, publish -----------------------------------
+    if (decode && tid < 32) {
+        if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
+            float fw = __ldg(A.fusion_weight);
+            if (A.dflags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
+            float t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = __shfl_sync(0xffffffffu, dtap, q);
+            dcx += fw * (dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky)));
+            dcy += fw * (dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky)));
+        }
+        if (tid == 0) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
     }
 
     // the (up to) four non-zero taps per channel of the offset gradient; the zero fill of these
@@ -559,12 +654,12 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int TM, int MINB>
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
-    const size_t smem = (size_t)N4 * 16 * ((CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
-                      + (size_t)((P.ec.lut_size + 3) & ~3) * 4 + (size_t)2 * NW * 8 * 4;
-    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, MINB>;
+    const size_t smem = (size_t)N4 * 16 * (1 + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
+                      + (size_t)(2 * NW * 16 + NW * 20) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
+    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, TM, MINB>;
     if (smem > 227 * 1024) return 1;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_kernel): %s", cudaGetErrorString(e));
@@ -576,10 +671,17 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     return check_launch("loss_tile_kernel");
 }
 
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB>
+static int launch_tile_tm(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetGlobal, MINB>(P, A, s, e0, e1);
+    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetOneHit, MINB>(P, A, s, e0, e1);
+    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetLut, MINB>(P, A, s, e0, e1);
+}
+
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
-    if (P.H == 64 && P.W == 48) return launch_tile_t<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);      // 192 threads, 16 px each
-    if (P.H == 96 && P.W == 72) return launch_tile_t<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);      // 288 threads, 24 px each
-    if (P.H == 128 && P.W == 128) return launch_tile_t<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);   // 512 threads, 32 px each
+    if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);      // 192 threads, 16 px each
+    if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);      // 288 threads, 24 px each
+    if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);   // 512 threads, 32 px each
     return 1;
 }
 
