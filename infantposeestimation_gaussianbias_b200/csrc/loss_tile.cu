@@ -26,6 +26,7 @@
 //
 // Algorithmic HBM bytes per tile: read hm, var (8N); write d_hm, d_var, d_off (16N).
 #include "loss_common.cuh"
+#include <stdlib.h>
 
 namespace gbc {
 
@@ -125,7 +126,6 @@ template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int TM, int MINB
 __global__ void __launch_bounds__(W4* ROWS, MINB)
 loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
     constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
-    constexpr int NWORD = (NIT + 1) / 2;            // tie-pattern words: 8 pixels x 4 partners each
     static_assert(TPB % 32 == 0 && TPB <= 1024, "CTA must be whole warps");
     static_assert(GBCODEC_MAX_PARTNERS == 4, "tie patterns are nibbles");
     if (A.plan && *A.plan != 2) return;      // backward recompute not needed
@@ -141,26 +141,24 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     float* lut = lutG + NW * 20;                                  // exp table of the target patch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = tid % W4, ty = tid / W4;
-    const int x0 = tx << 2;
-    const float fx0 = (float)x0, fty = (float)ty;
-    const int tile = blockIdx.x;
-    const int b = tile / P.K, k = tile - b * P.K;
+    const int k = blockIdx.x, b = blockIdx.y;                    // grid = (K, B): no division
+    const int tile = b * gridDim.x + k;
 
-    const bool grads = A.grad_hm != nullptr;
-    const bool backward_only = A.lam_eff != nullptr;
-    const bool decode = A.coords != nullptr;
-
+    // ---- bulk loads first: the tile into registers, the variance map into its sum ----------------
+    // (unconditional: whether the tile carries weight is only known one L2 round trip later)
+    const size_t toff = (size_t)tile * N4 + tid;
     const float4* hmb = reinterpret_cast<const float4*>(A.hm) + tid;
-    const float4* hm4 = hmb + (size_t)tile * N4;
-    float4* gh4 = grads ? reinterpret_cast<float4*>(A.grad_hm) + (size_t)tile * N4 + tid : nullptr;
-    float4* gv4 = (grads && A.grad_var) ? reinterpret_cast<float4*>(A.grad_var) + (size_t)tile * N4 + tid : nullptr;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // ---- loads first: the tile into registers, then every scalar the tile will need ------------
+    const float4* hm4 = reinterpret_cast<const float4*>(A.hm) + toff;
     float4 h[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) h[it] = ldg_stream(hm4 + it * TPB);
+    float4 vv[NIT];
+    if (A.var) {
+        const float4* var4 = reinterpret_cast<const float4*>(A.var) + toff;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) vv[it] = ldg_stream(var4 + it * TPB);
+    }
+    // then every scalar the tile will need
     const float w = __ldg(A.weff + tile);
     const int np = P.n_partner[k];
     const int4 pj4 = make_int4(P.partner[k][0], P.partner[k][1], P.partner[k][2], P.partner[k][3]);
@@ -175,22 +173,28 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     int4 gq = make_int4(0, 0, 0, 0);
     if (TM != kTargetGlobal) gq = __ldg(A.geom + tile);
 
-    const float wa = P.use_target_weight ? w : 1.f;
-    const bool heavy = (w != 0.f) || !P.use_target_weight;
-    float vsum = 0.f;
-    if (A.var && heavy) {
-        const float4* var4 = reinterpret_cast<const float4*>(A.var) + (size_t)tile * N4 + tid;
-        float4 v[NIT];
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) v[it] = ldg_stream(var4 + it * TPB);
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) vsum += (v[it].x + v[it].y) + (v[it].z + v[it].w);
-    }
+    const bool grads = A.grad_hm != nullptr;
+    const bool backward_only = A.lam_eff != nullptr;
+    const bool decode = A.coords != nullptr;
+    float4* gh4 = reinterpret_cast<float4*>(A.grad_hm) + toff;
+    float4* gv4 = (grads && A.grad_var) ? reinterpret_cast<float4*>(A.grad_var) + toff : nullptr;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // the offset gradient is zero except on (up to) four taps per channel, patched at the end
     if (grads) {
         float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
 #pragma unroll
         for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
+    }
+
+    const int tx = tid % W4, ty = tid / W4;
+    const int x0 = tx << 2;
+    const float fx0 = (float)x0, fty = (float)ty;
+    const float wa = P.use_target_weight ? w : 1.f;
+    const bool heavy = (w != 0.f) || !P.use_target_weight;
+    float vsum = 0.f;
+    if (A.var) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) vsum += (vv[it].x + vv[it].y) + (vv[it].z + vv[it].w);
     }
     // active partners (both weights non-zero), as a 4-bit mask; CTA-uniform
     unsigned act = 0;
@@ -394,17 +398,19 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
 
     // ---- limb partners: one visit each; sums for the overlap ratio, one tie bit per pixel -------------
-    unsigned words[NWORD];
+    // words[it]: one byte per pixel of the float4, holding (4-bit partner pattern) << 2 — a byte offset into
+    // the per-warp coefficient table of pass D
+    unsigned words[NIT];
 #pragma unroll
-    for (int q = 0; q < NWORD; ++q) words[q] = 0u;
-    bool anyeq = false;
+    for (int q = 0; q < NIT; ++q) words[q] = 0u;
+    float mind = INFINITY;                            // smallest |own - partner| logit difference seen (0 = a tie)
     while (cur >= 0) {
         const unsigned rest = act & ~((2u << cur) - 1u);
         const int nxt = rest ? __ffs(rest) - 1 : -1;
         const float4* src = hmb + ((size_t)b * P.K + pick4(nxt < 0 ? 0 : nxt, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        asm volatile("" : "+l"(src));                 // keep the pointer in registers instead of re-deriving it per row
         cp_async_wait_all();                          // this thread's slots hold partner `cur`
         float Sj = 0.f, M = 0.f;
-        unsigned tb = 0u;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             const float4 q4 = Qs[it * TPB + tid];
@@ -420,23 +426,25 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             for (int jj = 0; jj < 4; ++jj) sq[jj] = sigmoid_fast(qq[jj]);
             // the slot has been consumed (its value went through the sigmoid): refill it with the next partner
             if (nxt >= 0) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+            unsigned tw = 0u;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 Sj += sq[jj];
                 // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
-                const bool own_smaller = hv[jj] < qq[jj];
+                const float d = hv[jj] - qq[jj];
+                const bool own_smaller = d < 0.f;
                 M += own_smaller ? sk[jj] : sq[jj];
-                if (own_smaller) tb |= 1u << (it * 4 + jj);
-                anyeq |= hv[jj] == qq[jj];
+                if (own_smaller) tw |= 4u << (8 * jj);
+                mind = fminf(mind, fabsf(d));
             }
+            words[it] |= tw << cur;
         }
         cp_async_commit();
 #pragma unroll
         for (int s = 0; s < 4; ++s) if (cur == s) { r16[6 + 2 * s] = Sj; r16[7 + 2 * s] = M; }
-#pragma unroll
-        for (int q = 0; q < NWORD; ++q) words[q] |= spread8(tb >> (8 * q)) << cur;
         cur = nxt;
     }
+    const bool anyeq = mind == 0.f;
 
     // ---- reduction 3: entropy / variance sums and the partner sums in one go ------------------------------
     const float acc16 = block_sum1<16, NW>(r16, red0);
@@ -591,10 +599,9 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sv[j] = sigmoid_fast(hv[j]);
             }
-            const unsigned wd = words[it >> 1] >> ((it & 1) * 16);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float G = lutw[(wd >> (4 * j)) & 15u];
+                const float G = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lutw) + ((words[it] >> (8 * j)) & 0xFFu));
                 out[j] = fmaf(G, fmaf(-sv[j], sv[j], sv[j]), out[j]);
             }
         }
@@ -660,13 +667,13 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     const size_t smem = (size_t)N4 * 16 * (1 + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
                       + (size_t)(2 * NW * 16 + NW * 20) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
     auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, TM, MINB>;
-    if (smem > 227 * 1024) return 1;
+    if (smem > 227 * 1024 || P.B > 65535) return 1;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
     if (e0 && !A.plan) cudaEventRecord(e0, s);
-    kern<<<P.B * P.K, TPB, smem, s>>>(P, A);
+    kern<<<dim3(P.K, P.B), TPB, smem, s>>>(P, A);
     if (e1 && !A.plan) cudaEventRecord(e1, s);
     return check_launch("loss_tile_kernel");
 }
@@ -678,7 +685,23 @@ static int launch_tile_tm(const LossParams& P, const LossArgs& A, cudaStream_t s
     return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetLut, MINB>(P, A, s, e0, e1);
 }
 
+// GBCODEC_TILE_VARIANT=<n>: alternative CTA shapes for the 64x48 tile (measurement only)
+static int tile_variant() {
+    static const int v = [] { const char* e = getenv("GBCODEC_TILE_VARIANT"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    if (P.H == 64 && P.W == 48) {
+        switch (tile_variant()) {
+            case 1: return launch_tile_tm<12, 8, 8, true, true, true, 4>(P, A, s, e0, e1);     // 96 threads, 32 px each
+            case 2: return launch_tile_tm<12, 8, 8, false, true, true, 5>(P, A, s, e0, e1);
+            case 3: return launch_tile_tm<12, 16, 4, false, true, true, 5>(P, A, s, e0, e1);
+            case 4: return launch_tile_tm<12, 32, 2, true, true, true, 2>(P, A, s, e0, e1);    // 384 threads, 8 px each
+            case 5: return launch_tile_tm<12, 16, 4, true, true, true, 3>(P, A, s, e0, e1);
+            default: break;
+        }
+    }
     if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);      // 192 threads, 16 px each
     if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);      // 288 threads, 24 px each
     if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);   // 512 threads, 32 px each
