@@ -122,7 +122,10 @@ constexpr int kTargetGlobal = 1;   // read from HBM (stand-alone loss with d_tar
 constexpr int kTargetLut = 2;      // generated on the fly, any patch height
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int TM, int MINB>
+// ROLL = false: the tile stays in registers and the row loops are fully unrolled (most ILP, ~80 registers, large code).
+// ROLL = true : the tile is parked in a thread-private shared-memory slot as well and the row loops stay rolled
+//               (4x smaller loop code, <= 64 registers -> one more CTA per SM).
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB>
 __global__ void __launch_bounds__(W4* ROWS, MINB)
 loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
     constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
@@ -131,14 +134,17 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     if (A.plan && *A.plan != 2) return;      // backward recompute not needed
 
     extern __shared__ __align__(16) float smem[];
+    constexpr int UNR = ROLL ? 1 : NIT;
     float4* Qs = reinterpret_cast<float4*>(smem);                 // partner tile, thread-private slots
-    float4* Es = Qs + N4;                                         // exp(h - max), later softmax weight p
+    float4* Hs = Qs + (CQ ? N4 : 0);                              // own tile (ROLL only)
+    float4* Es = Hs + (ROLL ? N4 : 0);                            // exp(h - max), later softmax weight p
     float4* Ss = Es + (CE ? N4 : 0);                              // sigmoid(h)
     float4* As = Ss + (CS ? N4 : 0);                              // a = -log(p + eps) - p / (p + eps)
     float* red0 = reinterpret_cast<float*>(As + (CA ? N4 : 0));   // two reduction buffers of NW * 16 floats
     float* red1 = red0 + NW * 16;
     float* lutG = red1 + NW * 16;                                 // per warp: 16 overlap coefficients + 4 partner scales
-    float* lut = lutG + NW * 20;                                  // exp table of the target patch
+    unsigned* Ws = reinterpret_cast<unsigned*>(lutG + NW * 20);   // tie-pattern words (ROLL only), thread-private
+    float* lut = reinterpret_cast<float*>(Ws + (ROLL ? N4 : 0));  // exp table of the target patch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = blockIdx.x, b = blockIdx.y;                    // grid = (K, B): no division
@@ -150,8 +156,15 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const float4* hmb = reinterpret_cast<const float4*>(A.hm) + tid;
     const float4* hm4 = reinterpret_cast<const float4*>(A.hm) + toff;
     float4 h[NIT];
+    if (ROLL) {
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) h[it] = ldg_stream(hm4 + it * TPB);
+        for (int it = 0; it < NIT; ++it) cp_async16(Hs + it * TPB + tid, hm4 + it * TPB);
+        cp_async_commit();
+    } else {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) h[it] = ldg_stream(hm4 + it * TPB);
+    }
+    auto own4 = [&](int it) -> float4 { return ROLL ? Hs[it * TPB + tid] : h[it]; };
     float4 vv[NIT];
     if (A.var) {
         const float4* var4 = reinterpret_cast<const float4*>(A.var) + toff;
@@ -224,8 +237,9 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 
     // ---- reduction 1: tile maximum -----------------------------------------------------------
     float m = -INFINITY;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) m = fmaxf(m, fmaxf(fmaxf(h[it].x, h[it].y), fmaxf(h[it].z, h[it].w)));
+    if (ROLL) cp_async_wait_all();            // own slots only: no barrier needed
+#pragma unroll UNR
+    for (int it = 0; it < NIT; ++it) { const float4 o = own4(it); m = fmaxf(m, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w))); }
     m = block_max1<NW>(m, red0);             // the barrier also publishes the exp table
     const float ml = m * kLog2e;
 
@@ -252,9 +266,10 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     {
         float Ej[4] = {0.f, 0.f, 0.f, 0.f};
         float Yw = 0.f, Ssum_t = 0.f, mse = 0.f;
-#pragma unroll
+#pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
-            const float hv[4] = {h[it].x, h[it].y, h[it].z, h[it].w};
+            const float4 o = own4(it);
+            const float hv[4] = {o.x, o.y, o.z, o.w};
             float e[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) { e[j] = ex2(fmaf(hv[j], kLog2e, -ml)); Ej[j] += e[j]; }
@@ -315,7 +330,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     // ---- things that only need the soft-argmax: start their loads now ----------------------------
     // (1) first active partner's tile -> thread-private smem slots
     int cur = act ? __ffs(act) - 1 : -1;
-    if (cur >= 0) {
+    if (CQ && cur >= 0) {
         const float4* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) cp_async16(Qs + it * TPB + tid, src + it * TPB);
@@ -359,9 +374,10 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     {
         float A1 = 0.f, A2 = 0.f, Ry = 0.f, Ry2 = 0.f;
         float Rj[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
-            const float hv[4] = {h[it].x, h[it].y, h[it].z, h[it].w};
+            const float4 o = own4(it);
+            const float hv[4] = {o.x, o.y, o.z, o.w};
             float e[4];
             if (CE) { const float4 q = Es[it * TPB + tid]; e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w; }
             else {
@@ -402,19 +418,21 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     // the per-warp coefficient table of pass D
     unsigned words[NIT];
 #pragma unroll
-    for (int q = 0; q < NIT; ++q) words[q] = 0u;
+    for (int q = 0; q < NIT; ++q) { words[q] = 0u; if (ROLL) Ws[q * TPB + tid] = 0u; }
     float mind = INFINITY;                            // smallest |own - partner| logit difference seen (0 = a tie)
     while (cur >= 0) {
         const unsigned rest = act & ~((2u << cur) - 1u);
         const int nxt = rest ? __ffs(rest) - 1 : -1;
         const float4* src = hmb + ((size_t)b * P.K + pick4(nxt < 0 ? 0 : nxt, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         asm volatile("" : "+l"(src));                 // keep the pointer in registers instead of re-deriving it per row
-        cp_async_wait_all();                          // this thread's slots hold partner `cur`
+        const float4* srcc = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        if (CQ) cp_async_wait_all();                  // this thread's slots hold partner `cur`
         float Sj = 0.f, M = 0.f;
-#pragma unroll
+#pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
-            const float4 q4 = Qs[it * TPB + tid];
-            const float hv[4] = {h[it].x, h[it].y, h[it].z, h[it].w};
+            const float4 q4 = CQ ? Qs[it * TPB + tid] : ldg_stream(srcc + it * TPB);
+            const float4 o = own4(it);
+            const float hv[4] = {o.x, o.y, o.z, o.w};
             const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
             float sk[4], sq[4];
             if (CS) { const float4 s4 = Ss[it * TPB + tid]; sk[0] = s4.x; sk[1] = s4.y; sk[2] = s4.z; sk[3] = s4.w; }
@@ -425,7 +443,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) sq[jj] = sigmoid_fast(qq[jj]);
             // the slot has been consumed (its value went through the sigmoid): refill it with the next partner
-            if (nxt >= 0) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+            if (CQ && nxt >= 0) cp_async16(Qs + it * TPB + tid, src + it * TPB);
             unsigned tw = 0u;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -437,9 +455,9 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 if (own_smaller) tw |= 4u << (8 * jj);
                 mind = fminf(mind, fabsf(d));
             }
-            words[it] |= tw << cur;
+            if (ROLL) Ws[it * TPB + tid] |= tw << cur; else words[it] |= tw << cur;
         }
-        cp_async_commit();
+        if (CQ) cp_async_commit();
 #pragma unroll
         for (int s = 0; s < 4; ++s) if (cur == s) { r16[6 + 2 * s] = Sj; r16[7 + 2 * s] = M; }
         cur = nxt;
@@ -565,9 +583,10 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     float basej[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) basej[j] = dxj[j] * fxx;
-#pragma unroll
+#pragma unroll UNR
     for (int it = 0; it < NIT; ++it) {
-        const float hv[4] = {h[it].x, h[it].y, h[it].z, h[it].w};
+        const float4 o = own4(it);
+        const float hv[4] = {o.x, o.y, o.z, o.w};
         float p[4], a[4];
         if (CE) { const float4 q = Es[it * TPB + tid]; p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
         else {
@@ -599,9 +618,10 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sv[j] = sigmoid_fast(hv[j]);
             }
+            const unsigned wd = ROLL ? Ws[it * TPB + tid] : words[it];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float G = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lutw) + ((words[it] >> (8 * j)) & 0xFFu));
+                const float G = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lutw) + ((wd >> (8 * j)) & 0xFFu));
                 out[j] = fmaf(G, fmaf(-sv[j], sv[j], sv[j]), out[j]);
             }
         }
@@ -661,12 +681,12 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int TM, int MINB>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB>
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
-    const size_t smem = (size_t)N4 * 16 * (1 + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
-                      + (size_t)(2 * NW * 16 + NW * 20) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
-    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, TM, MINB>;
+    const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
+                      + (size_t)(2 * NW * 16 + NW * 20 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
+    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB>;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_kernel): %s", cudaGetErrorString(e));
@@ -678,11 +698,11 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     return check_launch("loss_tile_kernel");
 }
 
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB, bool CQ = true, bool ROLL = false>
 static int launch_tile_tm(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
-    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetGlobal, MINB>(P, A, s, e0, e1);
-    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetOneHit, MINB>(P, A, s, e0, e1);
-    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, kTargetLut, MINB>(P, A, s, e0, e1);
+    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetGlobal, MINB>(P, A, s, e0, e1);
+    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetOneHit, MINB>(P, A, s, e0, e1);
+    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetLut, MINB>(P, A, s, e0, e1);
 }
 
 // GBCODEC_TILE_VARIANT=<n>: alternative CTA shapes for the 64x48 tile (measurement only)
@@ -694,15 +714,15 @@ static int tile_variant() {
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     if (P.H == 64 && P.W == 48) {
         switch (tile_variant()) {
-            case 1: return launch_tile_tm<12, 8, 8, true, true, true, 4>(P, A, s, e0, e1);     // 96 threads, 32 px each
-            case 2: return launch_tile_tm<12, 8, 8, false, true, true, 5>(P, A, s, e0, e1);
-            case 3: return launch_tile_tm<12, 16, 4, false, true, true, 5>(P, A, s, e0, e1);
-            case 4: return launch_tile_tm<12, 32, 2, true, true, true, 2>(P, A, s, e0, e1);    // 384 threads, 8 px each
-            case 5: return launch_tile_tm<12, 16, 4, true, true, true, 3>(P, A, s, e0, e1);
+            case 1: return launch_tile_tm<12, 16, 4, false, true, true, 5, false, true>(P, A, s, e0, e1);   // rolled; H,S,A     39 KB, 5 CTAs
+            case 2: return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);                 // registers + unrolled; E,S,A,Q 51 KB, 4 CTAs
+            case 3: return launch_tile_tm<12, 16, 4, false, true, true, 4, true, true>(P, A, s, e0, e1);    // rolled; H,S,A,Q   51 KB, 4 CTAs
+            case 4: return launch_tile_tm<12, 16, 4, true, true, true, 4, true, true>(P, A, s, e0, e1);     // rolled; H,E,S,A,Q 63 KB, 3 CTAs
+            case 5: return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // rolled; H,S       27 KB, 6 CTAs
             default: break;
         }
     }
-    if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);      // 192 threads, 16 px each
+    if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true>(P, A, s, e0, e1);   // 192 threads, 16 px each; H,S,Q in smem
     if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);      // 288 threads, 24 px each
     if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);   // 512 threads, 32 px each
     return 1;
