@@ -135,6 +135,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 
     extern __shared__ __align__(16) float smem[];
     constexpr int UNR = ROLL ? 1 : NIT;
+    constexpr bool AQ = CQ && !CA;                  // the partner slot is free once the partners are done: park `a` there
     float4* Qs = reinterpret_cast<float4*>(smem);                 // partner tile, thread-private slots
     float4* Hs = Qs + (CQ ? N4 : 0);                              // own tile (ROLL only)
     float4* Es = Hs + (ROLL ? N4 : 0);                            // exp(h - max), later softmax weight p
@@ -142,8 +143,8 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     float4* As = Ss + (CS ? N4 : 0);                              // a = -log(p + eps) - p / (p + eps)
     float* red0 = reinterpret_cast<float*>(As + (CA ? N4 : 0));   // two reduction buffers of NW * 16 floats
     float* red1 = red0 + NW * 16;
-    float* lutG = red1 + NW * 16;                                 // per warp: 16 overlap coefficients + 4 partner scales
-    unsigned* Ws = reinterpret_cast<unsigned*>(lutG + NW * 20);   // tie-pattern words (ROLL only), thread-private
+    float* lutG = red1 + NW * 16;                                 // 12 tile coefficients + 16 overlap coefficients + 4 partner scales
+    unsigned* Ws = reinterpret_cast<unsigned*>(lutG + 32);        // tie-pattern words (ROLL only), thread-private
     float* lut = reinterpret_cast<float*>(Ws + (ROLL ? N4 : 0));  // exp table of the target patch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -178,11 +179,6 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     float wjv[4];
 #pragma unroll
     for (int pi = 0; pi < 4; ++pi) wjv[pi] = pi < np ? __ldg(A.weff + b * P.K + pick4(pi, pj4.x, pj4.y, pj4.z, pj4.w)) : 0.f;
-    const float gx = __ldg(A.gt + 2 * tile) * P.sx;
-    const float gy = __ldg(A.gt + 2 * tile + 1) * P.sy;
-    const float D = (float)__ldg(A.sums) + kEps;
-    const float D5 = (float)__ldg(A.sums + 1) + kEps;
-    const float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
     int4 gq = make_int4(0, 0, 0, 0);
     if (TM != kTargetGlobal) gq = __ldg(A.geom + tile);
 
@@ -242,6 +238,15 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     for (int it = 0; it < NIT; ++it) { const float4 o = own4(it); m = fmaxf(m, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w))); }
     m = block_max1<NW>(m, red0);             // the barrier also publishes the exp table
     const float ml = m * kLog2e;
+
+    // first active partner's tile -> thread-private smem slots; it has all of pass B to arrive
+    int cur = act ? __ffs(act) - 1 : -1;
+    if (CQ && cur >= 0) {
+        const float4* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+        cp_async_commit();
+    }
 
     // kTargetOneHit: the one row (if any) in which this thread meets the patch
     int hit_it = -1;
@@ -321,34 +326,35 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
     const float Ssum = lane_value<8>(acc8, 3), mse_sum = lane_value<8>(acc8, 4);
     const float mV = A.var ? lane_value<8>(acc8, 5) * P.inv_n : P.sigma;
-    float lam[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) lam[q] = backward_only ? __ldg(A.lam_eff + q) : P.lam[q] * gscale;
-    const float iD = rcp(D);
-    const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
 
-    // ---- things that only need the soft-argmax: start their loads now ----------------------------
-    // (1) first active partner's tile -> thread-private smem slots
-    int cur = act ? __ffs(act) - 1 : -1;
-    if (CQ && cur >= 0) {
-        const float4* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+    // ---- warp roles for the per-tile scalars (a warp each, the others do not repeat the work) ------------
+    //   warp RD: decode tail                       warp RO: offset term (8 taps, SmoothL1, its share of dL/dc)
+    //   warp RV: peak / variance / entropy terms    warp RP: limb overlap ratios and the tie-pattern table
+    constexpr int RD = 0, RO = 1 % NW, RV = 2 % NW, RP = 3 % NW;
+    // loads whose values are first needed after the partner visits: issue now, consume then
+    const float gtx = __ldg(A.gt + 2 * tile), gty = __ldg(A.gt + 2 * tile + 1);
+    const double sum_w = __ldg(A.sums), sum_p = __ldg(A.sums + 1);
+    const float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
+    float lam_eff[6];
+    if (backward_only) {
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) cp_async16(Qs + it * TPB + tid, src + it * TPB);
-        cp_async_commit();
+        for (int q = 0; q < 6; ++q) lam_eff[q] = __ldg(A.lam_eff + q);
     }
-    // (2) the 8 offset taps of the offset term (same addresses in every thread: one L1 line per warp)
-    const Taps tp = taps_setup(cx, cy, H, W);
-    float ov[2][4];
+    // offset term: the 8 taps around the soft-argmax (warp RO only)
+    float ov[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if (warp == RO) {
+        const Taps t0 = taps_setup(cx, cy, H, W);   // recomputed when the values are consumed: only the 8 loads stay live
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        ov[c][0] = __ldg(off_tile + c * N + tp.i00); ov[c][1] = __ldg(off_tile + c * N + tp.i01) * tp.okx;
-        ov[c][2] = __ldg(off_tile + c * N + tp.i10) * tp.oky; ov[c][3] = __ldg(off_tile + c * N + tp.i11) * (tp.okx * tp.oky);
+        for (int c = 0; c < 2; ++c) {
+            ov[c][0] = __ldg(off_tile + c * N + t0.i00); ov[c][1] = __ldg(off_tile + c * N + t0.i01);
+            ov[c][2] = __ldg(off_tile + c * N + t0.i10); ov[c][3] = __ldg(off_tile + c * N + t0.i11);
+        }
     }
-    // (3) decode stage 1 (warp 0): window taps around the rounded soft-argmax
+    // decode stage 1 (warp RD): window taps around the rounded soft-argmax
     const bool staged_decode = decode && (A.dflags & GBCODEC_DECODE_REFINE) && A.radius <= 2;
     float win = -INFINITY, winx = 0.f, winy = 0.f;
     bool win_ok = false;
-    if (staged_decode && tid < 32) {
+    if (staged_decode && warp == RD) {
         const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
         const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
         const int S = 2 * A.radius + 1;
@@ -357,62 +363,10 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         winx = (float)x; winy = (float)y;
         if (win_ok) win = __ldg(hm_tile + y * W + x);
     }
-    // (4) the variance-map gradient is uniform over the tile
-    if (gv4) {
-        const float g = lam[3] * kb * 2.f * (mV - P.sigma) * P.inv_n;
-        const float4 g4 = make_float4(g, g, g, g);
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) stg_stream(gv4 + it * TPB, g4);
-    }
 
-    // ---- pass C: entropy sums and relu moments about (cx, cy) ----------------------------------------
-    float dxj[4], dx2j[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { dxj[j] = (fx0 + (float)j) - cx; dx2j[j] = dxj[j] * dxj[j]; }
-    const float dy0 = fty - cy;
     float r16[16];
-    {
-        float A1 = 0.f, A2 = 0.f, Ry = 0.f, Ry2 = 0.f;
-        float Rj[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll UNR
-        for (int it = 0; it < NIT; ++it) {
-            const float4 o = own4(it);
-            const float hv[4] = {o.x, o.y, o.z, o.w};
-            float e[4];
-            if (CE) { const float4 q = Es[it * TPB + tid]; e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w; }
-            else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) e[j] = ex2(fmaf(hv[j], kLog2e, -ml));
-            }
-            float p[4], a[4], r[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                p[j] = e[j] * iZ;
-                const float u = p[j] + kEps;
-                const float l = lg2(u), rc = rcp(u);
-                A1 = fmaf(p[j], l, A1);
-                const float prc = p[j] * rc;
-                A2 = fmaf(p[j], prc, A2);
-                a[j] = fmaf(-kLn2, l, -prc);
-                r[j] = fmaxf(hv[j], 0.f);
-                Rj[j] += r[j];
-            }
-            if (CE) Es[it * TPB + tid] = make_float4(p[0], p[1], p[2], p[3]);
-            if (CA) As[it * TPB + tid] = make_float4(a[0], a[1], a[2], a[3]);
-            const float rs = (r[0] + r[1]) + (r[2] + r[3]);
-            const float dy = dy0 + (float)(it * ROWS);
-            Ry = fmaf(dy, rs, Ry);
-            Ry2 = fmaf(dy * dy, rs, Ry2);
-        }
-        r16[0] = A1; r16[1] = A2;
-        r16[2] = fmaf(dx2j[0], Rj[0], fmaf(dx2j[1], Rj[1], fmaf(dx2j[2], Rj[2], fmaf(dx2j[3], Rj[3], Ry2))));
-        r16[3] = fmaf(dxj[0], Rj[0], fmaf(dxj[1], Rj[1], fmaf(dxj[2], Rj[2], dxj[3] * Rj[3])));
-        r16[4] = Ry;
-        r16[5] = (Rj[0] + Rj[1]) + (Rj[2] + Rj[3]);
-#pragma unroll
-        for (int q = 6; q < 16; ++q) r16[q] = 0.f;
-    }
-
+    for (int q = 0; q < 16; ++q) r16[q] = 0.f;
     // ---- limb partners: one visit each; sums for the overlap ratio, one tie bit per pixel -------------
     // words[it]: one byte per pixel of the float4, holding (4-bit partner pattern) << 2 — a byte offset into
     // the per-warp coefficient table of pass D
@@ -464,13 +418,79 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
     const bool anyeq = mind == 0.f;
 
+    // the normalisers have arrived by now
+    const float D = (float)sum_w + kEps, D5 = (float)sum_p + kEps;
+    const float gx = gtx * P.sx, gy = gty * P.sy;
+    float lam[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) lam[q] = backward_only ? lam_eff[q] : P.lam[q] * gscale;
+    const float iD = rcp(D);
+    const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
+    // the variance-map gradient is uniform over the tile
+    if (gv4) {
+        const float g = lam[3] * kb * 2.f * (mV - P.sigma) * P.inv_n;
+        const float4 g4 = make_float4(g, g, g, g);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) stg_stream(gv4 + it * TPB, g4);
+    }
+
+    // ---- pass C: entropy sums and relu moments about (cx, cy) ----------------------------------------
+    float dxj[4], dx2j[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dxj[j] = (fx0 + (float)j) - cx; dx2j[j] = dxj[j] * dxj[j]; }
+    const float dy0 = fty - cy;
+    {
+        float A1 = 0.f, A2 = 0.f, Ry = 0.f, Ry2 = 0.f;
+        float Rj[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll UNR
+        for (int it = 0; it < NIT; ++it) {
+            const float4 o = own4(it);
+            const float hv[4] = {o.x, o.y, o.z, o.w};
+            float e[4];
+            if (CE) { const float4 q = Es[it * TPB + tid]; e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w; }
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) e[j] = ex2(fmaf(hv[j], kLog2e, -ml));
+            }
+            float p[4], a[4], r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                p[j] = e[j] * iZ;
+                const float u = p[j] + kEps;
+                const float l = lg2(u), rc = rcp(u);
+                A1 = fmaf(p[j], l, A1);
+                const float prc = p[j] * rc;
+                A2 = fmaf(p[j], prc, A2);
+                a[j] = fmaf(-kLn2, l, -prc);
+                r[j] = fmaxf(hv[j], 0.f);
+                Rj[j] += r[j];
+            }
+            if (CE) Es[it * TPB + tid] = make_float4(p[0], p[1], p[2], p[3]);
+            if (CA) As[it * TPB + tid] = make_float4(a[0], a[1], a[2], a[3]);
+            if (AQ) Qs[it * TPB + tid] = make_float4(a[0], a[1], a[2], a[3]);
+            const float rs = (r[0] + r[1]) + (r[2] + r[3]);
+            const float dy = dy0 + (float)(it * ROWS);
+            Ry = fmaf(dy, rs, Ry);
+            Ry2 = fmaf(dy * dy, rs, Ry2);
+        }
+        r16[0] = A1; r16[1] = A2;
+        r16[2] = fmaf(dx2j[0], Rj[0], fmaf(dx2j[1], Rj[1], fmaf(dx2j[2], Rj[2], fmaf(dx2j[3], Rj[3], Ry2))));
+        r16[3] = fmaf(dxj[0], Rj[0], fmaf(dxj[1], Rj[1], fmaf(dxj[2], Rj[2], dxj[3] * Rj[3])));
+        r16[4] = Ry;
+        r16[5] = (Rj[0] + Rj[1]) + (Rj[2] + Rj[3]);
+    }
+
     // ---- reduction 3: entropy / variance sums and the partner sums in one go ------------------------------
     const float acc16 = block_sum1<16, NW>(r16, red0);
 
-    // ---- decode stage 2 (warp 0): window softmax, blend, start the bilinear offset read ---------------
+    // ---- per-tile scalars, one warp per group; results meet in shared memory ---------------------------------
+    // coef[0..3] = c1, c4, k4, c6   coef[4] = pa   coef[5..6] = dL/dc from warp RV   coef[7..8] = dL/dc from warp RO
+    // coef[9] = 1 if any limb gradient is live;  tab[0..15] overlap coefficient per tie pattern, tab[16..19] partner scales
+    float* coef = lutG;                   // 12 floats
+    float* tab = lutG + 12;               // 20 floats
     float dcx = cx, dcy = cy, dtap = 0.f;
-    Bilinear dbl = Bilinear{};
-    if (decode && tid < 32) {
+    if (warp == RD && decode) {
+        // decode stage 2: window softmax, blend, start the bilinear offset read
         if (staged_decode) {
             const float vmax = warp_max(win);
             const float e = win_ok ? expf(win - vmax) : 0.f;
@@ -482,21 +502,19 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             refine_and_correct_cold(hm_tile, nullptr, A.alpha_param, nullptr, H, W, A.radius, GBCODEC_DECODE_REFINE, &dcx, &dcy);
         }
         if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
-            dbl = bilinear_setup(dcx, dcy, H, W);
+            const Bilinear dbl = bilinear_setup(dcx, dcy, H, W);
             // lane t < 8 fetches tap (t & 3) of channel (t >> 2)
             const int tap = lane & 3;
             const int yy = (tap & 2) ? dbl.y1 : dbl.y0, xx = (tap & 1) ? dbl.x1 : dbl.x0;
             if (lane < 8) dtap = __ldg(off_tile + (lane >> 2) * N + yy * W + xx);
         }
     }
-
-    // ---- per-tile scalars (every thread: nobody waits) ---------------------------------------------------
-    const float iRp = rcp(lane_value<16>(acc16, 5) + kEps);
-    float c1, c4, k4, c6, fxx, fyy, go0, go1, pa_;
-    {
+    if (warp == RO) {
+        const Taps tp = taps_setup(cx, cy, H, W);
         float sl1 = 0.f, sl1p[2], dsdx[2], dsdy[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+            ov[c][1] *= tp.okx; ov[c][2] *= tp.oky; ov[c][3] *= tp.okx * tp.oky;
             const float samp = tp.w00 * ov[c][0] + tp.w01 * ov[c][1] + tp.w10 * ov[c][2] + tp.w11 * ov[c][3];
             dsdx[c] = ((1.f - tp.fy) * (ov[c][1] - ov[c][0]) + tp.fy * (ov[c][3] - ov[c][2])) * tp.inx;
             dsdy[c] = ((1.f - tp.fx) * (ov[c][2] - ov[c][0]) + tp.fx * (ov[c][3] - ov[c][1])) * tp.iny;
@@ -505,41 +523,62 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             sl1 += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
             sl1p[c] = ad < 1.f ? d : (d > 0.f ? 1.f : -1.f);
         }
-        const float off_t = 0.5f * sl1;
+        const float h2 = lam[1] * ka * 0.5f;
+        if (lane == 0) {
+            if (!backward_only) A.partial[(size_t)tile * 8 + 1] = wa * (0.5f * sl1);
+            coef[7] = h2 * (sl1p[0] * (dsdx[0] + 1.f) + sl1p[1] * dsdx[1]);
+            coef[8] = h2 * (sl1p[0] * dsdy[0] + sl1p[1] * (dsdy[1] + 1.f));
+            if (grads) {
+                // the (up to) four non-zero taps per channel of the offset gradient; the zero fill of these
+                // addresses was issued before the first barrier, so it is ordered before these stores
+                float* go = A.grad_off + (size_t)tile * 2 * N;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    float* o = go + ch * N;
+                    const float gc = h2 * sl1p[ch];
+                    o[tp.i00] = gc * tp.w00;
+                    if (tp.okx != 0.f) o[tp.i01] = gc * tp.w01;
+                    if (tp.oky != 0.f) o[tp.i10] = gc * tp.w10;
+                    if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = gc * tp.w11;
+                }
+            }
+        }
+    }
+    if (warp == RV) {
+        const float iRp = rcp(lane_value<16>(acc16, 5) + kEps);
         const float peak_t = (cx - gx) * (cx - gx) + (cy - gy) * (cy - gy);
         const float v = lane_value<16>(acc16, 2) * iRp;
-        const float s = fsqrt_fast(v + kEps);
-        const float var_t = (s - P.sigma) * (s - P.sigma) + (A.var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
+        const float sd = fsqrt_fast(v + kEps);
+        const float var_t = (sd - P.sigma) * (sd - P.sigma) + (A.var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
         const float E = -kLn2 * lane_value<16>(acc16, 0);
         const float pa = E - lane_value<16>(acc16, 1);
         const float shape_t = (E - P.e_star) * (E - P.e_star);
-        if (tid == 0 && !backward_only) {
-            float* p = A.partial + (size_t)tile * 8;
-            p[0] = wa * (mse_sum * P.inv_n); p[1] = wa * off_t; p[2] = wa * peak_t;
-            p[3] = w * var_t; p[5] = w * shape_t;      // p[4] (limb overlap) below
-        }
-        c1 = lam[0] * ka * 2.f * P.inv_n;
-        const float a4 = lam[3] * kb * (s - P.sigma) * rcp(s);
-        c4 = a4 * iRp;
-        k4 = -c4 * v;
-        c6 = lam[5] * kb * 2.f * (E - P.e_star);
-        pa_ = pa;
+        const float a4 = lam[3] * kb * (sd - P.sigma) * rcp(sd);
+        const float c4 = a4 * iRp;
         const float dv_dcx = -2.f * lane_value<16>(acc16, 3) * iRp, dv_dcy = -2.f * lane_value<16>(acc16, 4) * iRp;
-        fxx = lam[2] * ka * 2.f * (cx - gx) + lam[1] * ka * 0.5f * (sl1p[0] * (dsdx[0] + 1.f) + sl1p[1] * dsdx[1]) + a4 * dv_dcx;
-        fyy = lam[2] * ka * 2.f * (cy - gy) + lam[1] * ka * 0.5f * (sl1p[0] * dsdy[0] + sl1p[1] * (dsdy[1] + 1.f)) + a4 * dv_dcy;
-        go0 = lam[1] * ka * 0.5f * sl1p[0];
-        go1 = lam[1] * ka * 0.5f * sl1p[1];
+        if (lane == 0) {
+            if (!backward_only) {
+                float* p = A.partial + (size_t)tile * 8;
+                p[0] = wa * (mse_sum * P.inv_n); p[2] = wa * peak_t; p[3] = w * var_t; p[5] = w * shape_t;
+            }
+            coef[0] = lam[0] * ka * 2.f * P.inv_n;
+            coef[1] = c4;
+            coef[2] = -c4 * v;
+            coef[3] = lam[5] * kb * 2.f * (E - P.e_star);
+            coef[4] = pa;
+            coef[5] = lam[2] * ka * 2.f * (cx - gx) + a4 * dv_dcx;
+            coef[6] = lam[2] * ka * 2.f * (cy - gy) + a4 * dv_dcy;
+        }
     }
-    // overlap ratios -> loss numerator and the per-partner gradient scale
-    bool g_live = false;
-    float* lutw = lutG + warp * 20;
-    {
+    if (warp == RP) {
+        // overlap ratios -> loss numerator and the per-partner gradient scale
         float cj[4] = {0.f, 0.f, 0.f, 0.f};
         float cst = 0.f, pair_loss = 0.f;
+        bool live = false;
         const float iD5 = rcp(D5);
 #pragma unroll
         for (int pi = 0; pi < 4; ++pi) {
-            if ((act >> pi) & 1u) {                     // CTA-uniform
+            if ((act >> pi) & 1u) {                     // warp-uniform
                 const float Sj = lane_value<16>(acc16, 6 + 2 * pi), M = lane_value<16>(acc16, 7 + 2 * pi);
                 const float imm = rcp(fminf(Ssum, Sj) + kEps);
                 const float rho = M * imm;
@@ -547,35 +586,44 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 if (grads && rho > 0.5f) {
                     cj[pi] = lam[4] * w * wjv[pi] * iD5 * imm;
                     cst += cj[pi] * rho * tie_rule(Ssum, Sj);
-                    g_live = true;
+                    live = true;
                 }
             }
         }
-        if (tid == 0 && !backward_only) A.partial[(size_t)tile * 8 + 4] = pair_loss;
-        if (g_live) {
-            // per warp: the overlap coefficient of a pixel as a function of its 4-bit tie pattern
-            if (lane < 16) {
-                float g = -cst;
+        if (lane == 0) {
+            if (!backward_only) A.partial[(size_t)tile * 8 + 4] = pair_loss;
+            coef[9] = live ? 1.f : 0.f;
+        }
+        // the overlap coefficient of a pixel as a function of its 4-bit tie pattern
+        if (lane < 16) {
+            float g = -cst;
 #pragma unroll
-                for (int pi = 0; pi < 4; ++pi) if ((lane >> pi) & 1) g += cj[pi];
-                lutw[lane] = g;
-            } else if (lane < 20) {
-                lutw[lane] = pick4(lane - 16, cj[0], cj[1], cj[2], cj[3]);
-            }
-            __syncwarp();
+            for (int pi = 0; pi < 4; ++pi) if ((lane >> pi) & 1) g += cj[pi];
+            tab[lane] = g;
+        } else if (lane < 20) {
+            tab[lane] = pick4(lane - 16, cj[0], cj[1], cj[2], cj[3]);
         }
     }
+    __syncthreads();
+    const float4 cf0 = *reinterpret_cast<const float4*>(coef), cf1 = *reinterpret_cast<const float4*>(coef + 4);
+    const float c1 = cf0.x, c4 = cf0.y, k4 = cf0.z, c6 = cf0.w, pa_ = cf1.x;
+    const float fxx = cf1.y + coef[7], fyy = cf1.z + coef[8];
+    const bool g_live = coef[9] != 0.f;
+    const float* lutw = tab;
     if (!grads) {
-        if (decode && tid < 32 && (A.dflags & GBCODEC_DECODE_APPLY_OFFSET)) {
+        if (decode && warp == RD && (A.dflags & GBCODEC_DECODE_APPLY_OFFSET)) {
             float fw = __ldg(A.fusion_weight);
             if (A.dflags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
+            const Bilinear dbl = bilinear_setup(dcx, dcy, H, W);
             float t[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) t[q] = __shfl_sync(0xffffffffu, dtap, q);
-            dcx += fw * (dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky)));
-            dcy += fw * (dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky)));
+            const float ox = dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky));
+            const float oy = dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky));
+            dcx += fw * ox;
+            dcy += fw * oy;
         }
-        if (decode && tid == 0) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
+        if (decode && tid == RD * 32) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
         return;
     }
 
@@ -593,7 +641,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
             for (int j = 0; j < 4; ++j) p[j] = ex2(fmaf(hv[j], kLog2e, -ml)) * iZ;
         }
-        if (CA) { const float4 q = As[it * TPB + tid]; a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w; }
+        if (CA || AQ) { const float4 q = CA ? As[it * TPB + tid] : Qs[it * TPB + tid]; a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w; }
         else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { const float u = p[j] + kEps; a[j] = fmaf(-kLn2, lg2(u), -p[j] * rcp(u)); }
@@ -650,33 +698,21 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         }
     }
 
-    // ---- decode stage 3 (warp 0): finish the bilinear read, publish -----------------------------------
-    if (decode && tid < 32) {
+    // ---- decode stage 3 (warp RD): finish the bilinear read, publish -----------------------------------
+    if (decode && warp == RD) {
         if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
             float fw = __ldg(A.fusion_weight);
             if (A.dflags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
+            const Bilinear dbl = bilinear_setup(dcx, dcy, H, W);
             float t[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) t[q] = __shfl_sync(0xffffffffu, dtap, q);
-            dcx += fw * (dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky)));
-            dcy += fw * (dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky)));
+            const float ox = dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky));
+            const float oy = dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky));
+            dcx += fw * ox;
+            dcy += fw * oy;
         }
-        if (tid == 0) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
-    }
-
-    // the (up to) four non-zero taps per channel of the offset gradient; the zero fill of these
-    // addresses was issued before the first barrier, so it is ordered before these stores
-    if (tid == 0) {
-        float* go = A.grad_off + (size_t)tile * 2 * N;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            float* o = go + ch * N;
-            const float gc = ch == 0 ? go0 : go1;
-            o[tp.i00] = gc * tp.w00;
-            if (tp.okx != 0.f) o[tp.i01] = gc * tp.w01;
-            if (tp.oky != 0.f) o[tp.i10] = gc * tp.w10;
-            if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = gc * tp.w11;
-        }
+        if (lane == 0) { A.coords[2 * tile] = dcx; A.coords[2 * tile + 1] = dcy; A.scores[tile] = m; }
     }
 }
 
@@ -685,7 +721,7 @@ template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool RO
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
     const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
-                      + (size_t)(2 * NW * 16 + NW * 20 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
+                      + (size_t)(2 * NW * 16 + 32 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
     auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB>;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
