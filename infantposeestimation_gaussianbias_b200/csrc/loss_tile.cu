@@ -753,14 +753,24 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
             case 1: return launch_tile_tm<12, 16, 4, false, true, true, 5, false, true>(P, A, s, e0, e1);   // rolled; H,S,A     39 KB, 5 CTAs
             case 2: return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);                 // registers + unrolled; E,S,A,Q 51 KB, 4 CTAs
             case 3: return launch_tile_tm<12, 16, 4, false, true, true, 4, true, true>(P, A, s, e0, e1);    // rolled; H,S,A,Q   51 KB, 4 CTAs
-            case 4: return launch_tile_tm<12, 16, 4, true, true, true, 4, true, true>(P, A, s, e0, e1);     // rolled; H,E,S,A,Q 63 KB, 3 CTAs
+            case 4: return launch_tile_tm<12, 32, 2, false, true, false, 3, true, true>(P, A, s, e0, e1);   // rolled; 384 threads, 8 px each
             case 5: return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // rolled; H,S       27 KB, 6 CTAs
             default: break;
         }
     }
     if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true>(P, A, s, e0, e1);   // 192 threads, 16 px each; H,S,Q in smem
-    if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);      // 288 threads, 24 px each
-    if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);   // 512 threads, 32 px each
+    if (P.H == 96 && P.W == 72) {
+        if (tile_variant() == 1) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);               // registers, 288 threads
+        if (tile_variant() == 2) return launch_tile_tm<18, 32, 3, false, true, false, 2, true, true>(P, A, s, e0, e1);  // rolled, 576 threads, 12 px each
+        if (tile_variant() == 3) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1); // rolled, 288 threads, no partner slot: 3 CTAs
+        return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);                          // rolled, 288 threads, 24 px each
+    }
+    if (P.H == 128 && P.W == 128) {
+        if (tile_variant() == 1) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);              // registers, 512 threads
+        if (tile_variant() == 2) return launch_tile_tm<32, 32, 4, false, true, false, 1, true, true>(P, A, s, e0, e1);  // rolled, 1024 threads, 16 px each
+        if (tile_variant() == 3) return launch_tile_tm<32, 16, 8, false, true, false, 1, false, true>(P, A, s, e0, e1); // rolled, 512 threads, no partner slot
+        return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);                          // rolled, 512 threads, 32 px each
+    }
     return 1;
 }
 
