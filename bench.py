@@ -294,7 +294,7 @@ def run_b200(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = B * K * BYTES_PER_HM / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "loss_kernel<256,3,2> (fused step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "loss_tile_kernel<12,16,4,...> (fused step: on-the-fly target + six-term loss fwd/bwd + decode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": B * K * BYTES_PER_HM}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")

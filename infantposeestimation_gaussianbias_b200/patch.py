@@ -1,0 +1,100 @@
+"""Drop-in shim: rebind the reference's codec entry points to the gbcodec CUDA ops.
+
+The reference files stay byte-identical; `patch_reference()` is run once (from a
+launcher or sitecustomize) before `train.py` / `validate.py` / `inference.py`
+build their model:
+
+    models.fusion_head.FusionPoseLoss.forward            -> FusionPoseLoss.forward  (this package)
+    models.fusion_head.HeatmapRegressionHead.decode      -> head_decode
+    models.pose_estimator.PoseEstimator.inference        -> inference (flip average fused into the decode)
+    models.pose_estimator.PoseEstimator.decode_heatmaps  -> decode_heatmaps
+    datasets.coco_dataset.COCOPoseDataset._generate_target (optional, `encode_on_device=True`)
+        -> returns an empty (K,0,0) placeholder + the exact target weights; the patched loss
+           then builds the target tiles inside the kernel from gt_keypoints (no target H2D copy)
+
+Signatures and return values are those of the reference.  The
+module objects are passed in (or imported by name) so that this file never
+needs the reference on its import path.
+"""
+from __future__ import annotations
+
+import importlib
+from types import ModuleType
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import fusion_head as fh
+from . import pose_estimator as pe
+
+_ORIGINALS: Dict[str, object] = {}
+
+
+def _loss_forward(self, outputs, target_heatmaps, target_weight, gt_keypoints,
+                  input_size=(192, 256), heatmap_size=(48, 64)):
+    """FusionPoseLoss.forward of the reference (fusion_head.py:745), routed to one kernel pass.
+    `self` is the REFERENCE module: its weights / sigma are read by attribute name (:608-635)."""
+    impl = getattr(self, "_gbcodec_impl", None)
+    if impl is None:
+        impl = fh.FusionPoseLoss(
+            heatmap_weight=self.heatmap_weight, offset_weight=self.offset_weight, peak_weight=self.peak_weight,
+            variance_weight=self.variance_weight, overlap_weight=self.overlap_weight, shape_weight=self.shape_weight,
+            target_sigma=getattr(self, "target_sigma", getattr(getattr(self, "gaussian_constraint", None), "target_sigma", 2.0)),
+            use_target_weight=getattr(self, "use_target_weight", True))
+        object.__setattr__(self, "_gbcodec_impl", impl)
+    return impl(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, heatmap_size)
+
+
+def _encode_placeholder(self, keypoints: np.ndarray, keypoints_visible: np.ndarray):
+    """COCOPoseDataset._generate_target for DataLoader workers when the tiles are built on the device:
+    the weights (visibility + the off-map rule, coco_dataset.py:214-229) are 17 scalar tests and stay
+    in numpy; the tile tensor is an empty placeholder that survives default_collate."""
+    K = self.num_keypoints
+    W, H = self.heatmap_size
+    stride = np.asarray(self.input_size, dtype=np.float64) / np.asarray(self.heatmap_size, dtype=np.float64)
+    weight = np.asarray(keypoints_visible, dtype=np.float32).reshape(K, 1).copy()
+    radius = self.sigma * 3
+    for k in range(K):
+        if weight[k, 0] < 0.5:
+            continue
+        mu = keypoints[k].astype(np.float64) / stride
+        ul = (int(mu[0] - radius), int(mu[1] - radius))
+        br = (int(mu[0] + radius + 1), int(mu[1] + radius + 1))
+        if ul[0] >= W or ul[1] >= H or br[0] < 0 or br[1] < 0:
+            weight[k, 0] = 0.0
+    return np.zeros((K, 0, 0), dtype=np.float32), weight
+
+
+def patch_reference(fusion_head: Optional[ModuleType] = None, pose_estimator: Optional[ModuleType] = None,
+                    coco_dataset: Optional[ModuleType] = None, encode_on_device: bool = False) -> Dict[str, object]:
+    """Rebind the reference's entry points.  Modules default to `models.fusion_head`,
+    `models.pose_estimator` (and `datasets.coco_dataset` when `encode_on_device`) imported by name.
+    Returns the original callables (also kept for `unpatch_reference`)."""
+    fusion_head = fusion_head or importlib.import_module("models.fusion_head")
+    pose_estimator = pose_estimator or importlib.import_module("models.pose_estimator")
+    saved = {
+        "FusionPoseLoss.forward": fusion_head.FusionPoseLoss.forward,
+        "HeatmapRegressionHead.decode": fusion_head.HeatmapRegressionHead.decode,
+        "PoseEstimator.inference": pose_estimator.PoseEstimator.inference,
+        "PoseEstimator.decode_heatmaps": pose_estimator.PoseEstimator.__dict__["decode_heatmaps"],
+    }
+    fusion_head.FusionPoseLoss.forward = _loss_forward
+    fusion_head.HeatmapRegressionHead.decode = lambda self, outputs, apply_offset=True: fh.head_decode(self, outputs, apply_offset)
+    pose_estimator.PoseEstimator.inference = lambda self, x, flip=True, flip_pairs=None: pe.inference(self, x, flip, flip_pairs)
+    pose_estimator.PoseEstimator.decode_heatmaps = staticmethod(pe.decode_heatmaps)
+    if encode_on_device:
+        coco_dataset = coco_dataset or importlib.import_module("datasets.coco_dataset")
+        saved["COCOPoseDataset._generate_target"] = coco_dataset.COCOPoseDataset._generate_target
+        coco_dataset.COCOPoseDataset._generate_target = _encode_placeholder
+    _ORIGINALS.update({k: (v, fusion_head, pose_estimator, coco_dataset) for k, v in saved.items()})
+    return saved
+
+
+def unpatch_reference() -> None:
+    for name, (fn, fusion_head, pose_estimator, coco_dataset) in list(_ORIGINALS.items()):
+        cls, attr = name.split(".")
+        mod = {"FusionPoseLoss": fusion_head, "HeatmapRegressionHead": fusion_head,
+               "PoseEstimator": pose_estimator, "COCOPoseDataset": coco_dataset}[cls]
+        setattr(getattr(mod, cls), attr, fn)
+        del _ORIGINALS[name]

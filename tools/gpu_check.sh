@@ -24,7 +24,7 @@ if [[ $what == all || $what == ncu ]]; then
   $CMD > $out/plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/launches.csv $CMD > $out/ncu_launches.log 2>&1
   $CMD > $out/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:loss_kernel -s 3 -c 2 -f -o $out/prof_loss $CMD > $out/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:loss_tile_kernel -s 3 -c 2 -f -o $out/prof_loss $CMD > $out/ncu_full.log 2>&1
   tail -3 $out/ncu_full.log
 fi
 exit $rc
