@@ -136,6 +136,9 @@ int gbcodec_loss_denominators_f32(const gbcodec_loss_desc* desc, const float* d_
  * grad pointers are given, d(total_loss)/d(hm, off, var) scaled by *d_grad_scale —
  * every heatmap tile is read from HBM once.
  *   d_hm (B,K,H,W)  d_off (B,K,2,H,W)  d_var (B,K,H,W) or NULL
+ *            d_off may also be a device-accessible (pinned, mapped) HOST pointer: the pass reads
+ *            at most 16 floats per tile from it, so a caller whose offset maps live in host
+ *            memory need not ship them over PCIe
  *   d_target (B,K,H,W), or NULL: tiles are generated on the fly from d_gt_kps and
  *            d_weight exactly as gbcodec_encode_f32 would (no HBM traffic for them)
  *   d_weight (B,K)   d_gt_kps (B,K,2) input-image pixels

@@ -18,28 +18,37 @@
 namespace gbc {
 
 // ---- weights after the encoder rule + the two batch sums ----------------------------
+// One thread per tile; a CTA owns 256 / K whole images so that the limb products of an image
+// stay inside one CTA.  The sums are accumulated in double: with the reference's weights
+// (visibility flags 0/1/2, coco_dataset.py:214) every partial sum is an exact integer, so the
+// order of the two atomics per CTA does not change the result.
 __global__ void __launch_bounds__(256)
 denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight,
               const float* __restrict__ gt, int target_given, float* __restrict__ weff, int4* __restrict__ geom,
               double* __restrict__ sums) {
-    // one image per thread: K weights, then the limb products
+    __shared__ float wsm[256];
     __shared__ double red[2][8];
+    const int ipb = 256 / P.K;                         // images per CTA
+    const int img0 = blockIdx.x * ipb;
+    const int nimg = min(ipb, P.B - img0);
+    const int local = threadIdx.x;
     double sw = 0.0, sp = 0.0;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.B; b += gridDim.x * blockDim.x) {
-        float w[GBCODEC_MAX_K];
-        for (int k = 0; k < P.K; ++k) {
-            const int t = b * P.K + k;
-            float wk = weight[t];
-            if (!target_given) {
-                const PatchGeom g = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec);
-                wk = g.weight;
-                if (geom) geom[t] = pack_geom(g);
-            }
-            w[k] = wk;
-            if (weff) weff[t] = wk;
-            sw += (double)wk;
+    if (local < nimg * P.K) {
+        const int t = img0 * P.K + local;
+        float wk = weight[t];
+        if (!target_given) {
+            const PatchGeom g = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec);
+            wk = g.weight;
+            if (geom) geom[t] = pack_geom(g);
         }
-        for (int p = 0; p < P.n_pairs; ++p) sp += (double)(w[P.pair_i[p]] * w[P.pair_j[p]]);
+        wsm[local] = wk;
+        if (weff) weff[t] = wk;
+        sw = (double)wk;
+    }
+    __syncthreads();
+    for (int q = local; q < nimg * P.n_pairs; q += 256) {
+        const int im = q / P.n_pairs, p = q - im * P.n_pairs;
+        sp += (double)(wsm[im * P.K + P.pair_i[p]] * wsm[im * P.K + P.pair_j[p]]);
     }
     for (int o = 16; o > 0; o >>= 1) {
         sw += __shfl_xor_sync(0xffffffffu, sw, o);
@@ -48,19 +57,19 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { red[0][warp] = sw; red[1][warp] = sp; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, c = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; c += red[1][i]; }
-        atomicAdd(sums, a);
-        atomicAdd(sums + 1, c);
+    if (threadIdx.x < 2) {
+        double a = 0.0;
+        for (int i = 0; i < 8; ++i) a += red[threadIdx.x][i];
+        atomicAdd(sums + threadIdx.x, a);
     }
 }
 
 __global__ void sums_to_float_kernel(const double* __restrict__ sums, float* __restrict__ out2) {
     if (threadIdx.x < 2) out2[threadIdx.x] = (float)sums[threadIdx.x];
 }
-__global__ void sums_from_float_kernel(const float* __restrict__ in2, double* __restrict__ sums) {
+__global__ void sums_from_float_kernel(const float* __restrict__ in2, double* __restrict__ sums, unsigned* __restrict__ ticket) {
     if (threadIdx.x < 2) sums[threadIdx.x] = (double)in2[threadIdx.x];
+    if (threadIdx.x == 2) *ticket = 0u;
 }
 // weights after the encoder rule only (the sums come from the caller)
 __global__ void __launch_bounds__(256)
@@ -429,15 +438,21 @@ loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossAr
 }
 
 // ---- second stage: fixed-order sum of the per-tile numerators -----------------------------
-__global__ void __launch_bounds__(1024)
+// Up to kFinBlocks CTAs each sum a contiguous slice of the tiles in double and publish six
+// partials; the CTA that draws the last ticket adds the partials in slice order and writes the
+// seven losses.  The order of every addition is fixed by the launch shape: bit-reproducible.
+__global__ void __launch_bounds__(256)
 finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ partial, const double* __restrict__ sums,
-                float* __restrict__ losses7) {
-    __shared__ double red[6][32];
+                double* __restrict__ bpart, unsigned* __restrict__ ticket, float* __restrict__ losses7) {
+    __shared__ double red[6][8];
+    __shared__ bool last;
     const int tiles = P.B * P.K;
+    const int per = (tiles + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(tiles, lo + per);
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-        const float4 a = *reinterpret_cast<const float4*>(partial + (size_t)t * 8);
-        const float4 c = *reinterpret_cast<const float4*>(partial + (size_t)t * 8 + 4);
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)t * 8));
+        const float4 c = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)t * 8 + 4));
         acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += c.x; acc[5] += c.y;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -447,19 +462,34 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
         if (lane == 0) red[q][warp] = acc[q];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 6) {
+        double s = 0.0;
+        for (int wp = 0; wp < 8; ++wp) s += red[threadIdx.x][wp];
+        bpart[blockIdx.x * 6 + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    __shared__ float term[6];
+    if (threadIdx.x < 6) {
+        const int q = threadIdx.x;
+        double s = 0.0;
+        for (int g = 0; g < (int)gridDim.x; ++g) s += __ldcg(bpart + g * 6 + q);
         const float D = (float)sums[0] + kEps, D5 = (float)sums[1] + kEps;
         const float Da = P.use_target_weight ? D : (float)tiles;
+        const float den = q < 3 ? Da : (q == 4 ? D5 : D);
+        term[q] = P.lam[q] * ((float)s / den);
+        losses7[q] = term[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         float total = 0.f;
-        for (int q = 0; q < 6; ++q) {
-            double s = 0.0;
-            for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) s += red[q][wp];
-            const float den = q < 3 ? Da : (q == 4 ? D5 : D);
-            const float v = P.lam[q] * ((float)s / den);
-            losses7[q] = v;
-            total += v;
-        }
+        for (int q = 0; q < 6; ++q) total += term[q];
         losses7[6] = total;
+        *ticket = 0u;
     }
 }
 
@@ -574,11 +604,13 @@ static int prepare_weights(const LossParams& P, const WsLayout& L, const float* 
                            int target_given, const float* denoms, cudaStream_t s) {
     if (denoms) {
         weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom);
-        sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums);
+        sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
     } else {
-        cudaError_t e = cudaMemsetAsync(L.sums, 0, 2 * sizeof(double), s);
+        // sums, plan and the finalize ticket share the first 32 bytes of the workspace
+        cudaError_t e = cudaMemsetAsync(L.sums, 0, 32, s);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-        const int grid = (P.B + 255) / 256 < 148 ? (P.B + 255) / 256 : 148;
+        const int ipb = 256 / P.K;
+        const int grid = (P.B + ipb - 1) / ipb;
         denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums);
     }
     return check_launch("denoms_kernel");
@@ -632,7 +664,9 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial;
     st = launch_loss_kernel(P, A, s);
     if (st) return st;
-    finalize_kernel<<<1, 1024, 0, s>>>(P, L.partial, L.sums, losses7);
+    const int tiles = P.B * P.K;
+    const int fin_blocks = (tiles + 255) / 256 < kFinBlocks ? (tiles + 255) / 256 : kFinBlocks;
+    finalize_kernel<<<fin_blocks, 256, 0, s>>>(P, L.partial, L.sums, L.bpart, L.ticket, losses7);
     return check_launch("finalize_kernel");
 }
 

@@ -42,9 +42,10 @@ struct LossArgs {
     const int* plan;                    // backward recompute: run only if *plan == 2
 };
 
-constexpr int kWsHeaderFloats = 64;     // sums (2 doubles), plan, lam_eff, ... ; 256 bytes
+constexpr int kFinBlocks = 32;          // CTAs of the second-stage reduction
+constexpr int kWsHeaderFloats = 512;    // sums (2 doubles), plan, ticket, lam_eff, second-stage partials; 2 KB
 struct WsLayout {
-    double* sums; int* plan; float* lam_eff; float* weff; int4* geom; float* partial;
+    double* sums; int* plan; unsigned* ticket; float* lam_eff; double* bpart; float* weff; int4* geom; float* partial;
 };
 static inline size_t ws_bytes(int B, int K) {
     return (size_t)(kWsHeaderFloats + (size_t)B * K * 13 + 8) * sizeof(float);
@@ -53,8 +54,10 @@ static inline WsLayout ws_carve(void* ws, int B, int K) {
     float* f = reinterpret_cast<float*>(ws);
     WsLayout l;
     l.sums = reinterpret_cast<double*>(f);          // f[0..3]
-    l.plan = reinterpret_cast<int*>(f + 4);         // f[4..7]
+    l.plan = reinterpret_cast<int*>(f + 4);         // f[4]
+    l.ticket = reinterpret_cast<unsigned*>(f + 5);  // f[5]
     l.lam_eff = f + 8;                              // f[8..15]
+    l.bpart = reinterpret_cast<double*>(f + 64);    // kFinBlocks * 6 doubles
     // geom rows are 16 bytes and partial rows 32 bytes: keep both aligned
     const size_t tiles = (size_t)B * K, tiles8 = (tiles + 7) & ~(size_t)7;
     l.geom = reinterpret_cast<int4*>(f + kWsHeaderFloats);

@@ -2,6 +2,10 @@
 
 The batch is cut into chunks of whole images; while chunk i is in the loss kernel,
 chunk i+1 is on its way over PCIe (copy stream + double-buffered device staging).
+Only the heatmaps and the variance maps are staged: of the offset maps (half of the
+input bytes) the step touches 16 floats per tile, at positions that are known only once the
+tile's soft-argmax is, so the kernel reads those taps straight from the pinned host
+buffer over PCIe (zero-copy) instead of shipping 2*H*W floats per tile.
 Chunks are shards in the sense of sharded.py: the two batch-global normalisers
 are computed first from the (tiny) keypoint/visibility arrays of the whole
 batch, every chunk is then normalised by them, and the per-chunk loss vectors
@@ -24,7 +28,7 @@ class HostCodecStep:
     def __init__(self, B: int, K: int, H: int, W: int, input_size: Sequence[int] = (192, 256), sigma: float = 2.0,
                  lambdas: Sequence[float] = (1.0, 1.0, 0.5, 0.1, 0.05, 0.05), chunk_images: int = 128,
                  device: Optional[torch.device] = None, with_grads: bool = True,
-                 skeleton: Sequence[Tuple[int, int]] = SKELETON):
+                 skeleton: Sequence[Tuple[int, int]] = SKELETON, stage_offsets: bool = False):
         self.B, self.K, self.H, self.W = B, K, H, W
         self.in_w, self.in_h = float(input_size[0]), float(input_size[1])
         self.sigma = float(sigma)
@@ -35,8 +39,9 @@ class HostCodecStep:
         self.pairs = ops.pairs_flat([(i, j) for (i, j) in skeleton if i < K and j < K])
         d, f = self.device, torch.float32
         C = self.chunk
-        self.stage = [dict(hm=torch.empty((C, K, H, W), dtype=f, device=d), off=torch.empty((C, K, 2, H, W), dtype=f, device=d),
-                           var=torch.empty((C, K, H, W), dtype=f, device=d)) for _ in range(2)]
+        self.stage_offsets = stage_offsets
+        self.stage = [dict(hm=torch.empty((C, K, H, W), dtype=f, device=d), var=torch.empty((C, K, H, W), dtype=f, device=d),
+                           off=torch.empty((C, K, 2, H, W), dtype=f, device=d) if stage_offsets else None) for _ in range(2)]
         self.kps_d = torch.empty((B, K, 2), dtype=f, device=d)
         self.vis_d = torch.empty((B, K), dtype=f, device=d)
         self.losses_d = torch.zeros(7, dtype=f, device=d)
@@ -54,8 +59,9 @@ class HostCodecStep:
 
     @property
     def h2d_bytes(self) -> int:
-        n = self.B * self.K * self.H * self.W * 4
-        return n * 4 + self.B * self.K * 12
+        n = self.B * self.K * self.H * self.W * 4                  # one (B,K,H,W) fp32 tensor
+        taps = self.B * self.K * 16 * 32                           # zero-copy: 16 taps per tile, a 32-byte sector each
+        return n * 2 + (n * 2 if self.stage_offsets else taps) + self.B * self.K * 12
 
     @property
     def d2h_bytes(self) -> int:
@@ -84,11 +90,13 @@ class HostCodecStep:
                 if c >= 2:
                     self.copy_stream.wait_event(self.consumed[c & 1])
                 s["hm"][:n].copy_(hm_h[lo:hi], non_blocking=True)
-                s["off"][:n].copy_(off_h[lo:hi], non_blocking=True)
+                if self.stage_offsets:
+                    s["off"][:n].copy_(off_h[lo:hi], non_blocking=True)
                 s["var"][:n].copy_(var_h[lo:hi], non_blocking=True)
                 self.staged[c & 1].record(self.copy_stream)
             main.wait_event(self.staged[c & 1])
-            res = ops.fusion_loss(s["hm"][:n], s["off"][:n], s["var"][:n], None, self.vis_d[lo:hi], self.kps_d[lo:hi],
+            off_c = s["off"][:n] if self.stage_offsets else off_h[lo:hi]
+            res = ops.fusion_loss(s["hm"][:n], off_c, s["var"][:n], None, self.vis_d[lo:hi], self.kps_d[lo:hi],
                                   den, None, self.in_w, self.in_h, self.lambdas, self.sigma, self.sigma, True, self.pairs,
                                   self.with_grads, True, self.alpha, self.fw, 2, N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)
             self.consumed[c & 1].record(main)

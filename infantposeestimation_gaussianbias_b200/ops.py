@@ -34,6 +34,19 @@ def _cuda_f32(name: str, t: Tensor, shape: Optional[Sequence[int]] = None) -> Te
     return t.contiguous()
 
 
+def _device_readable_f32(name: str, t: Tensor, shape: Sequence[int]) -> Tensor:
+    """A CUDA tensor, or a PINNED host tensor the kernels read in place over PCIe (zero-copy; with
+    unified addressing a cudaHostAlloc'd buffer has the same address on the device).  Only for
+    inputs of which a kernel touches a few bytes per tile — the offset maps (8 taps of 2*H*W)."""
+    if t.is_cuda:
+        return _cuda_f32(name, t, shape)
+    if not t.is_pinned():
+        raise RuntimeError(f"gbcodec: `{name}` must be a CUDA tensor or a pinned host tensor (this library has no CPU path)")
+    if t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise RuntimeError(f"gbcodec: pinned `{name}` must be contiguous float32 of shape {tuple(shape)}")
+    return t
+
+
 def _scalar(name: str, t: Optional[Tensor], like: Tensor) -> Optional[Tensor]:
     if t is None:
         return None
@@ -176,7 +189,7 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
     """-> losses7, grad_hm, grad_off, grad_var, coords, scores (empty tensors for what was not asked)."""
     B, K, H, W = hm.shape
     hm = _cuda_f32("heatmaps", hm)
-    off = _cuda_f32("offsets", off, (B, K, 2, H, W))
+    off = _device_readable_f32("offsets", off, (B, K, 2, H, W))
     if var is not None:
         var = _cuda_f32("variances", var, (B, K, H, W))
     if target is not None:
@@ -191,7 +204,7 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
     losses = torch.empty(7, dtype=torch.float32, device=dev)
     empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
     if with_grads:
-        ghm, goff = torch.empty_like(hm), torch.empty_like(off)
+        ghm, goff = torch.empty_like(hm), torch.empty(off.shape, dtype=torch.float32, device=dev)
         gvar = torch.empty_like(var) if var is not None else empty()
     else:
         ghm, goff, gvar = empty(), empty(), empty()

@@ -322,3 +322,33 @@ def test_errors_are_loud(gb):
         gb.decode_argmax(torch.zeros(1, 1, 8, 8).cuda(), 7)       # bad mode
     with pytest.raises(GbcodecError):
         gb.decode(torch.zeros(1, 1, 8, 8).cuda(), None, None, None, None, None, 2, 1)   # REFINE without alpha
+
+
+# ---------------------------------------------------------------------- host-buffer step
+@pytest.mark.parametrize("stage_offsets", [False, True])
+def test_host_buffer_step_matches_resident_step(gb, stage_offsets):
+    """HostCodecStep (pinned host buffers in, chunked H2D pipeline, offsets read in place over
+    PCIe or staged) must give what one resident pass over the whole batch gives."""
+    from infantposeestimation_gaussianbias_b200 import _native as N
+    from infantposeestimation_gaussianbias_b200.host_step import HostCodecStep
+    cfg = synth.CONFIGS["w32_256x192"]
+    B = 24
+    batch = synth.make_batch(cfg, seed=5, B=B)
+    K, (W, H) = cfg.K, cfg.heatmap_size
+    pin = lambda k: t(batch[k]).pin_memory()
+    hs = HostCodecStep(B, K, H, W, cfg.input_size, cfg.sigma, chunk_images=7, stage_offsets=stage_offsets)
+    out = hs(pin("heatmaps"), pin("offsets"), pin("variances"), pin("kps"), pin("vis"))
+    pairs = gb.pairs_flat(oc.COCO_SKELETON)
+    alpha, fw = torch.tensor([0.5]).cuda(), torch.tensor([0.6224593312018546]).cuda()
+    res = gb.fusion_loss(dev(batch["heatmaps"]), dev(batch["offsets"]), dev(batch["variances"]), None, dev(batch["vis"]),
+                         dev(batch["kps"]), None, None, float(cfg.input_size[0]), float(cfg.input_size[1]),
+                         list(oc.DEFAULT_LAMBDAS), cfg.sigma, cfg.sigma, True, pairs, True, True, alpha, fw, 2,
+                         N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)
+    np.testing.assert_allclose(out["losses"].numpy(), res[0].cpu().numpy(), rtol=2e-6)
+    assert np.array_equal(out["coords"].numpy(), res[4].cpu().numpy())
+    assert np.array_equal(out["scores"].numpy(), res[5].cpu().numpy())
+    # the last chunk's gradients are the resident gradients of those images
+    lo = (B // 7) * 7 if B % 7 else B - 7
+    for got, want in zip(hs.grads, res[1:4]):
+        assert torch.equal(got, want[lo:])
+    assert hs.h2d_bytes < (2 if not stage_offsets else 4) * B * K * H * W * 4 * 1.1
