@@ -755,6 +755,10 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
             case 3: return launch_tile_tm<12, 16, 4, false, true, true, 4, true, true>(P, A, s, e0, e1);    // rolled; H,S,A,Q   51 KB, 4 CTAs
             case 4: return launch_tile_tm<12, 32, 2, false, true, false, 3, true, true>(P, A, s, e0, e1);   // rolled; 384 threads, 8 px each
             case 5: return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // rolled; H,S       27 KB, 6 CTAs
+            case 6: return launch_tile_tm<12, 8, 8, false, true, false, 6, true, false>(P, A, s, e0, e1);   // 96 threads, 32 px each, registers; S,Q
+            case 7: return launch_tile_tm<12, 8, 8, false, true, false, 6, true, true>(P, A, s, e0, e1);    // 96 threads, 32 px each, rolled; H,S,Q
+            case 8: return launch_tile_tm<12, 8, 8, false, false, false, 8, true, false>(P, A, s, e0, e1);  // 96 threads, registers; Q only
+            case 9: return launch_tile_tm<12, 8, 8, false, true, false, 8, true, false>(P, A, s, e0, e1);   // 96 threads, registers; S,Q; 8 CTAs
             default: break;
         }
     }
