@@ -181,6 +181,115 @@ int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
                             float* d_grad_hm, float* d_grad_off, float* d_grad_var,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------- Gen-B family (next rows) ---
+ * The reference carries a second generation of the same codec ("Gen-B":
+ * data/, models/losses.py, utils/postprocess.py).  Same tile layout, same rules.
+ */
+
+/* Alternate encoders.
+ *   GBCODEC_ENCODE_PATCH          COCOPoseDataset._generate_target (datasets/coco_dataset.py:185-250);
+ *                                 what gbcodec_encode_f32 does
+ *   GBCODEC_ENCODE_PATCH_CLIPPED  PreemieCocoDataset._generate_heatmaps (data/coco_dataset.py:222-287):
+ *                                 mu in float32, weight binarised to 1, the joint must lie inside the
+ *                                 map (:250), and the patch origin is clamped to 0 BEFORE the patch
+ *                                 slice is derived (:262-263, :277) — for mu < 3 sigma the patch's own
+ *                                 top-left corner lands on pixel 0
+ *   GBCODEC_ENCODE_DENSE          GenerateTarget (data/pose_transforms.py:385-457): sub-pixel centre,
+ *                                 exp over the whole tile, weight 1/0 (visible and inside the map)
+ * d_vis (B,K): > 0 means visible for the two Gen-B modes. */
+#define GBCODEC_ENCODE_PATCH         0
+#define GBCODEC_ENCODE_PATCH_CLIPPED 1
+#define GBCODEC_ENCODE_DENSE         2
+int gbcodec_encode_mode_f32(const float* d_kps, const float* d_vis, float* d_target, float* d_weight,
+                            int B, int K, int H, int W, float in_w, float in_h, double sigma, int mode, void* stream);
+
+/* postprocess_predictions (utils/postprocess.py:296-340) in ONE pass over the heatmaps:
+ * fused_decode (:78-135: Taylor arg-max, optional scale to the 256-px image, confidence-adaptive
+ * blend with the regression branch) -> coordinate_refinement (:138-184) -> filter_low_confidence
+ * (:226-238) -> transform_preds (:270-292).  Every stage is optional, so the same entry point
+ * also serves fused_decode alone.
+ *   d_regression (B,K,2) or NULL.  The reference rescales it by image_size when its batch-wide
+ *                maximum is <= 1.0 (:119); that test runs on the device (d_workspace: 16 bytes).
+ *   d_center, d_scale (B,2) or NULL; required with scale_to_image or transform.
+ *   d_preds (B,K,2) out   d_maxvals (B,K) out   d_mask (B,K) out or NULL
+ */
+typedef struct gbcodec_postprocess_desc {
+    int32_t B, K, H, W;
+    int32_t argmax_mode;      /* GBCODEC_ARGMAX_*; fused_decode uses TAYLOR                          */
+    int32_t scale_to_image;   /* preds *= image_size / (W, H)            (postprocess.py:105-114)    */
+    float   image_size;       /* 256 in the reference                    (:108, :121)                */
+    int32_t refine_window;    /* coordinate_refinement window, 0 = skip  (:138)                      */
+    int32_t filter;           /* filter_low_confidence on/off            (:226)                      */
+    float   threshold;
+    int32_t transform;        /* transform_preds on/off                  (:270)                      */
+    float   input_w, input_h; /* its input_size (default 256, 256)                                    */
+} gbcodec_postprocess_desc;
+int gbcodec_postprocess_f32(const gbcodec_postprocess_desc* desc, const float* d_hm, const float* d_regression,
+                            const float* d_center, const float* d_scale,
+                            float* d_preds, float* d_maxvals, float* d_mask, void* d_workspace16, void* stream);
+
+/* Heatmap pixels -> input pixels -> original image (validate.py:31-36,102-119; inference.py:143-175):
+ *   c_in = c * (in / hm);   c_img = c_in / in * scale + center - scale / 2
+ * in exactly that order of float32 operations.  d_coords_in/out (B,K,2) (may alias), d_center/d_scale (B,2). */
+int gbcodec_coords_to_image_f32(const float* d_coords_in, const float* d_center, const float* d_scale,
+                                int B, int K, int H, int W, float in_w, float in_h, float* d_coords_out, void* stream);
+
+/* CombinedLoss (models/losses.py:205-290) and its parts, forward + backward in one pass:
+ *   heatmap    FusedPoseLoss (:10-47): mean_{B,K,H,W}(crit(p,t) * w)
+ *              with GBCODEC_CRIT_MSE_WEIGHTED: mean((p*w - t*w)^2) — KeypointMSELoss
+ *              (models/pose_estimator.py:102-143) and, with heatmap_scale = 0.5, JointsMSELoss (:174-202)
+ *   morph      MorphologyShapeLoss (:50-135): spatial mean / variance of pred and target
+ *   regression, refined   OffsetRegressionLoss (:138-171) on (B,K,2) coordinates
+ *   total = w_heatmap*heatmap + w_morph*morph + w_reg*(regression + refined)
+ * Algorithmic HBM bytes per tile: read pred, target (8N); write d_pred (4N).
+ */
+#define GBCODEC_CRIT_MSE          0
+#define GBCODEC_CRIT_SMOOTHL1     1
+#define GBCODEC_CRIT_L1           2   /* coordinates only */
+#define GBCODEC_CRIT_MSE_WEIGHTED 3   /* heatmaps only    */
+#define GBCODEC_TERM_HEATMAP    1u
+#define GBCODEC_TERM_MORPH      2u
+#define GBCODEC_TERM_REGRESSION 4u
+#define GBCODEC_TERM_REFINED    8u
+typedef struct gbcodec_combined_desc {
+    int32_t  B, K, H, W;
+    int32_t  norm_batch;          /* batch size in the means' denominators; 0 = B.  A rank holding a
+                                     shard passes the global batch and all-reduces the five scalars  */
+    uint32_t terms;               /* GBCODEC_TERM_* present in `predictions` / `targets`             */
+    int32_t  heatmap_criterion;   /* GBCODEC_CRIT_MSE | _SMOOTHL1 | _MSE_WEIGHTED                     */
+    int32_t  coord_criterion;     /* GBCODEC_CRIT_SMOOTHL1 | _L1 | _MSE                               */
+    int32_t  use_target_weight;   /* heatmap term only (:41); the other terms use w whenever given   */
+    float    heatmap_scale;       /* 1, or 0.5 for JointsMSELoss (:196)                               */
+    float    lambda_variance, lambda_mean;   /* MorphologyShapeLoss (:66-69)                          */
+    float    w_heatmap, w_morph, w_reg;      /* CombinedLoss (:228-231)                               */
+} gbcodec_combined_desc;
+
+size_t gbcodec_combined_workspace_bytes(int B, int K);
+
+/*   d_pred, d_target (B,K,H,W) — required with TERM_HEATMAP / TERM_MORPH
+ *   d_weight (B,K) or NULL
+ *   d_coords, d_refined, d_target_coords (B,K,2) — with TERM_REGRESSION / TERM_REFINED
+ *   d_grad_scale NULL (=1) or device scalar: upstream gradient of `total` assumed by the forward
+ *   d_losses5 out: heatmap, morph, regression, refined, total (absent terms are 0)
+ *   d_grad_pred (B,K,H,W), d_grad_coords, d_grad_refined (B,K,2): out, each NULL = not wanted
+ */
+int gbcodec_combined_loss_f32(const gbcodec_combined_desc* desc,
+                              const float* d_pred, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, float* d_losses5,
+                              float* d_grad_pred, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Backward for an arbitrary upstream gradient on the five outputs: returns inside the kernels if it
+ * equals what the forward assumed (d(total) = *d_grad_scale, nothing on the four terms), otherwise
+ * recomputes the gradients with per-term weights.  No host synchronisation. */
+int gbcodec_combined_loss_backward_f32(const gbcodec_combined_desc* desc,
+                              const float* d_pred, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, const float* d_grad_losses5,
+                              float* d_grad_pred, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement hook (bench.py): the next gbcodec_fusion_loss_f32 / _step_f32 calls made
  * by THIS host thread record `start_event` right before and `stop_event` right after
  * the per-tile loss kernel, on the stream of the call.  Both are cudaEvent_t passed as

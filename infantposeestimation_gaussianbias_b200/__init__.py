@@ -25,7 +25,7 @@ def __getattr__(name):
     if name in ("FusionPoseLoss", "decode_outputs", "head_decode", "soft_argmax", "SKELETON", "LOSS_KEYS"):
         from . import fusion_head
         return getattr(fusion_head, name)
-    if name in ("generate_heatmaps", "HeatmapGenerator"):
+    if name in ("generate_heatmaps", "HeatmapGenerator", "generate_heatmaps_clipped", "GenerateTarget"):
         from . import generate_heatmap
         return getattr(generate_heatmap, name)
     if name in ("decode_heatmaps", "inference", "flip_permutation"):
@@ -34,7 +34,11 @@ def __getattr__(name):
     if name == "patch_reference":
         from .patch import patch_reference
         return patch_reference
-    if name in ("ops", "postprocess", "sharded", "patch"):
+    if name in ("FusedPoseLoss", "MorphologyShapeLoss", "OffsetRegressionLoss", "JointsMSELoss", "KeypointMSELoss",
+                "CombinedLoss", "build_loss"):
+        from . import losses
+        return getattr(losses, name)
+    if name in ("ops", "postprocess", "sharded", "patch", "losses"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

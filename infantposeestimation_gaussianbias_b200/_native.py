@@ -22,6 +22,9 @@ DECODE_REFINE = 1
 DECODE_APPLY_OFFSET = 2
 DECODE_FUSION_WEIGHT_RAW = 4
 ARGMAX_PLAIN, ARGMAX_QUARTER, ARGMAX_TAYLOR = 0, 1, 2
+ENCODE_PATCH, ENCODE_PATCH_CLIPPED, ENCODE_DENSE = 0, 1, 2
+CRIT_MSE, CRIT_SMOOTHL1, CRIT_L1, CRIT_MSE_WEIGHTED = 0, 1, 2, 3
+TERM_HEATMAP, TERM_MORPH, TERM_REGRESSION, TERM_REFINED = 1, 2, 4, 8
 
 EXPORTS = (
     "gbcodec_abi_version", "gbcodec_status_string", "gbcodec_last_error",
@@ -29,6 +32,8 @@ EXPORTS = (
     "gbcodec_loss_workspace_bytes", "gbcodec_loss_denominators_f32",
     "gbcodec_fusion_loss_f32", "gbcodec_fusion_step_f32", "gbcodec_fusion_loss_backward_f32",
     "gbcodec_profile_loss_kernel",
+    "gbcodec_encode_mode_f32", "gbcodec_postprocess_f32", "gbcodec_coords_to_image_f32",
+    "gbcodec_combined_workspace_bytes", "gbcodec_combined_loss_f32", "gbcodec_combined_loss_backward_f32",
 )
 
 
@@ -41,6 +46,27 @@ class LossDesc(C.Structure):
         ("target_sigma", C.c_double), ("encode_sigma", C.c_double),
         ("use_target_weight", C.c_int32), ("n_pairs", C.c_int32),
         ("pairs", (C.c_int32 * 2) * MAX_PAIRS),
+    ]
+
+
+class PostprocessDesc(C.Structure):
+    """struct gbcodec_postprocess_desc"""
+    _fields_ = [
+        ("B", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("argmax_mode", C.c_int32), ("scale_to_image", C.c_int32), ("image_size", C.c_float),
+        ("refine_window", C.c_int32), ("filter", C.c_int32), ("threshold", C.c_float),
+        ("transform", C.c_int32), ("input_w", C.c_float), ("input_h", C.c_float),
+    ]
+
+
+class CombinedDesc(C.Structure):
+    """struct gbcodec_combined_desc"""
+    _fields_ = [
+        ("B", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("norm_batch", C.c_int32), ("terms", C.c_uint32),
+        ("heatmap_criterion", C.c_int32), ("coord_criterion", C.c_int32), ("use_target_weight", C.c_int32),
+        ("heatmap_scale", C.c_float), ("lambda_variance", C.c_float), ("lambda_mean", C.c_float),
+        ("w_heatmap", C.c_float), ("w_morph", C.c_float), ("w_reg", C.c_float),
     ]
 
 
@@ -90,6 +116,16 @@ def _declare(lib):
                                                           f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_fusion_loss_backward_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_profile_loss_kernel.argtypes = [_P, _P]
+    lib.gbcodec_encode_mode_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_float, C.c_float, C.c_double, C.c_int, _P]
+    lib.gbcodec_postprocess_f32.argtypes = [C.POINTER(PostprocessDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p, _P, _P]
+    lib.gbcodec_coords_to_image_f32.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                f32p, _P]
+    lib.gbcodec_combined_workspace_bytes.restype = C.c_size_t
+    lib.gbcodec_combined_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    comb = [C.POINTER(CombinedDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p]
+    lib.gbcodec_combined_loss_f32.argtypes = comb + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
+    lib.gbcodec_combined_loss_backward_f32.argtypes = comb + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = the library does not export what the header declares
 

@@ -24,7 +24,7 @@ int check_launch(const char* what) {
 }
 
 // encode.cu / decode.cu / loss.cu
-int launch_encode(const float*, const float*, float*, float*, int, int, int, int, float, float, double, cudaStream_t);
+int launch_encode(const float*, const float*, float*, float*, int, int, int, int, float, float, double, int, cudaStream_t);
 int launch_decode(const float*, const float*, const int32_t*, const float*, const float*, const float*, int, int, int, int,
                   int, unsigned, float*, float*, int32_t*, cudaStream_t);
 int launch_argmax(const float*, int, int, int, int, int, float*, float*, int32_t*, cudaStream_t);
@@ -37,6 +37,15 @@ int fusion_loss(const gbcodec_loss_desc*, const float*, const float*, const floa
 int fusion_loss_backward(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*,
                          const float*, const float*, const float*, const float*, float*, float*, float*, void*, size_t,
                          cudaStream_t);
+
+int launch_postprocess(const gbcodec_postprocess_desc*, const float*, const float*, const float*, const float*, float*, float*,
+                       float*, void*, cudaStream_t);
+int launch_coords_to_image(const float*, const float*, const float*, int, int, int, int, float, float, float*, cudaStream_t);
+size_t combined_workspace_bytes(int B, int K);
+int combined_loss(const gbcodec_combined_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
+                  const float*, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+int combined_loss_backward(const gbcodec_combined_desc*, const float*, const float*, const float*, const float*, const float*,
+                           const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t);
 
 void set_profile_events(cudaEvent_t, cudaEvent_t);
 
@@ -72,14 +81,19 @@ const char* gbcodec_status_string(int status) {
 
 const char* gbcodec_last_error(void) { return g_last_error; }
 
-int gbcodec_encode_f32(const float* d_kps, const float* d_vis, float* d_target, float* d_weight,
-                       int B, int K, int H, int W, float in_w, float in_h, double sigma, void* stream) {
+int gbcodec_encode_mode_f32(const float* d_kps, const float* d_vis, float* d_target, float* d_weight,
+                            int B, int K, int H, int W, float in_w, float in_h, double sigma, int mode, void* stream) {
     int st = check_tile_shape("encode", B, K, H, W);
     if (st) return st;
     if (!d_kps || !d_vis || !d_target || !d_weight) return fail(GBCODEC_ERR_NULL_POINTER, "encode: NULL pointer");
     if (!aligned16(d_target)) return fail(GBCODEC_ERR_UNALIGNED, "encode: d_target must be 16-byte aligned");
     if (!(sigma > 0.0) || !(in_w > 0.f) || !(in_h > 0.f)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "encode: sigma and input size must be positive");
-    return launch_encode(d_kps, d_vis, d_target, d_weight, B, K, H, W, in_w, in_h, sigma, (cudaStream_t)stream);
+    return launch_encode(d_kps, d_vis, d_target, d_weight, B, K, H, W, in_w, in_h, sigma, mode, (cudaStream_t)stream);
+}
+
+int gbcodec_encode_f32(const float* d_kps, const float* d_vis, float* d_target, float* d_weight,
+                       int B, int K, int H, int W, float in_w, float in_h, double sigma, void* stream) {
+    return gbcodec_encode_mode_f32(d_kps, d_vis, d_target, d_weight, B, K, H, W, in_w, in_h, sigma, GBCODEC_ENCODE_PATCH, stream);
 }
 
 int gbcodec_decode_f32(const float* d_hm, const float* d_hm_flipped, const int32_t* d_flip_perm,
@@ -115,6 +129,57 @@ int gbcodec_refine_centroid_f32(const float* d_hm, const float* d_coords_in, int
     if (!d_hm || !d_coords_in || !d_coords_out) return fail(GBCODEC_ERR_NULL_POINTER, "refine_centroid: NULL pointer");
     if (window < 1 || window > 31) return fail(GBCODEC_ERR_BAD_ARGUMENT, "refine_centroid: window=%d", window);
     return launch_centroid(d_hm, d_coords_in, B, K, H, W, window, d_coords_out, (cudaStream_t)stream);
+}
+
+int gbcodec_postprocess_f32(const gbcodec_postprocess_desc* desc, const float* d_hm, const float* d_regression,
+                            const float* d_center, const float* d_scale,
+                            float* d_preds, float* d_maxvals, float* d_mask, void* d_workspace16, void* stream) {
+    if (!desc) return fail(GBCODEC_ERR_NULL_POINTER, "postprocess: desc is NULL");
+    int st = check_tile_shape("postprocess", desc->B, desc->K, desc->H, desc->W);
+    if (st) return st;
+    if (!d_hm || !d_preds || !d_maxvals) return fail(GBCODEC_ERR_NULL_POINTER, "postprocess: NULL pointer");
+    if (!aligned16(d_hm)) return fail(GBCODEC_ERR_UNALIGNED, "postprocess: d_hm must be 16-byte aligned");
+    if (desc->argmax_mode < GBCODEC_ARGMAX_PLAIN || desc->argmax_mode > GBCODEC_ARGMAX_TAYLOR) return fail(GBCODEC_ERR_BAD_ARGUMENT, "postprocess: argmax_mode=%d", desc->argmax_mode);
+    if (desc->refine_window < 0 || desc->refine_window > 31) return fail(GBCODEC_ERR_BAD_ARGUMENT, "postprocess: refine_window=%d", desc->refine_window);
+    if (desc->transform && (!d_center || !d_scale)) return fail(GBCODEC_ERR_NULL_POINTER, "postprocess: transform needs d_center and d_scale");
+    if (desc->transform && (!(desc->input_w > 0.f) || !(desc->input_h > 0.f))) return fail(GBCODEC_ERR_BAD_ARGUMENT, "postprocess: input size must be positive");
+    if ((desc->scale_to_image || d_regression) && !(desc->image_size > 0.f)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "postprocess: image_size must be positive");
+    if (d_regression && !d_workspace16) return fail(GBCODEC_ERR_WORKSPACE, "postprocess: 16-byte workspace needed with d_regression");
+    return launch_postprocess(desc, d_hm, d_regression, d_center, d_scale, d_preds, d_maxvals, d_mask, d_workspace16, (cudaStream_t)stream);
+}
+
+int gbcodec_coords_to_image_f32(const float* d_coords_in, const float* d_center, const float* d_scale,
+                                int B, int K, int H, int W, float in_w, float in_h, float* d_coords_out, void* stream) {
+    if (B <= 0 || K <= 0 || H <= 0 || W <= 0) return fail(GBCODEC_ERR_BAD_SHAPE, "coords_to_image: B,K,H,W must be positive");
+    if (!d_coords_in || !d_center || !d_scale || !d_coords_out) return fail(GBCODEC_ERR_NULL_POINTER, "coords_to_image: NULL pointer");
+    if (!(in_w > 0.f) || !(in_h > 0.f)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "coords_to_image: input size must be positive");
+    return launch_coords_to_image(d_coords_in, d_center, d_scale, B, K, H, W, in_w, in_h, d_coords_out, (cudaStream_t)stream);
+}
+
+size_t gbcodec_combined_workspace_bytes(int B, int K) {
+    if (B <= 0 || K <= 0) return 0;
+    return combined_workspace_bytes(B, K);
+}
+
+int gbcodec_combined_loss_f32(const gbcodec_combined_desc* desc,
+                              const float* d_pred, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, float* d_losses5,
+                              float* d_grad_pred, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream) {
+    return combined_loss(desc, d_pred, d_target, d_weight, d_coords, d_refined, d_target_coords, d_grad_scale, d_losses5,
+                         d_grad_pred, d_grad_coords, d_grad_refined, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gbcodec_combined_loss_backward_f32(const gbcodec_combined_desc* desc,
+                              const float* d_pred, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, const float* d_grad_losses5,
+                              float* d_grad_pred, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream) {
+    return combined_loss_backward(desc, d_pred, d_target, d_weight, d_coords, d_refined, d_target_coords, d_grad_scale,
+                                  d_grad_losses5, d_grad_pred, d_grad_coords, d_grad_refined, d_workspace, workspace_bytes,
+                                  (cudaStream_t)stream);
 }
 
 size_t gbcodec_loss_workspace_bytes(int B, int K, int H, int W) {

@@ -1,0 +1,386 @@
+// genb_loss.cu — CombinedLoss of the reference's second codec generation (models/losses.py:205-290)
+// and its parts, forward and backward in one pass per tile:
+//
+//   heatmap     FusedPoseLoss            models/losses.py:10-47      mean(crit(p, t) * w)
+//               KeypointMSELoss          models/pose_estimator.py:102-143   mean((p w - t w)^2)
+//               JointsMSELoss            models/losses.py:174-202    0.5 * the same
+//   morph       MorphologyShapeLoss      models/losses.py:50-135     spatial mean / variance of p and t
+//   regression  OffsetRegressionLoss     models/losses.py:138-171    (B,K,2) coordinates
+//
+// One CTA per (image, keypoint) tile; both tiles are read from HBM once with 128-bit streaming
+// loads and stay in registers for the three passes (raw moments, central moments, gradient).
+// Roofline: HBM, 8N bytes read + 4N written per tile.  Closed-form backward:
+//   with S = sum(p) + 1e-8, m_c = sum(p c)/S, v_c = sum(p (c - m_c)^2)/S  (c = x, y)
+//   d m_c / d p_i = (c_i - m_c)/S         d v_c / d p_i = ((c_i - m_c)^2 - v_c)/S
+// (the cross term 2 (d m_c/d p_i) sum q (c - m_c) = 2 (d m_c/d p_i) m_c eps/S is below fp32 resolution).
+#include "common.cuh"
+#include <string.h>
+
+namespace gbc {
+
+struct GenbParams {
+    int B, K, H, W;
+    unsigned terms;
+    int heat_crit, coord_crit, use_target_weight;
+    float heat_scale, lam_var, lam_mean;
+    float w[4];              // multipliers of heatmap, morph, regression, refined in `total`
+    float inv_heat;          // 1 / (Bn K N)
+    float inv_pair;          // 1 / (Bn K 2)
+};
+
+struct GenbArgs {
+    const float* pred; const float* target; const float* weight;
+    const float* coords; const float* refined; const float* target_coords;
+    const float* grad_scale;
+    float* grad_pred; float* grad_coords; float* grad_refined;
+    float* partial;          // [B*K][4] un-normalised per-tile numerators
+    const float* eff;        // backward: device [4] effective upstream gradient per term
+    const int* plan;         // backward: run only if *plan != 0
+};
+
+constexpr int kGenbFinBlocks = 32;
+constexpr int kGenbHeaderFloats = 512;     // ticket, plan, eff[4], second-stage partials (32 x 4 doubles)
+struct GenbWs { unsigned* ticket; int* plan; float* eff; double* bpart; float* partial; };
+static inline size_t genb_ws_bytes(int B, int K) { return (size_t)(kGenbHeaderFloats + (size_t)B * K * 4) * sizeof(float); }
+static inline GenbWs genb_carve(void* ws) {
+    float* f = reinterpret_cast<float*>(ws);
+    GenbWs l;
+    l.ticket = reinterpret_cast<unsigned*>(f);
+    l.plan = reinterpret_cast<int*>(f + 1);
+    l.eff = f + 4;
+    l.bpart = reinterpret_cast<double*>(f + 64);
+    l.partial = f + kGenbHeaderFloats;
+    return l;
+}
+
+__device__ __forceinline__ float crit_value(int crit, float d) {
+    if (crit == GBCODEC_CRIT_SMOOTHL1) { const float a = fabsf(d); return a < 1.f ? 0.5f * d * d : a - 0.5f; }
+    if (crit == GBCODEC_CRIT_L1) return fabsf(d);
+    return d * d;
+}
+__device__ __forceinline__ float crit_slope(int crit, float d) {
+    if (crit == GBCODEC_CRIT_SMOOTHL1) return fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f);
+    if (crit == GBCODEC_CRIT_L1) return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    return 2.f * d;
+}
+
+// ---- per-tile heatmap + morphology terms ------------------------------------------------------
+template <int NITER>
+__global__ void __launch_bounds__(1024)
+genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ GenbArgs A) {
+    __shared__ float scratch[8 * 32 + 8];
+    if (A.plan && *A.plan == 0) return;               // stored gradients already right
+    const int tile = blockIdx.x;
+    const int n4 = (P.H * P.W) >> 2, w4 = P.W >> 2;
+    const float4* p4 = reinterpret_cast<const float4*>(A.pred) + (size_t)tile * n4;
+    const float4* t4 = reinterpret_cast<const float4*>(A.target) + (size_t)tile * n4;
+    constexpr int R = NITER > 0 ? NITER : 1;
+    float4 pv[R], tv[R];
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            pv[it] = ldg_stream(p4 + it * blockDim.x + threadIdx.x);
+            tv[it] = ldg_stream(t4 + it * blockDim.x + threadIdx.x);
+        }
+    }
+    const float wraw = A.weight ? __ldg(A.weight + tile) : 1.f;
+    const bool utw = P.use_target_weight && A.weight;
+    const float wh = P.heat_crit == GBCODEC_CRIT_MSE_WEIGHTED ? (utw ? wraw * wraw : 1.f) : (utw ? wraw : 1.f);
+    const float wm = wraw;
+    const int crit = P.heat_crit == GBCODEC_CRIT_MSE_WEIGHTED ? GBCODEC_CRIT_MSE : P.heat_crit;
+    const float gs = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
+    const float eh = A.eff ? __ldg(A.eff) : P.w[0] * gs;
+    const float em = A.eff ? __ldg(A.eff + 1) : P.w[1] * gs;
+
+    // ---- pass 1: raw moments of both tiles and the pixel criterion -----------------------------
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto pass1 = [&](const float4& p, const float4& t, int i) {
+        const int y = i / w4, x = (i - y * w4) << 2;
+        const float fx = (float)x, fy = (float)y;
+        const float sp = (p.x + p.y) + (p.z + p.w), st = (t.x + t.y) + (t.z + t.w);
+        acc[0] += sp;
+        acc[1] += fmaf(fx, sp, fmaf(3.f, p.w, fmaf(2.f, p.z, p.y)));
+        acc[2] = fmaf(fy, sp, acc[2]);
+        acc[3] += st;
+        acc[4] += fmaf(fx, st, fmaf(3.f, t.w, fmaf(2.f, t.z, t.y)));
+        acc[5] = fmaf(fy, st, acc[5]);
+        acc[6] += (crit_value(crit, p.x - t.x) + crit_value(crit, p.y - t.y)) + (crit_value(crit, p.z - t.z) + crit_value(crit, p.w - t.w));
+    };
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) pass1(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+    } else {
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) pass1(ldg_stream(p4 + i), ldg_stream(t4 + i), i);
+    }
+    block_sum<8>(acc, scratch);
+    const float Sp = acc[0] + kEps, St = acc[3] + kEps;
+    const float iSp = 1.f / Sp, iSt = 1.f / St;
+    const float pmx = acc[1] * iSp, pmy = acc[2] * iSp, tmx = acc[4] * iSt, tmy = acc[5] * iSt;
+    const float crit_sum = acc[6];
+
+    // ---- pass 2: central second moments about each tile's own mean ------------------------------
+    float c2[4] = {0.f, 0.f, 0.f, 0.f};
+    auto pass2 = [&](const float4& p, const float4& t, int i) {
+        const int y = i / w4, x = (i - y * w4) << 2;
+        const float fx = (float)x, fy = (float)y;
+        const float pe[4] = {p.x, p.y, p.z, p.w}, te[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float dp = (fx + (float)j) - pmx, dt = (fx + (float)j) - tmx;
+            c2[0] = fmaf(pe[j], dp * dp, c2[0]);
+            c2[2] = fmaf(te[j], dt * dt, c2[2]);
+        }
+        const float dyp = fy - pmy, dyt = fy - tmy;
+        c2[1] = fmaf((p.x + p.y) + (p.z + p.w), dyp * dyp, c2[1]);
+        c2[3] = fmaf((t.x + t.y) + (t.z + t.w), dyt * dyt, c2[3]);
+    };
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) pass2(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+    } else {
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) pass2(ldg_keep(p4 + i), ldg_keep(t4 + i), i);
+    }
+    block_sum<4>(c2, scratch);
+    const float pvx = c2[0] * iSp, pvy = c2[1] * iSp, tvx = c2[2] * iSt, tvy = c2[3] * iSt;
+    const float dvx = pvx - tvx, dvy = pvy - tvy, dmx = pmx - tmx, dmy = pmy - tmy;
+
+    if (threadIdx.x == 0 && !A.eff) {
+        float* out = A.partial + (size_t)tile * 4;
+        out[0] = (P.terms & GBCODEC_TERM_HEATMAP) ? wh * crit_sum : 0.f;
+        out[1] = (P.terms & GBCODEC_TERM_MORPH) ? wm * (P.lam_var * (dvx * dvx + dvy * dvy) + P.lam_mean * (dmx * dmx + dmy * dmy)) : 0.f;
+    }
+    if (!A.grad_pred) return;
+
+    // ---- pass 3: d(total)/d(pred) ----------------------------------------------------------------
+    const float ch = (P.terms & GBCODEC_TERM_HEATMAP) ? eh * P.heat_scale * wh * P.inv_heat : 0.f;
+    const float cm = (P.terms & GBCODEC_TERM_MORPH) ? em * wm * P.inv_pair * iSp : 0.f;
+    const float Ax = cm * 2.f * P.lam_var * dvx, Ay = cm * 2.f * P.lam_var * dvy;
+    const float Bx = cm * 2.f * P.lam_mean * dmx, By = cm * 2.f * P.lam_mean * dmy;
+    const float C0 = -(Ax * pvx + Ay * pvy);
+    float4* g4 = reinterpret_cast<float4*>(A.grad_pred) + (size_t)tile * n4;
+    auto pass3 = [&](const float4& p, const float4& t, int i) {
+        const int y = i / w4, x = (i - y * w4) << 2;
+        const float dy = (float)y - pmy;
+        const float rowc = fmaf(dy, fmaf(Ay, dy, By), C0);
+        const float pe[4] = {p.x, p.y, p.z, p.w}, te[4] = {t.x, t.y, t.z, t.w};
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float dx = ((float)x + (float)j) - pmx;
+            g[j] = fmaf(ch, crit_slope(crit, pe[j] - te[j]), fmaf(dx, fmaf(Ax, dx, Bx), rowc));
+        }
+        stg_stream(g4 + i, make_float4(g[0], g[1], g[2], g[3]));
+    };
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) pass3(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+    } else {
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) pass3(ldg_keep(p4 + i), ldg_keep(t4 + i), i);
+    }
+}
+
+// ---- coordinate terms: one thread per (image, keypoint) -----------------------------------------
+__global__ void __launch_bounds__(256)
+genb_coords_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ GenbArgs A, int zero_tile_terms) {
+    if (A.plan && *A.plan == 0) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.B * P.K) return;
+    const float w = A.weight ? A.weight[t] : 1.f;
+    const float gs = A.grad_scale ? *A.grad_scale : 1.f;
+    float num[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const unsigned bit = q == 0 ? GBCODEC_TERM_REGRESSION : GBCODEC_TERM_REFINED;
+        const float* src = q == 0 ? A.coords : A.refined;
+        float* dst = q == 0 ? A.grad_coords : A.grad_refined;
+        if (!(P.terms & bit)) continue;
+        const float e = A.eff ? A.eff[2 + q] : P.w[2 + q] * gs;
+        const float dx = src[2 * t] - A.target_coords[2 * t], dy = src[2 * t + 1] - A.target_coords[2 * t + 1];
+        num[q] = w * (crit_value(P.coord_crit, dx) + crit_value(P.coord_crit, dy));
+        if (dst) {
+            const float c = e * w * P.inv_pair;
+            dst[2 * t] = c * crit_slope(P.coord_crit, dx);
+            dst[2 * t + 1] = c * crit_slope(P.coord_crit, dy);
+        }
+    }
+    if (!A.eff) {
+        float* out = A.partial + (size_t)t * 4;
+        out[2] = num[0]; out[3] = num[1];
+        if (zero_tile_terms) { out[0] = 0.f; out[1] = 0.f; }
+    }
+}
+
+// ---- second stage: fixed-order sums, the five scalars ----------------------------------------------
+__global__ void __launch_bounds__(256)
+genb_finalize_kernel(const __grid_constant__ GenbParams P, const float* __restrict__ partial, double* __restrict__ bpart,
+                     unsigned* __restrict__ ticket, float* __restrict__ losses5) {
+    __shared__ double red[4][8];
+    __shared__ bool last;
+    const int tiles = P.B * P.K;
+    const int per = (tiles + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(tiles, lo + per);
+    double acc[4] = {0, 0, 0, 0};
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(partial) + t);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) red[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int wp = 0; wp < 8; ++wp) s += red[threadIdx.x][wp];
+        bpart[blockIdx.x * 4 + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    __shared__ float term[4];
+    if (threadIdx.x < 4) {
+        const int q = threadIdx.x;
+        double s = 0.0;
+        for (int g = 0; g < (int)gridDim.x; ++g) s += __ldcg(bpart + g * 4 + q);
+        const float v = q == 0 ? (float)s * P.inv_heat * P.heat_scale : (float)s * P.inv_pair;
+        term[q] = v;
+        losses5[q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+        for (int q = 0; q < 4; ++q) total += P.w[q] * term[q];
+        losses5[4] = total;
+        *ticket = 0u;
+    }
+}
+
+// backward plan: eff[q] = g5[4] * w[q] + g5[q]; plan = 0 if that is what the forward assumed
+__global__ void genb_plan_kernel(const __grid_constant__ GenbParams P, const float* __restrict__ g5,
+                                 const float* __restrict__ assumed, int* __restrict__ plan, float* __restrict__ eff) {
+    if (threadIdx.x != 0) return;
+    const float a = assumed ? *assumed : 1.f;
+    bool same = true;
+    for (int q = 0; q < 4; ++q) {
+        eff[q] = fmaf(g5[4], P.w[q], g5[q]);
+        if (eff[q] != P.w[q] * a) same = false;
+    }
+    *plan = same ? 0 : 1;
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static int make_genb_params(const gbcodec_combined_desc* d, GenbParams* P) {
+    if (!d) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: desc is NULL");
+    if (d->B <= 0 || d->K <= 0) return fail(GBCODEC_ERR_BAD_SHAPE, "combined_loss: B,K must be positive");
+    const bool tiles = d->terms & (GBCODEC_TERM_HEATMAP | GBCODEC_TERM_MORPH);
+    if (tiles) {
+        if (d->H <= 0 || d->W <= 0 || d->W % 4) return fail(GBCODEC_ERR_BAD_SHAPE, "combined_loss: H,W must be positive and W a multiple of 4 (got %d,%d)", d->H, d->W);
+        if ((long long)d->H * d->W > GBCODEC_MAX_TILE) return fail(GBCODEC_ERR_BAD_SHAPE, "combined_loss: tile %dx%d too large", d->H, d->W);
+    }
+    if (!d->terms || (d->terms & ~15u)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "combined_loss: terms=0x%x", d->terms);
+    if (d->heatmap_criterion != GBCODEC_CRIT_MSE && d->heatmap_criterion != GBCODEC_CRIT_SMOOTHL1 && d->heatmap_criterion != GBCODEC_CRIT_MSE_WEIGHTED)
+        return fail(GBCODEC_ERR_BAD_ARGUMENT, "combined_loss: heatmap_criterion=%d", d->heatmap_criterion);
+    if (d->coord_criterion != GBCODEC_CRIT_MSE && d->coord_criterion != GBCODEC_CRIT_SMOOTHL1 && d->coord_criterion != GBCODEC_CRIT_L1)
+        return fail(GBCODEC_ERR_BAD_ARGUMENT, "combined_loss: coord_criterion=%d", d->coord_criterion);
+    if (d->norm_batch < 0) return fail(GBCODEC_ERR_BAD_ARGUMENT, "combined_loss: norm_batch=%d", d->norm_batch);
+    memset(P, 0, sizeof(*P));
+    P->B = d->B; P->K = d->K; P->H = d->H; P->W = d->W;
+    P->terms = d->terms; P->heat_crit = d->heatmap_criterion; P->coord_crit = d->coord_criterion;
+    P->use_target_weight = d->use_target_weight;
+    P->heat_scale = d->heatmap_scale; P->lam_var = d->lambda_variance; P->lam_mean = d->lambda_mean;
+    P->w[0] = d->w_heatmap; P->w[1] = d->w_morph; P->w[2] = d->w_reg; P->w[3] = d->w_reg;
+    const double bn = (double)(d->norm_batch ? d->norm_batch : d->B) * d->K;
+    P->inv_heat = tiles ? (float)(1.0 / (bn * d->H * d->W)) : 0.f;
+    P->inv_pair = (float)(1.0 / (bn * 2.0));
+    return GBCODEC_OK;
+}
+
+static int check_genb(const GenbParams& P, const GenbArgs& A, const void* ws, size_t ws_size, bool backward) {
+    const bool tiles = P.terms & (GBCODEC_TERM_HEATMAP | GBCODEC_TERM_MORPH);
+    const bool coords = P.terms & (GBCODEC_TERM_REGRESSION | GBCODEC_TERM_REFINED);
+    if (tiles && (!A.pred || !A.target)) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_pred / d_target is NULL");
+    if ((P.terms & GBCODEC_TERM_REGRESSION) && !A.coords) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_coords is NULL");
+    if ((P.terms & GBCODEC_TERM_REFINED) && !A.refined) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_refined is NULL");
+    if (coords && !A.target_coords) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_target_coords is NULL");
+    if (!ws || ws_size < genb_ws_bytes(P.B, P.K)) return fail(GBCODEC_ERR_WORKSPACE, "combined_loss: workspace of %zu bytes needed", genb_ws_bytes(P.B, P.K));
+    if (!aligned16(ws) || (tiles && (!aligned16(A.pred) || !aligned16(A.target))) || (A.grad_pred && !aligned16(A.grad_pred)))
+        return fail(GBCODEC_ERR_UNALIGNED, "combined_loss: tensors must be 16-byte aligned");
+    if (backward && tiles && !A.grad_pred) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss backward: d_grad_pred is NULL");
+    return GBCODEC_OK;
+}
+
+static int launch_genb(const GenbParams& P, const GenbArgs& A, cudaStream_t s) {
+    const bool tiles = P.terms & (GBCODEC_TERM_HEATMAP | GBCODEC_TERM_MORPH);
+    const int nt = P.B * P.K;
+    genb_coords_kernel<<<(nt + 255) / 256, 256, 0, s>>>(P, A, tiles ? 0 : 1);
+    int st = check_launch("genb_coords_kernel");
+    if (st || !tiles) return st;
+    // both tiles stay in registers when the tile splits into <= 4 float4 per thread (64x48: 256 x 3,
+    // 96x72: 576 x 3, 128x128: 1024 x 4); other shapes re-read through L2
+    const int n4 = (P.H * P.W) >> 2;
+    int niter = 0, threads = 512;
+    for (int t = 256; t <= 1024; t += 32)
+        if (n4 % t == 0 && n4 / t <= 4) { threads = t; niter = n4 / t; break; }
+#define GBC_CASE(NI) case NI: genb_tile_kernel<NI><<<nt, threads, 0, s>>>(P, A); break;
+    switch (niter) {
+        GBC_CASE(1) GBC_CASE(2) GBC_CASE(3) GBC_CASE(4)
+        default: genb_tile_kernel<0><<<nt, threads, 0, s>>>(P, A); break;
+    }
+#undef GBC_CASE
+    return check_launch("genb_tile_kernel");
+}
+
+size_t combined_workspace_bytes(int B, int K) { return genb_ws_bytes(B, K); }
+
+int combined_loss(const gbcodec_combined_desc* d, const float* pred, const float* target, const float* weight,
+                  const float* coords, const float* refined, const float* target_coords, const float* grad_scale,
+                  float* losses5, float* gpred, float* gcoords, float* grefined, void* ws, size_t ws_size, cudaStream_t s) {
+    GenbParams P;
+    int st = make_genb_params(d, &P);
+    if (st) return st;
+    if (!losses5) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_losses5 is NULL");
+    GenbArgs A;
+    memset(&A, 0, sizeof(A));
+    A.pred = pred; A.target = target; A.weight = weight; A.coords = coords; A.refined = refined; A.target_coords = target_coords;
+    A.grad_scale = grad_scale; A.grad_pred = gpred; A.grad_coords = gcoords; A.grad_refined = grefined;
+    st = check_genb(P, A, ws, ws_size, false);
+    if (st) return st;
+    const GenbWs L = genb_carve(ws);
+    A.partial = L.partial;
+    cudaError_t e = cudaMemsetAsync(L.ticket, 0, 8, s);
+    if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    st = launch_genb(P, A, s);
+    if (st) return st;
+    const int nt = P.B * P.K;
+    const int fin = (nt + 255) / 256 < kGenbFinBlocks ? (nt + 255) / 256 : kGenbFinBlocks;
+    genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, losses5);
+    return check_launch("genb_finalize_kernel");
+}
+
+int combined_loss_backward(const gbcodec_combined_desc* d, const float* pred, const float* target, const float* weight,
+                           const float* coords, const float* refined, const float* target_coords, const float* grad_scale,
+                           const float* g5, float* gpred, float* gcoords, float* grefined, void* ws, size_t ws_size, cudaStream_t s) {
+    GenbParams P;
+    int st = make_genb_params(d, &P);
+    if (st) return st;
+    if (!g5) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss backward: d_grad_losses5 is NULL");
+    GenbArgs A;
+    memset(&A, 0, sizeof(A));
+    A.pred = pred; A.target = target; A.weight = weight; A.coords = coords; A.refined = refined; A.target_coords = target_coords;
+    A.grad_pred = gpred; A.grad_coords = gcoords; A.grad_refined = grefined;
+    st = check_genb(P, A, ws, ws_size, true);
+    if (st) return st;
+    const GenbWs L = genb_carve(ws);
+    A.partial = L.partial; A.eff = L.eff; A.plan = L.plan;
+    genb_plan_kernel<<<1, 32, 0, s>>>(P, g5, grad_scale, L.plan, L.eff);
+    st = check_launch("genb_plan_kernel");
+    if (st) return st;
+    return launch_genb(P, A, s);
+}
+
+}  // namespace gbc

@@ -46,3 +46,48 @@ class HeatmapGenerator:
         if keypoints.shape[-2] != self.num_keypoints:
             raise ValueError(f"expected {self.num_keypoints} keypoints, got {keypoints.shape[-2]}")
         return generate_heatmaps(keypoints, keypoints_visible, self.heatmap_size, self.input_size, self.sigma)
+
+
+def generate_heatmaps_clipped(joints: Tensor, joints_vis: Tensor, heatmap_size: Sequence[int] = (64, 48),
+                              image_size: Sequence[int] = (192, 256), sigma: float = 2.0) -> Tuple[Tensor, Tensor]:
+    """Batched PreemieCocoDataset._generate_heatmaps of the second-generation dataset
+    (data/coco_dataset.py:222-287), quirks included: heatmap_size is (H, W) and image_size (W_in, H_in)
+    as in that file; weight is 1.0 for a visible joint inside the map; the patch origin is clamped
+    to 0 before the patch slice is taken.  joints (B,K,2), joints_vis (B,K) or (B,K,1)."""
+    B, K = joints.shape[0], joints.shape[1]
+    H, W = int(heatmap_size[0]), int(heatmap_size[1])
+    from . import _native as N
+    return ops.encode_mode(joints.float(), joints_vis.float().reshape(B, K), H, W, float(image_size[0]), float(image_size[1]),
+                           float(sigma), N.ENCODE_PATCH_CLIPPED)
+
+
+class GenerateTarget:
+    """Batched, device-side GenerateTarget (data/pose_transforms.py:385-457): same `encoder` dict
+    (input_size (h, w), heatmap_size (h, w), sigma), same result keys.  results['keypoints'] is
+    (B,K,2|3) on the device, results['keypoints_visible'] (B,K) (default: all visible)."""
+
+    def __init__(self, encoder: dict):
+        self.encoder = encoder
+        self.input_size = encoder.get("input_size", (256, 256))
+        self.heatmap_size = encoder.get("heatmap_size", (64, 64))
+        self.sigma = encoder.get("sigma", 2.0)
+        self.use_udp = encoder.get("use_udp", False)
+
+    def __call__(self, results: dict) -> dict:
+        if "keypoints" not in results:
+            return results
+        from . import _native as N
+        kps = results["keypoints"]
+        squeeze = kps.dim() == 2
+        if squeeze:
+            kps = kps[None]
+        vis = results.get("keypoints_visible")
+        vis = torch.ones(kps.shape[:2], dtype=torch.float32, device=kps.device) if vis is None else vis.reshape(kps.shape[:2])
+        h, w = int(self.heatmap_size[0]), int(self.heatmap_size[1])
+        ih, iw = self.input_size
+        heat, weight = ops.encode_mode(kps[..., :2].float().contiguous(), vis.float(), h, w, float(iw), float(ih),
+                                       float(self.sigma), N.ENCODE_DENSE)
+        weight = weight[..., 0]
+        results["heatmaps"] = heat[0] if squeeze else heat
+        results["keypoint_weights"] = weight[0] if squeeze else weight
+        return results

@@ -295,3 +295,204 @@ def pairs_flat(pairs: Sequence[Tuple[int, int]]) -> List[int]:
     for a, b in pairs:
         out += [int(a), int(b)]
     return out
+
+
+# =========================================================================== Gen-B family
+@torch.library.custom_op(f"{_NS}::encode_mode", mutates_args=())
+def encode_mode(kps: Tensor, vis: Tensor, H: int, W: int, in_w: float, in_h: float, sigma: float, mode: int
+                ) -> Tuple[Tensor, Tensor]:
+    """mode: N.ENCODE_PATCH | N.ENCODE_PATCH_CLIPPED | N.ENCODE_DENSE -> target (B,K,H,W), weight (B,K,1)."""
+    B, K = kps.shape[0], kps.shape[1]
+    kps = _cuda_f32("keypoints", kps, (B, K, 2))
+    vis = _cuda_f32("visible", vis.reshape(B, K), (B, K))
+    target = torch.empty((B, K, H, W), dtype=torch.float32, device=kps.device)
+    weight = torch.empty((B, K, 1), dtype=torch.float32, device=kps.device)
+    with torch.cuda.device(kps.device):
+        N.check(N.lib().gbcodec_encode_mode_f32(_ptr(kps), _ptr(vis), _ptr(target), _ptr(weight), B, K, H, W,
+                                                in_w, in_h, sigma, mode, _stream(kps)), "encode_mode")
+    return target, weight
+
+
+@encode_mode.register_fake
+def _(kps, vis, H, W, in_w, in_h, sigma, mode):
+    B, K = kps.shape[0], kps.shape[1]
+    return kps.new_empty((B, K, H, W)), kps.new_empty((B, K, 1))
+
+
+@torch.library.custom_op(f"{_NS}::postprocess", mutates_args=())
+def postprocess(hm: Tensor, regression: Optional[Tensor], center: Optional[Tensor], scale: Optional[Tensor],
+                argmax_mode: int, scale_to_image: bool, image_size: float, refine_window: int,
+                filter_low: bool, threshold: float, transform: bool, input_w: float, input_h: float
+                ) -> Tuple[Tensor, Tensor, Tensor]:
+    """utils/postprocess.py:296-340 in one kernel -> preds (B,K,2), maxvals (B,K), mask (B,K)."""
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    dev = hm.device
+    if regression is not None:
+        regression = _cuda_f32("regression_coords", regression, (B, K, 2))
+    if center is not None:
+        center = _cuda_f32("center", center, (B, 2))
+    if scale is not None:
+        scale = _cuda_f32("scale", scale, (B, 2))
+    d = N.PostprocessDesc(B, K, H, W, argmax_mode, int(scale_to_image), image_size, refine_window, int(filter_low),
+                          threshold, int(transform), input_w, input_h)
+    preds = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    maxvals = torch.empty((B, K), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, K), dtype=torch.float32, device=dev)
+    ws = torch.empty(16, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().gbcodec_postprocess_f32(d, _ptr(hm), _ptr(regression), _ptr(center), _ptr(scale), _ptr(preds),
+                                                _ptr(maxvals), _ptr(mask), _ptr(ws), _stream(hm)), "postprocess")
+    return preds, maxvals, mask
+
+
+@postprocess.register_fake
+def _(hm, regression, center, scale, argmax_mode, scale_to_image, image_size, refine_window, filter_low, threshold,
+      transform, input_w, input_h):
+    B, K = hm.shape[0], hm.shape[1]
+    return hm.new_empty((B, K, 2)), hm.new_empty((B, K)), hm.new_empty((B, K))
+
+
+@torch.library.custom_op(f"{_NS}::coords_to_image", mutates_args=())
+def coords_to_image(coords: Tensor, center: Tensor, scale: Tensor, H: int, W: int, in_w: float, in_h: float) -> Tensor:
+    """validate.py:102-119 — heatmap px -> input px -> original image."""
+    B, K = coords.shape[0], coords.shape[1]
+    coords = _cuda_f32("coords", coords, (B, K, 2))
+    center = _cuda_f32("center", center, (B, 2))
+    scale = _cuda_f32("scale", scale, (B, 2))
+    out = torch.empty_like(coords)
+    with torch.cuda.device(coords.device):
+        N.check(N.lib().gbcodec_coords_to_image_f32(_ptr(coords), _ptr(center), _ptr(scale), B, K, H, W, in_w, in_h,
+                                                    _ptr(out), _stream(coords)), "coords_to_image")
+    return out
+
+
+@coords_to_image.register_fake
+def _(coords, center, scale, H, W, in_w, in_h):
+    return torch.empty_like(coords)
+
+
+def _combined_desc(B, K, H, W, norm_batch, terms, heat_crit, coord_crit, utw, heat_scale, lam_var, lam_mean, weights):
+    return N.CombinedDesc(B, K, H, W, norm_batch, terms, heat_crit, coord_crit, int(utw), heat_scale, lam_var, lam_mean,
+                          weights[0], weights[1], weights[2])
+
+
+def _combined_shapes(pred, coords, refined, target_coords):
+    if pred is not None:
+        return tuple(pred.shape)
+    c = coords if coords is not None else refined
+    return (c.shape[0], c.shape[1], 0, 0)
+
+
+@torch.library.custom_op(f"{_NS}::combined_loss", mutates_args=())
+def combined_loss(pred: Optional[Tensor], target: Optional[Tensor], weight: Optional[Tensor],
+                  coords: Optional[Tensor], refined: Optional[Tensor], target_coords: Optional[Tensor],
+                  grad_scale: Optional[Tensor], norm_batch: int, heat_crit: int, coord_crit: int,
+                  use_target_weight: bool, heat_scale: float, lam_var: float, lam_mean: float, weights: List[float],
+                  morph: bool, with_grads: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """models/losses.py:205-290 -> losses5 (heatmap, morph, regression, refined, total), grad_pred, grad_coords,
+    grad_refined (empty tensors for what was not asked / not present)."""
+    B, K, H, W = _combined_shapes(pred, coords, refined, target_coords)
+    some = pred if pred is not None else (coords if coords is not None else refined)
+    dev = some.device
+    terms = 0
+    if pred is not None:
+        pred = _cuda_f32("pred_heatmaps", pred, (B, K, H, W))
+        target = _cuda_f32("target_heatmaps", target, (B, K, H, W))
+        terms |= N.TERM_HEATMAP | (N.TERM_MORPH if morph else 0)
+    if coords is not None:
+        coords = _cuda_f32("pred_coords", coords, (B, K, 2))
+        terms |= N.TERM_REGRESSION
+    if refined is not None:
+        refined = _cuda_f32("refined_coords", refined, (B, K, 2))
+        terms |= N.TERM_REFINED
+    if target_coords is not None:
+        target_coords = _cuda_f32("target_coords", target_coords, (B, K, 2))
+    if weight is not None:
+        weight = _cuda_f32("target_weight", weight.reshape(B, K), (B, K))
+    grad_scale = _scalar("grad_scale", grad_scale, some)
+    desc = _combined_desc(B, K, H, W, norm_batch, terms, heat_crit, coord_crit, use_target_weight, heat_scale, lam_var,
+                          lam_mean, weights)
+    losses = torch.empty(5, dtype=torch.float32, device=dev)
+    empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pred) if (with_grads and pred is not None) else empty()
+    gc = torch.empty_like(coords) if (with_grads and coords is not None) else empty()
+    gr = torch.empty_like(refined) if (with_grads and refined is not None) else empty()
+    nbytes = N.lib().gbcodec_combined_workspace_bytes(B, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    opt = lambda t: _ptr(t) if t.numel() else None
+    with torch.cuda.device(dev):
+        N.check(N.lib().gbcodec_combined_loss_f32(desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined),
+                                                  _ptr(target_coords), _ptr(grad_scale), _ptr(losses), opt(gp), opt(gc), opt(gr),
+                                                  _ptr(ws), nbytes, _stream(some)), "combined_loss")
+    return losses, gp, gc, gr
+
+
+@combined_loss.register_fake
+def _(pred, target, weight, coords, refined, target_coords, grad_scale, norm_batch, heat_crit, coord_crit,
+      use_target_weight, heat_scale, lam_var, lam_mean, weights, morph, with_grads):
+    some = pred if pred is not None else (coords if coords is not None else refined)
+    e = lambda: some.new_empty(0)
+    g = lambda t: torch.empty_like(t) if (with_grads and t is not None) else e()
+    return some.new_empty(5), g(pred), g(coords), g(refined)
+
+
+@torch.library.custom_op(f"{_NS}::combined_loss_backward", mutates_args=("grad_pred", "grad_coords", "grad_refined"))
+def combined_loss_backward(grad_losses: Tensor, grad_pred: Tensor, grad_coords: Tensor, grad_refined: Tensor,
+                           pred: Optional[Tensor], target: Optional[Tensor], weight: Optional[Tensor],
+                           coords: Optional[Tensor], refined: Optional[Tensor], target_coords: Optional[Tensor],
+                           grad_scale: Optional[Tensor], norm_batch: int, heat_crit: int, coord_crit: int,
+                           use_target_weight: bool, heat_scale: float, lam_var: float, lam_mean: float,
+                           weights: List[float], morph: bool) -> None:
+    B, K, H, W = _combined_shapes(pred, coords, refined, target_coords)
+    some = pred if pred is not None else (coords if coords is not None else refined)
+    terms = 0
+    if pred is not None:
+        terms |= N.TERM_HEATMAP | (N.TERM_MORPH if morph else 0)
+    if coords is not None:
+        terms |= N.TERM_REGRESSION
+    if refined is not None:
+        terms |= N.TERM_REFINED
+    if weight is not None:
+        weight = weight.reshape(B, K)
+    desc = _combined_desc(B, K, H, W, norm_batch, terms, heat_crit, coord_crit, use_target_weight, heat_scale, lam_var,
+                          lam_mean, weights)
+    g5 = _cuda_f32("grad_losses", grad_losses.reshape(5), (5,))
+    nbytes = N.lib().gbcodec_combined_workspace_bytes(B, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=some.device)
+    opt = lambda t: _ptr(t) if t.numel() else None
+    with torch.cuda.device(some.device):
+        N.check(N.lib().gbcodec_combined_loss_backward_f32(
+            desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined), _ptr(target_coords), _ptr(grad_scale),
+            _ptr(g5), opt(grad_pred), opt(grad_coords), opt(grad_refined), _ptr(ws), nbytes, _stream(some)),
+            "combined_loss_backward")
+
+
+def _combined_setup_context(ctx, inputs, output):
+    (pred, target, weight, coords, refined, target_coords, grad_scale, norm_batch, heat_crit, coord_crit, utw, heat_scale,
+     lam_var, lam_mean, weights, morph, with_grads) = inputs
+    losses, gp, gc, gr = output
+    ctx.with_grads = with_grads
+    ctx.stash = (gp, gc, gr)
+    ctx.tensors = tuple(None if t is None else t.detach() for t in (pred, target, weight, coords, refined, target_coords, grad_scale))
+    ctx.scalars = (norm_batch, heat_crit, coord_crit, utw, heat_scale, lam_var, lam_mean, list(weights), morph)
+    ctx.set_materialize_grads(False)
+
+
+def _combined_backward(ctx, g_losses, g_gp, g_gc, g_gr):
+    none = [None] * 17
+    if g_losses is None:
+        return tuple(none)
+    if not ctx.with_grads:
+        raise RuntimeError("gbcodec::combined_loss was run with with_grads=False; its output is not differentiable")
+    gp, gc, gr = ctx.stash
+    contig = lambda t: None if t is None else t.contiguous()
+    torch.ops.gbcodec.combined_loss_backward(g_losses.contiguous(), gp, gc, gr, *[contig(t) for t in ctx.tensors], *ctx.scalars)
+    pred, target, weight, coords, refined, target_coords, grad_scale = ctx.tensors
+    none[0] = gp if pred is not None else None
+    none[3] = gc if coords is not None else None
+    none[4] = gr if refined is not None else None
+    return tuple(none)
+
+
+combined_loss.register_autograd(_combined_backward, setup_context=_combined_setup_context)

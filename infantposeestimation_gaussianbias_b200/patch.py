@@ -98,3 +98,92 @@ def unpatch_reference() -> None:
                "PoseEstimator": pose_estimator, "COCOPoseDataset": coco_dataset}[cls]
         setattr(getattr(mod, cls), attr, fn)
         del _ORIGINALS[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# second generation ("Gen-B"): utils/postprocess.py, models/losses.py, KeypointMSELoss
+# ------------------------------------------------------------------------------------------------
+_GENB_ORIGINALS: Dict[str, tuple] = {}
+_GENB_FUNCTIONS = ("get_max_preds", "get_max_preds_with_subpixel", "fused_decode", "coordinate_refinement",
+                   "filter_low_confidence", "transform_preds", "postprocess_predictions")
+
+
+def _genb_forwards():
+    """forward() bodies bound onto the REFERENCE's loss classes: `self` is the reference module, its
+    settings are read by the attribute names models/losses.py gives them."""
+    from . import losses as L
+
+    def fused(self, pred_heatmaps, target_heatmaps, target_weight=None):
+        if self.loss_type not in L._HEAT_CRIT:
+            raise ValueError(f"Unsupported loss type: {self.loss_type}")
+        return L._run(pred_heatmaps, target_heatmaps, target_weight, heat_crit=L._HEAT_CRIT[self.loss_type],
+                      use_target_weight=self.use_target_weight, weights=(1.0, 0.0, 0.0))[0]
+
+    def morph(self, pred_heatmaps, target_heatmaps, target_weight=None):
+        return L._run(pred_heatmaps, target_heatmaps, target_weight, lam_var=self.lambda_variance,
+                      lam_mean=self.lambda_mean, weights=(0.0, 1.0, 0.0), morph=True)[1]
+
+    def joints(self, output, target, target_weight):
+        return L._run(output, target, target_weight, heat_crit=L.N.CRIT_MSE_WEIGHTED,
+                      use_target_weight=self.use_target_weight, heat_scale=0.5, weights=(1.0, 0.0, 0.0))[0]
+
+    def keypoint_mse(self, pred, target, target_weight=None):
+        return L._run(pred, target, target_weight, heat_crit=L.N.CRIT_MSE_WEIGHTED,
+                      use_target_weight=self.use_target_weight, weights=(1.0, 0.0, 0.0))[0]
+
+    def offset(self, pred_coords, target_coords, target_weight=None):
+        name = type(self.criterion).__name__                 # nn.SmoothL1Loss | nn.L1Loss | nn.MSELoss (losses.py:145-152)
+        crit = {"SmoothL1Loss": L.N.CRIT_SMOOTHL1, "L1Loss": L.N.CRIT_L1, "MSELoss": L.N.CRIT_MSE}[name]
+        return L._run(coords=pred_coords, target_coords=target_coords, weight=target_weight, coord_crit=crit,
+                      weights=(0.0, 0.0, 1.0))[2]
+
+    def combined(self, predictions, targets):
+        impl = getattr(self, "_gbcodec_impl", None)
+        if impl is None:
+            import types as _t
+            cfg = _t.SimpleNamespace(LOSS=_t.SimpleNamespace(MORPH_LAMBDA=self.morph_loss.lambda_variance,
+                                                             MORPH_WEIGHT=self.w_morph, REG_WEIGHT=self.w_reg))
+            impl = L.CombinedLoss(cfg)
+            impl.w_heatmap = self.w_heatmap
+            impl.morph_loss.lambda_mean = self.morph_loss.lambda_mean
+            object.__setattr__(self, "_gbcodec_impl", impl)
+        return impl(predictions, targets)
+
+    return {"FusedPoseLoss": fused, "MorphologyShapeLoss": morph, "JointsMSELoss": joints,
+            "OffsetRegressionLoss": offset, "CombinedLoss": combined}, keypoint_mse
+
+
+def patch_reference_genb(postprocess: Optional[ModuleType] = None, losses: Optional[ModuleType] = None,
+                         pose_estimator: Optional[ModuleType] = None) -> Dict[str, object]:
+    """Rebind the second-generation entry points: the seven functions of `utils.postprocess`
+    (postprocess_predictions becomes one kernel), forward() of the five classes of `models.losses`
+    and of `models.pose_estimator.KeypointMSELoss`.  Modules default to an import by name; pass
+    `False` to skip one."""
+    from . import postprocess as pp
+    saved: Dict[str, object] = {}
+    if postprocess is not False:
+        postprocess = postprocess or importlib.import_module("utils.postprocess")
+        for fn in _GENB_FUNCTIONS:
+            saved[f"postprocess.{fn}"] = getattr(postprocess, fn)
+            _GENB_ORIGINALS[f"postprocess.{fn}"] = (postprocess, fn, getattr(postprocess, fn))
+            setattr(postprocess, fn, getattr(pp, fn))
+    forwards, keypoint_mse = _genb_forwards()
+    if losses is not False:
+        losses = losses or importlib.import_module("models.losses")
+        for cls, fwd in forwards.items():
+            saved[f"losses.{cls}.forward"] = getattr(losses, cls).forward
+            _GENB_ORIGINALS[f"losses.{cls}.forward"] = (getattr(losses, cls), "forward", getattr(losses, cls).forward)
+            getattr(losses, cls).forward = fwd
+    if pose_estimator is not False:
+        pose_estimator = pose_estimator or importlib.import_module("models.pose_estimator")
+        cls = pose_estimator.KeypointMSELoss
+        saved["pose_estimator.KeypointMSELoss.forward"] = cls.forward
+        _GENB_ORIGINALS["pose_estimator.KeypointMSELoss.forward"] = (cls, "forward", cls.forward)
+        cls.forward = keypoint_mse
+    return saved
+
+
+def unpatch_reference_genb() -> None:
+    for name, (owner, attr, fn) in list(_GENB_ORIGINALS.items()):
+        setattr(owner, attr, fn)
+        del _GENB_ORIGINALS[name]

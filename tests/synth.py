@@ -118,3 +118,22 @@ def digest(batch: Dict[str, np.ndarray]) -> str:
         a = np.ascontiguousarray(batch[key])
         h.update(key.encode()); h.update(str(a.dtype).encode()); h.update(str(a.shape).encode()); h.update(a.tobytes())
     return h.hexdigest()
+
+
+def make_genb_extras(cfg: CodecConfig, batch: Dict[str, np.ndarray], seed: int = 0) -> Dict[str, np.ndarray]:
+    """Extra seeded inputs of the second-generation ("Gen-B") family: a positive prediction map (its
+    losses and the linear-weight centroid normalise by the plain tile sum), regression-branch
+    coordinates in both conventions the reference accepts, crop centres / scales."""
+    rng = np.random.default_rng(seed + 1000)
+    B, K = batch["kps"].shape[:2]
+    W, H = cfg.heatmap_size
+    pred = (np.abs(batch["heatmaps"]) + np.float32(0.01)).astype(np.float32)
+    gt_hm = batch["kps"] * (np.array([W, H], np.float32) / np.array(cfg.input_size, np.float32))
+    reg_px = (gt_hm * (256.0 / np.array([W, H], np.float32)) + rng.normal(0, 3.0, size=(B, K, 2))).astype(np.float32)
+    reg_norm = np.clip(rng.uniform(0.02, 0.98, size=(B, K, 2)), 0, 1).astype(np.float32)
+    coords = (gt_hm + rng.normal(0, 1.2, size=(B, K, 2))).astype(np.float32)
+    refined = (gt_hm + rng.normal(0, 0.6, size=(B, K, 2))).astype(np.float32)
+    center = rng.uniform(100, 400, size=(B, 2)).astype(np.float32)
+    scale = rng.uniform(120, 380, size=(B, 2)).astype(np.float32)
+    return dict(pred=pred, reg_px=reg_px, reg_norm=reg_norm, coords=coords, refined=refined,
+                target_coords=gt_hm.astype(np.float32), center=center, scale=scale)

@@ -166,3 +166,143 @@ def test_patch_binds_on_the_real_reference_when_present():
         sys.path.remove(ref)
         for m in [m for m in sys.modules if m == "models" or m.startswith("models.")]:
             del sys.modules[m]
+
+
+# ------------------------------------------------------------------------------------------------
+# second generation: utils/postprocess.py, models/losses.py, KeypointMSELoss
+# ------------------------------------------------------------------------------------------------
+def _genb_stand_ins():
+    pp = types.ModuleType("utils.postprocess")
+    ls = types.ModuleType("models.losses")
+    pe = types.ModuleType("models.pose_estimator")
+    from infantposeestimation_gaussianbias_b200 import patch
+    for fn in patch._GENB_FUNCTIONS:
+        setattr(pp, fn, (lambda name: (lambda *a, **k: f"original-{name}"))(fn))
+
+    class FusedPoseLoss(nn.Module):                          # attribute names of models/losses.py
+        def __init__(self, use_target_weight=True, loss_type="mse"):
+            super().__init__()
+            self.use_target_weight, self.loss_type = use_target_weight, loss_type
+
+        def forward(self, *a, **k):
+            return "original"
+
+    class MorphologyShapeLoss(nn.Module):
+        def __init__(self, lambda_variance=1.0, lambda_mean=0.5):
+            super().__init__()
+            self.lambda_variance, self.lambda_mean = lambda_variance, lambda_mean
+
+        def forward(self, *a, **k):
+            return "original"
+
+    class OffsetRegressionLoss(nn.Module):
+        def __init__(self, loss_type="smoothl1"):
+            super().__init__()
+            self.criterion = {"smoothl1": nn.SmoothL1Loss, "l1": nn.L1Loss, "mse": nn.MSELoss}[loss_type](reduction="none")
+
+        def forward(self, *a, **k):
+            return "original"
+
+    class JointsMSELoss(nn.Module):
+        def __init__(self, use_target_weight=True):
+            super().__init__()
+            self.use_target_weight = use_target_weight
+
+        def forward(self, *a, **k):
+            return "original"
+
+    class CombinedLoss(nn.Module):
+        def __init__(self, config):
+            super().__init__()
+            self.heatmap_loss = FusedPoseLoss(True, "mse")
+            self.morph_loss = MorphologyShapeLoss(config.LOSS.MORPH_LAMBDA, 0.5)
+            self.regression_loss = OffsetRegressionLoss("smoothl1")
+            self.w_heatmap, self.w_morph, self.w_reg = 1.0, config.LOSS.MORPH_WEIGHT, config.LOSS.REG_WEIGHT
+
+        def forward(self, *a, **k):
+            return "original"
+
+    class KeypointMSELoss(nn.Module):
+        def __init__(self, use_target_weight=True):
+            super().__init__()
+            self.use_target_weight = use_target_weight
+
+        def forward(self, *a, **k):
+            return "original"
+
+    ls.FusedPoseLoss, ls.MorphologyShapeLoss, ls.OffsetRegressionLoss = FusedPoseLoss, MorphologyShapeLoss, OffsetRegressionLoss
+    ls.JointsMSELoss, ls.CombinedLoss = JointsMSELoss, CombinedLoss
+    pe.KeypointMSELoss = KeypointMSELoss
+    return pp, ls, pe
+
+
+def test_genb_patch_and_unpatch():
+    from infantposeestimation_gaussianbias_b200 import patch, postprocess
+    pp, ls, pe = _genb_stand_ins()
+    saved = patch.patch_reference_genb(pp, ls, pe)
+    assert len(saved) == 7 + 5 + 1
+    assert pp.postprocess_predictions is postprocess.postprocess_predictions and pp.fused_decode is postprocess.fused_decode
+    assert ls.FusedPoseLoss.forward.__name__ == "fused" and pe.KeypointMSELoss.forward.__name__ == "keypoint_mse"
+    patch.unpatch_reference_genb()
+    assert pp.fused_decode() == "original-fused_decode"
+    assert ls.CombinedLoss.forward(None) == "original" and pe.KeypointMSELoss.forward(None) == "original"
+
+
+def test_genb_patch_binds_on_the_real_reference_when_present():
+    import os
+    ref = os.environ.get("GBCODEC_REF", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "utils")):
+        pytest.skip("reference tree not present (GPU box)")
+    from infantposeestimation_gaussianbias_b200 import patch
+    sys.path.insert(0, ref)
+    try:
+        import importlib
+        pp = importlib.import_module("utils.postprocess")
+        ls = importlib.import_module("models.losses")
+        pe = importlib.import_module("models.pose_estimator")
+        before = (pp.fused_decode, ls.CombinedLoss.forward, pe.KeypointMSELoss.forward)
+        patch.patch_reference_genb(pp, ls, pe)
+        # the attributes the rebound forwards read exist on the reference's own modules
+        cfg = types.SimpleNamespace(LOSS=types.SimpleNamespace(MORPH_LAMBDA=1.2, MORPH_WEIGHT=0.15, REG_WEIGHT=0.6))
+        c = ls.CombinedLoss(cfg)
+        assert (c.w_heatmap, c.w_morph, c.w_reg) == (1.0, 0.15, 0.6) and c.morph_loss.lambda_variance == 1.2
+        assert type(ls.OffsetRegressionLoss("l1").criterion).__name__ == "L1Loss"
+        assert ls.FusedPoseLoss().loss_type == "mse" and pe.KeypointMSELoss().use_target_weight is True
+        patch.unpatch_reference_genb()
+        assert (pp.fused_decode, ls.CombinedLoss.forward, pe.KeypointMSELoss.forward) == before
+    finally:
+        sys.path.remove(ref)
+        for m in [m for m in sys.modules if m in ("models", "utils") or m.startswith("models.") or m.startswith("utils.")]:
+            del sys.modules[m]
+
+
+@pytest.mark.gpu
+def test_genb_patched_entry_points_run_the_cuda_ops():
+    import infantposeestimation_gaussianbias_b200 as pkg
+    pkg.load()
+    from infantposeestimation_gaussianbias_b200 import patch
+    from oracle import genb
+    pp, ls, pe = _genb_stand_ins()
+    patch.patch_reference_genb(pp, ls, pe)
+    try:
+        cfg = synth.CONFIGS["w32_256x192"]
+        batch = synth.make_batch(cfg, seed=3, B=4)
+        ex = synth.make_genb_extras(cfg, batch, seed=3)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        config = types.SimpleNamespace(LOSS=types.SimpleNamespace(MORPH_LAMBDA=1.2, MORPH_WEIGHT=0.15, REG_WEIGHT=0.6))
+        total, parts = ls.CombinedLoss(config)({"heatmaps": dev(ex["pred"]), "coords": dev(ex["coords"])},
+                                               {"heatmaps": dev(batch["target"]), "coords": dev(ex["target_coords"]), "weights": dev(batch["weight"])})
+        tw, pw = genb.combined_loss({"heatmaps": T(ex["pred"]), "coords": T(ex["coords"])},
+                                    {"heatmaps": T(batch["target"]), "coords": T(ex["target_coords"]), "weights": T(batch["weight"])}, 1.2, 0.15, 0.6)
+        for k in pw:
+            np.testing.assert_allclose(float(parts[k]), float(pw[k]), rtol=1e-5)
+        np.testing.assert_allclose(float(ls.OffsetRegressionLoss("l1")(dev(ex["coords"]), dev(ex["target_coords"]), dev(batch["weight"]))),
+                                   float(genb.offset_regression_loss(T(ex["coords"]), T(ex["target_coords"]), T(batch["weight"]), "l1")), rtol=1e-5)
+        np.testing.assert_allclose(float(pe.KeypointMSELoss()(dev(ex["pred"]), dev(batch["target"]), dev(batch["weight"]))),
+                                   float(genb.keypoint_mse_loss(T(ex["pred"]), T(batch["target"]), T(batch["weight"]))), rtol=1e-5)
+        c, v = pp.get_max_preds_with_subpixel(dev(batch["heatmaps"]))
+        wc, wv = genb.get_max_preds_with_subpixel(T(batch["heatmaps"]))
+        assert np.array_equal(c.cpu().numpy(), wc.numpy()) and np.array_equal(v.cpu().numpy(), wv.numpy())
+    finally:
+        patch.unpatch_reference_genb()
