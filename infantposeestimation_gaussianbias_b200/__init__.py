@@ -38,7 +38,7 @@ def __getattr__(name):
                 "CombinedLoss", "build_loss"):
         from . import losses
         return getattr(losses, name)
-    if name in ("ops", "postprocess", "sharded", "patch", "losses"):
+    if name in ("ops", "postprocess", "sharded", "patch", "losses", "generate_heatmap", "fusion_head", "pose_estimator", "host_step"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

@@ -162,7 +162,9 @@ __device__ __forceinline__ void subpixel_step(const float* __restrict__ t, int a
 }
 
 // coordinate_refinement (utils/postprocess.py:138-184) for one tile, by one warp: linear-weight
-// centroid of the window around trunc(ix, iy); an empty window keeps the input.  Result in every lane.
+// centroid of the window around trunc(ix, iy); an empty window keeps the input (so does a window that
+// lies wholly left of / above the map, where the reference's slice wraps around and its torch.arange
+// raises).  Result in every lane.
 __device__ __forceinline__ void centroid_window(const float* __restrict__ t, float ix, float iy, int H, int W, int window,
                                                 float& ox, float& oy) {
     const int lane = threadIdx.x & 31;
