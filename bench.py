@@ -197,18 +197,30 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        # a rank that dies must not leave the others waiting for the default 10 minutes
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     B = args.batch
     pairs = ops.pairs_flat(SKELETON)
     data = synth_device_batch(B, device, 1234 + rank, ops)
     alpha = torch.tensor([0.5], device=device)
     fw = torch.tensor([0.6224593312018546], device=device)
     dflags = N.DECODE_REFINE | N.DECODE_APPLY_OFFSET
-    # N=1: weights/normalisers + loss + finalize.  N>1: (normalisers + export) + (weights + import + loss + finalize)
-    launches_per_step = 3 if world == 1 else 6
+    # N=1: weights/normalisers + loss + finalize.  N>1 over NCCL: (normalisers + export) + (weights + import + loss
+    # + finalize); N>1 over peer memory: the same three kernels as N=1 (+ one 8-byte export of the global sums)
+    use_peer = world > 1 and args.exchange == "peer"
+    launches_per_step = 3 if world == 1 else (4 if use_peer else 6)
+    peer = None
+    if use_peer:
+        from infantposeestimation_gaussianbias_b200.sharded import PeerExchange
+        peer = PeerExchange(device=device)
 
     def step():
         den = None
+        if use_peer:
+            return ops.fusion_loss(data["hm"], data["off"], data["var"], None, data["vis"], data["kps"], None, None,
+                                   float(IN_W), float(IN_H), LAMBDAS, SIGMA, SIGMA, True, pairs, True, True, alpha, fw, 2, dflags,
+                                   peer.address)
         if world > 1:
             den = ops.loss_denominators(data["vis"], data["kps"], False, H, W, float(IN_W), float(IN_H), SIGMA, pairs)
             dist.all_reduce(den)
@@ -286,6 +298,10 @@ def run_b200(args):
         if world == 1 and abs(e2e["total_loss"] - check) > 1e-4 * abs(check):
             raise SystemExit(f"bench.py: host-buffer step disagrees with the resident step: {e2e['total_loss']} vs {check}")
 
+    if peer is not None:
+        nt = peer.timeouts()
+        if nt:
+            raise SystemExit(f"bench.py: rank {rank} gave up waiting for a peer mailbox {nt} time(s)")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,7 +334,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": ("none" if world == 1 else args.exchange),
                    "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
@@ -338,6 +354,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU")
     ap.add_argument("--chunk", type=int, default=128, help="images per chunk of the host-buffer pipeline")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the 2+7 loss scalars travel between ranks (NVLink peer-memory mailboxes written by the kernels, or NCCL all-reduces)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

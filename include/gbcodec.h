@@ -181,6 +181,43 @@ int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
                             float* d_grad_hm, float* d_grad_off, float* d_grad_var,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------- batch-sharded jobs ---
+ * One process per GPU, each rank holding whole images.  The data path needs no exchange; the
+ * loss needs two scalar ones per step: the batch normalisers before the tile
+ * kernel and the seven loss scalars after it.  Two ways to do them:
+ *   (a) portable: gbcodec_loss_denominators_f32 -> all-reduce (NCCL) -> d_denoms of
+ *       gbcodec_fusion_step_f32 -> all-reduce of d_losses7;
+ *   (b) gbcodec_fusion_step_sharded_f32: the kernels that produce those scalars write them into
+ *       every peer's mailbox over NVLink / NVSwitch (cudaIpc-mapped device memory) and read the
+ *       peers' values from their own — no NCCL call, no extra launch, fixed rank order (every
+ *       rank gets the same bits).  d_losses7 then holds the GLOBAL losses on every rank and the
+ *       gradients are this rank's share of the global-batch gradients.
+ * Set-up (these three calls allocate / map / free device memory and are NOT stream-ordered):
+ *   gbcodec_peer_create   allocates this rank's mailbox, returns its IPC handle (64 bytes)
+ *   gbcodec_peer_connect  maps the peers' mailboxes; all_handles = world x 64 bytes in rank order
+ *                         (gathered by the host program, e.g. torch.distributed.all_gather)
+ *   gbcodec_peer_destroy
+ * Every rank must make the same sequence of sharded calls.  A rank that waits for a dead peer
+ * gives up after a few seconds (bounded spin) and counts it: gbcodec_peer_status (synchronises).
+ */
+#define GBCODEC_PEER_HANDLE_BYTES 64
+#define GBCODEC_MAX_PEERS 16
+int gbcodec_peer_create(int rank, int world, void** ctx_out, unsigned char* handle_out);
+int gbcodec_peer_connect(void* ctx, const unsigned char* all_handles);
+int gbcodec_peer_status(void* ctx, int* h_timeouts);
+int gbcodec_peer_destroy(void* ctx);
+
+/* gbcodec_fusion_step_f32 for a rank of a sharded job.  d_coords/d_scores may both be NULL (loss
+ * only).  d_denoms_out: NULL or 2 device floats that receive the global raw sums (what the
+ * backward of gbcodec_fusion_loss_backward_f32 takes as d_denoms). */
+int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores, float* d_denoms_out,
+                            void* d_workspace, size_t workspace_bytes, void* peer_ctx, void* stream);
+
 /* ------------------------------------------------- Gen-B family (next rows) ---
  * The reference carries a second generation of the same codec ("Gen-B":
  * data/, models/losses.py, utils/postprocess.py).  Same tile layout, same rules.

@@ -25,7 +25,7 @@ namespace gbc {
 __global__ void __launch_bounds__(256)
 denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight,
               const float* __restrict__ gt, int target_given, float* __restrict__ weff, int4* __restrict__ geom,
-              double* __restrict__ sums) {
+              double* __restrict__ sums, unsigned* __restrict__ ticket, const __grid_constant__ PeerView peer) {
     __shared__ float wsm[256];
     __shared__ double red[2][8];
     const int ipb = 256 / P.K;                         // images per CTA
@@ -61,6 +61,38 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
         double a = 0.0;
         for (int i = 0; i < 8; ++i) a += red[threadIdx.x][i];
         atomicAdd(sums + threadIdx.x, a);
+    }
+    if (peer.world <= 1) return;
+    // ---- batch-sharded job: the CTA that draws the last ticket holds this rank's sums; it writes them into
+    // every peer's mailbox over NVLink, waits for the peers' sums in its own mailbox and leaves the GLOBAL
+    // sums (added in rank order: every rank gets the same bits) in the workspace.  No NCCL on this path.
+    __shared__ bool last;
+    __shared__ double gath[GBCODEC_MAX_PEERS][2];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int q = (int)(peer.seq & 1ull), r = threadIdx.x;
+    if (r < peer.world) {
+        const double sw = __ldcg(sums), sp = __ldcg(sums + 1);
+        PeerMail* dst = peer.mail[r];
+        dst->den[q][peer.rank][0] = sw;
+        dst->den[q][peer.rank][1] = sp;
+        __threadfence_system();
+        st_release_sys(&dst->den_seq[q][peer.rank], peer.seq);
+        PeerMail* mine = peer.mail[peer.rank];
+        wait_seq(&mine->den_seq[q][r], peer.seq, &mine->timeouts);
+        gath[r][0] = mine->den[q][r][0];
+        gath[r][1] = mine->den[q][r][1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double gw = 0.0, gp = 0.0;
+        for (int i = 0; i < peer.world; ++i) { gw += gath[i][0]; gp += gath[i][1]; }
+        sums[0] = gw; sums[1] = gp;
+        *ticket = 0u;
     }
 }
 
@@ -443,7 +475,8 @@ loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossAr
 // seven losses.  The order of every addition is fixed by the launch shape: bit-reproducible.
 __global__ void __launch_bounds__(256)
 finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ partial, const double* __restrict__ sums,
-                double* __restrict__ bpart, unsigned* __restrict__ ticket, float* __restrict__ losses7) {
+                double* __restrict__ bpart, unsigned* __restrict__ ticket, float* __restrict__ losses7,
+                const __grid_constant__ PeerView peer) {
     __shared__ double red[6][8];
     __shared__ bool last;
     const int tiles = P.B * P.K;
@@ -483,6 +516,36 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
         const float den = q < 3 ? Da : (q == 4 ? D5 : D);
         term[q] = P.lam[q] * ((float)s / den);
         losses7[q] = term[q];
+    }
+    __syncthreads();
+    if (peer.world <= 1) {
+        if (threadIdx.x == 0) {
+            float total = 0.f;
+            for (int q = 0; q < 6; ++q) total += term[q];
+            losses7[6] = total;
+            *ticket = 0u;
+        }
+        return;
+    }
+    // ---- batch-sharded job: every rank's terms are already divided by the GLOBAL normalisers, so the global
+    // losses are their sums over the ranks.  Same mailbox protocol as denoms_kernel; fixed rank order.
+    __shared__ float gl[GBCODEC_MAX_PEERS][8];
+    const int pq = (int)(peer.seq & 1ull), r = threadIdx.x;
+    if (r < peer.world) {
+        PeerMail* dst = peer.mail[r];
+        for (int q = 0; q < 6; ++q) dst->loss[pq][peer.rank][q] = term[q];
+        __threadfence_system();
+        st_release_sys(&dst->loss_seq[pq][peer.rank], peer.seq);
+        PeerMail* mine = peer.mail[peer.rank];
+        wait_seq(&mine->loss_seq[pq][r], peer.seq, &mine->timeouts);
+        for (int q = 0; q < 6; ++q) gl[r][q] = mine->loss[pq][r][q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = 0.f;
+        for (int i = 0; i < peer.world; ++i) v += gl[i][threadIdx.x];
+        term[threadIdx.x] = v;
+        losses7[threadIdx.x] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -600,8 +663,10 @@ static int check_common(const gbcodec_loss_desc* d, const float* hm, const float
     return GBCODEC_OK;
 }
 
+static const PeerView kNoPeers = {};
+
 static int prepare_weights(const LossParams& P, const WsLayout& L, const float* weight, const float* gt,
-                           int target_given, const float* denoms, cudaStream_t s) {
+                           int target_given, const float* denoms, cudaStream_t s, const PeerView& peer = kNoPeers) {
     if (denoms) {
         weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom);
         sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
@@ -611,7 +676,7 @@ static int prepare_weights(const LossParams& P, const WsLayout& L, const float* 
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         const int ipb = 256 / P.K;
         const int grid = (P.B + ipb - 1) / ipb;
-        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums);
+        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums, L.ticket, peer);
     }
     return check_launch("denoms_kernel");
 }
@@ -635,9 +700,17 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
                 const float* weight, const float* gt, const float* denoms, const float* grad_scale,
                 float* losses7, float* ghm, float* goff, float* gvar,
                 const float* alpha_param, const float* fusion_weight, int radius, unsigned dflags, float* coords, float* scores,
-                void* ws, size_t ws_size, cudaStream_t s) {
+                void* ws, size_t ws_size, cudaStream_t s, void* peer_ctx, float* denoms_out) {
     int st = check_common(d, hm, off, weight, gt, ws, ws_size);
     if (st) return st;
+    PeerView peer = kNoPeers;
+    if (peer_ctx) {
+        PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
+        if (!pc->connected) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: the peer context is not connected");
+        if (denoms) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: d_denoms and a peer context exclude each other");
+        pc->view.seq += 1;
+        peer = pc->view;
+    }
     if (!losses7) return fail(GBCODEC_ERR_NULL_POINTER, "loss: d_losses7 is NULL");
     const bool grads = ghm || goff || gvar;
     if (grads && (!ghm || !goff || (!gvar) != (!var))) return fail(GBCODEC_ERR_NULL_POINTER, "loss: give all gradient pointers or none (d_grad_var iff d_var)");
@@ -653,8 +726,13 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     st = make_params(d, &P);
     if (st) return st;
     const WsLayout L = ws_carve(ws, P.B, P.K);
-    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
+    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, peer);
     if (st) return st;
+    if (denoms_out) {
+        sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, denoms_out);
+        st = check_launch("sums_to_float_kernel");
+        if (st) return st;
+    }
     LossArgs A;
     memset(&A, 0, sizeof(A));
     A.hm = hm; A.off = off; A.var = var; A.target = target; A.weight = weight; A.gt = gt; A.grad_scale = grad_scale;
@@ -666,7 +744,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     if (st) return st;
     const int tiles = P.B * P.K;
     const int fin_blocks = (tiles + 255) / 256 < kFinBlocks ? (tiles + 255) / 256 : kFinBlocks;
-    finalize_kernel<<<fin_blocks, 256, 0, s>>>(P, L.partial, L.sums, L.bpart, L.ticket, losses7);
+    finalize_kernel<<<fin_blocks, 256, 0, s>>>(P, L.partial, L.sums, L.bpart, L.ticket, losses7, peer);
     return check_launch("finalize_kernel");
 }
 

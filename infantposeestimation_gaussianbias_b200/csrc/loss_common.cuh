@@ -80,6 +80,47 @@ __device__ __forceinline__ PatchGeom unpack_geom(const int4& v, float weight) {
     return g;
 }
 
+// ---- peer-memory exchange of a batch-sharded job (one process per GPU, NVLink / NVSwitch) -----------
+// Every rank owns one PeerMail in its own HBM; peers write into it with plain stores over NVLink
+// (cudaIpc-mapped pointers) and publish with a system-scope release store of the call's sequence
+// number; the owner polls its LOCAL copy with acquire loads.  Two parity slots: a peer can be at
+// most one call ahead (its call s+1 needs this rank's data of call s+1).
+struct PeerMail {
+    double den[2][GBCODEC_MAX_PEERS][2];                 // [parity][source rank]{sum w, sum w_i w_j}
+    unsigned long long den_seq[2][GBCODEC_MAX_PEERS];
+    float loss[2][GBCODEC_MAX_PEERS][8];                 // [parity][source rank] seven loss scalars
+    unsigned long long loss_seq[2][GBCODEC_MAX_PEERS];
+    unsigned int timeouts;                               // bounded spins that gave up (a peer died)
+};
+struct PeerView {
+    PeerMail* mail[GBCODEC_MAX_PEERS];                   // mail[rank] is the local one
+    int rank, world;
+    unsigned long long seq;
+};
+struct PeerCtx {
+    PeerView view;
+    cudaIpcMemHandle_t handle;
+    int connected;
+    int device;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Wait until a peer has published `seq`.  Bounded (a few seconds): a dead peer must not hang the GPU.
+__device__ __forceinline__ bool wait_seq(const unsigned long long* flag, unsigned long long seq, unsigned int* timeouts) {
+    for (unsigned it = 0; it < (1u << 22); ++it) {
+        if (ld_acquire_sys(flag) == seq) return true;
+        __nanosleep(200);
+    }
+    atomicAdd(timeouts, 1u);
+    return false;
+}
+
 // ---- bilinear helpers (same convention as decode.cu) ---------------------------------
 struct Taps {
     int i00, i01, i10, i11;          // flat indices inside a channel

@@ -41,7 +41,9 @@ class FusionPoseLoss(nn.Module):
       denominators -> (2,) tensor with the global batch sums for a rank holding a shard;
       grad_scale   -> scalar tensor, the upstream gradient the caller is going to use
           (e.g. the GradScaler scale); the in-pass gradients are pre-multiplied by it
-          so that backward() has nothing left to do.
+          so that backward() has nothing left to do;
+      peer         -> sharded.PeerExchange of a batch-sharded job: normalisers and losses are exchanged
+          with the other ranks inside the kernels (NVLink peer memory); the returned losses are global.
     """
 
     def __init__(self, heatmap_weight: float = 1.0, offset_weight: float = 1.0, peak_weight: float = 0.5,
@@ -71,7 +73,7 @@ class FusionPoseLoss(nn.Module):
     def forward(self, outputs: Dict[str, Tensor], target_heatmaps: Optional[Tensor], target_weight: Tensor,
                 gt_keypoints: Tensor, input_size: Tuple[int, int] = (192, 256),
                 heatmap_size: Tuple[int, int] = (48, 64), *, denominators: Optional[Tensor] = None,
-                grad_scale: Optional[Tensor] = None, decode: Optional[dict] = None) -> Dict[str, Tensor]:
+                grad_scale: Optional[Tensor] = None, decode: Optional[dict] = None, peer=None) -> Dict[str, Tensor]:
         # heatmap_size is accepted and ignored, as in the reference (it uses heatmaps.shape, :771)
         hm = _f32(outputs["heatmaps"])
         off = _f32(outputs["offsets"])
@@ -88,7 +90,7 @@ class FusionPoseLoss(nn.Module):
             float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
             bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads,
             bool(dec), dec.get("alpha_param"), dec.get("fusion_weight"), int(dec.get("radius", 2)),
-            int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)))
+            int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)), int(peer.address) if peer is not None else 0)
         losses7 = res[0]
         out = {k: losses7[i] for i, k in enumerate(LOSS_KEYS)}
         if dec:

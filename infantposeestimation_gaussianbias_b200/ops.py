@@ -185,8 +185,10 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
                 in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
                 use_target_weight: bool, pairs: List[int], with_grads: bool,
                 with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
-                decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """-> losses7, grad_hm, grad_off, grad_var, coords, scores (empty tensors for what was not asked)."""
+                decode_flags: int, peer_ctx: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> losses7, grad_hm, grad_off, grad_var, coords, scores, global_denoms (empty tensors for what was not
+    asked).  peer_ctx: address of a connected gbcodec peer context (sharded.PeerExchange) — the normalisers and
+    the losses are then exchanged with the other ranks inside the kernels, over NVLink peer memory."""
     B, K, H, W = hm.shape
     hm = _cuda_f32("heatmaps", hm)
     off = _device_readable_f32("offsets", off, (B, K, 2, H, W))
@@ -213,29 +215,42 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
     common = (desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(grad_scale),
               _ptr(losses), _ptr(ghm) if with_grads else None, _ptr(goff) if with_grads else None,
               _ptr(gvar) if (with_grads and var is not None) else None)
+    den_out = empty()
     with torch.cuda.device(dev):
         if with_decode:
             coords = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
             scores = torch.empty((B, K), dtype=torch.float32, device=dev)
             alpha_param = _scalar("alpha", alpha_param, hm)
             fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
+        else:
+            coords, scores = empty(), empty()
+        if peer_ctx:
+            if denoms is not None:
+                raise RuntimeError("gbcodec: `denominators` and a peer exchange exclude each other")
+            den_out = torch.empty(2, dtype=torch.float32, device=dev)
+            N.check(L.gbcodec_fusion_step_sharded_f32(
+                desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(grad_scale), *common[9:],
+                _ptr(alpha_param) if with_decode else None, _ptr(fusion_weight) if with_decode else None, radius, decode_flags,
+                _ptr(coords) if with_decode else None, _ptr(scores) if with_decode else None, _ptr(den_out),
+                _ptr(ws), ws.numel(), N._P(peer_ctx), _stream(hm)), "fusion_step_sharded")
+        elif with_decode:
             N.check(L.gbcodec_fusion_step_f32(*common, _ptr(alpha_param), _ptr(fusion_weight), radius, decode_flags,
                                               _ptr(coords), _ptr(scores), _ptr(ws), ws.numel(), _stream(hm)), "fusion_step")
         else:
-            coords, scores = empty(), empty()
             N.check(L.gbcodec_fusion_loss_f32(*common, _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss")
-    return losses, ghm, goff, gvar, coords, scores
+    return losses, ghm, goff, gvar, coords, scores, den_out
 
 
 @fusion_loss.register_fake
 def _(hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
-      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags):
+      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx=0):
     B, K = hm.shape[0], hm.shape[1]
     e = lambda: hm.new_empty(0)
     return (hm.new_empty(7),
             torch.empty_like(hm) if with_grads else e(), torch.empty_like(off) if with_grads else e(),
             torch.empty_like(var) if (with_grads and var is not None) else e(),
-            hm.new_empty((B, K, 2)) if with_decode else e(), hm.new_empty((B, K)) if with_decode else e())
+            hm.new_empty((B, K, 2)) if with_decode else e(), hm.new_empty((B, K)) if with_decode else e(),
+            hm.new_empty(2) if peer_ctx else e())
 
 
 @torch.library.custom_op(f"{_NS}::fusion_loss_backward", mutates_args=("grad_hm", "grad_off", "grad_var"))
@@ -257,8 +272,10 @@ def fusion_loss_backward(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor,
 
 def _loss_setup_context(ctx, inputs, output):
     (hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
-     utw, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags) = inputs
-    losses, ghm, goff, gvar, coords, scores = output
+     utw, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx) = inputs
+    losses, ghm, goff, gvar, coords, scores, den_out = output
+    if peer_ctx:
+        denoms = den_out          # the backward re-uses the global normalisers the forward exchanged
     ctx.with_grads = with_grads
     ctx.has_var = var is not None
     # Plain attributes, not save_for_backward: the backward adjusts the stored gradients in place.
@@ -268,8 +285,8 @@ def _loss_setup_context(ctx, inputs, output):
     ctx.set_materialize_grads(False)
 
 
-def _loss_backward(ctx, g_losses, g_ghm, g_goff, g_gvar, g_coords, g_scores):
-    n_in = 21
+def _loss_backward(ctx, g_losses, g_ghm, g_goff, g_gvar, g_coords, g_scores, g_den=None):
+    n_in = 22
     none = [None] * n_in
     if g_losses is None:
         return tuple(none)

@@ -9,6 +9,13 @@ collective; the loss needs two tiny ones:
 
 With the global normalisers the local gradients ARE the global-batch gradients
 restricted to the shard, so nothing else is exchanged.
+
+Two transports for those 2 + 7 scalars:
+  * NCCL all-reduces issued from here (default; also what the CPU/gloo tests exercise);
+  * `PeerExchange`: the kernels that produce the scalars write them into every peer's mailbox over
+    NVLink / NVSwitch peer memory and read the peers' values from their own (csrc/peer.cu,
+    denoms_kernel / finalize_kernel in csrc/loss.cu) — no collective call on the step at all;
+    torch.distributed is used once, to pass the 64-byte IPC handles around.
 """
 from __future__ import annotations
 
@@ -30,6 +37,48 @@ def _default_denominators(loss: FusionPoseLoss, weight, gt_keypoints, target_giv
                                  ops.pairs_flat(loss.pairs_for(K)))
 
 
+class PeerExchange:
+    """Mailboxes of a batch-sharded job (gbcodec_peer_* of include/gbcodec.h): one per rank, mapped into
+    every other rank of `group` through CUDA IPC.  Needs one process per GPU on one NVLink / NVSwitch
+    domain and an initialised process group (any backend) for the handle exchange."""
+
+    def __init__(self, group=None, device: Optional[torch.device] = None):
+        import ctypes as C
+        from . import _native as N
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > N.MAX_PEERS:
+            raise RuntimeError(f"PeerExchange: at most {N.MAX_PEERS} ranks")
+        self._lib = N.lib()
+        self._ctx = C.c_void_p()
+        handle = C.create_string_buffer(N.PEER_HANDLE_BYTES)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        with torch.cuda.device(dev):
+            N.check(self._lib.gbcodec_peer_create(self.rank, self.world, C.byref(self._ctx), handle), "peer_create")
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handle.raw, group=group)
+            N.check(self._lib.gbcodec_peer_connect(self._ctx, b"".join(gathered)), "peer_connect")
+        dist.barrier(group)       # nobody writes into a mailbox that is not mapped yet
+
+    @property
+    def address(self) -> int:
+        return int(self._ctx.value or 0)
+
+    def timeouts(self) -> int:
+        """Bounded spins that gave up so far on this rank (0 in a healthy job).  Synchronises the device."""
+        import ctypes as C
+        from . import _native as N
+        n = C.c_int(0)
+        N.check(self._lib.gbcodec_peer_status(self._ctx, C.byref(n)), "peer_status")
+        return int(n.value)
+
+    def close(self) -> None:
+        if self._ctx:
+            self._lib.gbcodec_peer_destroy(self._ctx)
+            self._ctx = None
+
+
 class ShardedFusionPoseLoss(FusionPoseLoss):
     """FusionPoseLoss for a rank that holds a shard of the global batch.
 
@@ -37,10 +86,11 @@ class ShardedFusionPoseLoss(FusionPoseLoss):
     exercised on CPU (gloo) with a stand-in for the CUDA ops; the defaults are the
     gbcodec ops."""
 
-    def __init__(self, *args, process_group=None,
+    def __init__(self, *args, process_group=None, peer: Optional[PeerExchange] = None,
                  local_denominators: Optional[Callable] = None, local_loss: Optional[Callable] = None, **kw):
         super().__init__(*args, **kw)
         self.process_group = process_group
+        self.peer = peer
         self._local_denominators = local_denominators
         self._local_loss = local_loss
 
@@ -55,6 +105,11 @@ class ShardedFusionPoseLoss(FusionPoseLoss):
 
     def forward(self, outputs: Dict[str, Tensor], target_heatmaps, target_weight, gt_keypoints,
                 input_size: Tuple[int, int] = (192, 256), heatmap_size: Tuple[int, int] = (48, 64), **kw):
+        if self.peer is not None:
+            # both exchanges happen inside the kernels: the values returned are the global losses, the
+            # gradients behind them this rank's share of the global-batch gradients
+            return super().forward(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, heatmap_size,
+                                   peer=self.peer, **kw)
         H, W = outputs["heatmaps"].shape[-2:]
         den = self.global_denominators(target_heatmaps, target_weight, gt_keypoints, (H, W), input_size)
         if self._local_loss is not None:
