@@ -55,6 +55,26 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// NV running sums per lane -> lane l holds the warp total of value l >> (5 - log2 NV) (halving butterfly:
+// each step exchanges half of the remaining values, so 4 values cost 2+1+3 shuffles instead of 20).
+template <int NV>
+__device__ __forceinline__ void warp_scatter_sum(float (&v)[NV], int lane) {
+#pragma unroll
+    for (int n = NV, o = 16; n > 1; n >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            const float keep = up ? v[j + n / 2] : v[j];
+            const float send = up ? v[j] : v[j + n / 2];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+#pragma unroll
+    for (int o = 16 / NV; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+template <int NV>
+__device__ __forceinline__ void warp_scatter_sum(float (&v)[NV]) { warp_scatter_sum<NV>(v, threadIdx.x & 31); }   // 1-D blocks
+
 // (value, index) maximum; on equal values the smaller index wins — torch.max's
 // first-occurrence rule (pose_estimator.py:352).
 __device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi) {

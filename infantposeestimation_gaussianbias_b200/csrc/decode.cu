@@ -13,19 +13,35 @@
 // bytes per tile (8*H*W with the flip average).
 #include "common.cuh"
 #include "decode_device.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace gbc {
 
-template <int NITER, bool FLIP>
-__global__ void __launch_bounds__(1024)
+// Schedule of one tile (NITER > 0: the tile fits the CTA's registers):
+//   1. the whole tile with 128-bit streaming loads; the two learnable scalars at once
+//   2. max            — one barrier (every warp finishes the cross-warp step itself)
+//   3. exp moments    — one barrier; every thread then knows the soft-argmax (cx, cy)
+//   4. the threads that hold pixels of the (2r+1)^2 window around round(cx, cy) drop them into
+//      shared memory (no second trip to L2), while warp 0 already has the 4x4x2 block of offset
+//      taps around floor(cx, cy) in flight — the one dependent DRAM access of the tail is issued
+//      before the coordinate it depends on is final, and covers |refined - global| <= 1 px
+//      (anything further takes the direct path)
+//   5. one barrier; warp 0: window softmax from shared memory, blend, taps picked by shuffle.
+constexpr int kMaxWin = 17 * 17;           // local_radius <= 8
+
+template <int NITER, bool FLIP, int MAXT = 1024, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 decode_kernel(const float* __restrict__ hm, const float* __restrict__ hmf, const int32_t* __restrict__ perm,
               const float* __restrict__ off, const float* __restrict__ alpha_param,
               const float* __restrict__ fusion_weight, int K, int H, int W, int radius, unsigned flags,
               float* __restrict__ coords, float* __restrict__ scores, int32_t* __restrict__ centre) {
-    __shared__ float scratch[4 * 32 + 8];
+    __shared__ float red0[32], red1[32 * 4];
+    __shared__ float win[kMaxWin];
     const int tile = blockIdx.x;
     const int b = tile / K, k = tile - b * K;
     const int n = H * W, n4 = n >> 2, w4 = W >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const float* hm_tile = hm + (size_t)tile * n;
     const float* hmf_tile = nullptr;
     if (FLIP) {
@@ -49,16 +65,31 @@ decode_kernel(const float* __restrict__ hm, const float* __restrict__ hmf, const
     float m = -INFINITY;
     if (NITER > 0) {
 #pragma unroll
-        for (int it = 0; it < R; ++it) v[it] = load(it * blockDim.x + threadIdx.x);
+        for (int it = 0; it < R; ++it) v[it] = load(it * blockDim.x + tid);
+    }
+    // scalars of the tail: issued now, consumed three barriers later
+    float a_raw = 0.f, fw = 0.f;
+    if (warp == 0) {
+        if (flags & GBCODEC_DECODE_REFINE) a_raw = __ldg(alpha_param);
+        if (flags & GBCODEC_DECODE_APPLY_OFFSET) fw = __ldg(fusion_weight);
+    }
+    const int S = 2 * radius + 1;
+    if (NITER > 0 && (flags & GBCODEC_DECODE_REFINE)) {
+        for (int c = tid; c < S * S; c += blockDim.x) win[c] = -INFINITY;       // off-map window cells stay -inf
+    }
+    if (NITER > 0) {
 #pragma unroll
         for (int it = 0; it < R; ++it) m = fmaxf(m, fmaxf(fmaxf(v[it].x, v[it].y), fmaxf(v[it].z, v[it].w)));
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        for (int i = tid; i < n4; i += blockDim.x) {
             const float4 t = load(i);
             m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
         }
     }
-    m = block_max(m, scratch);
+    m = warp_max(m);
+    if (lane == 0) red0[warp] = m;
+    __syncthreads();
+    m = warp_max(lane < nw ? red0[lane] : -INFINITY);
 
     float acc[3] = {0.f, 0.f, 0.f};     // sum e, sum e*x, sum e*y
     const float ml = m * kLog2e;
@@ -73,23 +104,313 @@ decode_kernel(const float* __restrict__ hm, const float* __restrict__ hmf, const
     };
     if (NITER > 0) {
 #pragma unroll
-        for (int it = 0; it < R; ++it) accumulate(v[it], it * blockDim.x + threadIdx.x);
+        for (int it = 0; it < R; ++it) accumulate(v[it], it * blockDim.x + tid);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) accumulate(load(i), i);
+        for (int i = tid; i < n4; i += blockDim.x) accumulate(load(i), i);
     }
-    block_sum<3>(acc, scratch);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) { red1[warp * 4] = acc[0]; red1[warp * 4 + 1] = acc[1]; red1[warp * 4 + 2] = acc[2]; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q] = warp_sum(lane < nw ? red1[lane * 4 + q] : 0.f);   // fixed order: same bits in every warp
+    float cx = acc[1] / acc[0], cy = acc[2] / acc[0];
 
-    if (threadIdx.x < 32) {
-        float cx = acc[1] / acc[0], cy = acc[2] / acc[0];
-        int px, py;
-        refine_and_correct(hm_tile, hmf_tile, off ? off + (size_t)tile * 2 * n : nullptr, alpha_param, fusion_weight,
-                           H, W, radius, flags, cx, cy, px, py);
-        if (threadIdx.x == 0) {
-            coords[2 * tile] = cx; coords[2 * tile + 1] = cy;
-            scores[tile] = m;
-            if (centre) { centre[2 * tile] = px; centre[2 * tile + 1] = py; }
+    if (NITER == 0) {
+        // generic shapes: the tail re-reads its few pixels through L2
+        if (tid < 32) {
+            int px, py;
+            refine_and_correct(hm_tile, hmf_tile, off ? off + (size_t)tile * 2 * n : nullptr, alpha_param, fusion_weight,
+                               H, W, radius, flags, cx, cy, px, py);
+            if (tid == 0) {
+                coords[2 * tile] = cx; coords[2 * tile + 1] = cy;
+                scores[tile] = m;
+                if (centre) { centre[2 * tile] = px; centre[2 * tile + 1] = py; }
+            }
+        }
+        return;
+    }
+
+    // torch.round is round-half-to-even == rintf in the default rounding mode
+    const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
+    const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
+    // offset taps: a 4x4 block per channel around floor(clamp(cx, cy)) - 1, one tap per lane of warp 0
+    const float* off_tile = off ? off + (size_t)tile * 2 * n : nullptr;
+    const bool want_off = (flags & GBCODEC_DECODE_APPLY_OFFSET) != 0;
+    const int bx = (int)floorf(fminf(fmaxf(cx, 0.f), (float)(W - 1))) - 1;
+    const int by = (int)floorf(fminf(fmaxf(cy, 0.f), (float)(H - 1))) - 1;
+    float pre = 0.f;
+    if (want_off && warp == 0) {
+        const int t = lane & 15;
+        const int tx = min(max(bx + (t & 3), 0), W - 1), ty = min(max(by + (t >> 2), 0), H - 1);
+        pre = __ldg(off_tile + (lane >> 4) * n + ty * W + tx);
+    }
+    if (flags & GBCODEC_DECODE_REFINE) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            const int i = it * blockDim.x + tid;
+            const int y = i / w4, x0 = (i - y * w4) << 2;
+            const int wy = y - py + radius;
+            if (wy >= 0 && wy < S && x0 + 3 >= px - radius && x0 <= px + radius) {
+                const float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int wx = x0 + j - px + radius;
+                    if (wx >= 0 && wx < S) win[wy * S + wx] = e[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp != 0) return;
+
+    if (flags & GBCODEC_DECODE_REFINE) {
+        float vmax = -INFINITY;
+        for (int c = lane; c < S * S; c += 32) vmax = fmaxf(vmax, win[c]);
+        vmax = warp_max(vmax);
+        float se = 0.f, sx = 0.f, sy = 0.f;
+        for (int c = lane; c < S * S; c += 32) {
+            const float wv = win[c];
+            if (wv != -INFINITY) {
+                const int x = px - radius + c % S, y = py - radius + c / S;
+                const float e = expf(wv - vmax);
+                se += e; sx += e * (float)x; sy += e * (float)y;
+            }
+        }
+        se = warp_sum(se); sx = warp_sum(sx); sy = warp_sum(sy);
+        const float a = sigmoid_acc(__shfl_sync(0xffffffffu, a_raw, 0));
+        cx = a * cx + (1.f - a) * (sx / se);
+        cy = a * cy + (1.f - a) * (sy / se);
+    }
+    if (want_off) {
+        if (flags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
+        const Bilinear bl = bilinear_setup(cx, cy, H, W);
+        float ox, oy;
+        const bool covered = bl.x0 >= bx && bl.x1 <= bx + 3 && bl.y0 >= by && bl.y1 <= by + 3;   // warp-uniform
+        if (covered) {
+            const int i00 = (bl.y0 - by) * 4 + (bl.x0 - bx), i01 = (bl.y0 - by) * 4 + (bl.x1 - bx);
+            const int i10 = (bl.y1 - by) * 4 + (bl.x0 - bx), i11 = (bl.y1 - by) * 4 + (bl.x1 - bx);
+            float t[2][4];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                t[c][0] = __shfl_sync(0xffffffffu, pre, c * 16 + i00);
+                t[c][1] = __shfl_sync(0xffffffffu, pre, c * 16 + i01) * bl.okx;
+                t[c][2] = __shfl_sync(0xffffffffu, pre, c * 16 + i10) * bl.oky;
+                t[c][3] = __shfl_sync(0xffffffffu, pre, c * 16 + i11) * (bl.okx * bl.oky);
+            }
+            ox = bl.w00 * t[0][0] + bl.w01 * t[0][1] + bl.w10 * t[0][2] + bl.w11 * t[0][3];
+            oy = bl.w00 * t[1][0] + bl.w01 * t[1][1] + bl.w10 * t[1][2] + bl.w11 * t[1][3];
+        } else {
+            ox = bilinear_read(off_tile, bl, W);
+            oy = bilinear_read(off_tile + n, bl, W);
+        }
+        const float f = __shfl_sync(0xffffffffu, fw, 0);
+        cx += f * ox;
+        cy += f * oy;
+    }
+    if (lane == 0) {
+        coords[2 * tile] = cx; coords[2 * tile + 1] = cy;
+        scores[tile] = m;
+        if (centre) { centre[2 * tile] = px; centre[2 * tile + 1] = py; }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Column-owner variant for the three tile shapes of the reference's configs (64x48, 96x72,
+// 128x128): TPB = (W/4) * ROWS threads, a thread owns the same four columns in every row it
+// visits, so there is no index arithmetic in the pixel loops (the generic kernel spends half
+// of its instructions on i / w4) and the x-moment factors out of the row loop:
+//   sum e x = x0 * Z_t + (E1 + 2 E2 + 3 E3),  E_j = column sums of this thread.
+// Same schedule otherwise (one barrier per reduction, window scatter, prefetched offset taps).
+// ---------------------------------------------------------------------------------
+// Reductions: ONE barrier for max and moments together.  A warp takes the softmax of its own pixels
+// relative to its own maximum; the per-warp {Z, sum e x, sum e y, max} meet in shared memory and
+// every warp rescales them to the tile maximum (exp2((m_w - m) log2 e), one per warp) while adding —
+// the same sum, 23 shuffles instead of 40 and one barrier less.
+__host__ __device__ constexpr int ceil_log2(int n) { return n <= 1 ? 0 : 1 + ceil_log2((n + 1) / 2); }
+
+template <int W4, int ROWS, int NIT, bool FLIP, int MINB>
+__global__ void __launch_bounds__(W4* ROWS, MINB)
+decode_tile_kernel(const float* __restrict__ hm, const float* __restrict__ hmf, const int32_t* __restrict__ perm,
+                   const float* __restrict__ off, const float* __restrict__ alpha_param,
+                   const float* __restrict__ fusion_weight, int K, int radius, unsigned flags,
+                   float* __restrict__ coords, float* __restrict__ scores, int32_t* __restrict__ centre) {
+    constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
+    constexpr int NWP = 1 << ceil_log2(NW);                    // lanes that take part in the cross-warp step
+    static_assert(TPB % 32 == 0 && NW <= 32, "CTA must be whole warps");
+    __shared__ float4 red[32];
+    __shared__ float win[kMaxWin];
+    const int tile = blockIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y;              // block = (W4, ROWS): the column group and first row of this thread
+    const int tid = ty * W4 + tx, lane = tid & 31, warp = tid >> 5;
+    const bool refine = (flags & GBCODEC_DECODE_REFINE) != 0, want_off = (flags & GBCODEC_DECODE_APPLY_OFFSET) != 0;
+    const float4* src = reinterpret_cast<const float4*>(hm + (size_t)tile * N) + tid;
+    float4 v[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) v[it] = ldg_stream(src + it * TPB);
+    float4 f[FLIP ? NIT : 1];
+    if (FLIP) {
+        const int b = tile / K, k = tile - b * K;
+        const int kk = perm ? __ldg(perm + k) : k;
+        // the mirrored float4 of the same row: column group W4-1-tx, lanes reversed
+        const float4* srcf = reinterpret_cast<const float4*>(hmf + ((size_t)b * K + kk) * N) + ty * W4 + (W4 - 1 - tx);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) f[it] = ldg_stream(srcf + it * TPB);
+    }
+    // the two learnable scalars and their sigmoids: in the shadow of the tile loads
+    float a = 0.f, fw = 0.f;
+    if (warp == 0) {
+        if (refine) a = sigmoid_acc(__ldg(alpha_param));
+        if (want_off) {
+            fw = __ldg(fusion_weight);
+            if (flags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
         }
     }
+    if (FLIP) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const float4 g = rev4(f[it]);
+            v[it].x = (v[it].x + g.x) * 0.5f; v[it].y = (v[it].y + g.y) * 0.5f;
+            v[it].z = (v[it].z + g.z) * 0.5f; v[it].w = (v[it].w + g.w) * 0.5f;
+        }
+    }
+    float mw = -INFINITY;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) mw = fmaxf(mw, fmaxf(fmaxf(v[it].x, v[it].y), fmaxf(v[it].z, v[it].w)));
+    mw = warp_max(mw);
+
+    const float mlw = mw * kLog2e;
+    float Ej[4] = {0.f, 0.f, 0.f, 0.f};
+    float Yw = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const float e0 = ex2(fmaf(v[it].x, kLog2e, -mlw)), e1 = ex2(fmaf(v[it].y, kLog2e, -mlw));
+        const float e2 = ex2(fmaf(v[it].z, kLog2e, -mlw)), e3 = ex2(fmaf(v[it].w, kLog2e, -mlw));
+        Ej[0] += e0; Ej[1] += e1; Ej[2] += e2; Ej[3] += e3;
+        Yw = fmaf((float)(it * ROWS), (e0 + e1) + (e2 + e3), Yw);
+    }
+    const float Zt = (Ej[0] + Ej[1]) + (Ej[2] + Ej[3]);
+    float acc[4];
+    acc[0] = Zt;
+    acc[1] = fmaf((float)(tx << 2), Zt, fmaf(3.f, Ej[3], fmaf(2.f, Ej[2], Ej[1])));
+    acc[2] = fmaf((float)ty, Zt, Yw);
+    acc[3] = 0.f;
+    warp_scatter_sum<4>(acc, lane);                                  // lane l: warp total of value l >> 3
+    if ((lane & 7) == 0) reinterpret_cast<float*>(red + warp)[lane >> 3] = lane == 24 ? mw : acc[0];
+    __syncthreads();
+    // every warp: rescale the per-warp moments to the tile maximum and add them, in lane order (same bits everywhere)
+    const float4 r = lane < NW ? red[lane] : make_float4(0.f, 0.f, 0.f, -INFINITY);
+    float m = r.w;
+#pragma unroll
+    for (int o = NWP / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    m = __shfl_sync(0xffffffffu, m, 0);
+    const float sc = lane < NW ? ex2((r.w - m) * kLog2e) : 0.f;
+    float Z = r.x * sc, X = r.y * sc, Y = r.z * sc;
+#pragma unroll
+    for (int o = NWP / 2; o > 0; o >>= 1) {
+        Z += __shfl_xor_sync(0xffffffffu, Z, o);
+        X += __shfl_xor_sync(0xffffffffu, X, o);
+        Y += __shfl_xor_sync(0xffffffffu, Y, o);
+    }
+    // lanes 0..NWP-1 hold the totals; the window scatter below needs them in every lane
+    const float iZ = 1.0f / __shfl_sync(0xffffffffu, Z, 0);
+    float cx = __shfl_sync(0xffffffffu, X, 0) * iZ, cy = __shfl_sync(0xffffffffu, Y, 0) * iZ;
+
+    // torch.round is round-half-to-even == rintf in the default rounding mode
+    const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
+    const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
+    const int S = 2 * radius + 1;
+    int bx = 0, by = 0;
+    float pre = 0.f;
+    const float* off_tile = nullptr;
+    if (want_off && warp == 0) {
+        off_tile = off + (size_t)tile * 2 * N;
+        bx = (int)floorf(fminf(fmaxf(cx, 0.f), (float)(W - 1))) - 1;
+        by = (int)floorf(fminf(fmaxf(cy, 0.f), (float)(H - 1))) - 1;
+        const int t = lane & 15;
+        const int qx = min(max(bx + (t & 3), 0), W - 1), qy = min(max(by + (t >> 2), 0), H - 1);
+        pre = __ldg(off_tile + (lane >> 4) * N + qy * W + qx);
+    }
+    if (refine) {
+        const int x0 = tx << 2;
+        if (x0 + 3 >= px - radius && x0 <= px + radius) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int wy = it * ROWS + ty - py + radius;
+                if (wy >= 0 && wy < S) {
+                    const float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int wx = x0 + j - px + radius;
+                        if (wx >= 0 && wx < S) win[wy * S + wx] = e[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp != 0) return;
+
+    if (refine) {
+        // window cells outside the map were never written: validity comes from the coordinates
+        float vmax = -INFINITY;
+        for (int c = lane; c < S * S; c += 32) {
+            const int x = px - radius + c % S, y = py - radius + c / S;
+            if (x >= 0 && x < W && y >= 0 && y < H) vmax = fmaxf(vmax, win[c]);
+        }
+        vmax = warp_max(vmax);
+        float sw[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = lane; c < S * S; c += 32) {
+            const int x = px - radius + c % S, y = py - radius + c / S;
+            if (x >= 0 && x < W && y >= 0 && y < H) {
+                const float e = expf(win[c] - vmax);
+                sw[0] += e; sw[1] += e * (float)x; sw[2] += e * (float)y;
+            }
+        }
+        warp_scatter_sum<4>(sw, lane);
+        const float se = __shfl_sync(0xffffffffu, sw[0], 0), sx = __shfl_sync(0xffffffffu, sw[0], 8), sy = __shfl_sync(0xffffffffu, sw[0], 16);
+        const float al = __shfl_sync(0xffffffffu, a, 0);
+        cx = al * cx + (1.f - al) * (sx / se);
+        cy = al * cy + (1.f - al) * (sy / se);
+    }
+    if (want_off) {
+        const Bilinear bl = bilinear_setup(cx, cy, H, W);
+        float ox, oy;
+        const bool covered = bl.x0 >= bx && bl.x1 <= bx + 3 && bl.y0 >= by && bl.y1 <= by + 3;   // warp-uniform
+        if (covered) {
+            const int i00 = (bl.y0 - by) * 4 + (bl.x0 - bx), i01 = (bl.y0 - by) * 4 + (bl.x1 - bx);
+            const int i10 = (bl.y1 - by) * 4 + (bl.x0 - bx), i11 = (bl.y1 - by) * 4 + (bl.x1 - bx);
+            float t[2][4];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                t[c][0] = __shfl_sync(0xffffffffu, pre, c * 16 + i00);
+                t[c][1] = __shfl_sync(0xffffffffu, pre, c * 16 + i01) * bl.okx;
+                t[c][2] = __shfl_sync(0xffffffffu, pre, c * 16 + i10) * bl.oky;
+                t[c][3] = __shfl_sync(0xffffffffu, pre, c * 16 + i11) * (bl.okx * bl.oky);
+            }
+            ox = bl.w00 * t[0][0] + bl.w01 * t[0][1] + bl.w10 * t[0][2] + bl.w11 * t[0][3];
+            oy = bl.w00 * t[1][0] + bl.w01 * t[1][1] + bl.w10 * t[1][2] + bl.w11 * t[1][3];
+        } else {
+            ox = bilinear_read(off_tile, bl, W);
+            oy = bilinear_read(off_tile + N, bl, W);
+        }
+        const float fq = __shfl_sync(0xffffffffu, fw, 0);
+        cx += fq * ox;
+        cy += fq * oy;
+    }
+    if (lane == 0) {
+        coords[2 * tile] = cx; coords[2 * tile + 1] = cy;
+        scores[tile] = m;
+        if (centre) { centre[2 * tile] = px; centre[2 * tile + 1] = py; }
+    }
+}
+
+template <int W4, int ROWS, int NIT, bool FLIP, int MINB>
+static int launch_decode_tile(const float* hm, const float* hmf, const int32_t* perm, const float* off, const float* ap,
+                              const float* fw, int tiles, int K, int radius, unsigned flags, float* coords, float* scores,
+                              int32_t* centre, cudaStream_t s) {
+    decode_tile_kernel<W4, ROWS, NIT, FLIP, MINB><<<tiles, dim3(W4, ROWS), 0, s>>>(hm, hmf, perm, off, ap, fw, K, radius, flags, coords, scores, centre);
+    return check_launch("decode_tile_kernel");
 }
 
 // Thread count T (multiple of 32) with n4 == T*NITER, NITER <= 8; 0 if none.
@@ -108,6 +429,11 @@ static void launch_decode_t(int niter, int grid, int threads, cudaStream_t s,
                             const float* hm, const float* hmf, const int32_t* perm, const float* off,
                             const float* ap, const float* fw, int K, int H, int W, int radius, unsigned flags,
                             float* coords, float* scores, int32_t* centre) {
+    // the 64x48 tile (256 threads x 3 float4): hold the register count down so that 6 CTAs (no flip) fit an SM
+    if (niter == 3 && threads == 256) {
+        decode_kernel<3, FLIP, 256, FLIP ? 5 : 6><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre);
+        return;
+    }
 #define GBC_CASE(NI) case NI: decode_kernel<NI, FLIP><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre); break;
     switch (niter) {
         GBC_CASE(1) GBC_CASE(2) GBC_CASE(3) GBC_CASE(4) GBC_CASE(5) GBC_CASE(6) GBC_CASE(7) GBC_CASE(8)
@@ -119,6 +445,20 @@ static void launch_decode_t(int niter, int grid, int threads, cudaStream_t s,
 int launch_decode(const float* hm, const float* hmf, const int32_t* perm, const float* off,
                   const float* alpha_param, const float* fusion_weight, int B, int K, int H, int W,
                   int radius, unsigned flags, float* coords, float* scores, int32_t* centre, cudaStream_t stream) {
+    // GBCODEC_DECODE_KERNEL=generic: the shape-agnostic kernel for every shape (A/B measurements)
+    static const bool generic = [] { const char* e = getenv("GBCODEC_DECODE_KERNEL"); return e && !strcmp(e, "generic"); }();
+    const int grid_t = B * K;
+#define GBC_TILE(W4, ROWS, NIT, MB_PLAIN, MB_FLIP)                                                                          \
+    do {                                                                                                                  \
+        if (hmf) return launch_decode_tile<W4, ROWS, NIT, true, MB_FLIP>(hm, hmf, perm, off, alpha_param, fusion_weight, grid_t, K, radius, flags, coords, scores, centre, stream); \
+        return launch_decode_tile<W4, ROWS, NIT, false, MB_PLAIN>(hm, hmf, perm, off, alpha_param, fusion_weight, grid_t, K, radius, flags, coords, scores, centre, stream); \
+    } while (0)
+    if (!generic) {
+        if (H == 64 && W == 48) GBC_TILE(12, 16, 4, 8, 6);      // 192 threads, 16 px each
+        if (H == 96 && W == 72) GBC_TILE(18, 16, 6, 4, 3);      // 288 threads, 24 px each
+        if (H == 128 && W == 128) GBC_TILE(32, 16, 8, 2, 2);    // 512 threads, 32 px each
+    }
+#undef GBC_TILE
     int niter = 0;
     int threads = pick_threads((H * W) >> 2, &niter);
     if (!threads) threads = 256;

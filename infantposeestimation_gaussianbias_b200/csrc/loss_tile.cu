@@ -31,26 +31,7 @@
 namespace gbc {
 
 // ---- one-barrier block reductions -------------------------------------------------------
-// Warp stage: NV running sums per lane -> lane l holds the warp total of value l >> (5 - log2 NV)
-// (halving butterfly: each step exchanges half of the remaining values, so 8 values cost
-// 4+2+1+2 shuffles instead of 40).
-template <int NV>
-__device__ __forceinline__ void warp_scatter_sum(float (&v)[NV]) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int n = NV, o = 16; n > 1; n >>= 1, o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int j = 0; j < n / 2; ++j) {
-            const float keep = up ? v[j + n / 2] : v[j];
-            const float send = up ? v[j] : v[j + n / 2];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-#pragma unroll
-    for (int o = 16 / NV; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-}
-
+// Warp stage: warp_scatter_sum (common.cuh).
 template <int NV> struct Log2 { static constexpr int value = 1 + Log2<NV / 2>::value; };
 template <> struct Log2<1> { static constexpr int value = 0; };
 

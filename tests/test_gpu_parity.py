@@ -175,7 +175,7 @@ def run_loss(gb, cfg, batch, *, on_the_fly, with_grads=True, utw=True, denoms=No
         dev(batch["weight"] if not on_the_fly else batch["vis"][..., None]), dev(batch["kps"]),
         denoms, grad_scale, float(cfg.input_size[0]), float(cfg.input_size[1]), list(lambdas),
         cfg.sigma, cfg.sigma, utw, pairs, with_grads, decode,
-        torch.tensor(0.5).cuda() if decode else None, torch.tensor(0.6224593312018546).cuda() if decode else None, 2, 3)
+        torch.tensor(0.5).cuda() if decode else None, torch.tensor(0.6224593312018546).cuda() if decode else None, 2, 3)[:6]
 
 
 @pytest.mark.parametrize("name", NAMES)

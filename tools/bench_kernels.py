@@ -79,7 +79,19 @@ loss = lambda target, grads, dec: ops.fusion_loss(d["hm"], d["off"], d["var"], t
 report("loss step (fused, on-the-fly target)", "cfg1 64x48 B=1024", B * K, 24 * n, timeit(lambda: loss(None, True, True)))
 report("loss fwd+bwd (target from HBM)", "cfg1 64x48 B=1024", B * K, 28 * n, timeit(lambda: loss(tgt, True, False)))
 report("loss fwd only (on-the-fly target)", "cfg1 64x48 B=1024", B * K, 8 * n, timeit(lambda: loss(None, False, False)))
-del d, tgt, wgt
+# second-generation family on the same shapes
+pred = d["hm"].abs().add_(0.01)
+wts = [1.0, 0.15, 0.6]
+comb = lambda grads: ops.combined_loss(pred, tgt, wgt, d["kps"], None, d["kps"], None, 0, N.CRIT_MSE, N.CRIT_SMOOTHL1, True, 1.0, 1.2, 0.5, wts, True, grads)
+report("genb_tile_kernel CombinedLoss fwd+bwd", "cfg1 64x48 B=1024", B * K, 12 * n, timeit(lambda: comb(True)))
+report("genb_tile_kernel CombinedLoss fwd", "cfg1 64x48 B=1024", B * K, 8 * n, timeit(lambda: comb(False)))
+cen = torch.rand(B, 2, device=dev) * 300 + 100
+scl = torch.rand(B, 2, device=dev) * 200 + 150
+report("postprocess_kernel (whole pipeline)", "cfg1 64x48 B=1024", B * K, 4 * n,
+       timeit(lambda: ops.postprocess(pred, d["kps"], cen, scl, N.ARGMAX_TAYLOR, True, 256.0, 5, True, 0.3, True, 256.0, 256.0)))
+report("encode_genb_kernel clipped", "cfg1 64x48 B=1024", B * K, 4 * n, timeit(lambda: ops.encode_mode(d["kps"], d["vis"], H, W, 192.0, 256.0, 2.0, N.ENCODE_PATCH_CLIPPED)))
+report("encode_genb_kernel dense", "cfg1 64x48 B=1024", B * K, 4 * n, timeit(lambda: ops.encode_mode(d["kps"], d["vis"], H, W, 192.0, 256.0, 2.0, N.ENCODE_DENSE)))
+del d, tgt, wgt, pred
 torch.cuda.empty_cache()
 
 # configs[2]: 96x72 decode + flip + offsets, B=4096
