@@ -26,6 +26,7 @@
 //
 // Algorithmic HBM bytes per tile: read hm, var (8N); write d_hm, d_var, d_off (16N).
 #include "loss_common.cuh"
+#include "f32x2.cuh"
 #include <stdlib.h>
 
 namespace gbc {
@@ -248,35 +249,39 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     };
 
     // ---- pass B: softmax moments, sigmoid mass, squared error ------------------------------------
+    // Pixel arithmetic runs on packed pairs (f32x2.cuh): (x, y) and (z, w) of the float4.
+    const f2 kL2E = splat2(kLog2e), kNL2E = splat2(-kLog2e), kNML = splat2(-ml), kOne = splat2(1.f);
     float r8[8];
     {
-        float Ej[4] = {0.f, 0.f, 0.f, 0.f};
-        float Yw = 0.f, Ssum_t = 0.f, mse = 0.f;
+        f2 E01 = splat2(0.f), E23 = splat2(0.f), S2 = splat2(0.f), mse2 = splat2(0.f);
+        float Yw = 0.f;
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
-            const float4 o = own4(it);
-            const float hv[4] = {o.x, o.y, o.z, o.w};
-            float e[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { e[j] = ex2(fmaf(hv[j], kLog2e, -ml)); Ej[j] += e[j]; }
-            if (CE) Es[it * TPB + tid] = make_float4(e[0], e[1], e[2], e[3]);
-            Yw = fmaf((float)(it * ROWS), (e[0] + e[1]) + (e[2] + e[3]), Yw);
+            const f4 hv = as_f4(own4(it));
+            const f2 t01 = fma2(hv.a, kL2E, kNML), t23 = fma2(hv.b, kL2E, kNML);
+            const f2 e01 = pack2(ex2(lo2(t01)), ex2(hi2(t01))), e23 = pack2(ex2(lo2(t23)), ex2(hi2(t23)));
+            E01 = add2(E01, e01); E23 = add2(E23, e23);
+            if (CE) Es[it * TPB + tid] = as_float4(f4{e01, e23});
+            Yw = fmaf((float)(it * ROWS), hsum2(add2(e01, e23)), Yw);
             if (heavy) {
-                float s[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) s[j] = sigmoid_fast(hv[j]);
-                if (CS) Ss[it * TPB + tid] = make_float4(s[0], s[1], s[2], s[3]);
-                Ssum_t += (s[0] + s[1]) + (s[2] + s[3]);
-                const float4 t = target4(it);
-                const float d0 = hv[0] - t.x, d1 = hv[1] - t.y, d2 = hv[2] - t.z, d3 = hv[3] - t.w;
-                mse += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+                const f2 u01 = mul2(hv.a, kNL2E), u23 = mul2(hv.b, kNL2E);
+                const f2 g01 = add2(pack2(ex2(lo2(u01)), ex2(hi2(u01))), kOne), g23 = add2(pack2(ex2(lo2(u23)), ex2(hi2(u23))), kOne);
+                const f2 s01 = pack2(rcp(lo2(g01)), rcp(hi2(g01))), s23 = pack2(rcp(lo2(g23)), rcp(hi2(g23)));
+                if (CS) Ss[it * TPB + tid] = as_float4(f4{s01, s23});
+                S2 = add2(S2, add2(s01, s23));
+                const f4 tv = as_f4(target4(it));
+                const f2 d01 = sub2(hv.a, tv.a), d23 = sub2(hv.b, tv.b);
+                mse2 = fma2(d01, d01, mse2);
+                mse2 = fma2(d23, d23, mse2);
             }
         }
+        float Ej[4];
+        unpack2(E01, Ej[0], Ej[1]); unpack2(E23, Ej[2], Ej[3]);
         const float Zt = (Ej[0] + Ej[1]) + (Ej[2] + Ej[3]);
         r8[0] = Zt;
         r8[1] = fmaf(fx0, Zt, fmaf(3.f, Ej[3], fmaf(2.f, Ej[2], Ej[1])));
         r8[2] = fmaf(fty, Zt, Yw);
-        r8[3] = Ssum_t; r8[4] = mse; r8[5] = vsum; r8[6] = 0.f; r8[7] = 0.f;
+        r8[3] = hsum2(S2); r8[4] = hsum2(mse2); r8[5] = vsum; r8[6] = 0.f; r8[7] = 0.f;
     }
     const float acc8 = block_sum1<8, NW>(r8, red1);
     const float iZ = rcp(lane_value<8>(acc8, 0));
@@ -362,36 +367,41 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         asm volatile("" : "+l"(src));                 // keep the pointer in registers instead of re-deriving it per row
         const float4* srcc = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         if (CQ) cp_async_wait_all();                  // this thread's slots hold partner `cur`
-        float Sj = 0.f, M = 0.f;
+        f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
             const float4 q4 = CQ ? Qs[it * TPB + tid] : ldg_stream(srcc + it * TPB);
             const float4 o = own4(it);
-            const float hv[4] = {o.x, o.y, o.z, o.w};
-            const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
-            float sk[4], sq[4];
+            const f4 hv = as_f4(o), qv = as_f4(q4);
+            float sk[4];
             if (CS) { const float4 s4 = Ss[it * TPB + tid]; sk[0] = s4.x; sk[1] = s4.y; sk[2] = s4.z; sk[3] = s4.w; }
             else {
+                const float hh[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) sk[jj] = sigmoid_fast(hv[jj]);
+                for (int jj = 0; jj < 4; ++jj) sk[jj] = sigmoid_fast(hh[jj]);
             }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) sq[jj] = sigmoid_fast(qq[jj]);
+            const f2 u01 = mul2(qv.a, kNL2E), u23 = mul2(qv.b, kNL2E);
+            const f2 g01 = add2(pack2(ex2(lo2(u01)), ex2(hi2(u01))), kOne), g23 = add2(pack2(ex2(lo2(u23)), ex2(hi2(u23))), kOne);
+            float sq[4] = {rcp(lo2(g01)), rcp(hi2(g01)), rcp(lo2(g23)), rcp(hi2(g23))};
             // the slot has been consumed (its value went through the sigmoid): refill it with the next partner
             if (CQ && nxt >= 0) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+            // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
+            const f2 d01 = sub2(hv.a, qv.a), d23 = sub2(hv.b, qv.b);
+            const float d[4] = {lo2(d01), hi2(d01), lo2(d23), hi2(d23)};
             unsigned tw = 0u;
+            float sel[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                Sj += sq[jj];
-                // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
-                const float d = hv[jj] - qq[jj];
-                const bool own_smaller = d < 0.f;
-                M += own_smaller ? sk[jj] : sq[jj];
+                const bool own_smaller = d[jj] < 0.f;
+                sel[jj] = own_smaller ? sk[jj] : sq[jj];
                 if (own_smaller) tw |= 4u << (8 * jj);
-                mind = fminf(mind, fabsf(d));
+                mind = fminf(mind, fabsf(d[jj]));
             }
+            Sj2 = add2(Sj2, add2(pack2(sq[0], sq[1]), pack2(sq[2], sq[3])));
+            M2 = add2(M2, add2(pack2(sel[0], sel[1]), pack2(sel[2], sel[3])));
             if (ROLL) Ws[it * TPB + tid] |= tw << cur; else words[it] |= tw << cur;
         }
+        const float Sj = hsum2(Sj2), M = hsum2(M2);
         if (CQ) cp_async_commit();
 #pragma unroll
         for (int s = 0; s < 4; ++s) if (cur == s) { r16[6 + 2 * s] = Sj; r16[7 + 2 * s] = M; }
@@ -420,41 +430,42 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
     for (int j = 0; j < 4; ++j) { dxj[j] = (fx0 + (float)j) - cx; dx2j[j] = dxj[j] * dxj[j]; }
     const float dy0 = fty - cy;
+    // the entropy derivative is parked negated: an = ln2 * lg2(p + eps) + p / (p + eps) = -a
     {
-        float A1 = 0.f, A2 = 0.f, Ry = 0.f, Ry2 = 0.f;
-        float Rj[4] = {0.f, 0.f, 0.f, 0.f};
+        const f2 kIZ = splat2(iZ), kEps2 = splat2(kEps), kLn2v = splat2(kLn2);
+        f2 A1 = splat2(0.f), A2 = splat2(0.f), R01 = splat2(0.f), R23 = splat2(0.f);
+        float Ry = 0.f, Ry2 = 0.f;
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
             const float4 o = own4(it);
-            const float hv[4] = {o.x, o.y, o.z, o.w};
-            float e[4];
-            if (CE) { const float4 q = Es[it * TPB + tid]; e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w; }
+            const f4 hv = as_f4(o);
+            f2 e01, e23;
+            if (CE) { const f4 q = as_f4(Es[it * TPB + tid]); e01 = q.a; e23 = q.b; }
             else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) e[j] = ex2(fmaf(hv[j], kLog2e, -ml));
+                const f2 t01 = fma2(hv.a, kL2E, kNML), t23 = fma2(hv.b, kL2E, kNML);
+                e01 = pack2(ex2(lo2(t01)), ex2(hi2(t01))); e23 = pack2(ex2(lo2(t23)), ex2(hi2(t23)));
             }
-            float p[4], a[4], r[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                p[j] = e[j] * iZ;
-                const float u = p[j] + kEps;
-                const float l = lg2(u), rc = rcp(u);
-                A1 = fmaf(p[j], l, A1);
-                const float prc = p[j] * rc;
-                A2 = fmaf(p[j], prc, A2);
-                a[j] = fmaf(-kLn2, l, -prc);
-                r[j] = fmaxf(hv[j], 0.f);
-                Rj[j] += r[j];
-            }
-            if (CE) Es[it * TPB + tid] = make_float4(p[0], p[1], p[2], p[3]);
-            if (CA) As[it * TPB + tid] = make_float4(a[0], a[1], a[2], a[3]);
-            if (AQ) Qs[it * TPB + tid] = make_float4(a[0], a[1], a[2], a[3]);
-            const float rs = (r[0] + r[1]) + (r[2] + r[3]);
+            const f2 p01 = mul2(e01, kIZ), p23 = mul2(e23, kIZ);
+            const f2 u01 = add2(p01, kEps2), u23 = add2(p23, kEps2);
+            const f2 l01 = pack2(lg2(lo2(u01)), lg2(hi2(u01))), l23 = pack2(lg2(lo2(u23)), lg2(hi2(u23)));
+            const f2 c01 = pack2(rcp(lo2(u01)), rcp(hi2(u01))), c23 = pack2(rcp(lo2(u23)), rcp(hi2(u23)));
+            A1 = fma2(p01, l01, A1); A1 = fma2(p23, l23, A1);
+            const f2 prc01 = mul2(p01, c01), prc23 = mul2(p23, c23);
+            A2 = fma2(p01, prc01, A2); A2 = fma2(p23, prc23, A2);
+            const f2 an01 = fma2(kLn2v, l01, prc01), an23 = fma2(kLn2v, l23, prc23);
+            const f2 r01 = pack2(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f)), r23 = pack2(fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            R01 = add2(R01, r01); R23 = add2(R23, r23);
+            if (CE) Es[it * TPB + tid] = as_float4(f4{p01, p23});
+            if (CA) As[it * TPB + tid] = as_float4(f4{an01, an23});
+            if (AQ) Qs[it * TPB + tid] = as_float4(f4{an01, an23});
+            const float rs = hsum2(add2(r01, r23));
             const float dy = dy0 + (float)(it * ROWS);
             Ry = fmaf(dy, rs, Ry);
             Ry2 = fmaf(dy * dy, rs, Ry2);
         }
-        r16[0] = A1; r16[1] = A2;
+        float Rj[4];
+        unpack2(R01, Rj[0], Rj[1]); unpack2(R23, Rj[2], Rj[3]);
+        r16[0] = hsum2(A1); r16[1] = hsum2(A2);
         r16[2] = fmaf(dx2j[0], Rj[0], fmaf(dx2j[1], Rj[1], fmaf(dx2j[2], Rj[2], fmaf(dx2j[3], Rj[3], Ry2))));
         r16[3] = fmaf(dxj[0], Rj[0], fmaf(dxj[1], Rj[1], fmaf(dxj[2], Rj[2], dxj[3] * Rj[3])));
         r16[4] = Ry;
@@ -609,52 +620,55 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
 
     // ---- pass D: the heatmap gradient ----------------------------------------------------------------------
-    float basej[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) basej[j] = dxj[j] * fxx;
+    // g = c1 (h - t) + p (c6 (a - pa) + (x - cx) Fx + (y - cy) Fy) + [h > 0] (c4 ((x-cx)^2 + (y-cy)^2) + k4) + overlap
+    // with an = -a parked by pass C: c6 (a - pa) = -c6 (an + pa)
+    {
+        const f2 kIZ = splat2(iZ), kEps2 = splat2(kEps), kLn2v = splat2(kLn2);
+        const f2 kC1 = splat2(c1), kNC6 = splat2(-c6), kPa = splat2(pa_), kC4 = splat2(c4), kK4 = splat2(k4);
+        const f2 base01 = pack2(dxj[0] * fxx, dxj[1] * fxx), base23 = pack2(dxj[2] * fxx, dxj[3] * fxx);
+        const f2 dx2_01 = pack2(dx2j[0], dx2j[1]), dx2_23 = pack2(dx2j[2], dx2j[3]);
 #pragma unroll UNR
-    for (int it = 0; it < NIT; ++it) {
-        const float4 o = own4(it);
-        const float hv[4] = {o.x, o.y, o.z, o.w};
-        float p[4], a[4];
-        if (CE) { const float4 q = Es[it * TPB + tid]; p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) p[j] = ex2(fmaf(hv[j], kLog2e, -ml)) * iZ;
-        }
-        if (CA || AQ) { const float4 q = CA ? As[it * TPB + tid] : Qs[it * TPB + tid]; a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w; }
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float u = p[j] + kEps; a[j] = fmaf(-kLn2, lg2(u), -p[j] * rcp(u)); }
-        }
-        const float4 t = target4(it);
-        const float tv[4] = {t.x, t.y, t.z, t.w};
-        const float dy = dy0 + (float)(it * ROWS);
-        const float dy2 = dy * dy, fyd = dy * fyy;
-        float out[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float g = c1 * (hv[j] - tv[j]);
-            g = fmaf(p[j], fmaf(c6, a[j] - pa_, basej[j] + fyd), g);
-            const float rterm = fmaf(c4, dx2j[j] + dy2, k4);
-            if (hv[j] > 0.f) g += rterm;
-            out[j] = g;
-        }
-        if (g_live) {
-            float sv[4];
-            if (CS) { const float4 s4 = Ss[it * TPB + tid]; sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w; }
+        for (int it = 0; it < NIT; ++it) {
+            const float4 o = own4(it);
+            const f4 hv = as_f4(o);
+            f2 p01, p23, an01, an23;
+            if (CE) { const f4 q = as_f4(Es[it * TPB + tid]); p01 = q.a; p23 = q.b; }
             else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sv[j] = sigmoid_fast(hv[j]);
+                const f2 t01 = fma2(hv.a, kL2E, kNML), t23 = fma2(hv.b, kL2E, kNML);
+                p01 = mul2(pack2(ex2(lo2(t01)), ex2(hi2(t01))), kIZ); p23 = mul2(pack2(ex2(lo2(t23)), ex2(hi2(t23))), kIZ);
             }
-            const unsigned wd = ROLL ? Ws[it * TPB + tid] : words[it];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float G = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lutw) + ((wd >> (8 * j)) & 0xFFu));
-                out[j] = fmaf(G, fmaf(-sv[j], sv[j], sv[j]), out[j]);
+            if (CA || AQ) { const f4 q = as_f4(CA ? As[it * TPB + tid] : Qs[it * TPB + tid]); an01 = q.a; an23 = q.b; }
+            else {
+                const f2 u01 = add2(p01, kEps2), u23 = add2(p23, kEps2);
+                const f2 l01 = pack2(lg2(lo2(u01)), lg2(hi2(u01))), l23 = pack2(lg2(lo2(u23)), lg2(hi2(u23)));
+                const f2 c01 = pack2(rcp(lo2(u01)), rcp(hi2(u01))), c23 = pack2(rcp(lo2(u23)), rcp(hi2(u23)));
+                an01 = fma2(kLn2v, l01, mul2(p01, c01)); an23 = fma2(kLn2v, l23, mul2(p23, c23));
             }
+            const f4 tv = as_f4(target4(it));
+            const float dy = dy0 + (float)(it * ROWS);
+            const f2 fyd = splat2(dy * fyy), dy2 = splat2(dy * dy);
+            f2 g01 = mul2(kC1, sub2(hv.a, tv.a)), g23 = mul2(kC1, sub2(hv.b, tv.b));
+            g01 = fma2(p01, fma2(kNC6, add2(an01, kPa), add2(base01, fyd)), g01);
+            g23 = fma2(p23, fma2(kNC6, add2(an23, kPa), add2(base23, fyd)), g23);
+            // relu branch of the variance term: rterm * [h > 0] (the mask is exactly 0 or 1)
+            const f2 rt01 = fma2(kC4, add2(dx2_01, dy2), kK4), rt23 = fma2(kC4, add2(dx2_23, dy2), kK4);
+            const f2 m01 = pack2(o.x > 0.f ? 1.f : 0.f, o.y > 0.f ? 1.f : 0.f), m23 = pack2(o.z > 0.f ? 1.f : 0.f, o.w > 0.f ? 1.f : 0.f);
+            g01 = fma2(rt01, m01, g01); g23 = fma2(rt23, m23, g23);
+            if (g_live) {
+                f2 s01, s23;
+                if (CS) { const f4 q = as_f4(Ss[it * TPB + tid]); s01 = q.a; s23 = q.b; }
+                else { s01 = pack2(sigmoid_fast(o.x), sigmoid_fast(o.y)); s23 = pack2(sigmoid_fast(o.z), sigmoid_fast(o.w)); }
+                const unsigned wd = ROLL ? Ws[it * TPB + tid] : words[it];
+                float G[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    G[j] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lutw) + ((wd >> (8 * j)) & 0xFFu));
+                const f2 kNeg = splat2(-1.f);
+                g01 = fma2(pack2(G[0], G[1]), fma2(mul2(s01, kNeg), s01, s01), g01);
+                g23 = fma2(pack2(G[2], G[3]), fma2(mul2(s23, kNeg), s23, s23), g23);
+            }
+            stg_stream(gh4 + it * TPB, as_float4(f4{g01, g23}));
         }
-        stg_stream(gh4 + it * TPB, make_float4(out[0], out[1], out[2], out[3]));
     }
 
     // rare: a logit of this thread equals its partner's — ATen's minimum splits that gradient evenly.
