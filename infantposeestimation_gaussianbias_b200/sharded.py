@@ -132,3 +132,41 @@ def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
     base, extra = divmod(B, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedCombinedLoss:
+    """CombinedLoss (models/losses.py:205-290) for a rank that holds a shard of the global batch.  Its terms
+    are plain means over the batch, so the only global quantity is the batch size: every rank runs the
+    one-pass kernel with `norm_batch` = global batch (its gradients are then exactly the global-batch
+    gradients restricted to the shard) and the five scalars are summed over the ranks for reporting.
+
+    `local_loss(predictions, targets, norm_batch)` is the stand-in hook for the CPU (gloo) test."""
+
+    def __init__(self, config, process_group=None, local_loss: Optional[Callable] = None):
+        self.process_group = process_group
+        self._local_loss = local_loss
+        if local_loss is None:
+            from .losses import CombinedLoss
+            self.impl = CombinedLoss(config)
+
+    def global_batch(self, local_batch: int, device) -> int:
+        if not (dist.is_available() and dist.is_initialized()):
+            return local_batch
+        n = torch.tensor([local_batch], dtype=torch.int64, device=device)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.process_group)
+        return int(n.item())
+
+    def __call__(self, predictions: Dict[str, Tensor], targets: Dict[str, Tensor], global_batch: Optional[int] = None):
+        some = next(iter(predictions.values()))
+        if global_batch is None:
+            global_batch = self.global_batch(some.shape[0], some.device)      # pass it in to avoid this host read
+        if self._local_loss is not None:
+            total, parts = self._local_loss(predictions, targets, global_batch)
+        else:
+            total, parts = self.impl(predictions, targets, norm_batch=global_batch)
+        keys = sorted(parts)
+        stacked = torch.stack([parts[k].detach() for k in keys])
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(stacked, op=dist.ReduceOp.SUM, group=self.process_group)
+        out = {k: parts[k] + (stacked[i] - parts[k].detach()) for i, k in enumerate(keys)}    # value global, gradient local
+        return out["total"], out

@@ -94,3 +94,66 @@ def test_shard_bounds_cover_the_batch_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# second generation: CombinedLoss sharded over the batch
+# ------------------------------------------------------------------------------------------------
+def _genb_worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from infantposeestimation_gaussianbias_b200.sharded import ShardedCombinedLoss, shard_bounds
+        from oracle import genb
+        cfg = synth.CONFIGS["w32_256x192"]
+        batch = synth.make_batch(cfg, seed=4, B=B)
+        ex = synth.make_genb_extras(cfg, batch, seed=4)
+        lo, hi = shard_bounds(B, rank, world)
+
+        def local_loss(predictions, targets, norm_batch):
+            # the oracle's means run over the local batch: rescale to the global one, as norm_batch does in the kernel
+            total, parts = genb.combined_loss(predictions, targets, 1.2, 0.15, 0.6)
+            f = predictions["heatmaps"].shape[0] / norm_batch
+            return total * f, {k: v * f for k, v in parts.items()}
+
+        loss = ShardedCombinedLoss(None, local_loss=local_loss)
+        p = torch.from_numpy(ex["pred"][lo:hi].copy()).requires_grad_(True)
+        c = torch.from_numpy(ex["coords"][lo:hi].copy()).requires_grad_(True)
+        total, parts = loss({"heatmaps": p, "coords": c},
+                            {"heatmaps": torch.from_numpy(batch["target"][lo:hi].copy()), "coords": torch.from_numpy(ex["target_coords"][lo:hi].copy()),
+                             "weights": torch.from_numpy(batch["weight"][lo:hi].copy())})
+        total.backward()
+        q.put((rank, lo, hi, {k: float(v) for k, v in parts.items()}, p.grad.numpy(), c.grad.numpy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_combined_loss_equals_global_batch():
+    from oracle import genb
+    B, world = 5, 2                      # uneven shards on purpose
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_genb_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=4, B=B)
+    ex = synth.make_genb_extras(cfg, batch, seed=4)
+    p = torch.from_numpy(ex["pred"]).requires_grad_(True)
+    c = torch.from_numpy(ex["coords"]).requires_grad_(True)
+    total, parts = genb.combined_loss({"heatmaps": p, "coords": c}, {"heatmaps": torch.from_numpy(batch["target"]), "coords": torch.from_numpy(ex["target_coords"]),
+                                                                      "weights": torch.from_numpy(batch["weight"])}, 1.2, 0.15, 0.6)
+    total.backward()
+    for rank, lo, hi, losses, gp, gc in got:
+        for k, v in parts.items():
+            np.testing.assert_allclose(losses[k], float(v), rtol=1e-5)
+        np.testing.assert_allclose(gp, p.grad.numpy()[lo:hi], rtol=1e-5, atol=1e-7 * np.abs(p.grad.numpy()).max())
+        np.testing.assert_allclose(gc, c.grad.numpy()[lo:hi], rtol=1e-5, atol=1e-9)
