@@ -104,7 +104,7 @@ def test_flip_decode_full_size_properties(gb):
     assert torch.isfinite(c).all()
     # (1) a strided sample against the oracle (flip average -> fusion decode)
     idx = torch.arange(0, B, 257, device="cuda")
-    avg = oc.flip_average(d["hm"][idx].cpu(), d["hmf"][idx].cpu(), d["perm"].cpu().numpy())
+    avg = oc.flip_average(d["hm"][idx].cpu(), d["hmf"][idx].cpu())          # COCO flip pairs = synth.flip_perm
     want_c, want_s = oc.fusion_decode(avg, d["off"][idx].cpu(), ALPHA, FW)
     frac = np.abs(oc.soft_argmax(avg)[0].numpy() % 1 - 0.5)
     ok = (frac > 1e-3).all(-1)

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # One gpurun call: GPU parity tests, smoke, bench, launch list, one full ncu capture of the loss kernel.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [tests|bench|ncu|all]'
+#   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [tests|bench|kernels|ncu|all]'
 # Everything lands in gpurun_out/.
 set -u
 what="${1:-all}"
@@ -18,6 +18,12 @@ if [[ $what == all || $what == bench ]]; then
   cat $out/bench.json
   python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref.json 2>> $out/bench.err || rc=1
   cat $out/bench_ref.json
+fi
+if [[ $what == all || $what == kernels ]]; then
+  timeout 300 python tools/bench_kernels.py > $out/kernels.log 2>&1 || rc=1
+  timeout 200 python tools/bench_decode.py > $out/decode.log 2>&1 || rc=1
+  timeout 60 tools/bench_mix 17408 > $out/mix.log 2>&1 || rc=1
+  tail -3 $out/kernels.log
 fi
 if [[ $what == all || $what == ncu ]]; then
   CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
