@@ -754,6 +754,10 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
             case 7: return launch_tile_tm<12, 8, 8, false, true, false, 6, true, true>(P, A, s, e0, e1);    // 96 threads, 32 px each, rolled; H,S,Q
             case 8: return launch_tile_tm<12, 8, 8, false, false, false, 8, true, false>(P, A, s, e0, e1);  // 96 threads, registers; Q only
             case 9: return launch_tile_tm<12, 8, 8, false, true, false, 8, true, false>(P, A, s, e0, e1);   // 96 threads, registers; S,Q; 8 CTAs
+            case 10: return launch_tile_tm<12, 16, 4, false, false, false, 5, false, true>(P, A, s, e0, e1); // rolled; own tile only in smem, 5 CTAs
+            case 11: return launch_tile_tm<12, 16, 4, false, false, false, 6, false, true>(P, A, s, e0, e1); // ... 6 CTAs (56 registers)
+            case 12: return launch_tile_tm<12, 16, 4, false, false, false, 7, false, true>(P, A, s, e0, e1); // ... 7 CTAs (48 registers)
+            case 13: return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // H,S; 6 CTAs
             default: break;
         }
     }
@@ -762,13 +766,23 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
         if (tile_variant() == 1) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);               // registers, 288 threads
         if (tile_variant() == 2) return launch_tile_tm<18, 32, 3, false, true, false, 2, true, true>(P, A, s, e0, e1);  // rolled, 576 threads, 12 px each
         if (tile_variant() == 3) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1); // rolled, 288 threads, no partner slot: 3 CTAs
-        return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);                          // rolled, 288 threads, 24 px each
+        if (tile_variant() == 4) return launch_tile_tm<18, 16, 6, false, false, false, 3, false, true>(P, A, s, e0, e1); // rolled, 288 threads, own tile only in smem
+        if (tile_variant() == 5) return launch_tile_tm<18, 32, 3, false, true, false, 2, false, true>(P, A, s, e0, e1);  // rolled, 576 threads, no partner slot
+        if (tile_variant() == 6) return launch_tile_tm<18, 16, 6, false, false, false, 4, false, true>(P, A, s, e0, e1); // own tile only, 4 CTAs (56 registers)
+        if (tile_variant() == 7) return launch_tile_tm<18, 16, 6, false, true, false, 4, false, true>(P, A, s, e0, e1);  // H,S, no partner slot, 4 CTAs
+        if (tile_variant() == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);  // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
+        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1);                         // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.666 ms)
     }
     if (P.H == 128 && P.W == 128) {
         if (tile_variant() == 1) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);              // registers, 512 threads
         if (tile_variant() == 2) return launch_tile_tm<32, 32, 4, false, true, false, 1, true, true>(P, A, s, e0, e1);  // rolled, 1024 threads, 16 px each
         if (tile_variant() == 3) return launch_tile_tm<32, 16, 8, false, true, false, 1, false, true>(P, A, s, e0, e1); // rolled, 512 threads, no partner slot
-        return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);                          // rolled, 512 threads, 32 px each
+        if (tile_variant() == 4) return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true>(P, A, s, e0, e1); // rolled, 512 threads, own tile only in smem: 2 CTAs
+        if (tile_variant() == 5) return launch_tile_tm<32, 32, 4, false, true, false, 1, false, true>(P, A, s, e0, e1);  // rolled, 1024 threads, no partner slot
+        if (tile_variant() == 6) return launch_tile_tm<32, 8, 16, false, false, false, 4, false, true>(P, A, s, e0, e1); // 256 threads, 64 px each, own tile only: 2-3 CTAs by smem
+        if (tile_variant() == 7) return launch_tile_tm<32, 16, 8, false, false, false, 2, true, true>(P, A, s, e0, e1);  // 512 threads, H,Q
+        if (tile_variant() == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);  // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
+        return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true>(P, A, s, e0, e1);                        // rolled, 512 threads, 32 px each; own tile only in smem: 2 CTAs (1.137 ms)
     }
     return 1;
 }
