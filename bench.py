@@ -175,7 +175,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -326,7 +326,7 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu:
-        v, cores, times = cpu_step_rate(sample_B=32, min_seconds=10.0, max_reps=20)
+        v, cores, times = cpu_step_rate(sample_B=32, min_seconds=10.0, max_reps=400)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"32 images x {K} heatmaps of the same workload, median of {len(times)} passes ({sum(times):.1f} s of CPU work)"}
 
@@ -340,10 +340,20 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         "total_loss": float(res[0][6].item()),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to
+    the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -360,6 +370,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.out = _json_only_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
