@@ -17,7 +17,8 @@
  *   - return value: GBCODEC_OK (0) or a negative gbcodec_status.  Nothing throws.
  *     gbcodec_last_error() returns a thread-local description of the last failure.
  *   - W must be a multiple of 4 and every tensor 16-byte aligned (128-bit
- *     loads); 1 <= K <= GBCODEC_MAX_K; H*W <= GBCODEC_MAX_TILE.
+ *     loads); 1 <= K <= GBCODEC_MAX_K; H*W <= GBCODEC_MAX_TILE (the six-term loss
+ *     keeps two tiles in shared memory: H*W <= 28 000 there, GBCODEC_ERR_BAD_SHAPE above).
  *   - there is no CPU fallback anywhere in this library.
  */
 #ifndef GBCODEC_H_
