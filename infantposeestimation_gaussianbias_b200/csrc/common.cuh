@@ -75,6 +75,28 @@ __device__ __forceinline__ void warp_scatter_sum(float (&v)[NV], int lane) {
 template <int NV>
 __device__ __forceinline__ void warp_scatter_sum(float (&v)[NV]) { warp_scatter_sum<NV>(v, threadIdx.x & 31); }   // 1-D blocks
 
+// Block-wide sums of NV (power of two, <= 16) values with ONE barrier and a run-time warp count: halving
+// butterfly inside the warp, then every warp adds the per-warp partials itself in a fixed order (deterministic,
+// the same bits in every thread).  `red` holds nw * NV floats and must not be in use by a previous reduction
+// that some warp may still be reading (alternate two buffers).  Results are written back into v[0..NV).
+template <int NV>
+__device__ __forceinline__ void block_sum_1bar(float (&v)[NV], float* red, int nw, int lane, int warp) {
+    constexpr int SUB = 32 / NV;                       // lanes that share one value after the warp stage
+    int sh = 0;
+#pragma unroll
+    for (int s = SUB; s > 1; s >>= 1) ++sh;            // log2(SUB)
+    warp_scatter_sum<NV>(v, lane);
+    const int idx = lane >> sh, q = lane & (SUB - 1);
+    if (q == 0) red[warp * NV + idx] = v[0];
+    __syncthreads();
+    float acc = 0.f;
+    for (int ww = q; ww < nw; ww += SUB) acc += red[ww * NV + idx];
+#pragma unroll
+    for (int o = SUB / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __shfl_sync(0xffffffffu, acc, k << sh);
+}
+
 // (value, index) maximum; on equal values the smaller index wins — torch.max's
 // first-occurrence rule (pose_estimator.py:352).
 __device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi) {

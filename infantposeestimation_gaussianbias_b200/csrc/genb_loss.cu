@@ -65,12 +65,13 @@ __device__ __forceinline__ float crit_slope(int crit, float d) {
 }
 
 // ---- per-tile heatmap + morphology terms ------------------------------------------------------
-template <int NITER>
-__global__ void __launch_bounds__(1024)
+template <int NITER, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ GenbArgs A) {
-    __shared__ float scratch[8 * 32 + 8];
+    __shared__ float red_a[8 * 32], red_b[4 * 32];
     if (A.plan && *A.plan == 0) return;               // stored gradients already right
     const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n4 = (P.H * P.W) >> 2, w4 = P.W >> 2;
     const float4* p4 = reinterpret_cast<const float4*>(A.pred) + (size_t)tile * n4;
     const float4* t4 = reinterpret_cast<const float4*>(A.target) + (size_t)tile * n4;
@@ -81,6 +82,16 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
         for (int it = 0; it < R; ++it) {
             pv[it] = ldg_stream(p4 + it * blockDim.x + threadIdx.x);
             tv[it] = ldg_stream(t4 + it * blockDim.x + threadIdx.x);
+        }
+    }
+    // pixel coordinates of the register-resident float4s, worked out once (y << 16 | x): one division per float4
+    // instead of one per float4 and pass
+    int yx[R];
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
+            const int i = it * blockDim.x + threadIdx.x, y = i / w4;
+            yx[it] = (y << 16) | ((i - y * w4) << 2);
         }
     }
     const float wraw = A.weight ? __ldg(A.weight + tile) : 1.f;
@@ -94,9 +105,8 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
 
     // ---- pass 1: raw moments of both tiles and the pixel criterion -----------------------------
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    auto pass1 = [&](const float4& p, const float4& t, int i) {
-        const int y = i / w4, x = (i - y * w4) << 2;
-        const float fx = (float)x, fy = (float)y;
+    auto pass1 = [&](const float4& p, const float4& t, int c) {
+        const float fx = (float)(c & 0xffff), fy = (float)(c >> 16);
         const float sp = (p.x + p.y) + (p.z + p.w), st = (t.x + t.y) + (t.z + t.w);
         acc[0] += sp;
         acc[1] += fmaf(fx, sp, fmaf(3.f, p.w, fmaf(2.f, p.z, p.y)));
@@ -108,11 +118,11 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
     };
     if (NITER > 0) {
 #pragma unroll
-        for (int it = 0; it < R; ++it) pass1(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+        for (int it = 0; it < R; ++it) pass1(pv[it], tv[it], yx[it]);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) pass1(ldg_stream(p4 + i), ldg_stream(t4 + i), i);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass1(ldg_stream(p4 + i), ldg_stream(t4 + i), (y << 16) | ((i - y * w4) << 2)); }
     }
-    block_sum<8>(acc, scratch);
+    block_sum_1bar<8>(acc, red_a, nw, lane, warp);
     const float Sp = acc[0] + kEps, St = acc[3] + kEps;
     const float iSp = 1.f / Sp, iSt = 1.f / St;
     const float pmx = acc[1] * iSp, pmy = acc[2] * iSp, tmx = acc[4] * iSt, tmy = acc[5] * iSt;
@@ -120,9 +130,8 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
 
     // ---- pass 2: central second moments about each tile's own mean ------------------------------
     float c2[4] = {0.f, 0.f, 0.f, 0.f};
-    auto pass2 = [&](const float4& p, const float4& t, int i) {
-        const int y = i / w4, x = (i - y * w4) << 2;
-        const float fx = (float)x, fy = (float)y;
+    auto pass2 = [&](const float4& p, const float4& t, int c) {
+        const float fx = (float)(c & 0xffff), fy = (float)(c >> 16);
         const float pe[4] = {p.x, p.y, p.z, p.w}, te[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -136,11 +145,11 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
     };
     if (NITER > 0) {
 #pragma unroll
-        for (int it = 0; it < R; ++it) pass2(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+        for (int it = 0; it < R; ++it) pass2(pv[it], tv[it], yx[it]);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) pass2(ldg_keep(p4 + i), ldg_keep(t4 + i), i);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass2(ldg_keep(p4 + i), ldg_keep(t4 + i), (y << 16) | ((i - y * w4) << 2)); }
     }
-    block_sum<4>(c2, scratch);
+    block_sum_1bar<4>(c2, red_b, nw, lane, warp);
     const float pvx = c2[0] * iSp, pvy = c2[1] * iSp, tvx = c2[2] * iSt, tvy = c2[3] * iSt;
     const float dvx = pvx - tvx, dvy = pvy - tvy, dmx = pmx - tmx, dmy = pmy - tmy;
 
@@ -158,9 +167,9 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
     const float Bx = cm * 2.f * P.lam_mean * dmx, By = cm * 2.f * P.lam_mean * dmy;
     const float C0 = -(Ax * pvx + Ay * pvy);
     float4* g4 = reinterpret_cast<float4*>(A.grad_pred) + (size_t)tile * n4;
-    auto pass3 = [&](const float4& p, const float4& t, int i) {
-        const int y = i / w4, x = (i - y * w4) << 2;
-        const float dy = (float)y - pmy;
+    auto pass3 = [&](const float4& p, const float4& t, int c, int i) {
+        const int x = c & 0xffff;
+        const float dy = (float)(c >> 16) - pmy;
         const float rowc = fmaf(dy, fmaf(Ay, dy, By), C0);
         const float pe[4] = {p.x, p.y, p.z, p.w}, te[4] = {t.x, t.y, t.z, t.w};
         float g[4];
@@ -173,9 +182,9 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
     };
     if (NITER > 0) {
 #pragma unroll
-        for (int it = 0; it < R; ++it) pass3(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+        for (int it = 0; it < R; ++it) pass3(pv[it], tv[it], yx[it], it * blockDim.x + threadIdx.x);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) pass3(ldg_keep(p4 + i), ldg_keep(t4 + i), i);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass3(ldg_keep(p4 + i), ldg_keep(t4 + i), (y << 16) | ((i - y * w4) << 2), i); }
     }
 }
 
@@ -320,16 +329,19 @@ static int launch_genb(const GenbParams& P, const GenbArgs& A, cudaStream_t s) {
     genb_coords_kernel<<<(nt + 255) / 256, 256, 0, s>>>(P, A, tiles ? 0 : 1);
     int st = check_launch("genb_coords_kernel");
     if (st || !tiles) return st;
-    // both tiles stay in registers when the tile splits into <= 4 float4 per thread (64x48: 256 x 3,
-    // 96x72: 576 x 3, 128x128: 1024 x 4); other shapes re-read through L2
+    // both tiles stay in registers: up to 3 float4 each per thread with CTAs of up to 1024 threads (64 registers:
+    // 64x48 -> 256 x 3, 96x72 -> 576 x 3), up to 8 with CTAs of up to 512 threads (128 registers: 128x128 -> 512 x 8);
+    // other shapes re-read through L2
     const int n4 = (P.H * P.W) >> 2;
     int niter = 0, threads = 512;
-    for (int t = 256; t <= 1024; t += 32)
-        if (n4 % t == 0 && n4 / t <= 4) { threads = t; niter = n4 / t; break; }
-#define GBC_CASE(NI) case NI: genb_tile_kernel<NI><<<nt, threads, 0, s>>>(P, A); break;
+    for (int t = 256; t <= 1024 && !niter; t += 32)
+        if (n4 % t == 0 && n4 / t <= 3) { threads = t; niter = n4 / t; }
+    for (int t = 128; t <= 512 && !niter; t += 32)
+        if (n4 % t == 0 && n4 / t <= 8) { threads = t; niter = n4 / t; }
+#define GBC_CASE(NI, MT) case NI: genb_tile_kernel<NI, MT><<<nt, threads, 0, s>>>(P, A); break;
     switch (niter) {
-        GBC_CASE(1) GBC_CASE(2) GBC_CASE(3) GBC_CASE(4)
-        default: genb_tile_kernel<0><<<nt, threads, 0, s>>>(P, A); break;
+        GBC_CASE(1, 1024) GBC_CASE(2, 1024) GBC_CASE(3, 1024) GBC_CASE(4, 512) GBC_CASE(5, 512) GBC_CASE(6, 512) GBC_CASE(7, 512) GBC_CASE(8, 512)
+        default: genb_tile_kernel<0, 1024><<<nt, threads, 0, s>>>(P, A); break;
     }
 #undef GBC_CASE
     return check_launch("genb_tile_kernel");
