@@ -207,9 +207,9 @@ def run_b200(args):
     fw = torch.tensor([0.6224593312018546], device=device)
     dflags = N.DECODE_REFINE | N.DECODE_APPLY_OFFSET
     # N=1: weights/normalisers + loss + finalize.  N>1 over NCCL: (normalisers + export) + (weights + import + loss
-    # + finalize); N>1 over peer memory: the same three kernels as N=1 (+ one 8-byte export of the global sums)
+    # + finalize); N>1 over peer memory: the same three kernels as N=1
     use_peer = world > 1 and args.exchange == "peer"
-    launches_per_step = 3 if world == 1 else (4 if use_peer else 6)
+    launches_per_step = 3 if world == 1 else (3 if use_peer else 6)
     peer = None
     if use_peer:
         from infantposeestimation_gaussianbias_b200.sharded import PeerExchange

@@ -25,7 +25,8 @@ namespace gbc {
 __global__ void __launch_bounds__(256)
 denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight,
               const float* __restrict__ gt, int target_given, float* __restrict__ weff, int4* __restrict__ geom,
-              double* __restrict__ sums, unsigned* __restrict__ ticket, const __grid_constant__ PeerView peer) {
+              double* __restrict__ sums, unsigned* __restrict__ ticket, const __grid_constant__ PeerView peer,
+              float* __restrict__ global_out) {
     __shared__ float wsm[256];
     __shared__ double red[2][8];
     const int ipb = 256 / P.K;                         // images per CTA
@@ -92,6 +93,7 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
         double gw = 0.0, gp = 0.0;
         for (int i = 0; i < peer.world; ++i) { gw += gath[i][0]; gp += gath[i][1]; }
         sums[0] = gw; sums[1] = gp;
+        if (global_out) { global_out[0] = (float)gw; global_out[1] = (float)gp; }    // what the backward takes as d_denoms
         *ticket = 0u;
     }
 }
@@ -666,7 +668,8 @@ static int check_common(const gbcodec_loss_desc* d, const float* hm, const float
 static const PeerView kNoPeers = {};
 
 static int prepare_weights(const LossParams& P, const WsLayout& L, const float* weight, const float* gt,
-                           int target_given, const float* denoms, cudaStream_t s, const PeerView& peer = kNoPeers) {
+                           int target_given, const float* denoms, cudaStream_t s, const PeerView& peer = kNoPeers,
+                           float* global_out = nullptr) {
     if (denoms) {
         weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom);
         sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
@@ -676,7 +679,7 @@ static int prepare_weights(const LossParams& P, const WsLayout& L, const float* 
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         const int ipb = 256 / P.K;
         const int grid = (P.B + ipb - 1) / ipb;
-        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums, L.ticket, peer);
+        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums, L.ticket, peer, peer.world > 1 ? global_out : nullptr);
     }
     return check_launch("denoms_kernel");
 }
@@ -726,9 +729,9 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     st = make_params(d, &P);
     if (st) return st;
     const WsLayout L = ws_carve(ws, P.B, P.K);
-    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, peer);
+    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, peer, denoms_out);
     if (st) return st;
-    if (denoms_out) {
+    if (denoms_out && peer.world <= 1) {                 // with peers the exchanging CTA has written them already
         sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, denoms_out);
         st = check_launch("sums_to_float_kernel");
         if (st) return st;
