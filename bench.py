@@ -179,6 +179,36 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore the pinned host buffers it is about to allocate: first touch) to the CPU
+    cores of the NUMA node the GPU hangs off.  With one process per GPU and ~54 GB/s of H2D per rank, buffers on
+    the far socket put the host-buffer step on the inter-socket link.  Best effort: returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                    # NVML pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -194,6 +224,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the codec has no CPU path (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
@@ -325,7 +356,7 @@ def run_b200(args):
             pass
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:                 # the CPU baseline is an N=1 figure (all host cores, nothing else running)
         v, cores, times = cpu_step_rate(sample_B=32, min_seconds=10.0, max_reps=400)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"32 images x {K} heatmaps of the same workload, median of {len(times)} passes ({sum(times):.1f} s of CPU work)"}
@@ -334,7 +365,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": ("none" if world == 1 else args.exchange),
+        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": ("none" if world == 1 else args.exchange), "numa_node_rank0": numa,
                    "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
