@@ -328,6 +328,25 @@ int gbcodec_combined_loss_backward_f32(const gbcodec_combined_desc* desc,
                               float* d_grad_pred, float* d_grad_coords, float* d_grad_refined,
                               void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The plain heatmap head (PoseEstimator with head_type='heatmap') in ONE pass over the heatmaps:
+ * KeypointMSELoss forward + backward (models/pose_estimator.py:102-143: mean((p w - t w)^2) over B*K*H*W),
+ * the target tiles generated on the fly as COCOPoseDataset._generate_target builds them
+ * (datasets/coco_dataset.py:185-250) unless d_target is given, and decode_heatmaps (:331-373) of the
+ * same tiles.  Algorithmic HBM bytes per tile: read hm (4N) + write d_hm (4N).
+ *   d_target NULL: tiles and weights come from d_gt_kps (B,K,2) and d_weight = visibility (B,K);
+ *            given: d_weight (B,K) or NULL is used as is
+ *   norm_batch  batch size in the mean's denominator; 0 = B (a rank holding a shard passes the global batch)
+ *   d_loss out, 1 float   d_grad_hm (B,K,H,W) out or NULL   d_grad_scale NULL (=1) or device scalar
+ *   d_coords (B,K,2), d_maxvals (B,K), d_index (B,K) int32: out or NULL — gbcodec_decode_argmax_f32's outputs
+ *   workspace: gbcodec_combined_workspace_bytes(B, K)
+ */
+int gbcodec_heatmap_step_f32(const float* d_hm, const float* d_target, const float* d_weight, const float* d_gt_kps,
+                             int B, int K, int H, int W, float in_w, float in_h, double sigma,
+                             int use_target_weight, int norm_batch, const float* d_grad_scale,
+                             float* d_loss, float* d_grad_hm, int argmax_mode,
+                             float* d_coords, float* d_maxvals, int32_t* d_index,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement hook (bench.py): the next gbcodec_fusion_loss_f32 / _step_f32 calls made
  * by THIS host thread record `start_event` right before and `stop_event` right after
  * the per-tile loss kernel, on the stream of the call.  Both are cudaEvent_t passed as

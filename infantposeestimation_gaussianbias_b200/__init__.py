@@ -28,7 +28,7 @@ def __getattr__(name):
     if name in ("generate_heatmaps", "HeatmapGenerator", "generate_heatmaps_clipped", "GenerateTarget"):
         from . import generate_heatmap
         return getattr(generate_heatmap, name)
-    if name in ("decode_heatmaps", "inference", "flip_permutation"):
+    if name in ("decode_heatmaps", "inference", "flip_permutation", "HeatmapHeadStep"):
         from . import pose_estimator
         return getattr(pose_estimator, name)
     if name == "patch_reference":

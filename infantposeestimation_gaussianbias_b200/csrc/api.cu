@@ -51,6 +51,9 @@ int combined_loss(const gbcodec_combined_desc*, const float*, const float*, cons
 int combined_loss_backward(const gbcodec_combined_desc*, const float*, const float*, const float*, const float*, const float*,
                            const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t);
 
+int heatmap_step(const float*, const float*, const float*, const float*, int, int, int, int, float, float, double, int, int,
+                 const float*, float*, float*, int, float*, float*, int32_t*, void*, size_t, cudaStream_t);
+
 void set_profile_events(cudaEvent_t, cudaEvent_t);
 
 static int check_tile_shape(const char* who, int B, int K, int H, int W) {
@@ -184,6 +187,20 @@ int gbcodec_combined_loss_backward_f32(const gbcodec_combined_desc* desc,
     return combined_loss_backward(desc, d_pred, d_target, d_weight, d_coords, d_refined, d_target_coords, d_grad_scale,
                                   d_grad_losses5, d_grad_pred, d_grad_coords, d_grad_refined, d_workspace, workspace_bytes,
                                   (cudaStream_t)stream);
+}
+
+int gbcodec_heatmap_step_f32(const float* d_hm, const float* d_target, const float* d_weight, const float* d_gt_kps,
+                             int B, int K, int H, int W, float in_w, float in_h, double sigma,
+                             int use_target_weight, int norm_batch, const float* d_grad_scale,
+                             float* d_loss, float* d_grad_hm, int argmax_mode,
+                             float* d_coords, float* d_maxvals, int32_t* d_index,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+    int st = check_tile_shape("heatmap_step", B, K, H, W);
+    if (st) return st;
+    if (argmax_mode < GBCODEC_ARGMAX_PLAIN || argmax_mode > GBCODEC_ARGMAX_TAYLOR) return fail(GBCODEC_ERR_BAD_ARGUMENT, "heatmap_step: argmax_mode=%d", argmax_mode);
+    if (!d_target && (!(in_w > 0.f) || !(in_h > 0.f))) return fail(GBCODEC_ERR_BAD_ARGUMENT, "heatmap_step: input size must be positive");
+    return heatmap_step(d_hm, d_target, d_weight, d_gt_kps, B, K, H, W, in_w, in_h, sigma, use_target_weight, norm_batch, d_grad_scale,
+                        d_loss, d_grad_hm, argmax_mode, d_coords, d_maxvals, d_index, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t gbcodec_loss_workspace_bytes(int B, int K, int H, int W) {

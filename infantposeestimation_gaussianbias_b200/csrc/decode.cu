@@ -467,40 +467,6 @@ int launch_decode(const float* hm, const float* hmf, const int32_t* perm, const 
     return check_launch("decode_kernel");
 }
 
-// Sub-pixel step of the arg-max family for the peak at flat index `at` of tile `t`.
-__device__ __forceinline__ void subpixel_step(const float* __restrict__ t, int at, int H, int W, int mode, float& fx, float& fy) {
-    const int x = at % W, y = at / W;
-    fx = (float)x; fy = (float)y;
-    if (mode == GBCODEC_ARGMAX_QUARTER) {
-        if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
-            const float dx = t[y * W + x + 1] - t[y * W + x - 1];
-            const float dy = t[(y + 1) * W + x] - t[(y - 1) * W + x];
-            fx += (dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f));
-            fy += (dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f));
-        }
-    } else if (mode == GBCODEC_ARGMAX_TAYLOR) {
-        // utils/postprocess.py:57-73: strict '1 <', fp32 differences, the division in double
-        if (x > 1 && x < W - 1 && y > 1 && y < H - 1) {
-            const float c = t[y * W + x];
-            const float xl = t[y * W + x - 1], xr = t[y * W + x + 1];
-            const float yu = t[(y - 1) * W + x], yd = t[(y + 1) * W + x];
-            const float dx = xr - xl, dy = yd - yu;
-            const float dxx = __fadd_rn(__fsub_rn(xr, __fmul_rn(2.f, c)), xl);
-            const float dyy = __fadd_rn(__fsub_rn(yd, __fmul_rn(2.f, c)), yu);
-            if (dxx < 0.f) {
-                double o = (double)dx / (2.0 * fabs((double)dxx));
-                o = fmin(fmax(o, -0.5), 0.5);
-                fx = __fadd_rn(fx, (float)o);
-            }
-            if (dyy < 0.f) {
-                double o = (double)dy / (2.0 * fabs((double)dyy));
-                o = fmin(fmax(o, -0.5), 0.5);
-                fy = __fadd_rn(fy, (float)o);
-            }
-        }
-    }
-}
-
 // coordinate_refinement (utils/postprocess.py:138-184) for one tile, by one warp: linear-weight
 // centroid of the window around trunc(ix, iy); an empty window keeps the input (so does a window that
 // lies wholly left of / above the map, where the reference's slice wraps around and its torch.arange

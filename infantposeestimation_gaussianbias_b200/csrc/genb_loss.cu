@@ -14,6 +14,7 @@
 //   d m_c / d p_i = (c_i - m_c)/S         d v_c / d p_i = ((c_i - m_c)^2 - v_c)/S
 // (the cross term 2 (d m_c/d p_i) sum q (c - m_c) = 2 (d m_c/d p_i) m_c eps/S is below fp32 resolution).
 #include "common.cuh"
+#include "decode_device.cuh"
 #include <string.h>
 
 namespace gbc {
@@ -222,7 +223,7 @@ genb_coords_kernel(const __grid_constant__ GenbParams P, const __grid_constant__
 // ---- second stage: fixed-order sums, the five scalars ----------------------------------------------
 __global__ void __launch_bounds__(256)
 genb_finalize_kernel(const __grid_constant__ GenbParams P, const float* __restrict__ partial, double* __restrict__ bpart,
-                     unsigned* __restrict__ ticket, float* __restrict__ losses5) {
+                     unsigned* __restrict__ ticket, float* __restrict__ losses5, float* __restrict__ single_out) {
     __shared__ double red[4][8];
     __shared__ bool last;
     const int tiles = P.B * P.K;
@@ -258,13 +259,14 @@ genb_finalize_kernel(const __grid_constant__ GenbParams P, const float* __restri
         for (int g = 0; g < (int)gridDim.x; ++g) s += __ldcg(bpart + g * 4 + q);
         const float v = q == 0 ? (float)s * P.inv_heat * P.heat_scale : (float)s * P.inv_pair;
         term[q] = v;
-        losses5[q] = v;
+        if (losses5) losses5[q] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         float total = 0.f;
         for (int q = 0; q < 4; ++q) total += P.w[q] * term[q];
-        losses5[4] = total;
+        if (losses5) losses5[4] = total;
+        if (single_out) *single_out = total;
         *ticket = 0u;
     }
 }
@@ -370,7 +372,7 @@ int combined_loss(const gbcodec_combined_desc* d, const float* pred, const float
     if (st) return st;
     const int nt = P.B * P.K;
     const int fin = (nt + 255) / 256 < kGenbFinBlocks ? (nt + 255) / 256 : kGenbFinBlocks;
-    genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, losses5);
+    genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, losses5, nullptr);
     return check_launch("genb_finalize_kernel");
 }
 
@@ -393,6 +395,159 @@ int combined_loss_backward(const gbcodec_combined_desc* d, const float* pred, co
     st = check_launch("genb_plan_kernel");
     if (st) return st;
     return launch_genb(P, A, s);
+}
+
+// ---- plain heatmap head: KeypointMSELoss fwd + bwd, on-the-fly targets, arg-max decode — one pass ---------
+// models/pose_estimator.py head_type='heatmap': loss = mean((p w - t w)^2) (:102-143), keypoints from
+// decode_heatmaps (:331-373); target tiles as COCOPoseDataset._generate_target builds them
+// (datasets/coco_dataset.py:185-250).  One CTA per tile, the tile in registers: read P (4N), write dP (4N).
+struct HeatArgs {
+    const float* hm; const float* target; const float* weight; const float* kps; const float* grad_scale;
+    float* grad_hm; float* coords; float* maxvals; int32_t* index; float* partial;
+    int H, W, mode, use_target_weight;
+    float in_w, in_h, inv_bkn;
+    EncodeConst ec;
+};
+
+template <int NITER, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+heatmap_step_kernel(const __grid_constant__ HeatArgs A) {
+    extern __shared__ float lut[];
+    __shared__ PatchGeom geom_s;
+    __shared__ float red_v[32], red_s[32];
+    __shared__ int red_i[32];
+    const int tile = blockIdx.x;
+    const int H = A.H, W = A.W, n = H * W, n4 = n >> 2, w4 = W >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float4* p4 = reinterpret_cast<const float4*>(A.hm) + (size_t)tile * n4;
+    constexpr int R = NITER > 0 ? NITER : 1;
+    float4 pv[R];
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) pv[it] = ldg_stream(p4 + it * blockDim.x + threadIdx.x);
+    }
+    if (!A.target) {
+        fill_patch_lut(lut, A.ec);
+        if (threadIdx.x == 0) geom_s = patch_geometry(A.kps[2 * tile], A.kps[2 * tile + 1], A.weight[tile], H, W, A.in_w, A.in_h, A.ec);
+        __syncthreads();
+    }
+    const PatchGeom g = A.target ? PatchGeom{} : geom_s;
+    const float wraw = A.target ? (A.weight ? __ldg(A.weight + tile) : 1.f) : g.weight;
+    const float w2 = (A.use_target_weight && A.weight) ? wraw * wraw : 1.f;      // (p w - t w)^2 = w^2 (p - t)^2
+    const float4* t4 = A.target ? reinterpret_cast<const float4*>(A.target) + (size_t)tile * n4 : nullptr;
+    auto target_at = [&](int i) -> float4 {
+        if (t4) return ldg_keep(t4 + i);
+        const int y = i / w4, x = (i - y * w4) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.active && y >= g.y_from && y < g.y_to && x + 3 >= g.x_from && x < g.x_to) {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = (x + j >= g.x_from && x + j < g.x_to) ? patch_value(lut, g, A.ec, x + j, y) : 0.f;
+            v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        return v;
+    };
+    // ---- one pass: squared error and the first maximum (ascending index per thread + strict '>') -------------
+    float sq = 0.f, best = -INFINITY;
+    int at = 0x7fffffff;
+    float4 tv[R];
+    auto visit = [&](const float4& p, const float4& t, int i) {
+        const float d0 = p.x - t.x, d1 = p.y - t.y, d2 = p.z - t.z, d3 = p.w - t.w;
+        sq += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+        const int base = i << 2;
+        if (p.x > best) { best = p.x; at = base; }
+        if (p.y > best) { best = p.y; at = base + 1; }
+        if (p.z > best) { best = p.z; at = base + 2; }
+        if (p.w > best) { best = p.w; at = base + 3; }
+    };
+    if (NITER > 0) {
+#pragma unroll
+        for (int it = 0; it < R; ++it) { tv[it] = target_at(it * blockDim.x + threadIdx.x); visit(pv[it], tv[it], it * blockDim.x + threadIdx.x); }
+    } else {
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) visit(ldg_stream(p4 + i), target_at(i), i);
+    }
+    if (at == 0x7fffffff) at = 0x7ffffffe;
+    sq = warp_sum(sq);
+    warp_argmax(best, at);
+    if (lane == 0) { red_s[warp] = sq; red_v[warp] = best; red_i[warp] = at; }
+    // ---- gradient: does not wait for the reductions --------------------------------------------------------------
+    if (A.grad_hm) {
+        const float gs = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
+        const float c = gs * 2.f * w2 * A.inv_bkn;
+        float4* g4 = reinterpret_cast<float4*>(A.grad_hm) + (size_t)tile * n4;
+        auto grad = [&](const float4& p, const float4& t, int i) {
+            stg_stream(g4 + i, make_float4(c * (p.x - t.x), c * (p.y - t.y), c * (p.z - t.z), c * (p.w - t.w)));
+        };
+        if (NITER > 0) {
+#pragma unroll
+            for (int it = 0; it < R; ++it) grad(pv[it], tv[it], it * blockDim.x + threadIdx.x);
+        } else {
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) grad(ldg_keep(p4 + i), target_at(i), i);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float s = 0.f, bv = red_v[0];
+    int bi = red_i[0];
+    for (int q = 0; q < nw; ++q) { s += red_s[q]; if (q) argmax_merge(bv, bi, red_v[q], red_i[q]); }
+    float4* out = reinterpret_cast<float4*>(A.partial) + tile;
+    *out = make_float4(w2 * s, 0.f, 0.f, 0.f);
+    if (A.coords) {
+        const float* t = A.hm + (size_t)tile * n;
+        if (bi >= n) { bi = 0; bv = t[0]; }
+        float fx, fy;
+        subpixel_step(t, bi, H, W, A.mode, fx, fy);
+        A.coords[2 * tile] = fx; A.coords[2 * tile + 1] = fy;
+        A.maxvals[tile] = bv;
+        if (A.index) A.index[tile] = bi;
+    }
+}
+
+int heatmap_step(const float* hm, const float* target, const float* weight, const float* kps, int B, int K, int H, int W,
+                 float in_w, float in_h, double sigma, int use_target_weight, int norm_batch, const float* grad_scale,
+                 float* loss, float* grad_hm, int argmax_mode, float* coords, float* maxvals, int32_t* index,
+                 void* ws, size_t ws_size, cudaStream_t s) {
+    if (!hm || !loss) return fail(GBCODEC_ERR_NULL_POINTER, "heatmap_step: d_hm / d_loss is NULL");
+    if (!target && (!weight || !kps)) return fail(GBCODEC_ERR_NULL_POINTER, "heatmap_step: on-the-fly targets need d_weight (visibility) and d_gt_kps");
+    if (coords && !maxvals) return fail(GBCODEC_ERR_NULL_POINTER, "heatmap_step: d_maxvals is NULL");
+    if (!ws || ws_size < genb_ws_bytes(B, K)) return fail(GBCODEC_ERR_WORKSPACE, "heatmap_step: workspace of %zu bytes needed", genb_ws_bytes(B, K));
+    if (!aligned16(hm) || !aligned16(ws) || (target && !aligned16(target)) || (grad_hm && !aligned16(grad_hm)))
+        return fail(GBCODEC_ERR_UNALIGNED, "heatmap_step: tensors must be 16-byte aligned");
+    if (norm_batch < 0 || !(sigma > 0.0)) return fail(GBCODEC_ERR_BAD_ARGUMENT, "heatmap_step: norm_batch / sigma");
+    HeatArgs A;
+    memset(&A, 0, sizeof(A));
+    A.hm = hm; A.target = target; A.weight = weight; A.kps = kps; A.grad_scale = grad_scale; A.grad_hm = grad_hm;
+    A.coords = coords; A.maxvals = maxvals; A.index = index;
+    A.H = H; A.W = W; A.mode = argmax_mode; A.use_target_weight = use_target_weight; A.in_w = in_w; A.in_h = in_h;
+    A.ec = make_encode_const(sigma);
+    const double bkn = (double)(norm_batch ? norm_batch : B) * K * H * W;
+    A.inv_bkn = (float)(1.0 / bkn);
+    const GenbWs L = genb_carve(ws);
+    A.partial = L.partial;
+    cudaError_t e = cudaMemsetAsync(L.ticket, 0, 8, s);
+    if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const size_t smem = target ? 0 : (size_t)A.ec.lut_size * sizeof(float);
+    if (smem > 40 * 1024) return fail(GBCODEC_ERR_BAD_ARGUMENT, "heatmap_step: sigma %g needs a %zu-byte patch table", sigma, smem);
+    const int nt = B * K, n4 = (H * W) >> 2;
+    int niter = 0, threads = 512;
+    for (int t = 256; t <= 1024 && !niter; t += 32)
+        if (n4 % t == 0 && n4 / t <= 3) { threads = t; niter = n4 / t; }
+    for (int t = 128; t <= 512 && !niter; t += 32)
+        if (n4 % t == 0 && n4 / t <= 8) { threads = t; niter = n4 / t; }
+#define GBC_CASE(NI, MT) case NI: heatmap_step_kernel<NI, MT><<<nt, threads, smem, s>>>(A); break;
+    switch (niter) {
+        GBC_CASE(1, 1024) GBC_CASE(2, 1024) GBC_CASE(3, 1024) GBC_CASE(4, 512) GBC_CASE(5, 512) GBC_CASE(6, 512) GBC_CASE(7, 512) GBC_CASE(8, 512)
+        default: heatmap_step_kernel<0, 1024><<<nt, threads, smem, s>>>(A); break;
+    }
+#undef GBC_CASE
+    int st = check_launch("heatmap_step_kernel");
+    if (st) return st;
+    GenbParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = B; P.K = K; P.heat_scale = 1.f; P.inv_heat = A.inv_bkn; P.w[0] = 1.f;
+    const int fin = (nt + 255) / 256 < kGenbFinBlocks ? (nt + 255) / 256 : kGenbFinBlocks;
+    genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, nullptr, loss);
+    return check_launch("genb_finalize_kernel");
 }
 
 }  // namespace gbc

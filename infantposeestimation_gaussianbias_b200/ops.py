@@ -513,3 +513,68 @@ def _combined_backward(ctx, g_losses, g_gp, g_gc, g_gr):
 
 
 combined_loss.register_autograd(_combined_backward, setup_context=_combined_setup_context)
+
+
+# --------------------------------------------------------------------------- plain heatmap head, one pass
+@torch.library.custom_op(f"{_NS}::heatmap_step", mutates_args=())
+def heatmap_step(hm: Tensor, target: Optional[Tensor], weight: Optional[Tensor], gt_kps: Optional[Tensor],
+                 in_w: float, in_h: float, sigma: float, use_target_weight: bool, norm_batch: int,
+                 grad_scale: Optional[Tensor], with_grads: bool, with_decode: bool, argmax_mode: int
+                 ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """KeypointMSELoss fwd (+ bwd) [+ decode_heatmaps] in one pass -> loss (0-dim), grad_hm, coords (B,K,2), maxvals (B,K);
+    target None: tiles and weights are generated in the kernel from gt_kps and weight (= visibility)."""
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    dev = hm.device
+    if target is not None:
+        target = _cuda_f32("target_heatmaps", target, (B, K, H, W))
+    if weight is not None:
+        weight = _cuda_f32("target_weight", weight.reshape(B, K), (B, K))
+    if gt_kps is not None:
+        gt_kps = _cuda_f32("gt_keypoints", gt_kps, (B, K, 2))
+    grad_scale = _scalar("grad_scale", grad_scale, hm)
+    empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ghm = torch.empty_like(hm) if with_grads else empty()
+    coords = torch.empty((B, K, 2), dtype=torch.float32, device=dev) if with_decode else empty()
+    maxvals = torch.empty((B, K), dtype=torch.float32, device=dev) if with_decode else empty()
+    nbytes = N.lib().gbcodec_combined_workspace_bytes(B, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().gbcodec_heatmap_step_f32(
+            _ptr(hm), _ptr(target), _ptr(weight), _ptr(gt_kps), B, K, H, W, in_w, in_h, sigma, int(use_target_weight), norm_batch,
+            _ptr(grad_scale), _ptr(loss), _ptr(ghm) if with_grads else None, argmax_mode,
+            _ptr(coords) if with_decode else None, _ptr(maxvals) if with_decode else None, None,
+            _ptr(ws), nbytes, _stream(hm)), "heatmap_step")
+    return loss, ghm, coords, maxvals
+
+
+@heatmap_step.register_fake
+def _(hm, target, weight, gt_kps, in_w, in_h, sigma, use_target_weight, norm_batch, grad_scale, with_grads, with_decode, argmax_mode):
+    B, K = hm.shape[0], hm.shape[1]
+    e = lambda: hm.new_empty(0)
+    return (hm.new_empty(()), torch.empty_like(hm) if with_grads else e(),
+            hm.new_empty((B, K, 2)) if with_decode else e(), hm.new_empty((B, K)) if with_decode else e())
+
+
+def _heatmap_step_setup(ctx, inputs, output):
+    ctx.with_grads = inputs[10]
+    ctx.grad_scale = inputs[9]
+    ctx.ghm = output[1]
+    ctx.mark_non_differentiable(output[1], output[2], output[3])      # the stored gradient, keypoints, max values
+    ctx.set_materialize_grads(False)
+
+
+def _heatmap_step_backward(ctx, g_loss, g_ghm, g_coords, g_maxvals):
+    none = [None] * 13
+    if g_loss is None:
+        return tuple(none)
+    if not ctx.with_grads:
+        raise RuntimeError("gbcodec::heatmap_step was run with with_grads=False; its output is not differentiable")
+    # the stored gradient assumes d(loss) = grad_scale (1 if absent): one scalar multiply otherwise, on the device
+    ratio = g_loss if ctx.grad_scale is None else g_loss / ctx.grad_scale.reshape(())
+    none[0] = ctx.ghm * ratio
+    return tuple(none)
+
+
+heatmap_step.register_autograd(_heatmap_step_backward, setup_context=_heatmap_step_setup)

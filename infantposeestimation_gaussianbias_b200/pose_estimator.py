@@ -53,3 +53,37 @@ def inference(model, x: Tensor, flip: bool = True, flip_pairs: Optional[list] = 
         back = torch.flip(flipped, dims=[-1])[:, perm.long()]
         heatmaps = (heatmaps + back) / 2
     return decode_heatmaps(heatmaps)
+
+
+class HeatmapHeadStep(torch.nn.Module):
+    """The training / validation step of the plain heatmap head (PoseEstimator with head_type='heatmap',
+    models/pose_estimator.py:209-215,259-273) in ONE pass over the heatmaps: KeypointMSELoss forward and
+    backward (:102-143), target tiles generated in the kernel from the batch's keypoints
+    (datasets/coco_dataset.py:185-250) unless `target` is given, and decode_heatmaps (:331-373).
+
+        loss, keypoints, max_vals = step(heatmaps, keypoints=gt_keypoints, keypoints_visible=vis)
+        loss.backward()
+    """
+
+    def __init__(self, input_size=(192, 256), sigma: float = 2.0, use_target_weight: bool = True, shift: bool = True):
+        super().__init__()
+        self.input_size = tuple(float(v) for v in input_size)
+        self.sigma = float(sigma)
+        self.use_target_weight = bool(use_target_weight)
+        self.shift = bool(shift)
+
+    def forward(self, heatmaps: Tensor, target: Optional[Tensor] = None, target_weight: Optional[Tensor] = None,
+                keypoints: Optional[Tensor] = None, keypoints_visible: Optional[Tensor] = None, *, decode: bool = True,
+                norm_batch: int = 0, grad_scale: Optional[Tensor] = None):
+        hm = _f32(heatmaps)
+        with_grads = torch.is_grad_enabled() and hm.requires_grad
+        if target is None:
+            if keypoints is None or keypoints_visible is None:
+                raise ValueError("HeatmapHeadStep: give `target` (+ `target_weight`) or `keypoints` + `keypoints_visible`")
+            weight, kps = _f32(keypoints_visible), _f32(keypoints)
+        else:
+            weight, kps = _f32(target_weight), None
+        loss, _, coords, maxvals = ops.heatmap_step(hm, _f32(target), weight, kps, self.input_size[0], self.input_size[1], self.sigma,
+                                                    self.use_target_weight, int(norm_batch), grad_scale, with_grads, bool(decode),
+                                                    N.ARGMAX_QUARTER if self.shift else N.ARGMAX_PLAIN)
+        return (loss, coords, maxvals) if decode else loss

@@ -302,3 +302,50 @@ def test_errors_are_loud(pkg):
         ops.encode_mode(torch.zeros(1, 1, 2).cuda(), torch.ones(1, 1).cuda(), 8, 8, 32.0, 32.0, 2.0, 9)   # bad mode
     with pytest.raises(GbcodecError):
         ops.postprocess(torch.zeros(1, 1, 8, 8).cuda(), None, None, None, N.ARGMAX_TAYLOR, False, 256.0, 5, True, 0.3, True, 256.0, 256.0)   # transform without centre
+
+
+# ------------------------------------------------------------------ plain heatmap head, one pass
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("on_the_fly", [False, True])
+def test_heatmap_head_step(pkg, name, on_the_fly):
+    """KeypointMSELoss fwd + bwd with (optionally on-the-fly) targets + decode_heatmaps in one kernel, against the
+    golden KeypointMSELoss value of the reference and the oracle's gradient / arg-max."""
+    from oracle import heatmap_codec as oc
+    cfg, batch, ex, g = goldens_genb.load(name)
+    step = pkg.pose_estimator.HeatmapHeadStep(input_size=cfg.input_size, sigma=cfg.sigma)
+    p = dev(ex["pred"]).requires_grad_(True)
+    if on_the_fly:
+        loss, kp, mv = step(p, keypoints=dev(batch["kps"]), keypoints_visible=dev(batch["vis"]))
+    else:
+        loss, kp, mv = step(p, dev(batch["target"]), dev(batch["weight"]))
+    (loss * 3.0).backward()
+    np.testing.assert_allclose(float(loss.detach()), float(g["kpmse_w"]), rtol=LOSS_RTOL)
+    pc = T(ex["pred"]).clone().requires_grad_(True)
+    (genb.keypoint_mse_loss(pc, T(batch["target"]), T(batch["weight"])) * 3.0).backward()
+    maxnorm_close(p.grad.cpu().numpy(), pc.grad.numpy(), what="d KeypointMSELoss / d pred")
+    wkp, wmv, _ = oc.decode_heatmaps(T(ex["pred"]), shift=True)
+    assert np.array_equal(kp.cpu().numpy(), wkp.numpy()) and np.array_equal(mv.cpu().numpy(), wmv.numpy())
+    # no weights: plain mean squared error
+    l2 = pkg.pose_estimator.HeatmapHeadStep(input_size=cfg.input_size, sigma=cfg.sigma)(dev(ex["pred"]), dev(batch["target"]), None, decode=False)
+    np.testing.assert_allclose(float(l2), float(g["kpmse_none"]), rtol=LOSS_RTOL)
+
+
+def test_heatmap_head_step_sharded_and_ties(pkg):
+    from oracle import heatmap_codec as oc
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=61, B=8)
+    step = pkg.pose_estimator.HeatmapHeadStep(input_size=cfg.input_size, sigma=cfg.sigma)
+    hm = batch["heatmaps"]                      # includes constant tiles and duplicated maxima (first-max rule)
+    def run(sl, nb=0):
+        p = dev(hm[sl]).requires_grad_(True)
+        loss, kp, mv = step(p, keypoints=dev(batch["kps"][sl]), keypoints_visible=dev(batch["vis"][sl]), norm_batch=nb)
+        loss.backward()
+        return float(loss.detach()), p.grad.cpu().numpy(), kp.cpu().numpy(), mv.cpu().numpy()
+    whole = run(slice(0, 8))
+    a, b = run(slice(0, 3), 8), run(slice(3, 8), 8)
+    np.testing.assert_allclose(a[0] + b[0], whole[0], rtol=2e-6)
+    assert np.array_equal(np.concatenate([a[1], b[1]]), whole[1])
+    wkp, wmv, _ = oc.decode_heatmaps(T(hm), shift=True)
+    assert np.array_equal(whole[2], wkp.numpy()) and np.array_equal(whole[3], wmv.numpy())
+    want = genb.keypoint_mse_loss(T(hm), T(batch["target"]), T(batch["weight"]))
+    np.testing.assert_allclose(whole[0], float(want), rtol=LOSS_RTOL)

@@ -89,6 +89,8 @@ cen = torch.rand(B, 2, device=dev) * 300 + 100
 scl = torch.rand(B, 2, device=dev) * 200 + 150
 report("postprocess_kernel (whole pipeline)", "cfg1 64x48 B=1024", B * K, 4 * n,
        timeit(lambda: ops.postprocess(pred, d["kps"], cen, scl, N.ARGMAX_TAYLOR, True, 256.0, 5, True, 0.3, True, 256.0, 256.0)))
+report("heatmap_step_kernel (KeypointMSELoss fwd+bwd, on-the-fly target, arg-max)", "cfg1 64x48 B=1024", B * K, 8 * n,
+       timeit(lambda: ops.heatmap_step(pred, None, d["vis"], d["kps"], 192.0, 256.0, 2.0, True, 0, None, True, True, N.ARGMAX_QUARTER)))
 report("encode_genb_kernel clipped", "cfg1 64x48 B=1024", B * K, 4 * n, timeit(lambda: ops.encode_mode(d["kps"], d["vis"], H, W, 192.0, 256.0, 2.0, N.ENCODE_PATCH_CLIPPED)))
 report("encode_genb_kernel dense", "cfg1 64x48 B=1024", B * K, 4 * n, timeit(lambda: ops.encode_mode(d["kps"], d["vis"], H, W, 192.0, 256.0, 2.0, N.ENCODE_DENSE)))
 del d, tgt, wgt, pred
