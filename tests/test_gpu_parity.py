@@ -352,3 +352,33 @@ def test_host_buffer_step_matches_resident_step(gb, stage_offsets):
     for got, want in zip(hs.grads, res[1:4]):
         assert torch.equal(got, want[lo:])
     assert hs.h2d_bytes < (2 if not stage_offsets else 4) * B * K * H * W * 4 * 1.1
+
+
+# ---------------------------------------------------------------------- AMP: fp16 head outputs (train.py:171)
+def test_fp16_head_outputs_under_autocast(gb):
+    """Under autocast the head's outputs reach the loss in fp16.  The mirror computes in fp32 on the up-cast values (what
+    ATen's softmax / mse do under autocast) and autograd hands fp16 gradients back: they must equal the fp32 path's
+    gradients on the same up-cast inputs, rounded to fp16; the decode must equal the fp32 decode of those inputs."""
+    from infantposeestimation_gaussianbias_b200 import FusionPoseLoss, decode_outputs
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=23, B=4)
+    half = {k: dev(batch[k]).half() for k in ("heatmaps", "offsets", "variances")}
+    loss_fn = FusionPoseLoss(target_sigma=cfg.sigma)
+    with torch.autocast("cuda", dtype=torch.float16):
+        o16 = {k: v.clone().requires_grad_(True) for k, v in half.items()}
+        out16 = loss_fn(o16, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size)
+        scale = torch.tensor(1024.0).cuda()                   # a GradScaler-style loss scale
+        (out16["total_loss"] * scale).backward()
+    o32 = {k: v.float().requires_grad_(True) for k, v in half.items()}
+    out32 = loss_fn(o32, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size)
+    (out32["total_loss"] * 1024.0).backward()
+    for k in oc.LOSS_KEYS:
+        assert out16[k].dtype == torch.float32 and float(out16[k]) == float(out32[k])
+    for k in o16:
+        assert o16[k].grad.dtype == torch.float16
+        assert torch.equal(o16[k].grad, o32[k].grad.half()), k
+    a = torch.tensor(0.5).cuda()
+    fw = torch.sigmoid(torch.tensor(0.5)).cuda()
+    c16, s16 = decode_outputs({**half, "fusion_weight": fw}, a)
+    c32, s32 = decode_outputs({**{k: v.float() for k, v in half.items()}, "fusion_weight": fw}, a)
+    assert torch.equal(c16, c32) and torch.equal(s16, s32) and c16.dtype == torch.float32
