@@ -41,9 +41,33 @@ SKELETON = ((0, 1), (0, 2), (1, 3), (2, 4), (5, 6), (5, 7), (7, 9), (6, 8), (8, 
 BYTES_PER_HM = 24 * H * W          # fused step: read P,V (8N); write dP,dV,dO (16N)  — SURVEY §8d / DESIGN.md
 
 
+WORKLOAD = "BASELINE configs[1]: HRNet-W32 256x192 (64x48 heatmaps, K=17, sigma=2)"
+SYNTH_CONFIG = "w32_256x192"        # tests/synth.py config of the CPU arm
+TILE_KERNEL = "loss_tile_kernel<12,16,4,...>"
+
+# The default (and the driver's) workload is BASELINE configs[1].  The other fused-step configurations of BASELINE.json
+# can be selected for a measurement of their own; they change the shapes only.
+WORKLOADS = {
+    "w32": None,
+    "hrformer": dict(K=17, H=96, W=72, IN_W=288, IN_H=384, SIGMA=2.0, SYNTH_CONFIG="hrformer_384x288", TILE_KERNEL="loss_tile_kernel<18,16,6,...>",
+                     WORKLOAD="BASELINE configs[2] shapes: HRFormer-base 384x288 (96x72 heatmaps, K=17, sigma=2)"),
+    "preemie": dict(K=13, H=128, W=128, IN_W=256, IN_H=256, SIGMA=1.5, SYNTH_CONFIG="preemie_256", TILE_KERNEL="loss_tile_kernel<32,16,8,...>",
+                    WORKLOAD="BASELINE configs[3]: preemie_optimized.yaml (128x128 heatmaps, K=13, sigma=1.5, 256x256 input), full six-term loss"),
+}
+
+
+def select_workload(name):
+    w = WORKLOADS[name]
+    if w is None:
+        return
+    g = globals()
+    g.update(w)
+    g["BYTES_PER_HM"] = 24 * g["H"] * g["W"]
+    g["METRIC"] = f"heatmaps/sec (Bx{g['K']}x{g['H']}x{g['W']}, encode+loss+decode)"
+
+
 def workload_name(B):
-    return (f"BASELINE configs[1]: HRNet-W32 256x192 (64x48 heatmaps, K=17, sigma=2) fused codec step "
-            f"(on-the-fly encode + six-term loss fwd/bwd + decode), batch {B} per GPU")
+    return f"{WORKLOAD} fused codec step (on-the-fly encode + six-term loss fwd/bwd + decode), batch {B} per GPU"
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -107,7 +131,7 @@ def synth_device_batch(B, device, seed, ops):
     u = r(B, K)
     vis = torch.where(u < 0.15, 0.0, torch.where(u < 0.40, 1.0, 2.0))
     kps = torch.stack(((r(B, K) * 1.2 - 0.1) * IN_W, (r(B, K) * 1.2 - 0.1) * IN_H), dim=-1)
-    jitter = rn(B, K, 2) * 1.5 * 4.0
+    jitter = rn(B, K, 2) * 1.5 * (IN_W / W)
     shifted, _ = ops.encode(kps + jitter, torch.full_like(vis, 2.0), H, W, float(IN_W), float(IN_H), SIGMA)
     amp = r(B, K, 1, 1) * 0.9 + 0.3
     hm = amp * shifted + 0.05 * rn(B, K, H, W)
@@ -125,7 +149,7 @@ def cpu_step_rate(sample_B: int, min_seconds: float, max_reps: int):
     from tests import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.CONFIGS["w32_256x192"]
+    cfg = synth.CONFIGS[SYNTH_CONFIG]
     batch = synth.make_batch(cfg, seed=0, B=sample_B)
     T = lambda k: torch.from_numpy(batch[k])
     args = (batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"))
@@ -153,7 +177,7 @@ def run_reference(args):
     from tests import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.CONFIGS["w32_256x192"]
+    cfg = synth.CONFIGS[SYNTH_CONFIG]
     batch = synth.make_batch(cfg, seed=0, B=sample_B)
     T = lambda k: torch.from_numpy(batch[k])
     call = lambda: oc.codec_step(batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"),
@@ -351,11 +375,11 @@ def run_b200(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = B * K * BYTES_PER_HM / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "loss_tile_kernel<12,16,4,...> (fused step: on-the-fly target + six-term loss fwd/bwd + decode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": f"{TILE_KERNEL} (fused step: on-the-fly target + six-term loss fwd/bwd + decode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_launches_timed": len(sampled),
                 "algorithmic_bytes_per_launch": B * K * BYTES_PER_HM}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_path):
+    if os.path.exists(traffic_path) and args.config == "w32":      # the ncu capture is of the default workload's kernel
         try:
             roofline["traffic"] = json.load(open(traffic_path)).get("loss_kernel_dram_bytes_per_launch")
         except Exception:
@@ -403,10 +427,12 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="images per chunk of the host-buffer pipeline")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the 2+7 loss scalars travel between ranks (NVLink peer-memory mailboxes written by the kernels, or NCCL all-reduces)")
+    ap.add_argument("--config", default="w32", choices=sorted(WORKLOADS), help="fused-step workload (default: BASELINE configs[1])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    select_workload(args.config)
     args.out = _json_only_stdout()
     if args.impl == "reference":
         return run_reference(args)
