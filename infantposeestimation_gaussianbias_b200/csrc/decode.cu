@@ -454,9 +454,9 @@ int launch_decode(const float* hm, const float* hmf, const int32_t* perm, const 
         return launch_decode_tile<W4, ROWS, NIT, false, MB_PLAIN>(hm, hmf, perm, off, alpha_param, fusion_weight, grid_t, K, radius, flags, coords, scores, centre, stream); \
     } while (0)
     if (!generic) {
-        if (H == 64 && W == 48) GBC_TILE(12, 16, 4, 8, 6);      // 192 threads, 16 px each
-        if (H == 96 && W == 72) GBC_TILE(18, 16, 6, 4, 3);      // 288 threads, 24 px each
-        if (H == 128 && W == 128) GBC_TILE(32, 16, 8, 2, 2);    // 512 threads, 32 px each
+        if (H == 64 && W == 48) GBC_TILE(12, 16, 4, 10, 8);     // 192 threads, 16 px each
+        if (H == 96 && W == 72) GBC_TILE(18, 16, 6, 5, 4);      // 288 threads, 24 px each
+        if (H == 128 && W == 128) GBC_TILE(32, 16, 8, 3, 2);    // 512 threads, 32 px each
     }
 #undef GBC_TILE
     int niter = 0;
