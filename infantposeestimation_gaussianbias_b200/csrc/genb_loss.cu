@@ -66,8 +66,8 @@ __device__ __forceinline__ float crit_slope(int crit, float d) {
 }
 
 // ---- per-tile heatmap + morphology terms ------------------------------------------------------
-template <int NITER, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+template <int NITER, int MAXT, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ GenbArgs A) {
     __shared__ float red_a[8 * 32], red_b[4 * 32];
     if (A.plan && *A.plan == 0) return;               // stored gradients already right
