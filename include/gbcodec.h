@@ -347,6 +347,34 @@ int gbcodec_heatmap_step_f32(const float* d_hm, const float* d_target, const flo
                              float* d_coords, float* d_maxvals, int32_t* d_index,
                              void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* float16 maps — what the head hands the loss under autocast (train.py:171).
+ * d_hm, d_off, d_var and the three gradients are IEEE binary16 (same shapes); losses, coordinates, scores, weights,
+ * keypoints and target tiles stay float32.  Values are up-cast where they enter the kernel and every sum runs in
+ * float32, so the losses and the decode are exactly those of the float32 entry points on the up-cast maps, at half the
+ * bytes.  A gradient has to meet its upstream factor — the loss scaler's 2^16 — BEFORE it is rounded to half, or it
+ * underflows.  So:
+ *   gbcodec_fusion_step_f16           stores gradients only if the gradient pointers are given, pre-multiplied by
+ *                                     *d_grad_scale: the upstream factor the caller EXPECTS (last step's loss scale);
+ *   gbcodec_fusion_loss_backward_f16  compares the actual upstream d_grad_losses7 with that assumption on the device
+ *                                     and returns inside the kernel if it held (gradients_stored != 0); otherwise, or if
+ *                                     nothing was stored, it computes the gradients with the actual per-term factors.
+ * In steady state a training step is ONE pass (12N bytes per tile instead of 24N), a changed loss scale costs one more.
+ * Tile shapes 64x48, 96x72, 128x128 (GBCODEC_ERR_BAD_SHAPE otherwise: up-cast and use the float32 entry points).
+ * Pixels whose logit equals a limb partner's exactly (frequent in half precision) take their half of the overlap gradient
+ * in a second store: those gradients are rounded twice (<= 1 ulp of half). */
+int gbcodec_fusion_step_f16(const gbcodec_loss_desc* desc,
+                            const void* d_hm, const void* d_off, const void* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps, const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, void* d_grad_hm, void* d_grad_off, void* d_grad_var,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores, void* d_workspace, size_t workspace_bytes, void* stream);
+int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,
+                            const void* d_hm, const void* d_off, const void* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps, const float* d_denoms,
+                            const float* d_grad_scale, int gradients_stored, const float* d_grad_losses7,
+                            void* d_grad_hm, void* d_grad_off, void* d_grad_var,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement hook (bench.py): the next gbcodec_fusion_loss_f32 / _step_f32 calls made
  * by THIS host thread record `start_event` right before and `stop_event` right after
  * the per-tile loss kernel, on the stream of the call.  Both are cudaEvent_t passed as

@@ -38,6 +38,7 @@ EXPORTS = (
     "gbcodec_combined_workspace_bytes", "gbcodec_combined_loss_f32", "gbcodec_combined_loss_backward_f32",
     "gbcodec_peer_create", "gbcodec_peer_connect", "gbcodec_peer_status", "gbcodec_peer_destroy",
     "gbcodec_fusion_step_sharded_f32", "gbcodec_heatmap_step_f32",
+    "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16",
 )
 
 
@@ -123,6 +124,10 @@ def _declare(lib):
     lib.gbcodec_heatmap_step_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                              C.c_double, C.c_int, C.c_int, f32p, f32p, f32p, C.c_int, f32p, f32p, _P,
                                              _P, C.c_size_t, _P]
+    lib.gbcodec_fusion_step_f16.argtypes = [C.POINTER(LossDesc), _P, _P, _P, f32p, f32p, f32p, f32p, f32p, f32p, _P, _P, _P,
+                                            f32p, f32p, C.c_int, C.c_uint, f32p, f32p, _P, C.c_size_t, _P]
+    lib.gbcodec_fusion_loss_backward_f16.argtypes = [C.POINTER(LossDesc), _P, _P, _P, f32p, f32p, f32p, f32p, f32p, C.c_int, f32p,
+                                                     _P, _P, _P, _P, C.c_size_t, _P]
     lib.gbcodec_peer_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
     lib.gbcodec_peer_connect.argtypes = [_P, C.c_char_p]
     lib.gbcodec_peer_status.argtypes = [_P, C.POINTER(C.c_int)]

@@ -33,14 +33,14 @@ size_t loss_workspace_bytes(int B, int K);
 int loss_denominators(const gbcodec_loss_desc*, const float*, const float*, int, float*, void*, size_t, cudaStream_t);
 int fusion_loss(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
                 const float*, const float*, float*, float*, float*, float*,
-                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*);
+                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*, int);
 int peer_create(int, int, void**, unsigned char*);
 int peer_connect(void*, const unsigned char*);
 int peer_status(void*, int*);
 int peer_destroy(void*);
 int fusion_loss_backward(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*,
                          const float*, const float*, const float*, const float*, float*, float*, float*, void*, size_t,
-                         cudaStream_t);
+                         cudaStream_t, int, int);
 
 int launch_postprocess(const gbcodec_postprocess_desc*, const float*, const float*, const float*, const float*, float*, float*,
                        float*, void*, cudaStream_t);
@@ -224,7 +224,7 @@ int gbcodec_fusion_loss_f32(const gbcodec_loss_desc* desc,
                             void* d_workspace, size_t workspace_bytes, void* stream) {
     return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
-                       nullptr, nullptr, 0, 0u, nullptr, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr);
+                       nullptr, nullptr, 0, 0u, nullptr, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0);
 }
 
 int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
@@ -239,7 +239,7 @@ int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
     return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
                        d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
-                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr);
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0);
 }
 
 int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
@@ -254,7 +254,7 @@ int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
     return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, nullptr, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
                        d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
-                       d_workspace, workspace_bytes, (cudaStream_t)stream, peer_ctx, d_denoms_out);
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, peer_ctx, d_denoms_out, 0);
 }
 
 int gbcodec_peer_create(int rank, int world, void** ctx_out, unsigned char* handle_out) { return peer_create(rank, world, ctx_out, handle_out); }
@@ -270,7 +270,31 @@ int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
                             void* d_workspace, size_t workspace_bytes, void* stream) {
     return fusion_loss_backward(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                                 d_grad_losses7, d_grad_hm, d_grad_off, d_grad_var, d_workspace, workspace_bytes,
-                                (cudaStream_t)stream);
+                                (cudaStream_t)stream, 0, 1);
+}
+
+int gbcodec_fusion_step_f16(const gbcodec_loss_desc* desc,
+                            const void* d_hm, const void* d_off, const void* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps, const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, void* d_grad_hm, void* d_grad_off, void* d_grad_var,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if ((d_coords == nullptr) != (d_scores == nullptr)) return fail(GBCODEC_ERR_NULL_POINTER, "step_f16: give d_coords and d_scores or neither");
+    return fusion_loss(desc, (const float*)d_hm, (const float*)d_off, (const float*)d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
+                       d_losses7, (float*)d_grad_hm, (float*)d_grad_off, (float*)d_grad_var,
+                       d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 1);
+}
+
+int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,
+                            const void* d_hm, const void* d_off, const void* d_var, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps, const float* d_denoms,
+                            const float* d_grad_scale, int gradients_stored, const float* d_grad_losses7,
+                            void* d_grad_hm, void* d_grad_off, void* d_grad_var,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    return fusion_loss_backward(desc, (const float*)d_hm, (const float*)d_off, (const float*)d_var, d_target, d_weight, d_gt_kps, d_denoms,
+                                d_grad_scale, d_grad_losses7, (float*)d_grad_hm, (float*)d_grad_off, (float*)d_grad_var,
+                                d_workspace, workspace_bytes, (cudaStream_t)stream, 1, gradients_stored ? 1 : 0);
 }
 
 int gbcodec_profile_loss_kernel(void* start_event, void* stop_event) {

@@ -1,15 +1,21 @@
 // decode_device.cuh — device helpers shared by decode.cu and the fused step in loss.cu.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace gbc {
 
 __device__ __forceinline__ float4 rev4(const float4& v) { return make_float4(v.w, v.z, v.y, v.x); }
 
+// one element as float: the maps are float32, or float16 under autocast (the values are up-cast, never the sums)
+__device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld1(const __half* p) { return __half2float(__ldg(p)); }
+
 // value of the (possibly flip-averaged) tile at one pixel; same arithmetic as the vector load path
-__device__ __forceinline__ float tile_at(const float* hm_tile, const float* hmf_tile, int W, int x, int y) {
-    float v = __ldg(hm_tile + y * W + x);
-    if (hmf_tile) v = (v + __ldg(hmf_tile + y * W + (W - 1 - x))) * 0.5f;
+template <typename T>
+__device__ __forceinline__ float tile_at(const T* hm_tile, const T* hmf_tile, int W, int x, int y) {
+    float v = ld1(hm_tile + y * W + x);
+    if (hmf_tile) v = (v + ld1(hmf_tile + y * W + (W - 1 - x))) * 0.5f;
     return v;
 }
 
@@ -36,17 +42,19 @@ __device__ __forceinline__ Bilinear bilinear_setup(float cx, float cy, int H, in
     b.w10 = (1.f - b.fx) * b.fy;         b.w11 = b.fx * b.fy;
     return b;
 }
-__device__ __forceinline__ float bilinear_read(const float* ch, const Bilinear& b, int W) {
-    const float v00 = __ldg(ch + b.y0 * W + b.x0);
-    const float v01 = __ldg(ch + b.y0 * W + b.x1) * b.okx;
-    const float v10 = __ldg(ch + b.y1 * W + b.x0) * b.oky;
-    const float v11 = __ldg(ch + b.y1 * W + b.x1) * (b.okx * b.oky);
+template <typename T>
+__device__ __forceinline__ float bilinear_read(const T* ch, const Bilinear& b, int W) {
+    const float v00 = ld1(ch + b.y0 * W + b.x0);
+    const float v01 = ld1(ch + b.y0 * W + b.x1) * b.okx;
+    const float v10 = ld1(ch + b.y1 * W + b.x0) * b.oky;
+    const float v11 = ld1(ch + b.y1 * W + b.x1) * (b.okx * b.oky);
     return b.w00 * v00 + b.w01 * v01 + b.w10 * v10 + b.w11 * v11;
 }
 
 // Steps 3-6 of the decode for one tile, executed by warp 0 once the global
 // soft-argmax (cx, cy) is known.  Result in lane 0.
-__device__ __forceinline__ void refine_and_correct(const float* hm_tile, const float* hmf_tile, const float* off_tile,
+template <typename T>
+__device__ __forceinline__ void refine_and_correct(const T* hm_tile, const T* hmf_tile, const T* off_tile,
                                                    const float* alpha_param, const float* fusion_weight,
                                                    int H, int W, int radius, unsigned flags,
                                                    float& cx, float& cy, int& px_out, int& py_out) {

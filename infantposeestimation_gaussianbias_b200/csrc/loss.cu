@@ -233,7 +233,7 @@ loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossAr
     // ---- fused decode (warp 0) ------------------------------------------------------------
     if (decode && tid < 32) {
         float dx_ = cx, dy_ = cy; int px, py;
-        refine_and_correct(A.hm + (size_t)tile * n, nullptr, A.off ? A.off + (size_t)tile * 2 * n : nullptr,
+        refine_and_correct<float>(A.hm + (size_t)tile * n, nullptr, A.off ? A.off + (size_t)tile * 2 * n : nullptr,
                            A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, dx_, dy_, px, py);
         if (tid == 0) { A.coords[2 * tile] = dx_; A.coords[2 * tile + 1] = dy_; A.scores[tile] = m; }
     }
@@ -641,9 +641,10 @@ static bool force_generic() {
 }
 
 static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s) {
-    if (!force_generic()) {
+    if (!force_generic() || A.half_io) {
         const int st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st != 1) return st;
+        if (A.half_io) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: float16 maps are supported for 64x48, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
     }
     const int n4 = (P.H * P.W) >> 2;
     if (n4 == 256 * 3) return launch_loss_t<256, 3, 2>(P, A, s);           // 64x48
@@ -703,7 +704,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
                 const float* weight, const float* gt, const float* denoms, const float* grad_scale,
                 float* losses7, float* ghm, float* goff, float* gvar,
                 const float* alpha_param, const float* fusion_weight, int radius, unsigned dflags, float* coords, float* scores,
-                void* ws, size_t ws_size, cudaStream_t s, void* peer_ctx, float* denoms_out) {
+                void* ws, size_t ws_size, cudaStream_t s, void* peer_ctx, float* denoms_out, int half_io) {
     int st = check_common(d, hm, off, weight, gt, ws, ws_size);
     if (st) return st;
     PeerView peer = kNoPeers;
@@ -743,6 +744,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.alpha_param = alpha_param; A.fusion_weight = fusion_weight; A.coords = coords; A.scores = scores;
     A.radius = radius; A.dflags = dflags;
     A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial;
+    A.half_io = half_io;
     st = launch_loss_kernel(P, A, s);
     if (st) return st;
     const int tiles = P.B * P.K;
@@ -753,7 +755,8 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
 
 int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const float* off, const float* var, const float* target,
                          const float* weight, const float* gt, const float* denoms, const float* grad_scale, const float* g7,
-                         float* ghm, float* goff, float* gvar, void* ws, size_t ws_size, cudaStream_t s) {
+                         float* ghm, float* goff, float* gvar, void* ws, size_t ws_size, cudaStream_t s, int half_io,
+                         int have_stash) {
     int st = check_common(d, hm, off, weight, gt, ws, ws_size);
     if (st) return st;
     if (!g7 || !ghm || !goff || (!gvar) != (!var)) return fail(GBCODEC_ERR_NULL_POINTER, "backward: NULL pointer");
@@ -765,16 +768,23 @@ int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const floa
     st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
     if (st) return st;
     plan_kernel<<<1, 32, 0, s>>>(P, g7, grad_scale, L.plan, L.lam_eff);
-    const size_t n4 = (size_t)P.B * P.K * P.H * P.W / 4;
-    const int grid = 148 * 8;
-    rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4);
-    rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(goff), 2 * n4);
-    if (gvar) rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(gvar), n4);
+    if (!half_io) {
+        const size_t n4 = (size_t)P.B * P.K * P.H * P.W / 4;
+        const int grid = 148 * 8;
+        rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4);
+        rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(goff), 2 * n4);
+        if (gvar) rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(gvar), n4);
+    }
     LossArgs A;
     memset(&A, 0, sizeof(A));
     A.hm = hm; A.off = off; A.var = var; A.target = target; A.weight = weight; A.gt = gt;
     A.grad_hm = ghm; A.grad_off = goff; A.grad_var = gvar;
-    A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial; A.lam_eff = L.lam_eff; A.plan = L.plan;
+    A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial; A.lam_eff = L.lam_eff;
+    // float16 maps: a gradient must meet its upstream factor before it is rounded to half.  Either the forward stored
+    // gradients for an ASSUMED upstream factor (d_grad_scale) and this call only re-computes them if the actual one
+    // differs (plan != 0), or it stored nothing and this call always computes them (per-term weights of plan_kernel)
+    A.plan = (half_io && !have_stash) ? nullptr : L.plan;
+    A.half_io = half_io;
     return launch_loss_kernel(P, A, s);
 }
 

@@ -40,6 +40,7 @@ struct LossArgs {
     float* partial;                     // [B*K][8] un-normalised per-tile loss numerators
     const float* lam_eff;               // backward recompute: device [6] per-term multipliers
     const int* plan;                    // backward recompute: run only if *plan == 2
+    int half_io;                        // hm, off, var and the three gradients are float16 (the pointers are then __half*)
 };
 
 constexpr int kFinBlocks = 32;          // CTAs of the second-stage reduction

@@ -27,6 +27,7 @@
 // Algorithmic HBM bytes per tile: read hm, var (8N); write d_hm, d_var, d_off (16N).
 #include "loss_common.cuh"
 #include "f32x2.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace gbc {
@@ -91,12 +92,64 @@ __device__ __forceinline__ T pick4(int i, T a, T b, T c, T d) { return i == 0 ? 
 
 // Out-of-line copy of the un-staged decode tail for the rare paths (weight-0 tiles, radius > 2),
 // so that the hot path's code stays small.
-__device__ __noinline__ void refine_and_correct_cold(const float* hm_tile, const float* off_tile, const float* alpha_param,
+template <typename T>
+__device__ __noinline__ void refine_and_correct_cold(const T* hm_tile, const T* off_tile, const float* alpha_param,
                                                      const float* fusion_weight, int H, int W, int radius, unsigned flags,
                                                      float* cx, float* cy) {
     int px, py;
-    refine_and_correct(hm_tile, nullptr, off_tile, alpha_param, fusion_weight, H, W, radius, flags, *cx, *cy, px, py);
+    refine_and_correct<T>(hm_tile, nullptr, off_tile, alpha_param, fusion_weight, H, W, radius, flags, *cx, *cy, px, py);
 }
+
+// ---- element type of the maps -------------------------------------------------------------------
+// float32, or float16 under autocast (train.py:171).  Half maps are up-cast value by value where they enter
+// (registers / the shared-memory slots hold float32 either way), gradients are rounded once where they leave;
+// everything in between is the same code.  A "vector" is four pixels: 16 bytes of float, 8 bytes of half.
+__device__ __forceinline__ float4 half4_to_float4(const uint2& r) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 float4_to_half4(const float4& v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const unsigned*>(&a); r.y = *reinterpret_cast<const unsigned*>(&b);
+    return r;
+}
+template <bool HALF> struct TileIO;
+template <> struct TileIO<false> {
+    using Vec = float4;
+    using Elem = float;
+    static __device__ __forceinline__ float4 load_stream(const Vec* p) { return ldg_stream(p); }
+    static __device__ __forceinline__ float4 load_keep(const Vec* p) { return ldg_keep(p); }
+    static __device__ __forceinline__ float4 load_plain(const Vec* p) { return *p; }
+    static __device__ __forceinline__ void store_stream(Vec* p, const float4& v) { stg_stream(p, v); }
+    static __device__ __forceinline__ void store_plain(Vec* p, const float4& v) { *p = v; }
+    static __device__ __forceinline__ void copy_async(float4* slot, const Vec* g) { cp_async16(slot, g); }
+    static __device__ __forceinline__ float4 from_slot(const float4* slot) { return *slot; }
+    static __device__ __forceinline__ void st1(Elem* p, float v) { *p = v; }
+};
+template <> struct TileIO<true> {
+    using Vec = uint2;
+    using Elem = __half;
+    static __device__ __forceinline__ float4 load_stream(const Vec* p) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return half4_to_float4(r);
+    }
+    static __device__ __forceinline__ float4 load_keep(const Vec* p) { return half4_to_float4(__ldg(p)); }
+    static __device__ __forceinline__ float4 load_plain(const Vec* p) { return half4_to_float4(*p); }
+    static __device__ __forceinline__ void store_stream(Vec* p, const float4& v) {
+        const uint2 r = float4_to_half4(v);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(r.x), "r"(r.y) : "memory");
+    }
+    static __device__ __forceinline__ void store_plain(Vec* p, const float4& v) { *p = float4_to_half4(v); }
+    // the raw halves land in the first 8 bytes of the thread's 16-byte slot; from_slot up-casts them
+    static __device__ __forceinline__ void copy_async(float4* slot, const Vec* g) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(slot);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(g) : "memory");
+    }
+    static __device__ __forceinline__ float4 from_slot(const float4* slot) { return half4_to_float4(*reinterpret_cast<const uint2*>(slot)); }
+    static __device__ __forceinline__ void st1(Elem* p, float v) { *p = __float2half_rn(v); }
+};
 
 // Target modes: where the target tile comes from
 constexpr int kTargetOneHit = 0;   // generated on the fly; the patch is no taller than ROWS, so a thread meets it in at most one row
@@ -107,13 +160,19 @@ constexpr int kTargetLut = 2;      // generated on the fly, any patch height
 // ROLL = false: the tile stays in registers and the row loops are fully unrolled (most ILP, ~80 registers, large code).
 // ROLL = true : the tile is parked in a thread-private shared-memory slot as well and the row loops stay rolled
 //               (4x smaller loop code, <= 64 registers -> one more CTA per SM).
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false>
 __global__ void __launch_bounds__(W4* ROWS, MINB)
 loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
+    using IO = TileIO<HALF>;
+    using Vec = typename IO::Vec;
+    using Elem = typename IO::Elem;
     constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
     static_assert(TPB % 32 == 0 && TPB <= 1024, "CTA must be whole warps");
     static_assert(GBCODEC_MAX_PARTNERS == 4, "tie patterns are nibbles");
-    if (A.plan && *A.plan != 2) return;      // backward recompute not needed
+    // backward call: nothing to do if the stored gradients are already right (plan 0); float32 gradients that are
+    // off by one common factor are rescaled in place by rescale_kernel (plan 1), float16 ones are computed again
+    // (a stored half cannot be rescaled without a second rounding)
+    if (A.plan && (HALF ? *A.plan == 0 : *A.plan != 2)) return;
 
     extern __shared__ __align__(16) float smem[];
     constexpr int UNR = ROLL ? 1 : NIT;
@@ -136,23 +195,23 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     // ---- bulk loads first: the tile into registers, the variance map into its sum ----------------
     // (unconditional: whether the tile carries weight is only known one L2 round trip later)
     const size_t toff = (size_t)tile * N4 + tid;
-    const float4* hmb = reinterpret_cast<const float4*>(A.hm) + tid;
-    const float4* hm4 = reinterpret_cast<const float4*>(A.hm) + toff;
+    const Vec* hmb = reinterpret_cast<const Vec*>(A.hm) + tid;
+    const Vec* hm4 = reinterpret_cast<const Vec*>(A.hm) + toff;
     float4 h[NIT];
     if (ROLL) {
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) cp_async16(Hs + it * TPB + tid, hm4 + it * TPB);
+        for (int it = 0; it < NIT; ++it) IO::copy_async(Hs + it * TPB + tid, hm4 + it * TPB);
         cp_async_commit();
     } else {
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) h[it] = ldg_stream(hm4 + it * TPB);
+        for (int it = 0; it < NIT; ++it) h[it] = IO::load_stream(hm4 + it * TPB);
     }
     auto own4 = [&](int it) -> float4 { return ROLL ? Hs[it * TPB + tid] : h[it]; };
     float4 vv[NIT];
     if (A.var) {
-        const float4* var4 = reinterpret_cast<const float4*>(A.var) + toff;
+        const Vec* var4 = reinterpret_cast<const Vec*>(A.var) + toff;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) vv[it] = ldg_stream(var4 + it * TPB);
+        for (int it = 0; it < NIT; ++it) vv[it] = IO::load_stream(var4 + it * TPB);
     }
     // then every scalar the tile will need
     const float w = __ldg(A.weff + tile);
@@ -167,14 +226,14 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const bool grads = A.grad_hm != nullptr;
     const bool backward_only = A.lam_eff != nullptr;
     const bool decode = A.coords != nullptr;
-    float4* gh4 = reinterpret_cast<float4*>(A.grad_hm) + toff;
-    float4* gv4 = (grads && A.grad_var) ? reinterpret_cast<float4*>(A.grad_var) + toff : nullptr;
+    Vec* gh4 = reinterpret_cast<Vec*>(A.grad_hm) + toff;
+    Vec* gv4 = (grads && A.grad_var) ? reinterpret_cast<Vec*>(A.grad_var) + toff : nullptr;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // the offset gradient is zero except on (up to) four taps per channel, patched at the end
     if (grads) {
-        float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
+        Vec* go4 = reinterpret_cast<Vec*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
 #pragma unroll
-        for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
+        for (int it = 0; it < 2 * NIT; ++it) IO::store_stream(go4 + it * TPB, z4);
     }
 
     const int tx = tid % W4, ty = tid / W4;
@@ -215,7 +274,13 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 
     // ---- reduction 1: tile maximum -----------------------------------------------------------
     float m = -INFINITY;
-    if (ROLL) cp_async_wait_all();            // own slots only: no barrier needed
+    if (ROLL) {
+        cp_async_wait_all();                  // own slots only: no barrier needed
+        if (HALF) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) Hs[it * TPB + tid] = IO::from_slot(Hs + it * TPB + tid);
+        }
+    }
 #pragma unroll UNR
     for (int it = 0; it < NIT; ++it) { const float4 o = own4(it); m = fmaxf(m, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w))); }
     m = block_max1<NW>(m, red0);             // the barrier also publishes the exp table
@@ -224,9 +289,9 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     // first active partner's tile -> thread-private smem slots; it has all of pass B to arrive
     int cur = act ? __ffs(act) - 1 : -1;
     if (CQ && cur >= 0) {
-        const float4* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        const Vec* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+        for (int it = 0; it < NIT; ++it) IO::copy_async(Qs + it * TPB + tid, src + it * TPB);
         cp_async_commit();
     }
 
@@ -287,14 +352,14 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const float iZ = rcp(lane_value<8>(acc8, 0));
     const float cx = lane_value<8>(acc8, 1) * iZ, cy = lane_value<8>(acc8, 2) * iZ;
 
-    const float* hm_tile = A.hm + (size_t)tile * N;
-    const float* off_tile = A.off + (size_t)tile * 2 * N;
+    const Elem* hm_tile = reinterpret_cast<const Elem*>(A.hm) + (size_t)tile * N;
+    const Elem* off_tile = reinterpret_cast<const Elem*>(A.off) + (size_t)tile * 2 * N;
 
     // ---- weight 0: every term carries a factor w -> zero loss and gradient; decode only ----------
     if (!heavy) {
         if (decode && tid < 32) {
             float dx_ = cx, dy_ = cy;
-            refine_and_correct_cold(hm_tile, off_tile, A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, &dx_, &dy_);
+            refine_and_correct_cold<Elem>(hm_tile, off_tile, A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, &dx_, &dy_);
             if (tid == 0) { A.coords[2 * tile] = dx_; A.coords[2 * tile + 1] = dy_; A.scores[tile] = m; }
         }
         if (tid == 0 && !backward_only) {
@@ -304,8 +369,8 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         if (grads) {
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                stg_stream(gh4 + it * TPB, z4);
-                if (gv4) stg_stream(gv4 + it * TPB, z4);
+                IO::store_stream(gh4 + it * TPB, z4);
+                if (gv4) IO::store_stream(gv4 + it * TPB, z4);
             }
         }
         return;
@@ -332,8 +397,8 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         const Taps t0 = taps_setup(cx, cy, H, W);   // recomputed when the values are consumed: only the 8 loads stay live
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            ov[c][0] = __ldg(off_tile + c * N + t0.i00); ov[c][1] = __ldg(off_tile + c * N + t0.i01);
-            ov[c][2] = __ldg(off_tile + c * N + t0.i10); ov[c][3] = __ldg(off_tile + c * N + t0.i11);
+            ov[c][0] = ld1(off_tile + c * N + t0.i00); ov[c][1] = ld1(off_tile + c * N + t0.i01);
+            ov[c][2] = ld1(off_tile + c * N + t0.i10); ov[c][3] = ld1(off_tile + c * N + t0.i11);
         }
     }
     // decode stage 1 (warp RD): window taps around the rounded soft-argmax
@@ -347,7 +412,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         const int x = px - A.radius + lane % S, y = py - A.radius + lane / S;
         win_ok = lane < S * S && x >= 0 && x < W && y >= 0 && y < H;
         winx = (float)x; winy = (float)y;
-        if (win_ok) win = __ldg(hm_tile + y * W + x);
+        if (win_ok) win = ld1(hm_tile + y * W + x);
     }
 
     float r16[16];
@@ -363,14 +428,14 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     while (cur >= 0) {
         const unsigned rest = act & ~((2u << cur) - 1u);
         const int nxt = rest ? __ffs(rest) - 1 : -1;
-        const float4* src = hmb + ((size_t)b * P.K + pick4(nxt < 0 ? 0 : nxt, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        const Vec* src = hmb + ((size_t)b * P.K + pick4(nxt < 0 ? 0 : nxt, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         asm volatile("" : "+l"(src));                 // keep the pointer in registers instead of re-deriving it per row
-        const float4* srcc = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        const Vec* srcc = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         if (CQ) cp_async_wait_all();                  // this thread's slots hold partner `cur`
         f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
-            const float4 q4 = CQ ? Qs[it * TPB + tid] : ldg_stream(srcc + it * TPB);
+            const float4 q4 = CQ ? IO::from_slot(Qs + it * TPB + tid) : IO::load_stream(srcc + it * TPB);
             const float4 o = own4(it);
             const f4 hv = as_f4(o), qv = as_f4(q4);
             float sk[4];
@@ -384,7 +449,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const f2 g01 = add2(pack2(ex2(lo2(u01)), ex2(hi2(u01))), kOne), g23 = add2(pack2(ex2(lo2(u23)), ex2(hi2(u23))), kOne);
             float sq[4] = {rcp(lo2(g01)), rcp(hi2(g01)), rcp(lo2(g23)), rcp(hi2(g23))};
             // the slot has been consumed (its value went through the sigmoid): refill it with the next partner
-            if (CQ && nxt >= 0) cp_async16(Qs + it * TPB + tid, src + it * TPB);
+            if (CQ && nxt >= 0) IO::copy_async(Qs + it * TPB + tid, src + it * TPB);
             // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
             const f2 d01 = sub2(hv.a, qv.a), d23 = sub2(hv.b, qv.b);
             const float d[4] = {lo2(d01), hi2(d01), lo2(d23), hi2(d23)};
@@ -422,7 +487,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         const float g = lam[3] * kb * 2.f * (mV - P.sigma) * P.inv_n;
         const float4 g4 = make_float4(g, g, g, g);
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) stg_stream(gv4 + it * TPB, g4);
+        for (int it = 0; it < NIT; ++it) IO::store_stream(gv4 + it * TPB, g4);
     }
 
     // ---- pass C: entropy sums and relu moments about (cx, cy) ----------------------------------------
@@ -491,14 +556,14 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             dcx = a * cx + (1.f - a) * (sx / se);
             dcy = a * cy + (1.f - a) * (sy / se);
         } else if (A.dflags & GBCODEC_DECODE_REFINE) {
-            refine_and_correct_cold(hm_tile, nullptr, A.alpha_param, nullptr, H, W, A.radius, GBCODEC_DECODE_REFINE, &dcx, &dcy);
+            refine_and_correct_cold<Elem>(hm_tile, nullptr, A.alpha_param, nullptr, H, W, A.radius, GBCODEC_DECODE_REFINE, &dcx, &dcy);
         }
         if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
             const Bilinear dbl = bilinear_setup(dcx, dcy, H, W);
             // lane t < 8 fetches tap (t & 3) of channel (t >> 2)
             const int tap = lane & 3;
             const int yy = (tap & 2) ? dbl.y1 : dbl.y0, xx = (tap & 1) ? dbl.x1 : dbl.x0;
-            if (lane < 8) dtap = __ldg(off_tile + (lane >> 2) * N + yy * W + xx);
+            if (lane < 8) dtap = ld1(off_tile + (lane >> 2) * N + yy * W + xx);
         }
     }
     if (warp == RO) {
@@ -523,15 +588,15 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             if (grads) {
                 // the (up to) four non-zero taps per channel of the offset gradient; the zero fill of these
                 // addresses was issued before the first barrier, so it is ordered before these stores
-                float* go = A.grad_off + (size_t)tile * 2 * N;
+                Elem* go = reinterpret_cast<Elem*>(A.grad_off) + (size_t)tile * 2 * N;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
-                    float* o = go + ch * N;
+                    Elem* o = go + ch * N;
                     const float gc = h2 * sl1p[ch];
-                    o[tp.i00] = gc * tp.w00;
-                    if (tp.okx != 0.f) o[tp.i01] = gc * tp.w01;
-                    if (tp.oky != 0.f) o[tp.i10] = gc * tp.w10;
-                    if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = gc * tp.w11;
+                    IO::st1(o + tp.i00, gc * tp.w00);
+                    if (tp.okx != 0.f) IO::st1(o + tp.i01, gc * tp.w01);
+                    if (tp.oky != 0.f) IO::st1(o + tp.i10, gc * tp.w10);
+                    if (tp.okx != 0.f && tp.oky != 0.f) IO::st1(o + tp.i11, gc * tp.w11);
                 }
             }
         }
@@ -667,7 +732,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 g01 = fma2(pack2(G[0], G[1]), fma2(mul2(s01, kNeg), s01, s01), g01);
                 g23 = fma2(pack2(G[2], G[3]), fma2(mul2(s23, kNeg), s23, s23), g23);
             }
-            stg_stream(gh4 + it * TPB, as_float4(f4{g01, g23}));
+            IO::store_stream(gh4 + it * TPB, as_float4(f4{g01, g23}));
         }
     }
 
@@ -677,17 +742,17 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         for (int pi = 0; pi < 4; ++pi) {
             const float cjp = lutw[16 + pi];
             if (!((act >> pi) & 1u) || cjp == 0.f) continue;
-            const float4* src = hmb + ((size_t)b * P.K + pick4(pi, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+            const Vec* src = hmb + ((size_t)b * P.K + pick4(pi, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
             for (int it = 0; it < NIT; ++it) {
-                const float4 q = ldg_keep(src + it * TPB), o = ldg_keep(hm4 + it * TPB);
+                const float4 q = IO::load_keep(src + it * TPB), o = IO::load_keep(hm4 + it * TPB);
                 if (q.x == o.x || q.y == o.y || q.z == o.z || q.w == o.w) {
-                    float4 g = gh4[it * TPB];
+                    float4 g = IO::load_plain(gh4 + it * TPB);
                     float s;
                     if (q.x == o.x) { s = sigmoid_fast(o.x); g.x = fmaf(0.5f * cjp * s, 1.f - s, g.x); }
                     if (q.y == o.y) { s = sigmoid_fast(o.y); g.y = fmaf(0.5f * cjp * s, 1.f - s, g.y); }
                     if (q.z == o.z) { s = sigmoid_fast(o.z); g.z = fmaf(0.5f * cjp * s, 1.f - s, g.z); }
                     if (q.w == o.w) { s = sigmoid_fast(o.w); g.w = fmaf(0.5f * cjp * s, 1.f - s, g.w); }
-                    gh4[it * TPB] = g;
+                    IO::store_plain(gh4 + it * TPB, g);
                 }
             }
         }
@@ -712,12 +777,12 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false>
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
     const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
                       + (size_t)(2 * NW * 16 + 32 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
-    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB>;
+    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF>;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_kernel): %s", cudaGetErrorString(e));
@@ -729,11 +794,11 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     return check_launch("loss_tile_kernel");
 }
 
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB, bool CQ = true, bool ROLL = false>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB, bool CQ = true, bool ROLL = false, bool HALF = false>
 static int launch_tile_tm(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
-    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetGlobal, MINB>(P, A, s, e0, e1);
-    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetOneHit, MINB>(P, A, s, e0, e1);
-    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetLut, MINB>(P, A, s, e0, e1);
+    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetGlobal, MINB, HALF>(P, A, s, e0, e1);
+    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetOneHit, MINB, HALF>(P, A, s, e0, e1);
+    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetLut, MINB, HALF>(P, A, s, e0, e1);
 }
 
 // GBCODEC_TILE_VARIANT=<n>: alternative CTA shapes for the 64x48 tile (measurement only)
@@ -743,6 +808,13 @@ static int tile_variant() {
 }
 
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    if (A.half_io) {
+        // float16 maps (autocast): the default instantiation of each shape; other shapes have no half path
+        if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, true>(P, A, s, e0, e1);
+        if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, true>(P, A, s, e0, e1);
+        if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, true>(P, A, s, e0, e1);
+        return 1;
+    }
     if (P.H == 64 && P.W == 48) {
         switch (tile_variant()) {
             case 1: return launch_tile_tm<12, 16, 4, false, true, true, 5, false, true>(P, A, s, e0, e1);   // rolled; H,S,A     39 KB, 5 CTAs

@@ -75,6 +75,8 @@ class FusionPoseLoss(nn.Module):
                 heatmap_size: Tuple[int, int] = (48, 64), *, denominators: Optional[Tensor] = None,
                 grad_scale: Optional[Tensor] = None, decode: Optional[dict] = None, peer=None) -> Dict[str, Tensor]:
         # heatmap_size is accepted and ignored, as in the reference (it uses heatmaps.shape, :771)
+        if self._half_maps(outputs) and denominators is None and grad_scale is None and peer is None:
+            return self._forward_f16(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, decode)
         hm = _f32(outputs["heatmaps"])
         off = _f32(outputs["offsets"])
         var = _f32(outputs.get("variances"))
@@ -96,6 +98,48 @@ class FusionPoseLoss(nn.Module):
         if dec:
             out["coords"], out["scores"] = res[4], res[5]
         return out
+
+
+def _fusion_loss_half_methods():
+    def _half_maps(self, outputs) -> bool:
+        """Autocast (train.py:171): the head's three maps arrive in float16 and the tile shape has a float16 kernel."""
+        hm, off, var = outputs["heatmaps"], outputs["offsets"], outputs.get("variances")
+        return (hm.dtype == torch.float16 and off.dtype == torch.float16 and (var is None or var.dtype == torch.float16)
+                and hm.is_cuda and tuple(hm.shape[-2:]) in ops.HALF_TILE_SHAPES)
+
+    def _forward_f16(self, outputs, target_heatmaps, target_weight, gt_keypoints, input_size, decode):
+        hm, off, var = outputs["heatmaps"], outputs["offsets"], outputs.get("variances")
+        K = hm.shape[1]
+        if target_heatmaps is not None and target_heatmaps.numel() == 0:
+            target_heatmaps = None
+        with_grads = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (hm, off, var))
+        # The upstream gradient this step will most likely see is the one the last step saw (the GradScaler's scale moves
+        # once in thousands of steps).  It lives on the device; the kernels compare, nothing is read back.
+        state = getattr(self, "_amp_upstream", None)
+        if with_grads and (state is None or state.device != hm.device):
+            state = torch.ones(1, dtype=torch.float32, device=hm.device)
+            object.__setattr__(self, "_amp_upstream", state)
+        sigma_enc = float(self.encode_sigma if self.encode_sigma is not None else self.target_sigma)
+        dec = decode or {}
+        losses7, coords, scores, _, _, _ = ops.fusion_loss_f16(
+            hm, off, var, _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), None, state if with_grads else None,
+            float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
+            bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads, bool(dec), dec.get("alpha_param"),
+            dec.get("fusion_weight"), int(dec.get("radius", 2)), int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)))
+        if with_grads and losses7.requires_grad:
+            def remember(g, st=state):          # what total_loss actually received, kept on the device for the next step
+                st.copy_(g[6:7])
+            losses7.register_hook(remember)
+        out = {k: losses7[i] for i, k in enumerate(LOSS_KEYS)}
+        if dec:
+            out["coords"], out["scores"] = coords, scores
+        return out
+
+    FusionPoseLoss._half_maps = _half_maps
+    FusionPoseLoss._forward_f16 = _forward_f16
+
+
+_fusion_loss_half_methods()
 
 
 def soft_argmax(heatmaps: Tensor) -> Tuple[Tensor, Tensor]:

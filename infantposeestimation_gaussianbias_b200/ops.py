@@ -578,3 +578,122 @@ def _heatmap_step_backward(ctx, g_loss, g_ghm, g_coords, g_maxvals):
 
 
 heatmap_step.register_autograd(_heatmap_step_backward, setup_context=_heatmap_step_setup)
+
+
+# --------------------------------------------------------------------------- float16 maps (autocast)
+HALF_TILE_SHAPES = ((64, 48), (96, 72), (128, 128))
+
+
+def _cuda_f16(name: str, t: Tensor, shape: Sequence[int]) -> Tensor:
+    if not t.is_cuda or t.dtype != torch.float16 or tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"gbcodec: `{name}` must be a CUDA float16 tensor of shape {tuple(shape)}")
+    return t.contiguous()
+
+
+@torch.library.custom_op(f"{_NS}::fusion_loss_f16", mutates_args=())
+def fusion_loss_f16(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor], weight: Tensor, gt_kps: Tensor,
+                    denoms: Optional[Tensor], expected_upstream: Optional[Tensor], in_w: float, in_h: float, lambdas: List[float],
+                    target_sigma: float, encode_sigma: float, use_target_weight: bool, pairs: List[int], with_grads: bool,
+                    with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
+                    decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """float16 heatmaps / offsets / variances -> losses7 (float32), coords, scores, grad_hm, grad_off, grad_var (float16).
+    With `with_grads` the pass also stores the gradients, pre-multiplied by `expected_upstream` (a 1-element float32
+    device tensor: the upstream gradient of total_loss the caller expects, i.e. the loss scale; None = 1) — the
+    backward keeps them if the expectation held and computes them again otherwise."""
+    B, K, H, W = hm.shape
+    hm = _cuda_f16("heatmaps", hm, (B, K, H, W))
+    off = _cuda_f16("offsets", off, (B, K, 2, H, W))
+    if var is not None:
+        var = _cuda_f16("variances", var, (B, K, H, W))
+    if target is not None:
+        target = _cuda_f32("target_heatmaps", target, (B, K, H, W))
+    weight = _cuda_f32("target_weight", weight.reshape(B, K), (B, K))
+    gt_kps = _cuda_f32("gt_keypoints", gt_kps, (B, K, 2))
+    if denoms is not None:
+        denoms = _cuda_f32("denominators", denoms.reshape(2), (2,))
+    expected_upstream = _scalar("expected_upstream", expected_upstream, hm)
+    dev = hm.device
+    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+    losses = torch.empty(7, dtype=torch.float32, device=dev)
+    empty = lambda dt=torch.float32: torch.empty(0, dtype=dt, device=dev)
+    coords = torch.empty((B, K, 2), dtype=torch.float32, device=dev) if with_decode else empty()
+    scores = torch.empty((B, K), dtype=torch.float32, device=dev) if with_decode else empty()
+    ghm = torch.empty_like(hm) if with_grads else empty(torch.float16)
+    goff = torch.empty_like(off) if with_grads else empty(torch.float16)
+    gvar = torch.empty_like(var) if (with_grads and var is not None) else empty(torch.float16)
+    if with_decode:
+        alpha_param = _scalar("alpha", alpha_param, hm)
+        fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
+    ws = _workspace(hm)
+    with torch.cuda.device(dev):
+        N.check(N.lib().gbcodec_fusion_step_f16(
+            desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(expected_upstream),
+            _ptr(losses), _ptr(ghm) if with_grads else None, _ptr(goff) if with_grads else None,
+            _ptr(gvar) if (with_grads and var is not None) else None,
+            _ptr(alpha_param) if with_decode else None, _ptr(fusion_weight) if with_decode else None, radius, decode_flags,
+            _ptr(coords) if with_decode else None, _ptr(scores) if with_decode else None, _ptr(ws), ws.numel(), _stream(hm)),
+            "fusion_step_f16")
+    return losses, coords, scores, ghm, goff, gvar
+
+
+@fusion_loss_f16.register_fake
+def _(hm, off, var, target, weight, gt_kps, denoms, expected_upstream, in_w, in_h, lambdas, target_sigma, encode_sigma,
+      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags):
+    B, K = hm.shape[0], hm.shape[1]
+    e = lambda dt=torch.float32: hm.new_empty(0, dtype=dt)
+    return (hm.new_empty(7, dtype=torch.float32), hm.new_empty((B, K, 2), dtype=torch.float32) if with_decode else e(),
+            hm.new_empty((B, K), dtype=torch.float32) if with_decode else e(),
+            torch.empty_like(hm) if with_grads else e(torch.float16), torch.empty_like(off) if with_grads else e(torch.float16),
+            torch.empty_like(var) if (with_grads and var is not None) else e(torch.float16))
+
+
+@torch.library.custom_op(f"{_NS}::fusion_loss_backward_f16", mutates_args=("grad_hm", "grad_off", "grad_var"))
+def fusion_loss_backward_f16(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor, grad_var: Optional[Tensor], stored: bool,
+                             hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor],
+                             weight: Tensor, gt_kps: Tensor, denoms: Optional[Tensor], expected_upstream: Optional[Tensor],
+                             in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
+                             use_target_weight: bool, pairs: List[int]) -> None:
+    B, K, H, W = hm.shape
+    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+    g7 = _cuda_f32("grad_losses", grad_losses.reshape(7), (7,))
+    ws = _workspace(hm)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().gbcodec_fusion_loss_backward_f16(
+            desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight.reshape(B, K)), _ptr(gt_kps), _ptr(denoms),
+            _ptr(expected_upstream), int(stored), _ptr(g7), _ptr(grad_hm), _ptr(grad_off), _ptr(grad_var),
+            _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward_f16")
+
+
+def _loss_f16_setup(ctx, inputs, output):
+    (hm, off, var, target, weight, gt_kps, denoms, expected_upstream, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs,
+     with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags) = inputs
+    losses, coords, scores, ghm, goff, gvar = output
+    ctx.stored = with_grads
+    ctx.stash = (ghm, goff, gvar if var is not None else None)
+    # the expectation the stored gradients were built on: a private copy, the caller's tensor moves on
+    ctx.expected = None if expected_upstream is None else expected_upstream.detach().to(torch.float32).reshape(1).clone()
+    ctx.tensors = tuple(None if t is None else t.detach() for t in (hm, off, var, target, weight, gt_kps, denoms))
+    ctx.scalars = (in_w, in_h, list(lambdas), target_sigma, encode_sigma, utw, list(pairs))
+    ctx.mark_non_differentiable(coords, scores, ghm, goff, gvar)
+    ctx.set_materialize_grads(False)
+
+
+def _loss_f16_backward(ctx, g_losses, g_coords, g_scores, g_ghm, g_goff, g_gvar):
+    none = [None] * 21
+    if g_losses is None:
+        return tuple(none)
+    hm, off, var, target, weight, gt_kps, denoms = ctx.tensors
+    ghm, goff, gvar = ctx.stash
+    if not ctx.stored:
+        ghm, goff = torch.empty_like(hm), torch.empty_like(off)
+        gvar = torch.empty_like(var) if var is not None else None
+    contig = lambda t: None if t is None else t.contiguous()
+    torch.ops.gbcodec.fusion_loss_backward_f16(
+        g_losses.contiguous(), ghm, goff, gvar, ctx.stored, contig(hm), contig(off), contig(var), contig(target),
+        weight.contiguous(), contig(gt_kps), denoms, ctx.expected, *ctx.scalars)
+    none[0], none[1] = ghm, goff
+    none[2] = gvar if var is not None else None
+    return tuple(none)
+
+
+fusion_loss_f16.register_autograd(_loss_f16_backward, setup_context=_loss_f16_setup)

@@ -79,6 +79,21 @@ loss = lambda target, grads, dec: ops.fusion_loss(d["hm"], d["off"], d["var"], t
 report("loss step (fused, on-the-fly target)", "cfg1 64x48 B=1024", B * K, 24 * n, timeit(lambda: loss(None, True, True)))
 report("loss fwd+bwd (target from HBM)", "cfg1 64x48 B=1024", B * K, 28 * n, timeit(lambda: loss(tgt, True, False)))
 report("loss fwd only (on-the-fly target)", "cfg1 64x48 B=1024", B * K, 8 * n, timeit(lambda: loss(None, False, False)))
+# float16 maps (autocast): the fused pass with the expected loss scale, the backward that finds its expectation met
+# (returns inside the kernel) and the one that does not (computes the gradients again)
+h16 = {k: d[k].half() for k in ("hm", "off", "var")}
+scale = torch.tensor([65536.0], device=dev)
+g7 = torch.zeros(7, device=dev); g7[6] = 65536.0
+g7b = torch.zeros(7, device=dev); g7b[6] = 32768.0
+f16 = lambda: ops.fusion_loss_f16(h16["hm"], h16["off"], h16["var"], None, d["vis"], d["kps"], None, scale, 192.0, 256.0, LAM, 2.0, 2.0, True, SK,
+                                  True, True, alpha, fw, 2, DF)
+res16 = f16()
+b16 = lambda g: ops.fusion_loss_backward_f16(g, res16[3], res16[4], res16[5], True, h16["hm"], h16["off"], h16["var"], None, d["vis"], d["kps"], None,
+                                             scale, 192.0, 256.0, LAM, 2.0, 2.0, True, SK)
+report("loss step f16 (fused: losses + decode + half gradients at the expected loss scale)", "cfg1 64x48 B=1024", B * K, 12 * n, timeit(f16))
+report("loss f16 backward, expectation met (no work)", "cfg1 64x48 B=1024", B * K, 0, timeit(lambda: b16(g7)))
+report("loss f16 backward, loss scale changed (gradients again)", "cfg1 64x48 B=1024", B * K, 12 * n, timeit(lambda: b16(g7b)))
+del h16, res16
 # second-generation family on the same shapes
 pred = d["hm"].abs().add_(0.01)
 wts = [1.0, 0.15, 0.6]
