@@ -160,19 +160,17 @@ constexpr int kTargetLut = 2;      // generated on the fly, any patch height
 // ROLL = false: the tile stays in registers and the row loops are fully unrolled (most ILP, ~80 registers, large code).
 // ROLL = true : the tile is parked in a thread-private shared-memory slot as well and the row loops stay rolled
 //               (4x smaller loop code, <= 64 registers -> one more CTA per SM).
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false>
-__global__ void __launch_bounds__(W4* ROWS, MINB)
-loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
+// The tile's work is a device function: the forward kernel runs it once per CTA (grid = (K, B)), the backward kernel
+// (loss_tile_backward_kernel below) walks a few tiles per CTA so that the common case — nothing to recompute — costs a
+// small grid of CTAs that read one word and leave, not one CTA per tile.
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, bool HALF>
+__device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossArgs& A, const int k, const int b, const int kdim) {
     using IO = TileIO<HALF>;
     using Vec = typename IO::Vec;
     using Elem = typename IO::Elem;
     constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
     static_assert(TPB % 32 == 0 && TPB <= 1024, "CTA must be whole warps");
     static_assert(GBCODEC_MAX_PARTNERS == 4, "tie patterns are nibbles");
-    // backward call: nothing to do if the stored gradients are already right (plan 0); float32 gradients that are
-    // off by one common factor are rescaled in place by rescale_kernel (plan 1), float16 ones are computed again
-    // (a stored half cannot be rescaled without a second rounding)
-    if (A.plan && (HALF ? *A.plan == 0 : *A.plan != 2)) return;
 
     extern __shared__ __align__(16) float smem[];
     constexpr int UNR = ROLL ? 1 : NIT;
@@ -189,8 +187,7 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     float* lut = reinterpret_cast<float*>(Ws + (ROLL ? N4 : 0));  // exp table of the target patch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = blockIdx.x, b = blockIdx.y;                    // grid = (K, B): no division
-    const int tile = b * gridDim.x + k;
+    const int tile = b * kdim + k;
 
     // ---- bulk loads first: the tile into registers, the variance map into its sum ----------------
     // (unconditional: whether the tile carries weight is only known one L2 round trip later)
@@ -776,21 +773,60 @@ loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     }
 }
 
+// forward (and fused step): one CTA per tile, grid = (K, B) — no division
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false>
+__global__ void __launch_bounds__(W4* ROWS, MINB)
+loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
+    loss_tile_body<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, HALF>(P, A, blockIdx.x, blockIdx.y, gridDim.x);
+}
+
+// backward call: nothing to do if the stored gradients are already right (plan 0); float32 gradients that are off by one
+// common factor are rescaled in place by rescale_kernel (plan 1), float16 ones are computed again (a stored half cannot be
+// rescaled without a second rounding).  The grid is one wave of resident CTAs; each walks its share of the tiles.
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false>
+__global__ void __launch_bounds__(W4* ROWS, MINB)
+loss_tile_backward_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A, const int tiles_per_cta) {
+    if (A.plan && (HALF ? *A.plan == 0 : *A.plan != 2)) return;
+    const int tiles = P.B * P.K;
+    const int t0 = blockIdx.x * tiles_per_cta, t1 = min(tiles, t0 + tiles_per_cta);
+    for (int t = t0; t < t1; ++t) {
+        const int b = t / P.K;
+        loss_tile_body<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, HALF>(P, A, t - b * P.K, b, P.K);
+        __syncthreads();                         // the next tile re-uses every shared-memory buffer
+    }
+}
+
 // ---- launcher ----------------------------------------------------------------------------------------
 template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false>
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
     const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
                       + (size_t)(2 * NW * 16 + 32 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
-    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF>;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
+    if (A.lam_eff != nullptr) {                        // fusion_loss_backward: per-term upstream weights on the device
+        auto bk = loss_tile_backward_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF>;
+        cudaError_t e = cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_backward_kernel): %s", cudaGetErrorString(e));
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        }
+        const int tiles = P.B * P.K, resident = sms * MINB;
+        const int per = (tiles + resident - 1) / resident;            // one wave: balanced when there is work, ~sms*MINB CTAs to dismiss when there is none
+        bk<<<(tiles + per - 1) / per, TPB, smem, s>>>(P, A, per);
+        return check_launch("loss_tile_backward_kernel");
+    }
+    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
-    if (e0 && !A.plan) cudaEventRecord(e0, s);
+    if (e0) cudaEventRecord(e0, s);
     kern<<<dim3(P.K, P.B), TPB, smem, s>>>(P, A);
-    if (e1 && !A.plan) cudaEventRecord(e1, s);
+    if (e1) cudaEventRecord(e1, s);
     return check_launch("loss_tile_kernel");
 }
 
@@ -815,46 +851,22 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
         if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, true>(P, A, s, e0, e1);
         return 1;
     }
+    // GBCODEC_TILE_VARIANT=<n> selects an alternative CTA shape / shared-memory budget (A/B measurements; DESIGN.md §4
+    // lists what was tried: 96- and 384-thread CTAs, register-resident unrolled loops, 4-8 CTAs per SM — all slower)
+    const int v = tile_variant();
     if (P.H == 64 && P.W == 48) {
-        switch (tile_variant()) {
-            case 1: return launch_tile_tm<12, 16, 4, false, true, true, 5, false, true>(P, A, s, e0, e1);   // rolled; H,S,A     39 KB, 5 CTAs
-            case 2: return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);                 // registers + unrolled; E,S,A,Q 51 KB, 4 CTAs
-            case 3: return launch_tile_tm<12, 16, 4, false, true, true, 4, true, true>(P, A, s, e0, e1);    // rolled; H,S,A,Q   51 KB, 4 CTAs
-            case 4: return launch_tile_tm<12, 32, 2, false, true, false, 3, true, true>(P, A, s, e0, e1);   // rolled; 384 threads, 8 px each
-            case 5: return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // rolled; H,S       27 KB, 6 CTAs
-            case 6: return launch_tile_tm<12, 8, 8, false, true, false, 6, true, false>(P, A, s, e0, e1);   // 96 threads, 32 px each, registers; S,Q
-            case 7: return launch_tile_tm<12, 8, 8, false, true, false, 6, true, true>(P, A, s, e0, e1);    // 96 threads, 32 px each, rolled; H,S,Q
-            case 8: return launch_tile_tm<12, 8, 8, false, false, false, 8, true, false>(P, A, s, e0, e1);  // 96 threads, registers; Q only
-            case 9: return launch_tile_tm<12, 8, 8, false, true, false, 8, true, false>(P, A, s, e0, e1);   // 96 threads, registers; S,Q; 8 CTAs
-            case 10: return launch_tile_tm<12, 16, 4, false, false, false, 5, false, true>(P, A, s, e0, e1); // rolled; own tile only in smem, 5 CTAs
-            case 11: return launch_tile_tm<12, 16, 4, false, false, false, 6, false, true>(P, A, s, e0, e1); // ... 6 CTAs (56 registers)
-            case 12: return launch_tile_tm<12, 16, 4, false, false, false, 7, false, true>(P, A, s, e0, e1); // ... 7 CTAs (48 registers)
-            case 13: return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // H,S; 6 CTAs
-            default: break;
-        }
+        if (v == 1) return launch_tile_tm<12, 16, 4, false, true, true, 5, false, true>(P, A, s, e0, e1);    // rolled; H,S,A in smem, partners through L2
+        if (v == 2) return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);                  // tile in registers, unrolled; E,S,A,Q
+        if (v == 13) return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // rolled; H,S; 6 CTAs
+        return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true>(P, A, s, e0, e1);                // 192 threads, 16 px each; H,S,Q in smem, 5 CTAs
     }
-    if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true>(P, A, s, e0, e1);   // 192 threads, 16 px each; H,S,Q in smem
     if (P.H == 96 && P.W == 72) {
-        if (tile_variant() == 1) return launch_tile_tm<18, 16, 6, true, true, true, 2>(P, A, s, e0, e1);               // registers, 288 threads
-        if (tile_variant() == 2) return launch_tile_tm<18, 32, 3, false, true, false, 2, true, true>(P, A, s, e0, e1);  // rolled, 576 threads, 12 px each
-        if (tile_variant() == 3) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1); // rolled, 288 threads, no partner slot: 3 CTAs
-        if (tile_variant() == 4) return launch_tile_tm<18, 16, 6, false, false, false, 3, false, true>(P, A, s, e0, e1); // rolled, 288 threads, own tile only in smem
-        if (tile_variant() == 5) return launch_tile_tm<18, 32, 3, false, true, false, 2, false, true>(P, A, s, e0, e1);  // rolled, 576 threads, no partner slot
-        if (tile_variant() == 6) return launch_tile_tm<18, 16, 6, false, false, false, 4, false, true>(P, A, s, e0, e1); // own tile only, 4 CTAs (56 registers)
-        if (tile_variant() == 7) return launch_tile_tm<18, 16, 6, false, true, false, 4, false, true>(P, A, s, e0, e1);  // H,S, no partner slot, 4 CTAs
-        if (tile_variant() == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);  // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
-        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1);                         // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.666 ms)
+        if (v == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);    // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
+        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1);               // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.666 ms)
     }
     if (P.H == 128 && P.W == 128) {
-        if (tile_variant() == 1) return launch_tile_tm<32, 16, 8, false, true, true, 1>(P, A, s, e0, e1);              // registers, 512 threads
-        if (tile_variant() == 2) return launch_tile_tm<32, 32, 4, false, true, false, 1, true, true>(P, A, s, e0, e1);  // rolled, 1024 threads, 16 px each
-        if (tile_variant() == 3) return launch_tile_tm<32, 16, 8, false, true, false, 1, false, true>(P, A, s, e0, e1); // rolled, 512 threads, no partner slot
-        if (tile_variant() == 4) return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true>(P, A, s, e0, e1); // rolled, 512 threads, own tile only in smem: 2 CTAs
-        if (tile_variant() == 5) return launch_tile_tm<32, 32, 4, false, true, false, 1, false, true>(P, A, s, e0, e1);  // rolled, 1024 threads, no partner slot
-        if (tile_variant() == 6) return launch_tile_tm<32, 8, 16, false, false, false, 4, false, true>(P, A, s, e0, e1); // 256 threads, 64 px each, own tile only: 2-3 CTAs by smem
-        if (tile_variant() == 7) return launch_tile_tm<32, 16, 8, false, false, false, 2, true, true>(P, A, s, e0, e1);  // 512 threads, H,Q
-        if (tile_variant() == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);  // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
-        return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true>(P, A, s, e0, e1);                        // rolled, 512 threads, 32 px each; own tile only in smem: 2 CTAs (1.137 ms)
+        if (v == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);    // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
+        return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true>(P, A, s, e0, e1);              // rolled, 512 threads, 32 px each; own tile only in smem: 2 CTAs (1.137 ms)
     }
     return 1;
 }
