@@ -266,9 +266,23 @@ def run_b200(args):
     use_peer = world > 1 and args.exchange == "peer"
     launches_per_step = 3 if world == 1 else (3 if use_peer else 6)
     peer = None
+    exchange = "none" if world == 1 else args.exchange
     if use_peer:
+        # CUDA IPC needs the ranks to share an IPC namespace; if any rank cannot map its peers, every rank takes NCCL
         from infantposeestimation_gaussianbias_b200.sharded import PeerExchange
-        peer = PeerExchange(device=device)
+        why = ""
+        try:
+            peer = PeerExchange(device=device)
+        except Exception as e:                                   # noqa: BLE001 — reported in the JSON line
+            why = f"{type(e).__name__}: {e}"[:160]
+        ok = torch.tensor([1 if peer is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer, use_peer = None, False
+            launches_per_step = 6
+            exchange = f"nccl (peer-memory set-up failed on some rank{': ' + why if why else ''})"
 
     def step():
         den = None
@@ -395,7 +409,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": ("none" if world == 1 else args.exchange), "numa_node_rank0": numa,
+        "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": exchange, "numa_node_rank0": numa,
                    "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,

@@ -54,12 +54,29 @@ class PeerExchange:
         self._ctx = C.c_void_p()
         handle = C.create_string_buffer(N.PEER_HANDLE_BYTES)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        error = None
         with torch.cuda.device(dev):
-            N.check(self._lib.gbcodec_peer_create(self.rank, self.world, C.byref(self._ctx), handle), "peer_create")
+            try:
+                N.check(self._lib.gbcodec_peer_create(self.rank, self.world, C.byref(self._ctx), handle), "peer_create")
+            except Exception as e:           # every rank must still take part in the collectives below
+                error = e
             gathered = [None] * self.world
-            dist.all_gather_object(gathered, handle.raw, group=group)
-            N.check(self._lib.gbcodec_peer_connect(self._ctx, b"".join(gathered)), "peer_connect")
-        dist.barrier(group)       # nobody writes into a mailbox that is not mapped yet
+            dist.all_gather_object(gathered, handle.raw if error is None else b"", group=group)
+            if error is None and all(len(h) == N.PEER_HANDLE_BYTES for h in gathered):
+                try:
+                    N.check(self._lib.gbcodec_peer_connect(self._ctx, b"".join(gathered)), "peer_connect")
+                except Exception as e:
+                    error = e
+            elif error is None:
+                error = RuntimeError("PeerExchange: another rank could not create its mailbox")
+            # one collective doubles as the barrier (nobody writes into a mailbox that is not mapped yet) and as the
+            # vote: either every rank is connected or every rank raises
+            ok = torch.tensor([0 if error is not None else 1], dtype=torch.int32, device=dev if dist.get_backend(group) == "nccl" else "cpu")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"PeerExchange: peer-memory set-up failed on at least one rank"
+                               f"{' (here: ' + str(error) + ')' if error is not None else ''}")
 
     @property
     def address(self) -> int:
