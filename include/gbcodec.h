@@ -167,6 +167,21 @@ int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
                             float* d_coords, float* d_scores,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* gbcodec_fusion_step_f32 for a head that reduces its variance branch to the per-tile mean itself (the Softplus +
+ * mean_N fused into the epilogue of its last convolution, fusion_head.py:245-251): the loss uses V only through
+ * mean_N(V) (:467-478), so the map need not exist.  d_var_mean (B,K) replaces d_var, d_grad_var_mean (B,K) =
+ * d(total)/d(mean_N(V)) replaces d_grad_var; d(total)/dV_i = d_grad_var_mean / N if the caller needs it.
+ * Algorithmic HBM bytes per tile: 16N instead of 24N.  Tile shapes 64x48, 96x72, 128x128.  d_coords/d_scores may both
+ * be NULL (loss only); gradients all given or all NULL. */
+int gbcodec_fusion_step_vmean_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var_mean, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var_mean,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Backward for an arbitrary upstream gradient on the seven outputs.  The
  * gradients written by the forward assume d(total)=*d_grad_scale and nothing on
  * the six terms.  This call reads the actual upstream vector on the device and

@@ -38,7 +38,7 @@ EXPORTS = (
     "gbcodec_combined_workspace_bytes", "gbcodec_combined_loss_f32", "gbcodec_combined_loss_backward_f32",
     "gbcodec_peer_create", "gbcodec_peer_connect", "gbcodec_peer_status", "gbcodec_peer_destroy",
     "gbcodec_fusion_step_sharded_f32", "gbcodec_heatmap_step_f32",
-    "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16",
+    "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16", "gbcodec_fusion_step_vmean_f32",
 )
 
 
@@ -128,6 +128,8 @@ def _declare(lib):
                                             f32p, f32p, C.c_int, C.c_uint, f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_fusion_loss_backward_f16.argtypes = [C.POINTER(LossDesc), _P, _P, _P, f32p, f32p, f32p, f32p, f32p, C.c_int, f32p,
                                                      _P, _P, _P, _P, C.c_size_t, _P]
+    lib.gbcodec_fusion_step_vmean_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_uint,
+                                                                f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_peer_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
     lib.gbcodec_peer_connect.argtypes = [_P, C.c_char_p]
     lib.gbcodec_peer_status.argtypes = [_P, C.POINTER(C.c_int)]

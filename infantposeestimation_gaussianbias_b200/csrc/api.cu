@@ -33,7 +33,7 @@ size_t loss_workspace_bytes(int B, int K);
 int loss_denominators(const gbcodec_loss_desc*, const float*, const float*, int, float*, void*, size_t, cudaStream_t);
 int fusion_loss(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
                 const float*, const float*, float*, float*, float*, float*,
-                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*, int);
+                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*, int, const float*, float*);
 int peer_create(int, int, void**, unsigned char*);
 int peer_connect(void*, const unsigned char*);
 int peer_status(void*, int*);
@@ -224,7 +224,7 @@ int gbcodec_fusion_loss_f32(const gbcodec_loss_desc* desc,
                             void* d_workspace, size_t workspace_bytes, void* stream) {
     return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
-                       nullptr, nullptr, 0, 0u, nullptr, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0);
+                       nullptr, nullptr, 0, 0u, nullptr, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr, nullptr);
 }
 
 int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
@@ -239,7 +239,7 @@ int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
     return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
                        d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
-                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0);
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr, nullptr);
 }
 
 int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
@@ -254,13 +254,29 @@ int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
     return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, nullptr, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
                        d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
-                       d_workspace, workspace_bytes, (cudaStream_t)stream, peer_ctx, d_denoms_out, 0);
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, peer_ctx, d_denoms_out, 0, nullptr, nullptr);
 }
 
 int gbcodec_peer_create(int rank, int world, void** ctx_out, unsigned char* handle_out) { return peer_create(rank, world, ctx_out, handle_out); }
 int gbcodec_peer_connect(void* ctx, const unsigned char* all_handles) { return peer_connect(ctx, all_handles); }
 int gbcodec_peer_status(void* ctx, int* h_timeouts) { return peer_status(ctx, h_timeouts); }
 int gbcodec_peer_destroy(void* ctx) { return peer_destroy(ctx); }
+
+int gbcodec_fusion_step_vmean_f32(const gbcodec_loss_desc* desc,
+                            const float* d_hm, const float* d_off, const float* d_var_mean, const float* d_target,
+                            const float* d_weight, const float* d_gt_kps,
+                            const float* d_denoms, const float* d_grad_scale,
+                            float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var_mean,
+                            const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
+                            float* d_coords, float* d_scores,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_var_mean) return fail(GBCODEC_ERR_NULL_POINTER, "step_vmean: d_var_mean is NULL");
+    if ((d_coords == nullptr) != (d_scores == nullptr)) return fail(GBCODEC_ERR_NULL_POINTER, "step_vmean: give d_coords and d_scores or neither");
+    return fusion_loss(desc, d_hm, d_off, nullptr, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
+                       d_losses7, d_grad_hm, d_grad_off, nullptr,
+                       d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, d_var_mean, d_grad_var_mean);
+}
 
 int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
                             const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
@@ -283,7 +299,7 @@ int gbcodec_fusion_step_f16(const gbcodec_loss_desc* desc,
     return fusion_loss(desc, (const float*)d_hm, (const float*)d_off, (const float*)d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                        d_losses7, (float*)d_grad_hm, (float*)d_grad_off, (float*)d_grad_var,
                        d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
-                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 1);
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 1, nullptr, nullptr);
 }
 
 int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,

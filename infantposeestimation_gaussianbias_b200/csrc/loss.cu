@@ -704,8 +704,11 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
                 const float* weight, const float* gt, const float* denoms, const float* grad_scale,
                 float* losses7, float* ghm, float* goff, float* gvar,
                 const float* alpha_param, const float* fusion_weight, int radius, unsigned dflags, float* coords, float* scores,
-                void* ws, size_t ws_size, cudaStream_t s, void* peer_ctx, float* denoms_out, int half_io) {
+                void* ws, size_t ws_size, cudaStream_t s, void* peer_ctx, float* denoms_out, int half_io,
+                const float* var_mean, float* grad_var_mean) {
     int st = check_common(d, hm, off, weight, gt, ws, ws_size);
+    if (var_mean && var) return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: give the variance maps or their per-tile means, not both");
+    if (var_mean && (ghm != nullptr) != (grad_var_mean != nullptr)) return fail(GBCODEC_ERR_NULL_POINTER, "loss: d_grad_var_mean goes with the other gradients");
     if (st) return st;
     PeerView peer = kNoPeers;
     if (peer_ctx) {
@@ -745,6 +748,12 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.radius = radius; A.dflags = dflags;
     A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial;
     A.half_io = half_io;
+    A.var_mean = var_mean; A.grad_var_mean = grad_var_mean;
+    if (var_mean) {
+        // only the tile kernels take the means
+        st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
+        if (st == 1) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: per-tile variance means are supported for 64x48, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
+    } else
     st = launch_loss_kernel(P, A, s);
     if (st) return st;
     const int tiles = P.B * P.K;

@@ -41,6 +41,10 @@ struct LossArgs {
     const float* lam_eff;               // backward recompute: device [6] per-term multipliers
     const int* plan;                    // backward recompute: run only if *plan == 2
     int half_io;                        // hm, off, var and the three gradients are float16 (the pointers are then __half*)
+    // the variance branch reduced to its per-tile mean by the caller (a head that fuses the mean into its last
+    // convolution's epilogue): replaces var / grad_var, 16N instead of 24N bytes per tile
+    const float* var_mean;              // (B,K) or null
+    float* grad_var_mean;               // (B,K): d(total)/d(mean_N(V))
 };
 
 constexpr int kFinBlocks = 32;          // CTAs of the second-stage reduction

@@ -369,11 +369,13 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
                 IO::store_stream(gh4 + it * TPB, z4);
                 if (gv4) IO::store_stream(gv4 + it * TPB, z4);
             }
+            if (A.grad_var_mean && tid == 0) A.grad_var_mean[tile] = 0.f;
         }
         return;
     }
     const float Ssum = lane_value<8>(acc8, 3), mse_sum = lane_value<8>(acc8, 4);
-    const float mV = A.var ? lane_value<8>(acc8, 5) * P.inv_n : P.sigma;
+    const bool has_var = A.var != nullptr || A.var_mean != nullptr;
+    const float mV = A.var ? lane_value<8>(acc8, 5) * P.inv_n : (A.var_mean ? __ldg(A.var_mean + tile) : P.sigma);
 
     // ---- warp roles for the per-tile scalars (a warp each, the others do not repeat the work) ------------
     //   warp RD: decode tail                       warp RO: offset term (8 taps, SmoothL1, its share of dL/dc)
@@ -486,6 +488,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
 #pragma unroll
         for (int it = 0; it < NIT; ++it) IO::store_stream(gv4 + it * TPB, g4);
     }
+    if (grads && A.grad_var_mean && tid == 0) A.grad_var_mean[tile] = lam[3] * kb * 2.f * (mV - P.sigma);
 
     // ---- pass C: entropy sums and relu moments about (cx, cy) ----------------------------------------
     float dxj[4], dx2j[4];
@@ -603,7 +606,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
         const float peak_t = (cx - gx) * (cx - gx) + (cy - gy) * (cy - gy);
         const float v = lane_value<16>(acc16, 2) * iRp;
         const float sd = fsqrt_fast(v + kEps);
-        const float var_t = (sd - P.sigma) * (sd - P.sigma) + (A.var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
+        const float var_t = (sd - P.sigma) * (sd - P.sigma) + (has_var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
         const float E = -kLn2 * lane_value<16>(acc16, 0);
         const float pa = E - lane_value<16>(acc16, 1);
         const float shape_t = (E - P.e_star) * (E - P.e_star);

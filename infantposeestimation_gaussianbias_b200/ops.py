@@ -697,3 +697,57 @@ def _loss_f16_backward(ctx, g_losses, g_coords, g_scores, g_ghm, g_goff, g_gvar)
 
 
 fusion_loss_f16.register_autograd(_loss_f16_backward, setup_context=_loss_f16_setup)
+
+
+# --------------------------------------------------------------------------- variance branch given as per-tile means
+@torch.library.custom_op(f"{_NS}::fusion_step_vmean", mutates_args=())
+def fusion_step_vmean(hm: Tensor, off: Tensor, var_mean: Tensor, target: Optional[Tensor], weight: Tensor, gt_kps: Tensor,
+                      denoms: Optional[Tensor], grad_scale: Optional[Tensor], in_w: float, in_h: float, lambdas: List[float],
+                      target_sigma: float, encode_sigma: float, use_target_weight: bool, pairs: List[int], with_grads: bool,
+                      with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
+                      decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """The fused step for a head that hands over mean_N(V) per tile instead of the variance map (16N instead of 24N bytes
+    per tile) -> losses7, grad_hm, grad_off, grad_var_mean (B,K) = d(total)/d(mean_N(V)) times grad_scale, coords, scores.
+    No autograd rule: the caller owns the head and wires the three gradients into its own backward."""
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    off = _cuda_f32("offsets", off, (B, K, 2, H, W))
+    var_mean = _cuda_f32("variance_means", var_mean.reshape(B, K), (B, K))
+    if target is not None:
+        target = _cuda_f32("target_heatmaps", target, (B, K, H, W))
+    weight = _cuda_f32("target_weight", weight.reshape(B, K), (B, K))
+    gt_kps = _cuda_f32("gt_keypoints", gt_kps, (B, K, 2))
+    if denoms is not None:
+        denoms = _cuda_f32("denominators", denoms.reshape(2), (2,))
+    grad_scale = _scalar("grad_scale", grad_scale, hm)
+    dev = hm.device
+    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+    losses = torch.empty(7, dtype=torch.float32, device=dev)
+    empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+    ghm = torch.empty_like(hm) if with_grads else empty()
+    goff = torch.empty_like(off) if with_grads else empty()
+    gvm = torch.empty((B, K), dtype=torch.float32, device=dev) if with_grads else empty()
+    coords = torch.empty((B, K, 2), dtype=torch.float32, device=dev) if with_decode else empty()
+    scores = torch.empty((B, K), dtype=torch.float32, device=dev) if with_decode else empty()
+    if with_decode:
+        alpha_param = _scalar("alpha", alpha_param, hm)
+        fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
+    ws = _workspace(hm)
+    opt = lambda t, on: _ptr(t) if on else None
+    with torch.cuda.device(dev):
+        N.check(N.lib().gbcodec_fusion_step_vmean_f32(
+            desc, _ptr(hm), _ptr(off), _ptr(var_mean), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(grad_scale),
+            _ptr(losses), opt(ghm, with_grads), opt(goff, with_grads), opt(gvm, with_grads),
+            opt(alpha_param, with_decode), opt(fusion_weight, with_decode), radius, decode_flags,
+            opt(coords, with_decode), opt(scores, with_decode), _ptr(ws), ws.numel(), _stream(hm)), "fusion_step_vmean")
+    return losses, ghm, goff, gvm, coords, scores
+
+
+@fusion_step_vmean.register_fake
+def _(hm, off, var_mean, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
+      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags):
+    B, K = hm.shape[0], hm.shape[1]
+    e = lambda: hm.new_empty(0)
+    return (hm.new_empty(7), torch.empty_like(hm) if with_grads else e(), torch.empty_like(off) if with_grads else e(),
+            hm.new_empty((B, K)) if with_grads else e(), hm.new_empty((B, K, 2)) if with_decode else e(),
+            hm.new_empty((B, K)) if with_decode else e())

@@ -420,3 +420,26 @@ def test_fp16_head_outputs_under_autocast(gb, name):
     c16, s16 = decode_outputs({**half, "fusion_weight": fw}, a)
     c32, s32 = decode_outputs({**{k: v.float() for k, v in half.items()}, "fusion_weight": fw}, a)
     assert torch.equal(c16, c32) and torch.equal(s16, s32) and c16.dtype == torch.float32
+
+
+# ---------------------------------------------------------------------- variance branch handed over as per-tile means
+@pytest.mark.parametrize("name", NAMES)
+def test_step_with_variance_means(gb, name):
+    """a head that reduces V to mean_N(V) in its last convolution's epilogue.  The loss uses V only through
+    that mean, so the step with the means must give the step with the maps: same losses, same d/d(heatmaps, offsets),
+    and d/d(mean) = N * d/dV_i."""
+    cfg, batch, g = goldens.load(name)
+    pairs = [v for p in oc.skeleton_for(cfg.K) for v in p]
+    a, f = torch.tensor(0.5).cuda(), torch.tensor(0.6224593312018546).cuda()
+    common = (float(cfg.input_size[0]), float(cfg.input_size[1]), list(oc.DEFAULT_LAMBDAS), cfg.sigma, cfg.sigma, True, pairs, True, True, a, f, 2, 3)
+    hm, off, var = dev(batch["heatmaps"]), dev(batch["offsets"]), dev(batch["variances"])
+    full = gb.fusion_loss(hm, off, var, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common)
+    vm = var.double().mean(dim=(2, 3)).float()
+    res = gb.fusion_step_vmean(hm, off, vm, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common)
+    np.testing.assert_allclose(res[0].cpu().numpy(), full[0].cpu().numpy(), rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(res[0].cpu().numpy(), g["loss_f32"], rtol=LOSS_RTOL, atol=1e-9)
+    assert torch.equal(res[1], full[1]) and torch.equal(res[2], full[2])           # the heatmap / offset gradients do not see V
+    assert torch.equal(res[4], full[4]) and torch.equal(res[5], full[5])
+    n = cfg.H * cfg.W
+    np.testing.assert_allclose(res[3].cpu().numpy(), full[3][:, :, 0, 0].cpu().numpy() * n, rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(res[3].cpu().numpy(), g["grad_var_tile"] * n, rtol=1e-4, atol=1e-12)

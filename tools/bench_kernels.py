@@ -79,6 +79,10 @@ loss = lambda target, grads, dec: ops.fusion_loss(d["hm"], d["off"], d["var"], t
 report("loss step (fused, on-the-fly target)", "cfg1 64x48 B=1024", B * K, 24 * n, timeit(lambda: loss(None, True, True)))
 report("loss fwd+bwd (target from HBM)", "cfg1 64x48 B=1024", B * K, 28 * n, timeit(lambda: loss(tgt, True, False)))
 report("loss fwd only (on-the-fly target)", "cfg1 64x48 B=1024", B * K, 8 * n, timeit(lambda: loss(None, False, False)))
+vm = d["var"].mean(dim=(2, 3))
+report("loss step with per-tile variance means (fused, on-the-fly target)", "cfg1 64x48 B=1024", B * K, 16 * n,
+       timeit(lambda: ops.fusion_step_vmean(d["hm"], d["off"], vm, None, d["vis"], d["kps"], None, None, 192.0, 256.0, LAM, 2.0, 2.0, True, SK,
+                                            True, True, alpha, fw, 2, DF)))
 # float16 maps (autocast): the fused pass with the expected loss scale, the backward that finds its expectation met
 # (returns inside the kernel) and the one that does not (computes the gradients again)
 h16 = {k: d[k].half() for k in ("hm", "off", "var")}
