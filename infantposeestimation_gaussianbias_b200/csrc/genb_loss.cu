@@ -409,8 +409,8 @@ struct HeatArgs {
     EncodeConst ec;
 };
 
-template <int NITER, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+template <int NITER, int MAXT, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 heatmap_step_kernel(const __grid_constant__ HeatArgs A) {
     extern __shared__ float lut[];
     __shared__ PatchGeom geom_s;
@@ -534,8 +534,13 @@ int heatmap_step(const float* hm, const float* target, const float* weight, cons
         if (n4 % t == 0 && n4 / t <= 3) { threads = t; niter = n4 / t; }
     for (int t = 128; t <= 512 && !niter; t += 32)
         if (n4 % t == 0 && n4 / t <= 8) { threads = t; niter = n4 / t; }
+    if (niter == 3 && threads == 256) {                     // 64x48: cap the registers for 8 resident CTAs
+        heatmap_step_kernel<3, 256, 8><<<nt, threads, smem, s>>>(A);
+        niter = -1;
+    }
 #define GBC_CASE(NI, MT) case NI: heatmap_step_kernel<NI, MT><<<nt, threads, smem, s>>>(A); break;
     switch (niter) {
+        case -1: break;
         GBC_CASE(1, 1024) GBC_CASE(2, 1024) GBC_CASE(3, 1024) GBC_CASE(4, 512) GBC_CASE(5, 512) GBC_CASE(6, 512) GBC_CASE(7, 512) GBC_CASE(8, 512)
         default: heatmap_step_kernel<0, 1024><<<nt, threads, smem, s>>>(A); break;
     }
