@@ -171,7 +171,7 @@ int gbcodec_fusion_step_f32(const gbcodec_loss_desc* desc,
  * mean_N fused into the epilogue of its last convolution, fusion_head.py:245-251): the loss uses V only through
  * mean_N(V) (:467-478), so the map need not exist.  d_var_mean (B,K) replaces d_var, d_grad_var_mean (B,K) =
  * d(total)/d(mean_N(V)) replaces d_grad_var; d(total)/dV_i = d_grad_var_mean / N if the caller needs it.
- * Algorithmic HBM bytes per tile: 16N instead of 24N.  Tile shapes 64x48, 96x72, 128x128.  d_coords/d_scores may both
+ * Algorithmic HBM bytes per tile: 16N instead of 24N.  Tile shapes 64x48, 64x64, 96x72, 128x128.  d_coords/d_scores may both
  * be NULL (loss only); gradients all given or all NULL. */
 int gbcodec_fusion_step_vmean_f32(const gbcodec_loss_desc* desc,
                             const float* d_hm, const float* d_off, const float* d_var_mean, const float* d_target,
@@ -374,7 +374,7 @@ int gbcodec_heatmap_step_f32(const float* d_hm, const float* d_target, const flo
  *                                     and returns inside the kernel if it held (gradients_stored != 0); otherwise, or if
  *                                     nothing was stored, it computes the gradients with the actual per-term factors.
  * In steady state a training step is ONE pass (12N bytes per tile instead of 24N), a changed loss scale costs one more.
- * Tile shapes 64x48, 96x72, 128x128 (GBCODEC_ERR_BAD_SHAPE otherwise: up-cast and use the float32 entry points).
+ * Tile shapes 64x48, 64x64, 96x72, 128x128 (GBCODEC_ERR_BAD_SHAPE otherwise: up-cast and use the float32 entry points).
  * Pixels whose logit equals a limb partner's exactly (frequent in half precision) take their half of the overlap gradient
  * in a second store: those gradients are rounded twice (<= 1 ulp of half). */
 int gbcodec_fusion_step_f16(const gbcodec_loss_desc* desc,

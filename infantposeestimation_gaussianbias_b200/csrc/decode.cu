@@ -455,6 +455,7 @@ int launch_decode(const float* hm, const float* hmf, const int32_t* perm, const 
     } while (0)
     if (!generic) {
         if (H == 64 && W == 48) GBC_TILE(12, 16, 4, 10, 8);     // 192 threads, 16 px each
+        if (H == 64 && W == 64) GBC_TILE(16, 16, 4, 8, 6);      // 256 threads, 16 px each
         if (H == 96 && W == 72) GBC_TILE(18, 16, 6, 5, 4);      // 288 threads, 24 px each
         if (H == 128 && W == 128) GBC_TILE(32, 16, 8, 3, 2);    // 512 threads, 32 px each
     }

@@ -644,7 +644,7 @@ static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream
     if (!force_generic() || A.half_io) {
         const int st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st != 1) return st;
-        if (A.half_io) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: float16 maps are supported for 64x48, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
+        if (A.half_io) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: float16 maps are supported for 64x48, 64x64, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
     }
     const int n4 = (P.H * P.W) >> 2;
     if (n4 == 256 * 3) return launch_loss_t<256, 3, 2>(P, A, s);           // 64x48
@@ -752,7 +752,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     if (var_mean) {
         // only the tile kernels take the means
         st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
-        if (st == 1) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: per-tile variance means are supported for 64x48, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
+        if (st == 1) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: per-tile variance means are supported for 64x48, 64x64, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
     } else
     st = launch_loss_kernel(P, A, s);
     if (st) return st;

@@ -852,6 +852,7 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
         if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, true>(P, A, s, e0, e1);
         if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, true>(P, A, s, e0, e1);
         if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, true>(P, A, s, e0, e1);
+        if (P.H == 64 && P.W == 64) return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, true>(P, A, s, e0, e1);
         return 1;
     }
     // GBCODEC_TILE_VARIANT=<n> selects an alternative CTA shape / shared-memory budget (A/B measurements; DESIGN.md §4
@@ -867,6 +868,8 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
         if (v == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);    // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
         return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true>(P, A, s, e0, e1);               // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.666 ms)
     }
+    if (P.H == 64 && P.W == 64)          // the reference's other default map (data/pose_transforms.py:391): 256 threads, H,S,Q in smem, 4 CTAs
+        return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true>(P, A, s, e0, e1);
     if (P.H == 128 && P.W == 128) {
         if (v == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);    // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
         return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true>(P, A, s, e0, e1);              // rolled, 512 threads, 32 px each; own tile only in smem: 2 CTAs (1.137 ms)

@@ -581,7 +581,7 @@ heatmap_step.register_autograd(_heatmap_step_backward, setup_context=_heatmap_st
 
 
 # --------------------------------------------------------------------------- float16 maps (autocast)
-HALF_TILE_SHAPES = ((64, 48), (96, 72), (128, 128))
+HALF_TILE_SHAPES = ((64, 48), (64, 64), (96, 72), (128, 128))
 
 
 def _cuda_f16(name: str, t: Tensor, shape: Sequence[int]) -> Tensor:

@@ -165,3 +165,25 @@ def test_limits_are_enforced(pkg):
         ops.decode_argmax(torch.zeros(1, 65, 8, 8).cuda(), 0)             # K above GBCODEC_MAX_K
     with pytest.raises(GbcodecError):
         ops.encode(torch.zeros(1, 1, 2).cuda(), torch.ones(1, 1).cuda(), 8, 8, 32.0, 32.0, 0.0)    # sigma
+
+
+def test_64x64_takes_the_tile_kernels_in_every_mode(pkg):
+    """64x64 (the reference's other default map, data/pose_transforms.py:391) has its own instantiations: float32, float16
+    maps and per-tile variance means must agree with each other there too."""
+    cfg = SHAPES["64x64"]
+    ops = pkg.ops
+    batch = synth.make_batch(cfg, seed=29)
+    pairs = [v for p in oc.skeleton_for(cfg.K) for v in p]
+    a, f = torch.tensor(0.5).cuda(), torch.tensor(0.62).cuda()
+    common = (float(cfg.input_size[0]), float(cfg.input_size[1]), list(oc.DEFAULT_LAMBDAS), cfg.sigma, cfg.sigma, True, pairs)
+    half = {k: dev(batch[k]).half() for k in ("heatmaps", "offsets", "variances")}
+    up = {k: v.float() for k, v in half.items()}
+    full = ops.fusion_loss(up["heatmaps"], up["offsets"], up["variances"], None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common, True, True, a, f, 2, 3)
+    h16 = ops.fusion_loss_f16(half["heatmaps"], half["offsets"], half["variances"], None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common,
+                              True, True, a, f, 2, 3)
+    assert torch.equal(h16[0], full[0]) and torch.equal(h16[1], full[4]) and torch.equal(h16[2], full[5])
+    assert (h16[3] == full[1].half()).float().mean().item() > 0.9999
+    vm = up["variances"].double().mean(dim=(2, 3)).float()
+    res = ops.fusion_step_vmean(up["heatmaps"], up["offsets"], vm, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common, True, True, a, f, 2, 3)
+    np.testing.assert_allclose(res[0].cpu().numpy(), full[0].cpu().numpy(), rtol=2e-6, atol=1e-9)
+    assert torch.equal(res[1], full[1]) and torch.equal(res[2], full[2])
