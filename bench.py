@@ -53,7 +53,16 @@ WORKLOADS = {
                      WORKLOAD="BASELINE configs[2] shapes: HRFormer-base 384x288 (96x72 heatmaps, K=17, sigma=2)"),
     "preemie": dict(K=13, H=128, W=128, IN_W=256, IN_H=256, SIGMA=1.5, SYNTH_CONFIG="preemie_256", TILE_KERNEL="loss_tile_kernel<32,16,8,...>",
                     WORKLOAD="BASELINE configs[3]: preemie_optimized.yaml (128x128 heatmaps, K=13, sigma=1.5, 256x256 input), full six-term loss"),
+    # decode-only workloads (their own metric: the step is one decode call, no loss)
+    "decode_flip": dict(K=17, H=96, W=72, IN_W=288, IN_H=384, SIGMA=2.0, SYNTH_CONFIG="hrformer_384x288", DECODE="flip", DEFAULT_BATCH=4096,
+                        TILE_KERNEL="decode_tile_kernel<18,16,6,flip>",
+                        WORKLOAD="BASELINE configs[2]: HRFormer-base 384x288 (96x72 heatmaps, K=17) decode with flip test + offset correction"),
+    "decode": dict(K=17, H=64, W=48, IN_W=192, IN_H=256, SIGMA=2.0, SYNTH_CONFIG="w32_256x192", DECODE="plain", DEFAULT_BATCH=16384,
+                   TILE_KERNEL="decode_tile_kernel<12,16,4>",
+                   WORKLOAD="BASELINE configs[4]: decode-only sweep point (64x48 heatmaps, K=17), sub-pixel refinement + offset correction"),
 }
+DECODE = None                       # None: fused step; "flip" / "plain": decode-only workloads
+DEFAULT_BATCH = 1024
 
 
 def select_workload(name):
@@ -62,6 +71,10 @@ def select_workload(name):
         return
     g = globals()
     g.update(w)
+    if g["DECODE"]:
+        g["BYTES_PER_HM"] = (8 if g["DECODE"] == "flip" else 4) * g["H"] * g["W"]     # read P (and the flipped pass); SURVEY §8d
+        g["METRIC"] = f"heatmaps/sec (Bx{g['K']}x{g['H']}x{g['W']}, decode{' with flip test' if g['DECODE'] == 'flip' else ''} + offset correction)"
+        return
     g["BYTES_PER_HM"] = 24 * g["H"] * g["W"]
     g["METRIC"] = f"heatmaps/sec (Bx{g['K']}x{g['H']}x{g['W']}, encode+loss+decode)"
 
@@ -121,7 +134,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- inputs
-def synth_device_batch(B, device, seed, ops):
+def synth_device_batch(B, device, seed, ops, with_var=True):
     """Synthetic batch created on the device (SURVEY §8d recipe): peaked heatmaps around
     jittered keypoints + noise, gaussian offsets, softplus variances."""
     import torch
@@ -136,7 +149,9 @@ def synth_device_batch(B, device, seed, ops):
     amp = r(B, K, 1, 1) * 0.9 + 0.3
     hm = amp * shifted + 0.05 * rn(B, K, H, W)
     off = 0.3 * rn(B, K, 2, H, W)
-    var = torch.nn.functional.softplus(rn(B, K, H, W))
+    var = torch.nn.functional.softplus(rn(B, K, H, W)) if with_var else None
+    if not with_var:
+        return dict(hm=hm.contiguous(), off=off.contiguous())
     return dict(kps=kps.contiguous(), vis=vis.contiguous(), hm=hm.contiguous(), off=off.contiguous(), var=var.contiguous())
 
 
@@ -421,6 +436,210 @@ def run_b200(args):
     return 0
 
 
+# ----------------------------------------------------------------------------- decode-only workloads
+def decode_workload_name(B):
+    return f"{WORKLOAD}, batch {B} per GPU"
+
+
+def cpu_decode_rate(sample_B: int, min_seconds: float, max_reps: int):
+    """Oracle port of the reference decode (per-tile window loop of LocalGaussianRefinement, fusion_head.py:84-128,
+    after the flip-test average when the workload has one) on the host cores."""
+    import torch
+    from oracle import heatmap_codec as oc
+    from tests import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.CONFIGS[SYNTH_CONFIG]
+    batch = synth.make_batch(cfg, seed=0, B=sample_B)
+    hm, off = torch.from_numpy(batch["heatmaps"]), torch.from_numpy(batch["offsets"])
+    flipped = torch.from_numpy(batch["heatmaps_flip"]) if DECODE == "flip" else None
+
+    def one():
+        t0 = time.perf_counter()
+        oc.fusion_decode(hm, off, 0.5, 0.6224593312018546, True, True, 2, heatmaps_of_flipped_input=flipped, loop=True)
+        return time.perf_counter() - t0
+
+    one()
+    times, t_start = [], time.perf_counter()
+    while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
+        times.append(one())
+    return sample_B * K / statistics.median(times), cores, times
+
+
+def run_reference_decode(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    sample_B = 64
+    import torch
+    from oracle import heatmap_codec as oc
+    from tests import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.CONFIGS[SYNTH_CONFIG]
+    batch = synth.make_batch(cfg, seed=0, B=sample_B)
+    hm, off = torch.from_numpy(batch["heatmaps"]), torch.from_numpy(batch["offsets"])
+    flipped = torch.from_numpy(batch["heatmaps_flip"]) if DECODE == "flip" else None
+    call = lambda: oc.fusion_decode(hm, off, 0.5, 0.6224593312018546, True, True, 2, heatmaps_of_flipped_input=flipped, loop=True)
+    for _ in range(max(1, min(args.warmup, 3))):
+        call()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call()
+    dt = time.perf_counter() - t0
+    value = sample_B * K * args.steps / dt
+    sample = f"{sample_B} images x {K} heatmaps per step (a bounded sample of the {args.batch}-image batch), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": decode_workload_name(args.batch), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), file=args.out, flush=True)
+    return 0
+
+
+def run_decode_b200(args):
+    """Decode-only workloads (BASELINE configs[2] and [4]).  No rank needs anything from another: N ranks decode N
+    shards of the same size (weak scaling), the only collectives are the bench's own barriers and max-over-ranks."""
+    import torch
+    import torch.distributed as dist
+    import infantposeestimation_gaussianbias_b200 as pkg
+    pkg.load()
+    from infantposeestimation_gaussianbias_b200 import _native as N
+    from infantposeestimation_gaussianbias_b200 import ops
+    from infantposeestimation_gaussianbias_b200.host_step import HostDecode
+    from infantposeestimation_gaussianbias_b200.pose_estimator import flip_permutation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the codec has no CPU path (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
+    B = args.batch
+    flip = DECODE == "flip"
+    flip_pairs = ((1, 2), (3, 4), (5, 6), (7, 8), (9, 10), (11, 12), (13, 14), (15, 16))     # configs/config.py:41-43
+    perm = flip_permutation(K, flip_pairs, device) if flip else None
+    alpha = torch.tensor([0.5], device=device)
+    fw = torch.tensor([0.6224593312018546], device=device)
+    dflags = N.DECODE_REFINE | N.DECODE_APPLY_OFFSET
+    in_bytes = B * K * BYTES_PER_HM
+    # inputs smaller than a few L2s are rotated so that no timed launch finds its heatmaps in the 126 MB L2
+    n_rot = max(1, min(8, -(-512_000_000 // in_bytes)))
+    sets = []
+    for r in range(n_rot):
+        d = synth_device_batch(B, device, 1234 + rank + 97 * r, ops, with_var=False)
+        if r > 0:
+            d["off"] = sets[0]["off"]                                  # 8 taps per tile are read: one copy of the offset maps
+        if flip:
+            g = torch.Generator(device=device).manual_seed(4321 + rank + r)
+            d["flip"] = (torch.flip(d["hm"][:, perm.long()], dims=[-1]) + 0.02 * torch.randn(B, K, H, W, generator=g, device=device)).contiguous()
+        sets.append(d)
+
+    def step(i):
+        d = sets[i % n_rot]
+        return ops.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        res = step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_a.record()
+    for i in range(args.steps):
+        res = step(i)
+    t_b.record()
+    barrier()
+    ms = torch.tensor([t_a.elapsed_time(t_b)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    # a step IS one launch of the decode kernel (on torch's current stream, where the two events are recorded), so the
+    # average launch duration is the timed region over its launches; the gaps between launches count against the kernel
+    kern_ms = total_ms / args.steps
+    clocks = None
+    if rank == 0:
+        t_end, i = time.time() + 1.0, 0
+        while time.time() < t_end:
+            step(i); i += 1
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    value = world * B * K * args.steps / (total_ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        d = sets[0]
+        host = {k: v.cpu().pin_memory() for k, v in d.items()}
+        hd = HostDecode(B, K, H, W, flip=flip, chunk_images=max(args.chunk, 256), device=device, flip_pairs=flip_pairs)
+        for _ in range(2):
+            out = hd(host["hm"], host.get("flip"), host["off"])
+        n_e2e = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = hd(host["hm"], host.get("flip"), host["off"])       # synchronises
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        want = ops.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
+        if not torch.equal(out["coords"], want[0].cpu()) or not torch.equal(out["scores"], want[1].cpu()):
+            raise SystemExit("bench.py: host-buffer decode disagrees with the resident decode")
+        e2e = {"value": world * B * K * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": hd.h2d_bytes,
+               "d2h_bytes_per_step": hd.d2h_bytes, "steps": n_e2e, "chunk_images": hd.chunk}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy: a 1:1 read:write mix; read-only streams run above it)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = in_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"{TILE_KERNEL} (soft-argmax + window refinement + offset taps{', flip average in the load' if flip else ''})",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kern_ms, "kernel_launches_timed": args.steps, "algorithmic_bytes_per_launch": in_bytes}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        v, cores, times = cpu_decode_rate(sample_B=32, min_seconds=10.0, max_reps=400)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"32 images x {K} heatmaps of the same workload, median of {len(times)} passes ({sum(times):.1f} s of CPU work)"}
+    l2 = (f"heatmaps {in_bytes / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed" if n_rot == 1 else
+          f"heatmaps {in_bytes / 1e6:.0f} MB per step: {n_rot} input sets ({n_rot * in_bytes / 1e6:.0f} MB) visited in rotation, so a launch never finds its heatmaps in the 126 MB L2")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": decode_workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "exchange": "none (shards are independent)", "numa_node_rank0": numa, "l2": l2},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), file=args.out, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def _json_only_stdout():
     """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
     communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to
@@ -437,7 +656,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: 1024; decode_flip 4096; decode 16384)")
     ap.add_argument("--chunk", type=int, default=128, help="images per chunk of the host-buffer pipeline")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the 2+7 loss scalars travel between ranks (NVLink peer-memory mailboxes written by the kernels, or NCCL all-reduces)")
@@ -447,10 +666,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     select_workload(args.config)
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH
     args.out = _json_only_stdout()
     if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+        return run_reference_decode(args) if DECODE else run_reference(args)
+    return run_decode_b200(args) if DECODE else run_b200(args)
 
 
 if __name__ == "__main__":

@@ -110,3 +110,85 @@ class HostCodecStep:
         self.out_h["scores"].copy_(self.scores_d, non_blocking=True)
         main.synchronize()
         return self.out_h
+
+
+class HostDecode:
+    """Keypoint decode (HeatmapRegressionHead.decode, models/fusion_head.py:309-365, with the flip-test average of
+    PoseEstimator.inference, models/pose_estimator.py:303-327, in front) on HOST buffers.
+
+    Same pipeline as HostCodecStep: chunks of whole images cross PCIe on a copy stream into double-buffered device
+    staging while the previous chunk is in the decode kernel; the offset maps stay in pinned host memory (the kernel
+    reads its 8 taps per tile in place); coordinates and scores come back to pinned host memory.  Nothing couples two
+    chunks, so the result is that of one call over the whole batch.
+    """
+
+    def __init__(self, B: int, K: int, H: int, W: int, flip: bool = False, apply_offset: bool = True, refine: bool = True,
+                 radius: int = 2, chunk_images: int = 256, device: Optional[torch.device] = None,
+                 flip_pairs: Optional[Sequence[Tuple[int, int]]] = None):
+        from .pose_estimator import flip_permutation
+        self.B, self.K, self.H, self.W = B, K, H, W
+        self.flip, self.apply_offset, self.refine, self.radius = flip, apply_offset, refine, radius
+        self.chunk = min(chunk_images, B)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        d, f, C = self.device, torch.float32, self.chunk
+        self.stage = [dict(hm=torch.empty((C, K, H, W), dtype=f, device=d),
+                           flip=torch.empty((C, K, H, W), dtype=f, device=d) if flip else None) for _ in range(2)]
+        self.perm = flip_permutation(K, flip_pairs, d) if flip else None
+        self.flags = (N.DECODE_REFINE if refine else 0) | (N.DECODE_APPLY_OFFSET if apply_offset else 0)
+        self.alpha = torch.tensor([0.5], dtype=f, device=d)
+        self.fw = torch.tensor([0.6224593312018546], dtype=f, device=d)
+        self.coords_d = torch.empty((B, K, 2), dtype=f, device=d)
+        self.scores_d = torch.empty((B, K), dtype=f, device=d)
+        self.copy_stream = torch.cuda.Stream(device=d)
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.out_h = dict(coords=torch.empty((B, K, 2), dtype=f).pin_memory(), scores=torch.empty((B, K), dtype=f).pin_memory())
+        self.launches = 0
+
+    @property
+    def h2d_bytes(self) -> int:
+        n = self.B * self.K * self.H * self.W * 4
+        taps = self.B * self.K * 8 * 32 if self.apply_offset else 0     # zero-copy: 8 taps per tile, a 32-byte sector each
+        return n * (2 if self.flip else 1) + taps
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.B * self.K * 12
+
+    def set_decode_params(self, alpha_param: Tensor, fusion_weight: Tensor):
+        self.alpha.copy_(alpha_param.reshape(1)); self.fw.copy_(fusion_weight.reshape(1))
+
+    def __call__(self, hm_h: Tensor, hm_flip_h: Optional[Tensor] = None, off_h: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """Pinned host tensors in; pinned host {coords (B,K,2), scores (B,K)} out; synchronises before returning."""
+        B, C = self.B, self.chunk
+        if self.flip and hm_flip_h is None:
+            raise RuntimeError("gbcodec: HostDecode(flip=True) needs the heatmaps of the flipped input")
+        if self.apply_offset and off_h is None:
+            raise RuntimeError("gbcodec: HostDecode(apply_offset=True) needs the offset maps")
+        main = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(main)
+        self.launches = 0
+        for c in range((B + C - 1) // C):
+            lo, hi = c * C, min(B, (c + 1) * C)
+            n = hi - lo
+            s = self.stage[c & 1]
+            with torch.cuda.stream(self.copy_stream):
+                if c >= 2:
+                    self.copy_stream.wait_event(self.consumed[c & 1])
+                s["hm"][:n].copy_(hm_h[lo:hi], non_blocking=True)
+                if self.flip:
+                    s["flip"][:n].copy_(hm_flip_h[lo:hi], non_blocking=True)
+                self.staged[c & 1].record(self.copy_stream)
+            main.wait_event(self.staged[c & 1])
+            coords, scores, _ = ops.decode(s["hm"][:n], s["flip"][:n] if self.flip else None, self.perm,
+                                           off_h[lo:hi] if self.apply_offset else None,
+                                           self.alpha if self.refine else None, self.fw if self.apply_offset else None,
+                                           self.radius, self.flags)
+            self.consumed[c & 1].record(main)
+            self.coords_d[lo:hi] = coords
+            self.scores_d[lo:hi] = scores
+            self.launches += 1
+        self.out_h["coords"].copy_(self.coords_d, non_blocking=True)
+        self.out_h["scores"].copy_(self.scores_d, non_blocking=True)
+        main.synchronize()
+        return self.out_h

@@ -89,7 +89,7 @@ def decode(hm: Tensor, hm_flipped: Optional[Tensor], flip_perm: Optional[Tensor]
         if flip_perm.numel() != K:
             raise RuntimeError("gbcodec: flip_perm must hold K entries")
     if off is not None:
-        off = _cuda_f32("offsets", off, (B, K, 2, H, W))
+        off = _device_readable_f32("offsets", off, (B, K, 2, H, W))     # 8 taps per tile: may stay in pinned host memory
     alpha_param = _scalar("alpha", alpha_param, hm)
     fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
     coords = torch.empty((B, K, 2), dtype=torch.float32, device=hm.device)

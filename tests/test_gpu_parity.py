@@ -354,6 +354,37 @@ def test_host_buffer_step_matches_resident_step(gb, stage_offsets):
     assert hs.h2d_bytes < (2 if not stage_offsets else 4) * B * K * H * W * 4 * 1.1
 
 
+@pytest.mark.parametrize("flip", [False, True])
+def test_host_buffer_decode_matches_resident_decode(gb, flip):
+    """HostDecode (pinned heatmaps in, chunked H2D pipeline, offsets read in place over PCIe) gives the resident
+    decode's coordinates and scores bit for bit, and those agree with the oracle (1e-4 px away from H1 tiles)."""
+    from infantposeestimation_gaussianbias_b200 import _native as N
+    from infantposeestimation_gaussianbias_b200.host_step import HostDecode
+    from infantposeestimation_gaussianbias_b200.pose_estimator import flip_permutation
+    cfg = synth.CONFIGS["hrformer_384x288"]
+    B = 19
+    batch = synth.make_batch(cfg, seed=6, B=B)
+    K, (W, H) = cfg.K, cfg.heatmap_size
+    pin = lambda k: t(batch[k]).pin_memory()
+    hd = HostDecode(B, K, H, W, flip=flip, chunk_images=5, flip_pairs=oc.COCO_FLIP_PAIRS)
+    out = hd(pin("heatmaps"), pin("heatmaps_flip") if flip else None, pin("offsets"))
+    perm = flip_permutation(K, oc.COCO_FLIP_PAIRS, torch.device("cuda")) if flip else None
+    alpha, fw = torch.tensor([0.5]).cuda(), torch.tensor([0.6224593312018546]).cuda()
+    c, s, _ = gb.decode(dev(batch["heatmaps"]), dev(batch["heatmaps_flip"]) if flip else None, perm, dev(batch["offsets"]),
+                        alpha, fw, 2, N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)
+    assert np.array_equal(out["coords"].numpy(), c.cpu().numpy())
+    assert np.array_equal(out["scores"].numpy(), s.cpu().numpy())
+    hm = t(batch["heatmaps"])
+    flipped = t(batch["heatmaps_flip"]) if flip else None
+    want_c, want_s = oc.fusion_decode(hm, t(batch["offsets"]), 0.5, 0.6224593312018546, True, True, 2, heatmaps_of_flipped_input=flipped)
+    coarse, _ = oc.soft_argmax(oc.flip_average(hm, flipped) if flip else hm)
+    safe = ((coarse - torch.floor(coarse) - 0.5).abs() > 1e-3).all(dim=-1).numpy()          # H1: away from the rounding boundary
+    assert safe.mean() > 0.9
+    np.testing.assert_allclose(out["coords"].numpy()[safe], want_c.numpy()[safe], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(out["scores"].numpy(), want_s.numpy(), rtol=1e-6 if flip else 0, atol=0)
+    assert hd.h2d_bytes < (2 if flip else 1) * B * K * H * W * 4 * 1.1 and hd.launches == 4
+
+
 # ---------------------------------------------------------------------- AMP: fp16 head outputs (train.py:171, SURVEY Q20)
 def same_up_to_tie_pixels(g16, g32, what):
     # 1024 = 2^10: scaling commutes with every rounding, so the two paths agree bit for bit — except on pixels whose
