@@ -198,7 +198,7 @@ constexpr int kTargetLut = 2;      // generated on the fly, any patch height
 // MG = true : the tile maximum is not reduced on its own: pass B runs relative to each warp's maximum and the moments
 //              are rescaled where the warps' sums meet (one barrier and one sweep over the tile less); the squared
 //              error then waits for pass C, since the target's exp table is published by that same barrier.
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, bool HALF, bool MG = false>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, bool HALF, bool MG = false, bool VSLOT = false>
 __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossArgs& A, const int k, const int b, const int kdim) {
     using IO = TileIO<HALF>;
     using Vec = typename IO::Vec;
@@ -230,10 +230,19 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     const size_t toff = (size_t)tile * N4 + tid;
     const Vec* hmb = reinterpret_cast<const Vec*>(A.hm) + tid;
     const Vec* hm4 = reinterpret_cast<const Vec*>(A.hm) + toff;
+    // VS: the variance tile is needed for its sum only; it rides through the (still unused) sigmoid slots as an
+    // asynchronous copy and is added up by pass B just before a slot receives its sigmoid — no registers held
+    // across the wait for HBM, no second wait
+    constexpr bool VS = ROLL && CS && VSLOT;
     float4 h[NIT];
     if (ROLL) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) IO::copy_async(Hs + it * TPB + tid, hm4 + it * TPB);
+        if (VS && A.var) {
+            const Vec* var4 = reinterpret_cast<const Vec*>(A.var) + toff;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) IO::copy_async(Ss + it * TPB + tid, var4 + it * TPB);
+        }
         cp_async_commit();
     } else {
 #pragma unroll
@@ -241,7 +250,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     }
     auto own4 = [&](int it) -> float4 { return ROLL ? Hs[it * TPB + tid] : h[it]; };
     float4 vv[NIT];
-    if (A.var) {
+    if (A.var && !VS) {
         const Vec* var4 = reinterpret_cast<const Vec*>(A.var) + toff;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) vv[it] = IO::load_stream(var4 + it * TPB);
@@ -275,7 +284,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     const float wa = P.use_target_weight ? w : 1.f;
     const bool heavy = (w != 0.f) || !P.use_target_weight;
     float vsum = 0.f;
-    if (A.var) {
+    if (A.var && !VS) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) vsum += (vv[it].x + vv[it].y) + (vv[it].z + vv[it].w);
     }
@@ -367,6 +376,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
             E01 = add2(E01, e01); E23 = add2(E23, e23);
             if (CE) Es[it * TPB + tid] = as_float4(f4{e01, e23});
             Yw = fmaf((float)(it * ROWS), hsum2(add2(e01, e23)), Yw);
+            if (VS && A.var) { const float4 v4 = IO::from_slot(Ss + it * TPB + tid); vsum += (v4.x + v4.y) + (v4.z + v4.w); }
             if (heavy) {
                 const f2 u01 = mul2(hv.a, kNL2E), u23 = mul2(hv.b, kNL2E);
                 const f2 g01 = add2(pack2(ex2(lo2(u01)), ex2(hi2(u01))), kOne), g23 = add2(pack2(ex2(lo2(u23)), ex2(hi2(u23))), kOne);
@@ -837,16 +847,16 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
 }
 
 // forward (and fused step): one CTA per tile, grid = (K, B) — no division
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false, bool MG = false>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false, bool MG = false, bool VSLOT = false>
 __global__ void __launch_bounds__(W4* ROWS, MINB)
 loss_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
-    loss_tile_body<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, HALF, MG>(P, A, blockIdx.x, blockIdx.y, gridDim.x);
+    loss_tile_body<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, HALF, MG, VSLOT>(P, A, blockIdx.x, blockIdx.y, gridDim.x);
 }
 
 // backward call: nothing to do if the stored gradients are already right (plan 0); float32 gradients that are off by one
 // common factor are rescaled in place by rescale_kernel (plan 1), float16 ones are computed again (a stored half cannot be
 // rescaled without a second rounding).  The grid is one wave of resident CTAs; each walks its share of the tiles.
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false, bool MG = false>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false, bool MG = false, bool VSLOT = false>
 __global__ void __launch_bounds__(W4* ROWS, MINB)
 loss_tile_backward_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A, const int tiles_per_cta) {
     if (A.plan && (HALF ? *A.plan == 0 : *A.plan != 2)) return;
@@ -854,20 +864,20 @@ loss_tile_backward_kernel(const __grid_constant__ LossParams P, const __grid_con
     const int t0 = blockIdx.x * tiles_per_cta, t1 = min(tiles, t0 + tiles_per_cta);
     for (int t = t0; t < t1; ++t) {
         const int b = t / P.K;
-        loss_tile_body<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, HALF, MG>(P, A, t - b * P.K, b, P.K);
+        loss_tile_body<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, HALF, MG, VSLOT>(P, A, t - b * P.K, b, P.K);
         __syncthreads();                         // the next tile re-uses every shared-memory buffer
     }
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false, bool MG = false>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool ROLL, int TM, int MINB, bool HALF = false, bool MG = false, bool VSLOT = false>
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
     const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
                       + (size_t)(2 * NW * 16 + 32 + 8 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
     if (A.lam_eff != nullptr) {                        // fusion_loss_backward: per-term upstream weights on the device
-        auto bk = loss_tile_backward_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF, MG>;
+        auto bk = loss_tile_backward_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF, MG, VSLOT>;
         cudaError_t e = cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_backward_kernel): %s", cudaGetErrorString(e));
@@ -882,7 +892,7 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
         bk<<<(tiles + per - 1) / per, TPB, smem, s>>>(P, A, per);
         return check_launch("loss_tile_backward_kernel");
     }
-    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF, MG>;
+    auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF, MG, VSLOT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -893,11 +903,11 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     return check_launch("loss_tile_kernel");
 }
 
-template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB, bool CQ = true, bool ROLL = false, bool HALF = false, bool MG = false>
+template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, int MINB, bool CQ = true, bool ROLL = false, bool HALF = false, bool MG = false, bool VSLOT = false>
 static int launch_tile_tm(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
-    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetGlobal, MINB, HALF, MG>(P, A, s, e0, e1);
-    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetOneHit, MINB, HALF, MG>(P, A, s, e0, e1);
-    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetLut, MINB, HALF, MG>(P, A, s, e0, e1);
+    if (A.target) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetGlobal, MINB, HALF, MG, VSLOT>(P, A, s, e0, e1);
+    if (P.ec.ntap <= ROWS) return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetOneHit, MINB, HALF, MG, VSLOT>(P, A, s, e0, e1);
+    return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetLut, MINB, HALF, MG, VSLOT>(P, A, s, e0, e1);
 }
 
 // GBCODEC_TILE_VARIANT=<n>: alternative CTA shapes for the 64x48 tile (measurement only)
@@ -907,14 +917,16 @@ static int tile_variant() {
 }
 
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
+    // The instantiations with sigmoid slots (CS) take the variance tile through them as an asynchronous copy (VSLOT): no
+    // registers held across the first wait for HBM (64x48 0.2755 -> 0.2670 ms, 96x72 0.659 -> 0.616, 64x64 0.360 -> 0.345).
     // Every default instantiation merges the maximum into the moment reduction (MG): 1-2 % faster on all four shapes than
     // a reduction of its own (64x48 0.2790 -> 0.2756 ms, 96x72 0.665 -> 0.659, 128x128 K=13 1.147 -> 1.121, 64x64 0.364 -> 0.360).
     if (A.half_io) {
         // float16 maps (autocast): the default instantiation of each shape; other shapes have no half path
-        if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, true, true>(P, A, s, e0, e1);
-        if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, true, true>(P, A, s, e0, e1);
+        if (P.H == 64 && P.W == 48) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, true, true, true>(P, A, s, e0, e1);
+        if (P.H == 96 && P.W == 72) return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, true, true, true>(P, A, s, e0, e1);
         if (P.H == 128 && P.W == 128) return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, true, true>(P, A, s, e0, e1);
-        if (P.H == 64 && P.W == 64) return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, true, true>(P, A, s, e0, e1);
+        if (P.H == 64 && P.W == 64) return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, true, true, true>(P, A, s, e0, e1);
         return 1;
     }
     // GBCODEC_TILE_VARIANT=<n> selects an alternative CTA shape / shared-memory budget (A/B measurements; DESIGN.md §4
@@ -925,14 +937,15 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
         if (v == 2) return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);                  // tile in registers, unrolled; E,S,A,Q
         if (v == 13) return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true>(P, A, s, e0, e1);  // rolled; H,S; 6 CTAs
         if (v == 21) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true>(P, A, s, e0, e1);   // the default with a maximum reduction of its own (one more barrier)
-        return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, false, true>(P, A, s, e0, e1);   // 192 threads, 16 px each; H,S,Q in smem, 5 CTAs
+        if (v == 22) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, false, true>(P, A, s, e0, e1);   // the default with the variance tile loaded into registers (0.2755 ms against 0.2665)
+        return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, false, true, true>(P, A, s, e0, e1);   // 192 threads, 16 px each; H,S,Q in smem, 5 CTAs
     }
     if (P.H == 96 && P.W == 72) {
         if (v == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);    // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
-        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, false, true>(P, A, s, e0, e1);  // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.659 ms)
+        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, false, true, true>(P, A, s, e0, e1);  // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.616 ms)
     }
     if (P.H == 64 && P.W == 64)          // the reference's other default map (data/pose_transforms.py:391): 256 threads, H,S,Q in smem, 4 CTAs
-        return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, false, true>(P, A, s, e0, e1);
+        return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, false, true, true>(P, A, s, e0, e1);
     if (P.H == 128 && P.W == 128) {
         if (v == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);    // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
         return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, false, true>(P, A, s, e0, e1); // rolled, 512 threads, 32 px each; own tile only in smem: 2 CTAs (1.121 ms)
