@@ -204,7 +204,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     using Vec = typename IO::Vec;
     using Elem = typename IO::Elem;
     constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
-    static_assert(TPB % 32 == 0 && TPB <= 1024, "CTA must be whole warps");
+    static_assert(TPB % 32 == 0 && TPB <= 1024, "CTA must be whole warps");      // NW <= 32: redm holds 32 floats
     static_assert(GBCODEC_MAX_PARTNERS == 4, "tie patterns are nibbles");
 
     extern __shared__ __align__(16) float smem[];
@@ -218,8 +218,8 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     float* red0 = reinterpret_cast<float*>(As + (CA ? N4 : 0));   // two reduction buffers of NW * 16 floats
     float* red1 = red0 + NW * 16;
     float* lutG = red1 + NW * 16;                                 // 12 tile coefficients + 16 overlap coefficients + 4 partner scales
-    float* redm = lutG + 32;                                      // per-warp maxima (MG), 8 floats
-    unsigned* Ws = reinterpret_cast<unsigned*>(redm + 8);         // tie-pattern words (ROLL only), thread-private
+    float* redm = lutG + 32;                                      // per-warp maxima (MG), one float per warp of the largest CTA
+    unsigned* Ws = reinterpret_cast<unsigned*>(redm + 32);        // tie-pattern words (ROLL only), thread-private
     float* lut = reinterpret_cast<float*>(Ws + (ROLL ? N4 : 0));  // exp table of the target patch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -234,6 +234,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     // asynchronous copy and is added up by pass B just before a slot receives its sigmoid — no registers held
     // across the wait for HBM, no second wait
     constexpr bool VS = ROLL && CS && VSLOT;
+    constexpr bool QPIPE = true;                    // (false: each row's partner vector is requested where it is consumed)
     float4 h[NIT];
     if (ROLL) {
 #pragma unroll
@@ -494,9 +495,15 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
         const Vec* srcc = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         if (CQ) cp_async_wait_all();                  // this thread's slots hold partner `cur`
         f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
+        // partners straight from L2 (no slot): the next row's vector is requested before this row's is consumed
+        float4 qn = z4;
+        if (!CQ && QPIPE) qn = IO::load_stream(srcc);
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
-            const float4 q4 = CQ ? IO::from_slot(Qs + it * TPB + tid) : IO::load_stream(srcc + it * TPB);
+            float4 q4;
+            if (CQ) q4 = IO::from_slot(Qs + it * TPB + tid);
+            else if (QPIPE) { q4 = qn; if (it + 1 < NIT) qn = IO::load_stream(srcc + (it + 1) * TPB); }
+            else q4 = IO::load_stream(srcc + it * TPB);
             const float4 o = own4(it);
             const f4 hv = as_f4(o), qv = as_f4(q4);
             float sk[4];
@@ -874,7 +881,7 @@ template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool RO
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
     const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
-                      + (size_t)(2 * NW * 16 + 32 + 8 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
+                      + (size_t)(2 * NW * 16 + 32 + 32 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
     if (A.lam_eff != nullptr) {                        // fusion_loss_backward: per-term upstream weights on the device
         auto bk = loss_tile_backward_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF, MG, VSLOT>;

@@ -61,7 +61,21 @@ def step(gb, cfg, d, sl=slice(None), denoms=None, var=None):
                           True, pairs, True, True, a, f, 2, 3)
 
 
-@pytest.mark.parametrize("name,B", [("w32_256x192", 1024), ("preemie_256", 1024)])
+@pytest.mark.parametrize("name,B", [("w32_256x192", 512), ("hrformer_384x288", 512), ("preemie_256", 512)])
+def test_fused_step_is_bit_reproducible(gb, name, B):
+    """No float atomics, fixed-order sums: the same inputs give the same bits, launch after launch — losses, every
+    gradient, coordinates and scores (CTAs of 6, 9 and 16 warps; the reductions exchange per-warp partials)."""
+    cfg = synth.CONFIGS[name]
+    d = device_batch(cfg, B, 23, gb)
+    var = torch.nn.functional.softplus(torch.randn(B, cfg.K, cfg.H, cfg.W, device="cuda"))
+    first = [t.clone() for t in step(gb, cfg, d, var=var)[:6]]
+    for _ in range(6):
+        again = step(gb, cfg, d, var=var)[:6]
+        for a, b in zip(first, again):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,B", [("w32_256x192", 1024), ("hrformer_384x288", 512), ("preemie_256", 1024)])
 def test_fused_step_full_size_properties(gb, name, B):
     cfg = synth.CONFIGS[name]
     d = device_batch(cfg, B, 11, gb)
