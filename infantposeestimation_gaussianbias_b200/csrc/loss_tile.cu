@@ -111,6 +111,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 // bit i of the low byte -> bit 4*i
 __device__ __forceinline__ unsigned spread8(unsigned t) {
     unsigned x = t & 0xFFu;
@@ -210,8 +211,12 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     extern __shared__ __align__(16) float smem[];
     constexpr int UNR = ROLL ? 1 : NIT;
     constexpr bool AQ = CQ && !CA;                  // the partner slot is free once the partners are done: park `a` there
+    // QRING: no room for a whole partner tile -> its rows stream through a two-row ring of thread-private slots, each
+    // row requested (cp.async) two rows before it is consumed, the next partner's first rows during the last two
+    constexpr bool QRING = !CQ && ROLL;
+    static_assert(!QRING || NIT % 2 == 0, "the ring's slot parity must carry over from one partner to the next");
     float4* Qs = reinterpret_cast<float4*>(smem);                 // partner tile, thread-private slots
-    float4* Hs = Qs + (CQ ? N4 : 0);                              // own tile (ROLL only)
+    float4* Hs = Qs + (CQ ? N4 : (QRING ? 2 * TPB : 0));          // own tile (ROLL only)
     float4* Es = Hs + (ROLL ? N4 : 0);                            // exp(h - max), later softmax weight p
     float4* Ss = Es + (CE ? N4 : 0);                              // sigmoid(h)
     float4* As = Ss + (CS ? N4 : 0);                              // a = -log(p + eps) - p / (p + eps)
@@ -337,6 +342,13 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
         const Vec* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) IO::copy_async(Qs + it * TPB + tid, src + it * TPB);
+        cp_async_commit();
+    }
+    if (QRING && cur >= 0) {
+        const Vec* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+        IO::copy_async(Qs + tid, src);
+        cp_async_commit();
+        IO::copy_async(Qs + TPB + tid, src + TPB);
         cp_async_commit();
     }
 
@@ -497,11 +509,12 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
         f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
         // partners straight from L2 (no slot): the next row's vector is requested before this row's is consumed
         float4 qn = z4;
-        if (!CQ && QPIPE) qn = IO::load_stream(srcc);
+        if (!CQ && !QRING && QPIPE) qn = IO::load_stream(srcc);
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
             float4 q4;
             if (CQ) q4 = IO::from_slot(Qs + it * TPB + tid);
+            else if (QRING) { cp_async_wait_but_one(); q4 = IO::from_slot(Qs + (it & 1) * TPB + tid); }   // one group per row: all but the newest have landed
             else if (QPIPE) { q4 = qn; if (it + 1 < NIT) qn = IO::load_stream(srcc + (it + 1) * TPB); }
             else q4 = IO::load_stream(srcc + it * TPB);
             const float4 o = own4(it);
@@ -518,6 +531,11 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
             float sq[4] = {rcp(lo2(g01)), rcp(hi2(g01)), rcp(lo2(g23)), rcp(hi2(g23))};
             // the slot has been consumed (its value went through the sigmoid): refill it with the next partner
             if (CQ && nxt >= 0) IO::copy_async(Qs + it * TPB + tid, src + it * TPB);
+            if (QRING) {
+                if (it + 2 < NIT) IO::copy_async(Qs + (it & 1) * TPB + tid, srcc + (it + 2) * TPB);
+                else if (nxt >= 0) IO::copy_async(Qs + (it & 1) * TPB + tid, src + (it + 2 - NIT) * TPB);
+                cp_async_commit();
+            }
             // min(sigma(a), sigma(b)) = sigma(min(a, b)): decide on the logits; equal logits give equal sigmoids
             const f2 d01 = sub2(hv.a, qv.a), d23 = sub2(hv.b, qv.b);
             const float d[4] = {lo2(d01), hi2(d01), lo2(d23), hi2(d23)};
@@ -881,6 +899,7 @@ template <int W4, int ROWS, int NIT, bool CE, bool CS, bool CA, bool CQ, bool RO
 static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int TPB = W4 * ROWS, N4 = TPB * NIT, NW = TPB / 32;
     const size_t smem = (size_t)N4 * 16 * ((CQ ? 1 : 0) + (ROLL ? 1 : 0) + (CE ? 1 : 0) + (CS ? 1 : 0) + (CA ? 1 : 0))
+                      + (size_t)((!CQ && ROLL) ? 2 * TPB * 16 : 0)
                       + (size_t)(2 * NW * 16 + 32 + 32 + (ROLL ? N4 : 0)) * 4 + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
     if (smem > 227 * 1024 || P.B > 65535) return 1;
     if (A.lam_eff != nullptr) {                        // fusion_loss_backward: per-term upstream weights on the device
