@@ -239,6 +239,10 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     // asynchronous copy and is added up by pass B just before a slot receives its sigmoid — no registers held
     // across the wait for HBM, no second wait
     constexpr bool VS = ROLL && CS && VSLOT;
+    // no sigmoid slots, but a partner ring: the variance rows go through the ring ahead of the first partner's
+    constexpr bool VRING = !CQ && ROLL && !VS;
+    const bool vring = VRING && A.var != nullptr;
+    const Vec* var4r = reinterpret_cast<const Vec*>(A.var) + toff;
     constexpr bool QPIPE = true;                    // (false: each row's partner vector is requested where it is consumed)
     float4 h[NIT];
     if (ROLL) {
@@ -250,13 +254,19 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
             for (int it = 0; it < NIT; ++it) IO::copy_async(Ss + it * TPB + tid, var4 + it * TPB);
         }
         cp_async_commit();
+        if (vring) {
+            IO::copy_async(Qs + tid, var4r);
+            cp_async_commit();
+            IO::copy_async(Qs + TPB + tid, var4r + TPB);
+            cp_async_commit();
+        }
     } else {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) h[it] = IO::load_stream(hm4 + it * TPB);
     }
     auto own4 = [&](int it) -> float4 { return ROLL ? Hs[it * TPB + tid] : h[it]; };
     float4 vv[NIT];
-    if (A.var && !VS) {
+    if (A.var && !VS && !vring) {
         const Vec* var4 = reinterpret_cast<const Vec*>(A.var) + toff;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) vv[it] = IO::load_stream(var4 + it * TPB);
@@ -290,7 +300,7 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     const float wa = P.use_target_weight ? w : 1.f;
     const bool heavy = (w != 0.f) || !P.use_target_weight;
     float vsum = 0.f;
-    if (A.var && !VS) {
+    if (A.var && !VS && !vring) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) vsum += (vv[it].x + vv[it].y) + (vv[it].z + vv[it].w);
     }
@@ -344,7 +354,8 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
         for (int it = 0; it < NIT; ++it) IO::copy_async(Qs + it * TPB + tid, src + it * TPB);
         cp_async_commit();
     }
-    if (QRING && cur >= 0) {
+    const Vec* src_first = hmb + ((size_t)b * P.K + pick4(cur < 0 ? 0 : cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
+    if (QRING && cur >= 0 && !vring) {
         const Vec* src = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         IO::copy_async(Qs + tid, src);
         cp_async_commit();
@@ -390,6 +401,16 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
             if (CE) Es[it * TPB + tid] = as_float4(f4{e01, e23});
             Yw = fmaf((float)(it * ROWS), hsum2(add2(e01, e23)), Yw);
             if (VS && A.var) { const float4 v4 = IO::from_slot(Ss + it * TPB + tid); vsum += (v4.x + v4.y) + (v4.z + v4.w); }
+            if (vring) {
+                // the ring's row `it` is a variance row; its slot then takes variance row it + 2 or, in the last two
+                // rounds, the first partner's rows 0 and 1
+                cp_async_wait_but_one();
+                const float4 v4 = IO::from_slot(Qs + (it & 1) * TPB + tid);
+                vsum += (v4.x + v4.y) + (v4.z + v4.w);
+                if (it + 2 < NIT) IO::copy_async(Qs + (it & 1) * TPB + tid, var4r + (it + 2) * TPB);
+                else if (cur >= 0) IO::copy_async(Qs + (it & 1) * TPB + tid, src_first + (it + 2 - NIT) * TPB);
+                cp_async_commit();
+            }
             if (heavy) {
                 const f2 u01 = mul2(hv.a, kNL2E), u23 = mul2(hv.b, kNL2E);
                 const f2 g01 = add2(pack2(ex2(lo2(u01)), ex2(hi2(u01))), kOne), g23 = add2(pack2(ex2(lo2(u23)), ex2(hi2(u23))), kOne);
@@ -968,13 +989,13 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
     }
     if (P.H == 96 && P.W == 72) {
         if (v == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);    // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
-        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, false, true, true>(P, A, s, e0, e1);  // rolled, 288 threads, 24 px each; H,S in smem, partners through L2: 3 CTAs (0.616 ms)
+        return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, false, true, true>(P, A, s, e0, e1);  // rolled, 288 threads, 24 px each; H,S in smem, partners through a two-row ring: 3 CTAs (0.581 ms)
     }
     if (P.H == 64 && P.W == 64)          // the reference's other default map (data/pose_transforms.py:391): 256 threads, H,S,Q in smem, 4 CTAs
         return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, false, true, true>(P, A, s, e0, e1);
     if (P.H == 128 && P.W == 128) {
         if (v == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);    // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
-        return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, false, true>(P, A, s, e0, e1); // rolled, 512 threads, 32 px each; own tile only in smem: 2 CTAs (1.121 ms)
+        return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, false, true>(P, A, s, e0, e1); // rolled, 512 threads, 32 px each; own tile + a two-row ring for the variance and partner rows in smem: 2 CTAs (1.067 ms)
     }
     return 1;
 }
