@@ -55,6 +55,14 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream still runs — once every CTA of the predecessor has executed
+// pdl_launch_dependents() (or exited) — and must execute pdl_wait() before it touches anything the predecessor
+// writes; pdl_wait() returns when the predecessor grid has completed and its writes are visible.  Both are no-ops in a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // NV running sums per lane -> lane l holds the warp total of value l >> (5 - log2 NV) (halving butterfly:
 // each step exchanges half of the remaining values, so 4 values cost 2+1+3 shuffles instead of 20).
 template <int NV>

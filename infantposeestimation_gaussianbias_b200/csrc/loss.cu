@@ -29,6 +29,7 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
               float* __restrict__ global_out) {
     __shared__ float wsm[256];
     __shared__ double red[2][8];
+    pdl_launch_dependents();                           // the tile kernel may start its bulk loads; it waits before it reads weff / geom / sums
     const int ipb = 256 / P.K;                         // images per CTA
     const int img0 = blockIdx.x * ipb;
     const int nimg = min(ipb, P.B - img0);
@@ -481,6 +482,7 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
                 const __grid_constant__ PeerView peer) {
     __shared__ double red[6][8];
     __shared__ bool last;
+    pdl_wait();                                        // launched while the tile kernel's last wave is still running
     const int tiles = P.B * P.K;
     const int per = (tiles + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(tiles, lo + per);
@@ -758,7 +760,17 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     if (st) return st;
     const int tiles = P.B * P.K;
     const int fin_blocks = (tiles + 255) / 256 < kFinBlocks ? (tiles + 255) / 256 : kFinBlocks;
-    finalize_kernel<<<fin_blocks, 256, 0, s>>>(P, L.partial, L.sums, L.bpart, L.ticket, losses7, peer);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(fin_blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const float* partial_c = L.partial; const double* sums_c = L.sums;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, finalize_kernel, P, partial_c, sums_c, L.bpart, L.ticket, losses7, peer);
+        if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(finalize_kernel): %s", cudaGetErrorString(e));
+    }
     return check_launch("finalize_kernel");
 }
 

@@ -271,7 +271,10 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
 #pragma unroll
         for (int it = 0; it < NIT; ++it) vv[it] = IO::load_stream(var4 + it * TPB);
     }
-    // then every scalar the tile will need
+    // then every scalar the tile will need.  The forward kernel is launched programmatically dependent on the kernel that
+    // writes them (the bulk copies above are already on their way); the finalize kernel may be scheduled from here on.
+    pdl_wait();
+    pdl_launch_dependents();
     const float w = __ldg(A.weff + tile);
     const int np = P.n_partner[k];
     const int4 pj4 = make_int4(P.partner[k][0], P.partner[k][1], P.partner[k][2], P.partner[k][3]);
@@ -945,7 +948,16 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e));
     if (e0) cudaEventRecord(e0, s);
-    kern<<<dim3(P.K, P.B), TPB, smem, s>>>(P, A);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(P.K, P.B); cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, P, A);
+        if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(loss_tile_kernel): %s", cudaGetErrorString(e));
+    }
     if (e1) cudaEventRecord(e1, s);
     return check_launch("loss_tile_kernel");
 }
