@@ -243,7 +243,6 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
     constexpr bool VRING = !CQ && ROLL && !VS;
     const bool vring = VRING && A.var != nullptr;
     const Vec* var4r = reinterpret_cast<const Vec*>(A.var) + toff;
-    constexpr bool QPIPE = true;                    // (false: each row's partner vector is requested where it is consumed)
     float4 h[NIT];
     if (ROLL) {
 #pragma unroll
@@ -531,16 +530,12 @@ __device__ __forceinline__ void loss_tile_body(const LossParams& P, const LossAr
         const Vec* srcc = hmb + ((size_t)b * P.K + pick4(cur, pj4.x, pj4.y, pj4.z, pj4.w)) * N4;
         if (CQ) cp_async_wait_all();                  // this thread's slots hold partner `cur`
         f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
-        // partners straight from L2 (no slot): the next row's vector is requested before this row's is consumed
-        float4 qn = z4;
-        if (!CQ && !QRING && QPIPE) qn = IO::load_stream(srcc);
 #pragma unroll UNR
         for (int it = 0; it < NIT; ++it) {
             float4 q4;
             if (CQ) q4 = IO::from_slot(Qs + it * TPB + tid);
             else if (QRING) { cp_async_wait_but_one(); q4 = IO::from_slot(Qs + (it & 1) * TPB + tid); }   // one group per row: all but the newest have landed
-            else if (QPIPE) { q4 = qn; if (it + 1 < NIT) qn = IO::load_stream(srcc + (it + 1) * TPB); }
-            else q4 = IO::load_stream(srcc + it * TPB);
+            else q4 = IO::load_stream(srcc + it * TPB);                  // register-resident tile without slots: straight from L2
             const float4 o = own4(it);
             const f4 hv = as_f4(o), qv = as_f4(q4);
             float sk[4];

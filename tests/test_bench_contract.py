@@ -22,6 +22,20 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and "model" not in d["config"] and d["gpu_launches"] == 0
 
 
+def test_reference_arm_of_the_decode_workloads():
+    """--config decode_flip / decode: the same contract, their own metric (BASELINE configs[2] and [4])."""
+    for config, what in (("decode_flip", "96x72, decode with flip test"), ("decode", "64x48, decode + offset")):
+        r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--config", config, "--steps", "1", "--warmup", "1"], cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1, r.stdout
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and what in d["metric"] and d["unit"] == "heatmaps/s" and d["value"] > 0
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["gpu_launches"] == 0
+        assert "BASELINE configs" in d["config"]["workload"] and "model" not in d["config"]
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], cwd=ROOT,
