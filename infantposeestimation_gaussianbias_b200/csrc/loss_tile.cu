@@ -1,4 +1,4 @@
-// loss_tile.cu — register-resident tile kernel of the six-term fusion loss (forward + backward
+// loss_tile.cu — tile kernel of the six-term fusion loss (forward + backward
 // + optional keypoint decode in one pass).  Same arithmetic as the generic kernel in loss.cu
 // (FusionPoseLoss.forward, models/fusion_head.py:745-806, terms :637-743 and :405-559, and the
 // autograd backward of train.py:182 in closed form); different schedule:
@@ -6,19 +6,22 @@
 //   * one CTA per (image, keypoint) tile, TPB = (W/4) * ROWS threads; a thread owns the same four
 //     columns in every row it visits, so every x-dependent factor is a per-thread constant and
 //     the column moments factor out of the row loop;
-//   * the tile lives in REGISTERS (NIT float4 per thread, loaded once with 128-bit streaming
-//     loads); the per-pixel intermediates a later pass needs (softmax weight, sigmoid, entropy
-//     derivative) are parked in thread-private shared-memory slots — no cross-thread traffic,
-//     conflict-free 128-bit accesses;
+//   * the tile is copied once (cp.async, 16 B per thread and row) into thread-private shared-memory
+//     slots and every pass reads it from there with rolled row loops (the shipped instantiations;
+//     ROLL = false keeps it in registers with unrolled loops); the per-pixel intermediates a later
+//     pass needs (sigmoid, entropy derivative) are parked in slots of the same kind — no
+//     cross-thread traffic, conflict-free 128-bit accesses; the variance tile, needed for its sum
+//     only, takes the same road through slots that are still unused at that time;
 //   * two block reductions per tile, ONE barrier each (halving butterfly inside the warp,
 //     then every warp finishes the cross-warp sum redundantly); the tile maximum has no
 //     reduction of its own: the softmax moments are accumulated relative to each warp's
 //     maximum and rescaled where the warps' partial sums meet;
-//   * the limb partners' tiles (some other CTA's own tile: L2 hits) stream through a
-//     thread-private shared-memory slot with cp.async, the next partner's copy in flight while
-//     the current one is consumed; each is visited once, the per-pixel tie pattern the gradient
-//     needs is kept as one bit per pixel and partner, and the gradient pass turns the 4-bit
-//     pattern of a pixel into its overlap coefficient with one table look-up;
+//   * the limb partners' tiles (some other CTA's own tile: L2 hits) stream through thread-private
+//     slots with cp.async — a whole tile where shared memory has room for it (the next partner's
+//     copy in flight while the current one is consumed), a two-row ring where it has not; each is
+//     visited once, the per-pixel tie pattern the gradient needs is kept as one bit per pixel and
+//     partner, and the gradient pass turns the 4-bit pattern of a pixel into its overlap
+//     coefficient with one table look-up;
 //   * stores are spread over the kernel's lifetime: the (almost all zero) offset-gradient tile
 //     leaves right after the loads are issued, the uniform variance-gradient tile once the
 //     first reduction is known, the heatmap gradient at the end;
