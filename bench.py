@@ -11,6 +11,10 @@ For N > 1 the driver launches one rank per GPU (torch.distributed.run); the batc
 sharded by image, per-GPU work fixed (weak scaling), the only collectives are the
 2-float normaliser all-reduce before and the 7-float loss all-reduce after the kernel.
 
+`--config decode_flip` / `--config decode [--batch B]` measure the decode-only workloads of
+BASELINE.json (configs[2]: 96x72, B=4096, flip test + offset correction; configs[4]: the
+64x48 sweep) under the same contract; `--config hrformer|preemie` the other fused-step shapes.
+
 `--impl reference` times the reference's CPU implementation of the same step on the
 host cores.  The reference is Python and cannot travel to the GPU box, so this is
 the oracle port (oracle/heatmap_codec.py, pinned to the reference by tests/golden).
@@ -406,7 +410,7 @@ def run_b200(args):
     achieved = B * K * BYTES_PER_HM / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": f"{TILE_KERNEL} (fused step: on-the-fly target + six-term loss fwd/bwd + decode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_launches_timed": len(sampled),
-                "algorithmic_bytes_per_launch": B * K * BYTES_PER_HM}
+                "algorithmic_bytes_per_launch": B * K * BYTES_PER_HM, "frac_of_nominal_8TBps": achieved / 8000.0}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path) and args.config == "w32":      # the ncu capture is of the default workload's kernel
         try:
@@ -617,7 +621,8 @@ def run_decode_b200(args):
     achieved = in_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": f"{TILE_KERNEL} (soft-argmax + window refinement + offset taps{', flip average in the load' if flip else ''})",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms": kern_ms, "kernel_launches_timed": args.steps, "algorithmic_bytes_per_launch": in_bytes}
+                "kernel_ms": kern_ms, "kernel_launches_timed": args.steps, "algorithmic_bytes_per_launch": in_bytes,
+                "frac_of_nominal_8TBps": achieved / 8000.0}
     cpu = None
     if not args.no_cpu and world == 1:
         v, cores, times = cpu_decode_rate(sample_B=32, min_seconds=10.0, max_reps=400)
