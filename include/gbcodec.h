@@ -74,7 +74,8 @@ int gbcodec_encode_f32(const float* d_kps, const float* d_vis, float* d_target, 
  *   d_hm           (B,K,H,W)
  *   d_hm_flipped   (B,K,H,W) raw head output for the W-flipped image, or NULL
  *   d_flip_perm    K int32, channel permutation of the flip pairs (NULL = identity)
- *   d_off          (B,K,2,H,W), required with GBCODEC_DECODE_APPLY_OFFSET
+ *   d_off          (B,K,2,H,W), required with GBCODEC_DECODE_APPLY_OFFSET; may also be a device-accessible
+ *                  (pinned, mapped) HOST pointer: 8 taps per tile are read, in place
  *   d_alpha_param  device scalar, raw learnable alpha (sigmoid applied here), required with REFINE
  *   d_fusion_weight device scalar; already sigmoid-ed as the head publishes it
  *                  (fusion_head.py:306) unless GBCODEC_DECODE_FUSION_WEIGHT_RAW
