@@ -8,8 +8,10 @@ sigma=2), batch 1024 per GPU; one step = one pass of the hot path over one batch
 target tiles generated on the fly from the keypoints, the six-term loss forward and
 backward, and the keypoint decode, every heatmap read from HBM once.
 For N > 1 the driver launches one rank per GPU (torch.distributed.run); the batch is
-sharded by image, per-GPU work fixed (weak scaling), the only collectives are the
-2-float normaliser all-reduce before and the 7-float loss all-reduce after the kernel.
+sharded by image, per-GPU work fixed (weak scaling); the only data that crosses GPUs are
+2 normaliser sums before and 7 loss scalars after the tile kernel, written by the kernels
+themselves into the peers' NVLink-mapped mailboxes (`--exchange peer`, default) or
+all-reduced by NCCL (`--exchange nccl`).
 
 `--config decode_flip` / `--config decode [--batch B]` measure the decode-only workloads of
 BASELINE.json (configs[2]: 96x72, B=4096, flip test + offset correction; configs[4]: the
