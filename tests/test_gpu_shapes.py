@@ -187,3 +187,24 @@ def test_64x64_takes_the_tile_kernels_in_every_mode(pkg):
     res = ops.fusion_step_vmean(up["heatmaps"], up["offsets"], vm, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common, True, True, a, f, 2, 3)
     np.testing.assert_allclose(res[0].cpu().numpy(), full[0].cpu().numpy(), rtol=2e-6, atol=1e-9)
     assert torch.equal(res[1], full[1]) and torch.equal(res[2], full[2])
+
+
+@pytest.mark.parametrize("name", ["hrformer_384x288", "preemie_256"])
+def test_float16_maps_on_the_ring_instantiations(pkg, name):
+    """96x72 and 128x128 have no whole-tile partner slots: partner rows (and at 128x128 the variance rows) stream through a
+    two-row ring.  With float16 maps the ring carries raw halves; losses, decode and gradients must still be those of the
+    float32 path on the up-cast maps (gradients rounded once to half, up to the tie pixels that are stored twice)."""
+    cfg = synth.CONFIGS[name]
+    ops = pkg.ops
+    batch = synth.make_batch(cfg, seed=31, B=5)
+    pairs = [v for p in oc.skeleton_for(cfg.K) for v in p]
+    a, f = torch.tensor(0.5).cuda(), torch.tensor(0.62).cuda()
+    common = (float(cfg.input_size[0]), float(cfg.input_size[1]), list(oc.DEFAULT_LAMBDAS), cfg.sigma, cfg.sigma, True, pairs)
+    half = {k: dev(batch[k]).half() for k in ("heatmaps", "offsets", "variances")}
+    up = {k: v.float() for k, v in half.items()}
+    full = ops.fusion_loss(up["heatmaps"], up["offsets"], up["variances"], None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common, True, True, a, f, 2, 3)
+    h16 = ops.fusion_loss_f16(half["heatmaps"], half["offsets"], half["variances"], None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common,
+                              True, True, a, f, 2, 3)
+    assert torch.equal(h16[0], full[0]) and torch.equal(h16[1], full[4]) and torch.equal(h16[2], full[5])
+    assert (h16[3] == full[1].half()).float().mean().item() > 0.9999
+    assert torch.equal(h16[4], full[2].half()) and torch.equal(h16[5], full[3].half())
