@@ -22,9 +22,12 @@ namespace gbc {
 // stay inside one CTA.  The sums are accumulated in double: with the reference's weights
 // (visibility flags 0/1/2, coco_dataset.py:214) every partial sum is an exact integer, so the
 // order of the two atomics per CTA does not change the result.
+// `sums` may be null (the caller supplies the normalisers): the kernel then only prepares the weights, the patch
+// geometry and the tile descriptors.
 __global__ void __launch_bounds__(256)
 denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight,
               const float* __restrict__ gt, int target_given, float* __restrict__ weff, int4* __restrict__ geom,
+              TileDesc* __restrict__ desc,
               double* __restrict__ sums, unsigned* __restrict__ ticket, const __grid_constant__ PeerView peer,
               float* __restrict__ global_out) {
     __shared__ float wsm[256];
@@ -35,19 +38,48 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
     const int nimg = min(ipb, P.B - img0);
     const int local = threadIdx.x;
     double sw = 0.0, sp = 0.0;
+    int4 gpk = make_int4(0, 0, 0, 0);
     if (local < nimg * P.K) {
         const int t = img0 * P.K + local;
         float wk = weight[t];
         if (!target_given) {
             const PatchGeom g = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec);
             wk = g.weight;
-            if (geom) geom[t] = pack_geom(g);
+            gpk = pack_geom(g);
+            if (geom) geom[t] = gpk;
         }
         wsm[local] = wk;
         if (weff) weff[t] = wk;
         sw = (double)wk;
     }
     __syncthreads();
+    // the tile's descriptor for the persistent step kernel: its weight, target geometry, ground truth in heatmap pixels
+    // and the limb partners that carry weight (compacted, in partner order)
+    if (desc && local < nimg * P.K) {
+        const int t = img0 * P.K + local;
+        const int im = local / P.K, k = local - im * P.K;
+        TileDesc d;
+        d.geom = gpk;
+        d.w = wsm[local];
+        d.gx = gt ? gt[2 * t] * P.sx : 0.f; d.gy = gt ? gt[2 * t + 1] * P.sy : 0.f;
+        unsigned nact = 0, own = 0, pj = 0;
+        d.wj[0] = d.wj[1] = d.wj[2] = d.wj[3] = 0.f;
+        for (int pi = 0; pi < P.n_partner[k]; ++pi) {
+            const int j = P.partner[k][pi];
+            const float wj = wsm[im * P.K + j];
+            if (d.w != 0.f && wj != 0.f) {
+                d.wj[nact] = wj;
+                pj |= (unsigned)j << (8 * nact);
+                if ((P.owner[k] >> pi) & 1) own |= 1u << nact;
+                ++nact;
+            }
+        }
+        d.pk = nact | (own << 4);
+        d.pj = pj;
+        d.pad[0] = d.pad[1] = d.pad[2] = 0u;
+        desc[t] = d;
+    }
+    if (!sums) return;
     for (int q = local; q < nimg * P.n_pairs; q += 256) {
         const int im = q / P.n_pairs, p = q - im * P.n_pairs;
         sp += (double)(wsm[im * P.K + P.pair_i[p]] * wsm[im * P.K + P.pair_j[p]]);
@@ -104,23 +136,8 @@ __global__ void sums_to_float_kernel(const double* __restrict__ sums, float* __r
 }
 __global__ void sums_from_float_kernel(const float* __restrict__ in2, double* __restrict__ sums, unsigned* __restrict__ ticket) {
     if (threadIdx.x < 2) sums[threadIdx.x] = (double)in2[threadIdx.x];
-    if (threadIdx.x == 2) *ticket = 0u;
+    if (threadIdx.x == 2) { ticket[0] = 0u; ticket[1] = 0u; }      // ticket and the step kernel's tile counter (adjacent words)
 }
-// weights after the encoder rule only (the sums come from the caller)
-__global__ void __launch_bounds__(256)
-weff_kernel(const __grid_constant__ LossParams P, const float* __restrict__ weight, const float* __restrict__ gt,
-            int target_given, float* __restrict__ weff, int4* __restrict__ geom) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.B * P.K) return;
-    float wk = weight[t];
-    if (!target_given) {
-        const PatchGeom g = patch_geometry(gt[2 * t], gt[2 * t + 1], wk, P.H, P.W, P.in_w, P.in_h, P.ec);
-        wk = g.weight;
-        geom[t] = pack_geom(g);
-    }
-    weff[t] = wk;
-}
-
 template <int TPB, int NITER, int CACHE>
 __global__ void __launch_bounds__(TPB)
 loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
@@ -643,6 +660,11 @@ static bool force_generic() {
 }
 
 static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s) {
+    if (!force_generic()) {
+        // the persistent step kernel covers float32 maps with the target generated on the fly
+        const int st = launch_step_tile(P, A, s, g_prof_start, g_prof_stop);
+        if (st != 1) return st;
+    }
     if (!force_generic() || A.half_io) {
         const int st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st != 1) return st;
@@ -673,16 +695,16 @@ static const PeerView kNoPeers = {};
 static int prepare_weights(const LossParams& P, const WsLayout& L, const float* weight, const float* gt,
                            int target_given, const float* denoms, cudaStream_t s, const PeerView& peer = kNoPeers,
                            float* global_out = nullptr) {
+    const int ipb = 256 / P.K;
+    const int grid = (P.B + ipb - 1) / ipb;
     if (denoms) {
-        weff_kernel<<<(P.B * P.K + 255) / 256, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom);
         sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
+        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, nullptr, L.ticket, kNoPeers, nullptr);
     } else {
-        // sums, plan and the finalize ticket share the first 32 bytes of the workspace
+        // sums, plan, the finalize ticket and the step kernel's tile counter share the first 32 bytes of the workspace
         cudaError_t e = cudaMemsetAsync(L.sums, 0, 32, s);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-        const int ipb = 256 / P.K;
-        const int grid = (P.B + ipb - 1) / ipb;
-        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.sums, L.ticket, peer, peer.world > 1 ? global_out : nullptr);
+        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, L.sums, L.ticket, peer, peer.world > 1 ? global_out : nullptr);
     }
     return check_launch("denoms_kernel");
 }
@@ -749,6 +771,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.alpha_param = alpha_param; A.fusion_weight = fusion_weight; A.coords = coords; A.scores = scores;
     A.radius = radius; A.dflags = dflags;
     A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial;
+    A.desc = L.desc; A.tile_counter = L.tile_counter;
     A.half_io = half_io;
     A.var_mean = var_mean; A.grad_var_mean = grad_var_mean;
     if (var_mean) {

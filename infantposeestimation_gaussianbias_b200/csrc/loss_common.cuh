@@ -45,15 +45,32 @@ struct LossArgs {
     // convolution's epilogue): replaces var / grad_var, 16N instead of 24N bytes per tile
     const float* var_mean;              // (B,K) or null
     float* grad_var_mean;               // (B,K): d(total)/d(mean_N(V))
+    // persistent step kernel (step_tile.cu): per-tile descriptors written by denoms_kernel, dynamic tile counter
+    const struct TileDesc* desc;
+    unsigned* tile_counter;
 };
+
+// Everything the persistent step kernel needs to know about one tile besides its pixels, in one 64-byte record
+// (one bulk copy per tile instead of a chain of dependent scalar loads).  Written by denoms_kernel.
+struct __align__(16) TileDesc {
+    int4 geom;            // packed patch geometry of the on-the-fly target (pack_geom)
+    float w;              // weight after the encoder's rule
+    float gx, gy;         // ground-truth keypoint in heatmap pixels (fusion_head.py:679-684)
+    unsigned pk;          // bits 0-2: number of ACTIVE limb partners (both weights non-zero), bits 4-7: owner bits (compacted)
+    float wj[4];          // weights of the active partners, in partner order
+    unsigned pj;          // channels of the active partners, one byte each
+    unsigned pad[3];
+};
+static_assert(sizeof(TileDesc) == 64, "one 64-byte bulk copy per tile");
 
 constexpr int kFinBlocks = 32;          // CTAs of the second-stage reduction
 constexpr int kWsHeaderFloats = 512;    // sums (2 doubles), plan, ticket, lam_eff, second-stage partials; 2 KB
 struct WsLayout {
-    double* sums; int* plan; unsigned* ticket; float* lam_eff; double* bpart; float* weff; int4* geom; float* partial;
+    double* sums; int* plan; unsigned* ticket; unsigned* tile_counter; float* lam_eff; double* bpart; float* weff; int4* geom; float* partial;
+    TileDesc* desc;
 };
 static inline size_t ws_bytes(int B, int K) {
-    return (size_t)(kWsHeaderFloats + (size_t)B * K * 13 + 8) * sizeof(float);
+    return (size_t)(kWsHeaderFloats + (size_t)B * K * (13 + 16) + 8 + 16) * sizeof(float);
 }
 static inline WsLayout ws_carve(void* ws, int B, int K) {
     float* f = reinterpret_cast<float*>(ws);
@@ -61,6 +78,7 @@ static inline WsLayout ws_carve(void* ws, int B, int K) {
     l.sums = reinterpret_cast<double*>(f);          // f[0..3]
     l.plan = reinterpret_cast<int*>(f + 4);         // f[4]
     l.ticket = reinterpret_cast<unsigned*>(f + 5);  // f[5]
+    l.tile_counter = reinterpret_cast<unsigned*>(f + 6);   // f[6]: inside the 32 bytes every call clears
     l.lam_eff = f + 8;                              // f[8..15]
     l.bpart = reinterpret_cast<double*>(f + 64);    // kFinBlocks * 6 doubles
     // geom rows are 16 bytes and partial rows 32 bytes: keep both aligned
@@ -68,6 +86,8 @@ static inline WsLayout ws_carve(void* ws, int B, int K) {
     l.geom = reinterpret_cast<int4*>(f + kWsHeaderFloats);
     l.partial = f + kWsHeaderFloats + 4 * tiles8;
     l.weff = l.partial + 8 * tiles;
+    // 64-byte records, 16-byte aligned (the workspace is)
+    l.desc = reinterpret_cast<TileDesc*>(f + kWsHeaderFloats + 4 * tiles8 + 8 * tiles + ((tiles + 3) & ~(size_t)3));
     return l;
 }
 
@@ -170,5 +190,8 @@ struct TileCoef {
 // loss_tile.cu: register-resident kernel for tiles whose rows split evenly over the CTA;
 // returns 1 if it has no instantiation for this shape (the caller then uses the generic kernel).
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+// step_tile.cu: persistent kernel (bulk-copy pipeline, one block reduction per tile) for float32 maps with the target
+// generated on the fly; returns 1 if it does not cover this call (the caller then uses launch_loss_tile).
+int launch_step_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t ev_start, cudaEvent_t ev_stop);
 
 }  // namespace gbc
