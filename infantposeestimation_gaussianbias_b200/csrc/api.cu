@@ -1,5 +1,6 @@
 // api.cu — the C ABI declared in include/gbcodec.h: argument checks, status
 // mapping and launches.  No torch types, no allocation, no synchronisation.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -17,8 +18,18 @@ int fail(int status, const char* fmt, ...) {
     return status;
 }
 
+// GBCODEC_SYNC_DEBUG=1: wait for the device after every launch and report the kernel that faulted (debugging only:
+// it serialises the host with the device and defeats programmatic dependent launch)
+static bool sync_debug() {
+    static const int v = [] { const char* e = getenv("GBCODEC_SYNC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v != 0;
+}
 int check_launch(const char* what) {
-    const cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && sync_debug()) {
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) fprintf(stderr, "[gbcodec] %s faulted: %s\n", what, cudaGetErrorString(e));
+    }
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return GBCODEC_OK;
 }

@@ -29,12 +29,7 @@
 #include "f32x2.cuh"
 #include <stdlib.h>
 #include <type_traits>
-#ifdef STEP_DEBUG
 #include <stdio.h>
-#define DBG(...) printf(__VA_ARGS__)
-#else
-#define DBG(...)
-#endif
 
 namespace gbc {
 
@@ -189,10 +184,8 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             unsigned nxt = atomicAdd(A.tile_counter, 1u) + gridDim.x;
             unsigned nxt2 = atomicAdd(A.tile_counter, 1u) + gridDim.x;         // two ahead: the atomic's latency is off the path
             unsigned pq = 0;                                                  // partner copies started so far
-            DBG("producer start cur=%u nxt=%u nxt2=%u tiles=%d\n", cur, nxt, nxt2, tiles);
             for (unsigned j = 0;; ++j) {
                 const unsigned s = j & 1u;
-                DBG("producer j=%u cur=%u\n", j, cur);
                 if (j >= 2) mbar_wait(hempty + s, ((j - 2) >> 1) & 1u);
                 if (cur >= (unsigned)tiles) { tids[s] = -1; mbar_arrive(hfull + s); break; }
                 if (j > 0) {
@@ -228,9 +221,6 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         return;
     }
     auto compute_barrier = [] { asm volatile("bar.sync 1, %0;" :: "n"(TPB) : "memory"); };
-#if defined(STEP_BISECT) && STEP_BISECT == 1
-    return;
-#endif
 
     StepConst C;
     {
@@ -257,13 +247,7 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         // ---- this tile ----------------------------------------------------------------------------------
         mbar_wait(hfull + s, (i >> 1) & 1u);
         const int tile = tids[s];
-        if (tid == 0) DBG("compute i=%u tile=%d\n", i, tile);
         if (tile < 0) break;
-#if defined(STEP_BISECT) && STEP_BISECT == 2
-        __syncwarp();
-        if (lane == 0) { if (has_var) mbar_arrive(vempty); mbar_arrive(hempty + s); }
-        continue;
-#endif
         const TileDesc* dsc = Db + s;
         const int4 gq = dsc->geom;
         const float4 d1 = *reinterpret_cast<const float4*>(&dsc->w);          // w, gx, gy, pk
@@ -478,14 +462,7 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         }
         if (lane == 0) { redMb[warp * 2] = mw; redMb[warp * 2 + 1] = mnw; }
         if (heavy && warp == 1) tapw[s * 32 + lane] = tapv;
-        if (tid == 0) DBG("compute before barrier\n");
         compute_barrier();
-        if (tid == 0) DBG("compute after barrier heavy=%d nact=%d\n", (int)heavy, nact);
-#if defined(STEP_BISECT) && STEP_BISECT == 3
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hempty + s);
-        continue;
-#endif
         float m = redMb[0], hmin = redMb[1];
 #pragma unroll
         for (int ww = 1; ww < NW; ++ww) { m = fmaxf(m, redMb[2 * ww]); hmin = fminf(hmin, redMb[2 * ww + 1]); }
@@ -860,11 +837,9 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
             if (lane == 0) { A.coords[2 * tile] = dcx_; A.coords[2 * tile + 1] = dcy_; A.scores[tile] = m; }
         }
-        if (tid == 0) DBG("compute tile done\n");
         __syncwarp();
         if (lane == 0) mbar_arrive(hempty + s);
     }
-    if (tid == 0) DBG("compute exit\n");
 }
 
 // ---- launcher ------------------------------------------------------------------------------------------
@@ -888,7 +863,10 @@ static int launch_step_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
     if (e0) cudaEventRecord(e0, s);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(L::TPB + 32);      // compute warps + the producer warp cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(L::TPB + 32);                  // compute warps + the producer warp
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
