@@ -54,6 +54,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
                  "DONE_%=:\n"
                  "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the producer warp's waits: back off between polls so that its spinning does not take issue slots from the compute warps
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity) {
+    while (!mbar_test(bar, parity)) __nanosleep(128);
+}
 // global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -98,15 +108,13 @@ struct StepPlan {
     static constexpr int oTab = oTap + 2 * 32 * 4;               // NW x 16 floats (overlap coefficient per tie pattern)
     static constexpr int oBar = oTab + NW * 16 * 4;              // 10 mbarriers
     static constexpr int oTid = oBar + 10 * 8;                   // 2 tile indices (+ pad)
-    static constexpr int oLut = oTid + 16;                       // exp table of the target patch
+    static constexpr int oDec = oTid + 16;                       // 2 x float4: soft-argmax and maximum handed to the producer warp
+    static constexpr int oLut = oDec + 32;                       // exp table of the target patch
     static_assert(TPB % 32 == 0 && NW >= 2, "whole warps; the tap window needs a second warp");
     static_assert((oBar % 8) == 0 && (oDesc % 16) == 0 && (oLut % 16) == 0, "alignment");
 };
 
 // ---- small pieces ---------------------------------------------------------------------------------
-struct StepConst {       // per CTA
-    float iD, iD5, lam[6];
-};
 
 // NV running sums per lane -> block totals, lane-distributed (value k in lanes k*SUB .. k*SUB+SUB-1 after the final
 // shuffle: fetch with lane k * SUB).  First NSC values carry softmax scaling relative to the warp's maximum.
@@ -136,6 +144,7 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     float* const tabs = reinterpret_cast<float*>(smraw + L::oTab);
     uint64_t* const bars = reinterpret_cast<uint64_t*>(smraw + L::oBar);
     int* const tids = reinterpret_cast<int*>(smraw + L::oTid);
+    float4* const decs = reinterpret_cast<float4*>(smraw + L::oDec);
     float* const lut = reinterpret_cast<float*>(smraw + L::oLut);
     uint64_t* const hfull = bars;          // [2] tile + descriptor landed
     uint64_t* const vfull = bars + 2;      // variance tile landed
@@ -173,28 +182,56 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     pdl_wait();
     pdl_launch_dependents();
 
-    // ---- producer warp: one thread keeps the copies of the next tile in flight ------------------------------------------
-    // Per tile j (buffer s = j & 1): wait until the compute warps have left tile j - 2, start the tile + descriptor
-    // copy, read the descriptor when it has landed, start the partner copies as partner buffers come free, then the
-    // variance tile.  The compute warps never wait for one another except at their one block barrier.
+    // ---- producer warp -------------------------------------------------------------------------------------------------
+    // Per tile j (buffer s = j & 1): wait until the compute warps have left tile j - 2 and finish that tile's keypoint
+    // decode (local refinement + offset correction from its soft-argmax, handed over through shared memory: dependent
+    // loads that would otherwise sit on the compute warps' path); then lane 0 starts the tile + descriptor copy, reads the
+    // descriptor when it has landed, starts the partner copies as partner buffers come free, then the variance tile.
+    // The compute warps never wait for one another except at their one block barrier.
     if (producer) {
+        if (lane == 0) bulk_g2s(Db, A.desc + blockIdx.x, 64, hfull);
+        unsigned cur = blockIdx.x, nxt = 0, nxt2 = 0;
         if (lane == 0) {
-            bulk_g2s(Db, A.desc + blockIdx.x, 64, hfull);
-            unsigned cur = blockIdx.x;
-            unsigned nxt = atomicAdd(A.tile_counter, 1u) + gridDim.x;
-            unsigned nxt2 = atomicAdd(A.tile_counter, 1u) + gridDim.x;         // two ahead: the atomic's latency is off the path
-            unsigned pq = 0;                                                  // partner copies started so far
-            for (unsigned j = 0;; ++j) {
-                const unsigned s = j & 1u;
-                if (j >= 2) mbar_wait(hempty + s, ((j - 2) >> 1) & 1u);
-                if (cur >= (unsigned)tiles) { tids[s] = -1; mbar_arrive(hfull + s); break; }
+            nxt = atomicAdd(A.tile_counter, 1u) + gridDim.x;
+            nxt2 = atomicAdd(A.tile_counter, 1u) + gridDim.x;     // two ahead: the atomic's latency is off the path
+        }
+        unsigned pq = 0;                                          // partner copies started so far (lane 0)
+        int told[2] = {-1, -1};                                   // tiles whose decode is still to be finished, per buffer
+        auto finish_decode = [&](unsigned sb) {
+            const int t = told[sb];
+            if (t < 0 || !decode) return;
+            const float4 d = decs[sb];
+            float dx_ = d.x, dy_ = d.y;
+            int px, py;
+            refine_and_correct<float>(hm + (size_t)t * N, nullptr, A.off + (size_t)t * 2 * N, A.alpha_param, A.fusion_weight,
+                                      H, W, A.radius, A.dflags, dx_, dy_, px, py);
+            if (lane == 0) { A.coords[2 * t] = dx_; A.coords[2 * t + 1] = dy_; A.scores[t] = d.z; }
+        };
+        for (unsigned j = 0;; ++j) {
+            const unsigned s = j & 1u;
+            if (j >= 2) {
+                mbar_wait_backoff(hempty + s, ((j - 2) >> 1) & 1u);
+                finish_decode(s);
+            }
+            cur = __shfl_sync(0xffffffffu, cur, 0);
+            if (cur >= (unsigned)tiles) {
+                if (lane == 0) { tids[s] = -1; mbar_arrive(hfull + s); }
+                // the tile in the other buffer is the last one this CTA has taken
+                if (j >= 1) {
+                    mbar_wait_backoff(hempty + (s ^ 1u), ((j - 1) >> 1) & 1u);
+                    finish_decode(s ^ 1u);
+                }
+                break;
+            }
+            told[s] = (int)cur;
+            if (lane == 0) {
                 if (j > 0) {
                     tids[s] = (int)cur;
                     mbar_arrive_expect_tx(hfull + s, kTile + 64);
                     bulk_g2s(Hb + s * N4, hm + (size_t)cur * N, kTile, hfull + s);
                     bulk_g2s(Db + s, A.desc + cur, 64, hfull + s);
                 }
-                mbar_wait(hfull + s, (j >> 1) & 1u);
+                mbar_wait_backoff(hfull + s, (j >> 1) & 1u);
                 const TileDesc* nd = Db + s;
                 const int nn = (int)(nd->pk & 7u);
                 const unsigned pj = nd->pj;
@@ -202,34 +239,30 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     const size_t b = cur / (unsigned)P.K;
                     for (int n = 0; n < nn; ++n) {
                         const unsigned q = pq & 1u;
-                        if (pq >= 2) mbar_wait(qempty + q, ((pq - 2) >> 1) & 1u);
+                        if (pq >= 2) mbar_wait_backoff(qempty + q, ((pq - 2) >> 1) & 1u);
                         mbar_arrive_expect_tx(qfull + q, kTile);
                         bulk_g2s(Qb + q * N4, hm + (b * P.K + ((pj >> (8 * n)) & 0xFFu)) * N, kTile, qfull + q);
                         ++pq;
                     }
                 }
                 if (has_var && j > 0) {
-                    mbar_wait(vfull, (j - 1) & 1u);                // a weight-0 tile's variance copy is awaited by nobody else
-                    mbar_wait(vempty, (j - 1) & 1u);
+                    mbar_wait_backoff(vfull, (j - 1) & 1u);        // a weight-0 tile's variance copy is awaited by nobody else
+                    mbar_wait_backoff(vempty, (j - 1) & 1u);
                     mbar_arrive_expect_tx(vfull, kTile);
                     bulk_g2s(Vb, A.var + (size_t)cur * N, kTile, vfull);
                 }
                 cur = nxt; nxt = nxt2;
                 if (nxt2 < (unsigned)tiles) nxt2 = atomicAdd(A.tile_counter, 1u) + gridDim.x;
             }
+            __syncwarp();
         }
         return;
     }
     auto compute_barrier = [] { asm volatile("bar.sync 1, %0;" :: "n"(TPB) : "memory"); };
 
-    StepConst C;
-    {
-        const float D = (float)__ldg(A.sums) + kEps, D5 = (float)__ldg(A.sums + 1) + kEps;
-        C.iD = rcp(D); C.iD5 = rcp(D5);
-        const float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) C.lam[q] = P.lam[q] * gscale;
-    }
+    // per-CTA scalars (the loss weights stay in the constant bank: lam[q] = P.lam[q] * gscale where they are used)
+    const float iD = rcp((float)__ldg(A.sums) + kEps), iD5 = rcp((float)__ldg(A.sums + 1) + kEps);
+    const float gscale = A.grad_scale ? __ldg(A.grad_scale) : 1.f;
 
     // thread geometry: four columns x0 .. x0+3 of rows ty, ty + ROWS, ...
     const int tx = tid % W4, ty = tid / W4;
@@ -494,15 +527,10 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 
         // ---- weight 0: every term carries a factor w -> zero loss and gradient; decode only ------------------------
         if (!heavy) {
-            if (decode && warp == 0) {
-                float dx_ = cx, dy_ = cy;
-                int px, py;
-                refine_and_correct<float>(hm + (size_t)tile * N, nullptr, off_tile, A.alpha_param, A.fusion_weight, H, W, A.radius, A.dflags, dx_, dy_, px, py);
-                if (lane == 0) { A.coords[2 * tile] = dx_; A.coords[2 * tile + 1] = dy_; A.scores[tile] = m; }
-            }
             if (tid == 0) {
                 float4* p = reinterpret_cast<float4*>(A.partial + (size_t)tile * 8);
                 p[0] = z4; p[1] = z4;
+                decs[s] = make_float4(cx, cy, m, 0.f);         // the producer warp finishes the decode
             }
             if (GRADS) {
 #pragma unroll
@@ -519,7 +547,7 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         // ---- per-tile scalars, derived by every warp from the same sums in the same order --------------------------
         const float ET = val(3), Ssum = val(4), Vsum = val(5), Rm = val(6), Rxa = val(7), Rya = val(8), M2a = val(9), mse_sum = val(10);
         const float mV = has_var ? Vsum * P.inv_n : P.sigma;
-        const float ka = P.use_target_weight ? wa * C.iD : 1.f / (float)(P.B * P.K), kb = w * C.iD;
+        const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
         // relu moments shifted from the tile centre to (cx, cy)
         const float dcx = cx - ax, dcy = cy - ay;
         const float sh1 = dcx * Rxa, sh2 = dcy * Rya, dd = dcx * dcx + dcy * dcy;
@@ -592,10 +620,10 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         const float iRp = rcp(Rm + kEps);
         const float v = M2c * iRp;
         const float sd = sqrt_approx(v + kEps);
-        const float a4 = C.lam[3] * kb * (sd - P.sigma) * rcp(sd);
+        const float a4 = (P.lam[3] * gscale) * kb * (sd - P.sigma) * rcp(sd);
         const float c4 = a4 * iRp, k4 = -c4 * v;
-        const float c1 = C.lam[0] * ka * 2.f * P.inv_n;
-        const float c6 = C.lam[5] * kb * 2.f * (Ent - P.e_star);
+        const float c1 = (P.lam[0] * gscale) * ka * 2.f * P.inv_n;
+        const float c6 = (P.lam[5] * gscale) * kb * 2.f * (Ent - P.e_star);
         // offset term: the eight taps around the soft-argmax
         const Taps tp = taps_setup(cx, cy, H, W);
         float ov[2][4];
@@ -625,9 +653,9 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             sl1 += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
             sl1p[c] = ad < 1.f ? d : (d > 0.f ? 1.f : -1.f);
         }
-        const float h2c = C.lam[1] * ka * 0.5f;
-        const float fxx = C.lam[2] * ka * 2.f * (cx - gx) + a4 * (-2.f * sXc * iRp) + h2c * (sl1p[0] * (dsdx[0] + 1.f) + sl1p[1] * dsdx[1]);
-        const float fyy = C.lam[2] * ka * 2.f * (cy - gy) + a4 * (-2.f * sYc * iRp) + h2c * (sl1p[0] * dsdy[0] + sl1p[1] * (dsdy[1] + 1.f));
+        const float h2c = (P.lam[1] * gscale) * ka * 0.5f;
+        const float fxx = (P.lam[2] * gscale) * ka * 2.f * (cx - gx) + a4 * (-2.f * sXc * iRp) + h2c * (sl1p[0] * (dsdx[0] + 1.f) + sl1p[1] * dsdx[1]);
+        const float fyy = (P.lam[2] * gscale) * ka * 2.f * (cy - gy) + a4 * (-2.f * sYc * iRp) + h2c * (sl1p[0] * dsdy[0] + sl1p[1] * (dsdy[1] + 1.f));
         // limb overlap: ratios -> loss numerator and the per-partner gradient scale
         float cj[4] = {0.f, 0.f, 0.f, 0.f};
         float cst = 0.f, pair_loss = 0.f;
@@ -660,7 +688,7 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     const float rho = M * imm;
                     if ((pk >> (4 + n)) & 1u) pair_loss += w * wjv[n] * fmaxf(rho - 0.5f, 0.f);
                     if (GRADS && rho > 0.5f) {
-                        cj[n] = C.lam[4] * w * wjv[n] * C.iD5 * imm;
+                        cj[n] = (P.lam[4] * gscale) * w * wjv[n] * iD5 * imm;
                         cst += cj[n] * rho * tie_rule(Ssum, Sj);
                         g_live = true;
                     }
@@ -677,35 +705,8 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             p[1] = make_float4(pair_loss, w * shape_t, 0.f, 0.f);
         }
 
-        // ---- decode tail, stages 1 and 2 (warp 0): window soft-argmax from the tile in shared memory, blend, start
-        //      the bilinear offset read; finished after the gradient pass ---------------------------------------------
-        float dcx_ = cx, dcy_ = cy, dtap = 0.f;
-        if (decode && warp == 0) {
-            if ((A.dflags & GBCODEC_DECODE_REFINE) && A.radius <= 2) {
-                const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
-                const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
-                const int S = 2 * A.radius + 1;
-                const int x = px - A.radius + lane % S, y = py - A.radius + lane / S;
-                const bool win_ok = lane < S * S && x >= 0 && x < W && y >= 0 && y < H;
-                const float win = win_ok ? reinterpret_cast<const float*>(Hs)[y * W + x] : -INFINITY;
-                const float vmax = warp_max(win);
-                const float e = win_ok ? expf(win - vmax) : 0.f;
-                const float se = warp_sum(e), sx = warp_sum(e * (float)x), sy = warp_sum(e * (float)y);
-                const float a = sigmoid_acc(__ldg(A.alpha_param));
-                dcx_ = a * cx + (1.f - a) * (sx / se);
-                dcy_ = a * cy + (1.f - a) * (sy / se);
-            } else if (A.dflags & GBCODEC_DECODE_REFINE) {
-                int px, py;
-                refine_and_correct<float>(hm + (size_t)tile * N, nullptr, nullptr, A.alpha_param, nullptr, H, W, A.radius, GBCODEC_DECODE_REFINE, dcx_, dcy_, px, py);
-                dcx_ = __shfl_sync(0xffffffffu, dcx_, 0); dcy_ = __shfl_sync(0xffffffffu, dcy_, 0);
-            }
-            if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
-                const Bilinear dbl = bilinear_setup(dcx_, dcy_, H, W);
-                const int tap = lane & 3;                      // lane t < 8 fetches tap (t & 3) of channel (t >> 2)
-                const int yy = (tap & 2) ? dbl.y1 : dbl.y0, xx = (tap & 1) ? dbl.x1 : dbl.x0;
-                if (lane < 8) dtap = __ldg(off_tile + (lane >> 2) * N + yy * W + xx);
-            }
-        }
+        // the producer warp finishes the decode (local refinement + offset correction) from the soft-argmax
+        if (tid == 0) decs[s] = make_float4(cx, cy, m, 0.f);
 
         if (GRADS) {
             // overlap coefficient of a pixel as a function of its tie pattern: per-warp table
@@ -728,7 +729,7 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const float dy0 = fty - cy;
             const f2 kIZ = splat2(iZ), kNML = splat2(-ml), kC1 = splat2(c1), kC4 = splat2(c4), kK4 = splat2(k4);
             const f2 dx2_01 = pack2(dx2j[0], dx2j[1]), dx2_23 = pack2(dx2j[2], dx2j[3]);
-            const float gvar = C.lam[3] * kb * 2.f * (mV - P.sigma) * P.inv_n;
+            const float gvar = (P.lam[3] * gscale) * kb * 2.f * (mV - P.sigma) * P.inv_n;
             const float4 gv = make_float4(gvar, gvar, gvar, gvar);
             auto pass_d = [&](auto flat_c) {
                 constexpr bool FLAT = decltype(flat_c)::value;
@@ -821,22 +822,6 @@ step_tile_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
         }
 
-        // ---- decode stage 3 (warp 0): finish the bilinear read, publish ------------------------------------------------
-        if (decode && warp == 0) {
-            if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
-                float fw = __ldg(A.fusion_weight);
-                if (A.dflags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
-                const Bilinear dbl = bilinear_setup(dcx_, dcy_, H, W);
-                float t[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) t[q] = __shfl_sync(0xffffffffu, dtap, q);
-                const float ox = dbl.w00 * t[0] + dbl.w01 * (t[1] * dbl.okx) + dbl.w10 * (t[2] * dbl.oky) + dbl.w11 * (t[3] * (dbl.okx * dbl.oky));
-                const float oy = dbl.w00 * t[4] + dbl.w01 * (t[5] * dbl.okx) + dbl.w10 * (t[6] * dbl.oky) + dbl.w11 * (t[7] * (dbl.okx * dbl.oky));
-                dcx_ += fw * ox;
-                dcy_ += fw * oy;
-            }
-            if (lane == 0) { A.coords[2 * tile] = dcx_; A.coords[2 * tile + 1] = dcy_; A.scores[tile] = m; }
-        }
         __syncwarp();
         if (lane == 0) mbar_arrive(hempty + s);
     }
