@@ -183,19 +183,26 @@ int gbcodec_fusion_step_vmean_f32(const gbcodec_loss_desc* desc,
                             float* d_coords, float* d_scores,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* Backward for an arbitrary upstream gradient on the seven outputs.  The
- * gradients written by the forward assume d(total)=*d_grad_scale and nothing on
- * the six terms.  This call reads the actual upstream vector on the device and
- *   - returns immediately inside the kernels if it matches the assumption,
- *   - rescales the three gradient tensors in place if all six effective term
- *     gradients are equal,
+/* Backward for an arbitrary upstream gradient on the seven outputs (the autograd backward of train.py:182 for
+ * whatever reaches the loss dict of fusion_head.py:795-806).  The gradients written by the forward assume
+ * d(total)=*d_grad_scale and nothing on the six terms.  This call reads the actual upstream vector on the device and
+ *   - returns immediately inside the kernels if the stored gradients already carry it,
+ *   - rescales the three gradient tensors in place if they are off by one common factor,
  *   - otherwise recomputes them with per-term weights.
- * No host synchronisation in any case. */
+ * No host synchronisation in any case (three launches, the usual answer costs a few microseconds).
+ *   d_held6   NULL, or 6 device floats the caller keeps with the stored gradients: the upstream factor each term's
+ *             share of them carries.  The call compares against it (held_valid != 0) or against *d_grad_scale
+ *             (held_valid == 0: first backward after the forward) and writes the new factors back, so that a second
+ *             backward through the same stored gradients (retain_graph; per-term losses, then total_loss) is right.
+ *             With NULL every call assumes the forward's state: correct for one backward per forward only.
+ *   workspace_from_forward != 0: d_workspace is the forward's workspace, untouched since; the weights, patch geometry
+ *             and normalisers in it are reused instead of being computed again. */
 int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
                             const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
                             const float* d_weight, const float* d_gt_kps,
                             const float* d_denoms, const float* d_grad_scale, const float* d_grad_losses7,
                             float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            float* d_held6, int held_valid, int workspace_from_forward,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------- batch-sharded jobs ---
@@ -389,6 +396,7 @@ int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,
                             const float* d_weight, const float* d_gt_kps, const float* d_denoms,
                             const float* d_grad_scale, int gradients_stored, const float* d_grad_losses7,
                             void* d_grad_hm, void* d_grad_off, void* d_grad_var,
+                            float* d_held6, int held_valid, int workspace_from_forward,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement hook (bench.py): the next gbcodec_fusion_loss_f32 / _step_f32 calls made

@@ -119,7 +119,7 @@ def _declare(lib):
     lib.gbcodec_fusion_loss_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_fusion_step_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_uint,
                                                           f32p, f32p, _P, C.c_size_t, _P]
-    lib.gbcodec_fusion_loss_backward_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
+    lib.gbcodec_fusion_loss_backward_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, _P, C.c_size_t, _P]
     lib.gbcodec_profile_loss_kernel.argtypes = [_P, _P]
     lib.gbcodec_heatmap_step_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                              C.c_double, C.c_int, C.c_int, f32p, f32p, f32p, C.c_int, f32p, f32p, _P,
@@ -127,7 +127,7 @@ def _declare(lib):
     lib.gbcodec_fusion_step_f16.argtypes = [C.POINTER(LossDesc), _P, _P, _P, f32p, f32p, f32p, f32p, f32p, f32p, _P, _P, _P,
                                             f32p, f32p, C.c_int, C.c_uint, f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_fusion_loss_backward_f16.argtypes = [C.POINTER(LossDesc), _P, _P, _P, f32p, f32p, f32p, f32p, f32p, C.c_int, f32p,
-                                                     _P, _P, _P, _P, C.c_size_t, _P]
+                                                     _P, _P, _P, f32p, C.c_int, C.c_int, _P, C.c_size_t, _P]
     lib.gbcodec_fusion_step_vmean_f32.argtypes = loss_common + [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_uint,
                                                                 f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_peer_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]

@@ -51,7 +51,7 @@ int peer_status(void*, int*);
 int peer_destroy(void*);
 int fusion_loss_backward(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*,
                          const float*, const float*, const float*, const float*, float*, float*, float*, void*, size_t,
-                         cudaStream_t, int, int);
+                         cudaStream_t, int, int, float*, int, int);
 
 int launch_postprocess(const gbcodec_postprocess_desc*, const float*, const float*, const float*, const float*, float*, float*,
                        float*, void*, cudaStream_t);
@@ -294,10 +294,11 @@ int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
                             const float* d_weight, const float* d_gt_kps,
                             const float* d_denoms, const float* d_grad_scale, const float* d_grad_losses7,
                             float* d_grad_hm, float* d_grad_off, float* d_grad_var,
+                            float* d_held6, int held_valid, int workspace_from_forward,
                             void* d_workspace, size_t workspace_bytes, void* stream) {
     return fusion_loss_backward(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms, d_grad_scale,
                                 d_grad_losses7, d_grad_hm, d_grad_off, d_grad_var, d_workspace, workspace_bytes,
-                                (cudaStream_t)stream, 0, 1);
+                                (cudaStream_t)stream, 0, 1, d_held6, held_valid, workspace_from_forward);
 }
 
 int gbcodec_fusion_step_f16(const gbcodec_loss_desc* desc,
@@ -318,10 +319,12 @@ int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,
                             const float* d_weight, const float* d_gt_kps, const float* d_denoms,
                             const float* d_grad_scale, int gradients_stored, const float* d_grad_losses7,
                             void* d_grad_hm, void* d_grad_off, void* d_grad_var,
+                            float* d_held6, int held_valid, int workspace_from_forward,
                             void* d_workspace, size_t workspace_bytes, void* stream) {
     return fusion_loss_backward(desc, (const float*)d_hm, (const float*)d_off, (const float*)d_var, d_target, d_weight, d_gt_kps, d_denoms,
                                 d_grad_scale, d_grad_losses7, (float*)d_grad_hm, (float*)d_grad_off, (float*)d_grad_var,
-                                d_workspace, workspace_bytes, (cudaStream_t)stream, 1, gradients_stored ? 1 : 0);
+                                d_workspace, workspace_bytes, (cudaStream_t)stream, 1, gradients_stored ? 1 : 0,
+                                d_held6, held_valid, workspace_from_forward);
 }
 
 int gbcodec_profile_loss_kernel(void* start_event, void* stop_event) {

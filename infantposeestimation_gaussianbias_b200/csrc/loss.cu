@@ -578,26 +578,44 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
 }
 
 // ---- backward for an arbitrary upstream gradient --------------------------------------------
-// plan: 0 = stored gradients already right, 1 = scale them by ratio, 2 = recompute with lam_eff
+// plan: 0 = stored gradients already right, 1 = scale them by ratio, 2 = recompute with lam_eff.
+// `held` (6 floats, caller-owned for the lifetime of one forward's stored gradients) records the upstream factor each
+// term's share of the stored gradients carries NOW: a backward may rescale or recompute them in place, so the next
+// backward through the same graph (retain_graph, per-term losses followed by total_loss) compares with what is there,
+// not with what the forward assumed.  held_valid == 0: first backward, every term carries *assumed (1 if NULL).
 __global__ void plan_kernel(const __grid_constant__ LossParams P, const float* __restrict__ g7,
-                            const float* __restrict__ assumed, int* __restrict__ plan, float* __restrict__ lam_eff) {
+                            const float* __restrict__ assumed, float* __restrict__ held, int held_valid,
+                            int* __restrict__ plan, float* __restrict__ lam_eff) {
     if (threadIdx.x != 0) return;
     const float a = assumed ? *assumed : 1.f;
-    float r[6];
-    bool uniform = true;
-    for (int q = 0; q < 6; ++q) { r[q] = g7[6] + g7[q]; lam_eff[q] = P.lam[q] * r[q]; if (r[q] != r[0]) uniform = false; }
-    if (uniform && r[0] == a) plan[0] = 0;
-    else if (uniform && a != 0.f) { plan[0] = 1; lam_eff[6] = r[0] / a; }
+    float r[6], h[6];
+    bool r_uniform = true, h_uniform = true, same = true;
+    for (int q = 0; q < 6; ++q) {
+        r[q] = g7[6] + g7[q];
+        h[q] = (held && held_valid) ? held[q] : a;
+        lam_eff[q] = P.lam[q] * r[q];
+        if (r[q] != r[0]) r_uniform = false;
+        if (h[q] != h[0]) h_uniform = false;
+        if (r[q] != h[q]) same = false;
+    }
+    const float ratio = r[0] / h[0];
+    if (same) plan[0] = 0;
+    else if (r_uniform && h_uniform && h[0] != 0.f && isfinite(ratio)) { plan[0] = 1; lam_eff[6] = ratio; }
     else plan[0] = 2;
+    if (held) for (int q = 0; q < 6; ++q) held[q] = r[q];
 }
+// plan 1: the three gradient tensors times one factor, one launch (n4a + n4b + n4c float4s)
 __global__ void __launch_bounds__(256)
-rescale_kernel(const int* __restrict__ plan, const float* __restrict__ lam_eff, float4* __restrict__ g, size_t n4) {
+rescale_kernel(const int* __restrict__ plan, const float* __restrict__ lam_eff, float4* __restrict__ ga, size_t n4a,
+               float4* __restrict__ gb, size_t n4b, float4* __restrict__ gc, size_t n4c) {
     if (*plan != 1) return;
     const float r = lam_eff[6];
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 v = g[i];
+    const size_t n = n4a + n4b + n4c;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4* g = i < n4a ? ga + i : (i < n4a + n4b ? gb + (i - n4a) : gc + (i - n4a - n4b));
+        float4 v = *g;
         v.x *= r; v.y *= r; v.z *= r; v.w *= r;
-        g[i] = v;
+        *g = v;
     }
 }
 
@@ -800,24 +818,26 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
 int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const float* off, const float* var, const float* target,
                          const float* weight, const float* gt, const float* denoms, const float* grad_scale, const float* g7,
                          float* ghm, float* goff, float* gvar, void* ws, size_t ws_size, cudaStream_t s, int half_io,
-                         int have_stash) {
+                         int have_stash, float* held, int held_valid, int ws_from_forward) {
     int st = check_common(d, hm, off, weight, gt, ws, ws_size);
     if (st) return st;
     if (!g7 || !ghm || !goff || (!gvar) != (!var)) return fail(GBCODEC_ERR_NULL_POINTER, "backward: NULL pointer");
+    if (held_valid && !held) return fail(GBCODEC_ERR_NULL_POINTER, "backward: held_valid without d_held6");
     LossParams P;
     st = make_params(d, &P);
     if (st) return st;
     const WsLayout L = ws_carve(ws, P.B, P.K);
-    // the workspace still holds weff and the sums of the forward only if the caller kept it; recompute, it is cheap
-    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
-    if (st) return st;
-    plan_kernel<<<1, 32, 0, s>>>(P, g7, grad_scale, L.plan, L.lam_eff);
-    if (!half_io) {
+    // the workspace still holds the weights, patch geometry and sums of the forward if the caller kept it
+    // (ws_from_forward); otherwise they are computed again, which is cheap
+    if (!ws_from_forward) {
+        st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
+        if (st) return st;
+    }
+    plan_kernel<<<1, 32, 0, s>>>(P, g7, grad_scale, held, held_valid, L.plan, L.lam_eff);
+    if (!half_io && have_stash) {
         const size_t n4 = (size_t)P.B * P.K * P.H * P.W / 4;
-        const int grid = 148 * 8;
-        rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4);
-        rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(goff), 2 * n4);
-        if (gvar) rescale_kernel<<<grid, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(gvar), n4);
+        rescale_kernel<<<148 * 8, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4,
+                                                reinterpret_cast<float4*>(goff), 2 * n4, reinterpret_cast<float4*>(gvar), gvar ? n4 : 0);
     }
     LossArgs A;
     memset(&A, 0, sizeof(A));
@@ -827,7 +847,7 @@ int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const floa
     // float16 maps: a gradient must meet its upstream factor before it is rounded to half.  Either the forward stored
     // gradients for an ASSUMED upstream factor (d_grad_scale) and this call only re-computes them if the actual one
     // differs (plan != 0), or it stored nothing and this call always computes them (per-term weights of plan_kernel)
-    A.plan = (half_io && !have_stash) ? nullptr : L.plan;
+    A.plan = have_stash ? L.plan : nullptr;
     A.half_io = half_io;
     return launch_loss_kernel(P, A, s);
 }

@@ -185,9 +185,10 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
                 in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
                 use_target_weight: bool, pairs: List[int], with_grads: bool,
                 with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
-                decode_flags: int, peer_ctx: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """-> losses7, grad_hm, grad_off, grad_var, coords, scores, global_denoms (empty tensors for what was not
-    asked).  peer_ctx: address of a connected gbcodec peer context (sharded.PeerExchange) — the normalisers and
+                decode_flags: int, peer_ctx: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> losses7, grad_hm, grad_off, grad_var, coords, scores, global_denoms, workspace (empty tensors for what was
+    not asked; the workspace holds the pass's per-tile weights / patch geometry / normalisers and is what the backward
+    reuses).  peer_ctx: address of a connected gbcodec peer context (sharded.PeerExchange) — the normalisers and
     the losses are then exchanged with the other ranks inside the kernels, over NVLink peer memory."""
     B, K, H, W = hm.shape
     hm = _cuda_f32("heatmaps", hm)
@@ -238,7 +239,7 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
                                               _ptr(coords), _ptr(scores), _ptr(ws), ws.numel(), _stream(hm)), "fusion_step")
         else:
             N.check(L.gbcodec_fusion_loss_f32(*common, _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss")
-    return losses, ghm, goff, gvar, coords, scores, den_out
+    return losses, ghm, goff, gvar, coords, scores, den_out, ws
 
 
 @fusion_loss.register_fake
@@ -250,42 +251,72 @@ def _(hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lamb
             torch.empty_like(hm) if with_grads else e(), torch.empty_like(off) if with_grads else e(),
             torch.empty_like(var) if (with_grads and var is not None) else e(),
             hm.new_empty((B, K, 2)) if with_decode else e(), hm.new_empty((B, K)) if with_decode else e(),
-            hm.new_empty(2) if peer_ctx else e())
+            hm.new_empty(2) if peer_ctx else e(), hm.new_empty(0, dtype=torch.uint8))
 
 
-@torch.library.custom_op(f"{_NS}::fusion_loss_backward", mutates_args=("grad_hm", "grad_off", "grad_var"))
+def _backward_call(half: bool, g7: Tensor, ghm: Tensor, goff: Tensor, gvar: Optional[Tensor], stored: bool,
+                   hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor], weight: Tensor, gt_kps: Tensor,
+                   denoms: Optional[Tensor], assumed: Optional[Tensor], scalars, held: Optional[Tensor], held_valid: bool,
+                   ws: Optional[Tensor]) -> None:
+    """gbcodec_fusion_loss_backward_f32 / _f16 through ctypes.  `held`: 6 device floats that travel with the stored
+    gradients (which upstream factor each term's share of them carries now); `ws`: the forward's workspace."""
+    B, K, H, W = hm.shape
+    desc = _desc(hm, *scalars)
+    from_forward = ws is not None and ws.numel() > 0
+    if not from_forward:
+        ws = _workspace(hm)
+    with torch.cuda.device(hm.device):
+        if half:
+            N.check(N.lib().gbcodec_fusion_loss_backward_f16(
+                desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(assumed),
+                int(stored), _ptr(g7), _ptr(ghm), _ptr(goff), _ptr(gvar), _ptr(held), int(held_valid), int(from_forward),
+                _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward_f16")
+        else:
+            N.check(N.lib().gbcodec_fusion_loss_backward_f32(
+                desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(assumed),
+                _ptr(g7), _ptr(ghm), _ptr(goff), _ptr(gvar), _ptr(held), int(held_valid), int(from_forward),
+                _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward")
+
+
+@torch.library.custom_op(f"{_NS}::fusion_loss_backward", mutates_args=("grad_hm", "grad_off", "grad_var", "held"))
 def fusion_loss_backward(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor, grad_var: Optional[Tensor],
                          hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor], weight: Tensor,
                          gt_kps: Tensor, denoms: Optional[Tensor], grad_scale: Optional[Tensor],
                          in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
-                         use_target_weight: bool, pairs: List[int]) -> None:
-    B, K, H, W = hm.shape
-    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+                         use_target_weight: bool, pairs: List[int], held: Optional[Tensor] = None,
+                         held_valid: bool = False) -> None:
+    """The stored gradients (written by fusion_loss for d(total) = grad_scale) brought to the upstream vector
+    `grad_losses` (7): nothing / an in-place rescale / a recompute, decided on the device.  `held` (6 floats, optional)
+    carries across calls what the stored gradients hold, see include/gbcodec.h."""
+    B, K = hm.shape[0], hm.shape[1]
     g7 = _cuda_f32("grad_losses", grad_losses.reshape(7), (7,))
-    weight = weight.reshape(B, K)
-    ws = _workspace(hm)
-    with torch.cuda.device(hm.device):
-        N.check(N.lib().gbcodec_fusion_loss_backward_f32(
-            desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(grad_scale),
-            _ptr(g7), _ptr(grad_hm), _ptr(grad_off), _ptr(grad_var), _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward")
+    _backward_call(False, g7, grad_hm, grad_off, grad_var, True, hm, off, var, target, weight.reshape(B, K), gt_kps, denoms,
+                   grad_scale, (in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs), held, held_valid, None)
 
 
 def _loss_setup_context(ctx, inputs, output):
     (hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
      utw, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx) = inputs
-    losses, ghm, goff, gvar, coords, scores, den_out = output
+    losses, ghm, goff, gvar, coords, scores, den_out, ws = output
     if peer_ctx:
         denoms = den_out          # the backward re-uses the global normalisers the forward exchanged
     ctx.with_grads = with_grads
     ctx.has_var = var is not None
-    # Plain attributes, not save_for_backward: the backward adjusts the stored gradients in place.
+    # Plain attributes, not save_for_backward: the backward adjusts the stored gradients in place, and `held` (allocated
+    # by the first backward) records which upstream factors they carry afterwards.
     ctx.stash = (ghm, goff, gvar if var is not None else None)
-    ctx.tensors = tuple(None if t is None else t.detach() for t in (hm, off, var, target, weight, gt_kps, denoms, grad_scale))
+    ctx.ws = ws
+    ctx.held = None
+    B, K = hm.shape[0], hm.shape[1]
+    contig = lambda t: None if t is None else t.detach().contiguous()
+    ctx.tensors = (contig(hm), contig(off), contig(var), contig(target), weight.detach().reshape(B, K).contiguous(),
+                   contig(gt_kps), contig(denoms), _scalar("grad_scale", grad_scale, hm))
     ctx.scalars = (in_w, in_h, list(lambdas), target_sigma, encode_sigma, utw, list(pairs))
+    ctx.mark_non_differentiable(ghm, goff, gvar, coords, scores, den_out, ws)
     ctx.set_materialize_grads(False)
 
 
-def _loss_backward(ctx, g_losses, g_ghm, g_goff, g_gvar, g_coords, g_scores, g_den=None):
+def _loss_backward(ctx, g_losses, *_unused):
     n_in = 22
     none = [None] * n_in
     if g_losses is None:
@@ -294,11 +325,14 @@ def _loss_backward(ctx, g_losses, g_ghm, g_goff, g_gvar, g_coords, g_scores, g_d
         raise RuntimeError("gbcodec::fusion_loss was run with with_grads=False; its output is not differentiable")
     ghm, goff, gvar = ctx.stash
     hm, off, var, target, weight, gt_kps, denoms, grad_scale = ctx.tensors
-    B, K = hm.shape[0], hm.shape[1]
-    contig = lambda t: None if t is None else t.contiguous()
-    torch.ops.gbcodec.fusion_loss_backward(
-        g_losses.contiguous(), ghm, goff, gvar, contig(hm), contig(off), contig(var), contig(target),
-        weight.reshape(B, K).contiguous(), contig(gt_kps), denoms, grad_scale, *ctx.scalars)
+    held_valid = ctx.held is not None
+    if not held_valid:
+        ctx.held = torch.empty(6, dtype=torch.float32, device=hm.device)
+    g7 = g_losses.detach().reshape(7).to(torch.float32).contiguous()
+    # straight through ctypes: this runs inside the autograd engine, where the dispatcher's bookkeeping for a
+    # mutating custom op (tens of microseconds of host time) buys nothing
+    _backward_call(False, g7, ghm, goff, gvar, True, hm, off, var, target, weight, gt_kps, denoms, grad_scale, ctx.scalars,
+                   ctx.held, held_valid, ctx.ws)
     none[0], none[1] = ghm, goff
     none[2] = gvar
     return tuple(none)
@@ -595,8 +629,9 @@ def fusion_loss_f16(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Opti
                     denoms: Optional[Tensor], expected_upstream: Optional[Tensor], in_w: float, in_h: float, lambdas: List[float],
                     target_sigma: float, encode_sigma: float, use_target_weight: bool, pairs: List[int], with_grads: bool,
                     with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
-                    decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """float16 heatmaps / offsets / variances -> losses7 (float32), coords, scores, grad_hm, grad_off, grad_var (float16).
+                    decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """float16 heatmaps / offsets / variances -> losses7 (float32), coords, scores, grad_hm, grad_off, grad_var (float16),
+    workspace.
     With `with_grads` the pass also stores the gradients, pre-multiplied by `expected_upstream` (a 1-element float32
     device tensor: the upstream gradient of total_loss the caller expects, i.e. the loss scale; None = 1) — the
     backward keeps them if the expectation held and computes them again otherwise."""
@@ -633,7 +668,7 @@ def fusion_loss_f16(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Opti
             _ptr(alpha_param) if with_decode else None, _ptr(fusion_weight) if with_decode else None, radius, decode_flags,
             _ptr(coords) if with_decode else None, _ptr(scores) if with_decode else None, _ptr(ws), ws.numel(), _stream(hm)),
             "fusion_step_f16")
-    return losses, coords, scores, ghm, goff, gvar
+    return losses, coords, scores, ghm, goff, gvar, ws
 
 
 @fusion_loss_f16.register_fake
@@ -644,53 +679,57 @@ def _(hm, off, var, target, weight, gt_kps, denoms, expected_upstream, in_w, in_
     return (hm.new_empty(7, dtype=torch.float32), hm.new_empty((B, K, 2), dtype=torch.float32) if with_decode else e(),
             hm.new_empty((B, K), dtype=torch.float32) if with_decode else e(),
             torch.empty_like(hm) if with_grads else e(torch.float16), torch.empty_like(off) if with_grads else e(torch.float16),
-            torch.empty_like(var) if (with_grads and var is not None) else e(torch.float16))
+            torch.empty_like(var) if (with_grads and var is not None) else e(torch.float16), hm.new_empty(0, dtype=torch.uint8))
 
 
-@torch.library.custom_op(f"{_NS}::fusion_loss_backward_f16", mutates_args=("grad_hm", "grad_off", "grad_var"))
+@torch.library.custom_op(f"{_NS}::fusion_loss_backward_f16", mutates_args=("grad_hm", "grad_off", "grad_var", "held"))
 def fusion_loss_backward_f16(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor, grad_var: Optional[Tensor], stored: bool,
                              hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor],
                              weight: Tensor, gt_kps: Tensor, denoms: Optional[Tensor], expected_upstream: Optional[Tensor],
                              in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
-                             use_target_weight: bool, pairs: List[int]) -> None:
-    B, K, H, W = hm.shape
-    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+                             use_target_weight: bool, pairs: List[int], held: Optional[Tensor] = None,
+                             held_valid: bool = False) -> None:
+    B, K = hm.shape[0], hm.shape[1]
     g7 = _cuda_f32("grad_losses", grad_losses.reshape(7), (7,))
-    ws = _workspace(hm)
-    with torch.cuda.device(hm.device):
-        N.check(N.lib().gbcodec_fusion_loss_backward_f16(
-            desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight.reshape(B, K)), _ptr(gt_kps), _ptr(denoms),
-            _ptr(expected_upstream), int(stored), _ptr(g7), _ptr(grad_hm), _ptr(grad_off), _ptr(grad_var),
-            _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward_f16")
+    _backward_call(True, g7, grad_hm, grad_off, grad_var, stored, hm, off, var, target, weight.reshape(B, K), gt_kps, denoms,
+                   expected_upstream, (in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs), held, held_valid, None)
 
 
 def _loss_f16_setup(ctx, inputs, output):
     (hm, off, var, target, weight, gt_kps, denoms, expected_upstream, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs,
      with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags) = inputs
-    losses, coords, scores, ghm, goff, gvar = output
+    losses, coords, scores, ghm, goff, gvar, ws = output
     ctx.stored = with_grads
     ctx.stash = (ghm, goff, gvar if var is not None else None)
+    ctx.ws = ws
+    ctx.held = None
     # the expectation the stored gradients were built on: a private copy, the caller's tensor moves on
     ctx.expected = None if expected_upstream is None else expected_upstream.detach().to(torch.float32).reshape(1).clone()
-    ctx.tensors = tuple(None if t is None else t.detach() for t in (hm, off, var, target, weight, gt_kps, denoms))
+    B, K = hm.shape[0], hm.shape[1]
+    contig = lambda t: None if t is None else t.detach().contiguous()
+    ctx.tensors = (contig(hm), contig(off), contig(var), contig(target), weight.detach().reshape(B, K).contiguous(), contig(gt_kps),
+                   contig(denoms))
     ctx.scalars = (in_w, in_h, list(lambdas), target_sigma, encode_sigma, utw, list(pairs))
-    ctx.mark_non_differentiable(coords, scores, ghm, goff, gvar)
+    ctx.mark_non_differentiable(coords, scores, ghm, goff, gvar, ws)
     ctx.set_materialize_grads(False)
 
 
-def _loss_f16_backward(ctx, g_losses, g_coords, g_scores, g_ghm, g_goff, g_gvar):
+def _loss_f16_backward(ctx, g_losses, *_unused):
     none = [None] * 21
     if g_losses is None:
         return tuple(none)
     hm, off, var, target, weight, gt_kps, denoms = ctx.tensors
     ghm, goff, gvar = ctx.stash
     if not ctx.stored:
+        # nothing was stored (forward under no expectation of a backward): fresh buffers, always computed
         ghm, goff = torch.empty_like(hm), torch.empty_like(off)
         gvar = torch.empty_like(var) if var is not None else None
-    contig = lambda t: None if t is None else t.contiguous()
-    torch.ops.gbcodec.fusion_loss_backward_f16(
-        g_losses.contiguous(), ghm, goff, gvar, ctx.stored, contig(hm), contig(off), contig(var), contig(target),
-        weight.contiguous(), contig(gt_kps), denoms, ctx.expected, *ctx.scalars)
+    held_valid = ctx.held is not None
+    if not held_valid:
+        ctx.held = torch.empty(6, dtype=torch.float32, device=hm.device)
+    g7 = g_losses.detach().reshape(7).to(torch.float32).contiguous()
+    _backward_call(True, g7, ghm, goff, gvar, ctx.stored, hm, off, var, target, weight, gt_kps, denoms, ctx.expected, ctx.scalars,
+                   ctx.held if ctx.stored else None, held_valid and ctx.stored, ctx.ws)
     none[0], none[1] = ghm, goff
     none[2] = gvar if var is not None else None
     return tuple(none)

@@ -80,12 +80,12 @@ def test_fused_step_full_size_properties(gb, name, B):
     cfg = synth.CONFIGS[name]
     d = device_batch(cfg, B, 11, gb)
     var = torch.nn.functional.softplus(torch.randn(B, cfg.K, cfg.H, cfg.W, device="cuda"))
-    losses, ghm, goff, gvar, coords, scores, _ = step(gb, cfg, d, var=var)
+    losses, ghm, goff, gvar, coords, scores = step(gb, cfg, d, var=var)[:6]
     assert torch.isfinite(losses).all() and torch.isfinite(ghm).all()
     # (1) permutation of the images
     p = torch.randperm(B, device="cuda")
     dp = {k: v[p].contiguous() for k, v in d.items()}
-    l2, ghm2, goff2, gvar2, coords2, scores2, _ = step(gb, cfg, dp, var=var[p].contiguous())
+    l2, ghm2, goff2, gvar2, coords2, scores2 = step(gb, cfg, dp, var=var[p].contiguous())[:6]
     np.testing.assert_allclose(l2.cpu().numpy(), losses.cpu().numpy(), rtol=2e-6)
     assert torch.equal(coords2, coords[p]) and torch.equal(scores2, scores[p])
     assert torch.equal(ghm2, ghm[p]) and torch.equal(gvar2, gvar[p]) and torch.equal(goff2, goff[p])
@@ -93,7 +93,7 @@ def test_fused_step_full_size_properties(gb, name, B):
     pairs = [v for q in oc.skeleton_for(cfg.K) for v in q]
     den = gb.loss_denominators(d["vis"], d["kps"], False, cfg.H, cfg.W, float(cfg.input_size[0]), float(cfg.input_size[1]), cfg.sigma, pairs)
     sl = slice(B // 2, B // 2 + 16)
-    _, ghm_s, goff_s, gvar_s, coords_s, _, _ = step(gb, cfg, d, sl, denoms=den, var=var)
+    _, ghm_s, goff_s, gvar_s, coords_s, _ = step(gb, cfg, d, sl, denoms=den, var=var)[:6]
     assert torch.equal(ghm_s, ghm[sl]) and torch.equal(goff_s, goff[sl]) and torch.equal(gvar_s, gvar[sl]) and torch.equal(coords_s, coords[sl])
     # (3) that slice against the CPU oracle (gradients scale with the normalisers: compare after rescaling)
     T = lambda t: t[sl].cpu()

@@ -7,6 +7,9 @@ the reference itself.  Tolerances are BASELINE.json's:
   loss values and gradients   1e-5 relative
   decoded coordinates         1e-4 px
 """
+import contextlib
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -30,6 +33,23 @@ def gb():
 
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@contextlib.contextmanager
+def tile_kernel():
+    """The float32 entry point through the one-CTA-per-tile kernel (csrc/loss_tile.cu) instead of the persistent step
+    kernel: the float16 and per-tile-mean entry points are instantiations of that kernel, and the tests that compare
+    them with the float32 path BIT FOR BIT need the same arithmetic on both sides.  (The step kernel itself is checked
+    against the goldens and the oracle like everything else.)"""
+    old = os.environ.get("GBCODEC_STEP_KERNEL")
+    os.environ["GBCODEC_STEP_KERNEL"] = "tile"
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ["GBCODEC_STEP_KERNEL"]
+        else:
+            os.environ["GBCODEC_STEP_KERNEL"] = old
 
 
 def t(a):
@@ -287,6 +307,56 @@ def test_module_autograd_and_scaling(gb):
     assert float(o["offsets"].grad.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("half", [False, True])
+def test_backward_twice_on_one_graph(gb, half):
+    """the backward adjusts the stored gradients in place (rescale / per-term recompute), so a second backward
+    through the same graph must compare the upstream it gets with what the stored gradients hold NOW, not with what the
+    forward assumed.  Sequence on ONE graph: heatmap_loss alone (recompute) -> total_loss (would be "nothing to do"
+    against the forward's assumption) -> 3 * total_loss (rescale) -> 3 * total_loss again (nothing to do); each against
+    the oracle's autograd for the same upstream."""
+    from infantposeestimation_gaussianbias_b200 import FusionPoseLoss
+    cfg, batch, g = goldens.load("w32_256x192")
+    loss_fn = FusionPoseLoss(target_sigma=cfg.sigma)
+    cast = (lambda x: x.half()) if half else (lambda x: x)
+    base = {k: cast(dev(batch[k])) for k in ("heatmaps", "offsets", "variances")}
+    o = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+    ref_in = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in base.items()}
+    rl = oc.fusion_loss(ref_in["heatmaps"], ref_in["offsets"], ref_in["variances"], t(batch["target"]), t(batch["weight"]), t(batch["kps"]),
+                        input_size=cfg.input_size, target_sigma=cfg.sigma)
+    out = loss_fn(o, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size)
+    assert not out["total_loss"].requires_grad or out["total_loss"].grad_fn is not None
+    steps = [("heatmap_loss alone", lambda d: d["heatmap_loss"]), ("total_loss", lambda d: d["total_loss"]),
+             ("3 x total_loss", lambda d: 3.0 * d["total_loss"]), ("3 x total_loss again", lambda d: 3.0 * d["total_loss"]),
+             ("shape + total", lambda d: d["shape_loss"] + d["total_loss"])]
+    for what, pick in steps:
+        for v in o.values():
+            v.grad = None
+        for v in ref_in.values():
+            v.grad = None
+        pick(out).backward(retain_graph=True)
+        pick(rl).backward(retain_graph=True)
+        for k in ("heatmaps", "variances"):
+            got = o[k].grad.float().cpu().numpy()
+            want = np.zeros_like(got) if ref_in[k].grad is None else ref_in[k].grad.numpy()     # a term that does not see this map
+            tol = 2e-3 if half else LOSS_RTOL              # half: the gradient is rounded to float16 once
+            assert np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-30) + 1e-12, (what, k)
+        go = o["offsets"].grad.float().cpu().numpy()
+        wo = ref_in["offsets"].grad
+        wo = np.zeros_like(go) if wo is None else wo.numpy()
+        assert np.abs(go - wo).max() <= (2e-3 if half else 3e-5) * max(np.abs(wo).max(), 1e-30) + 1e-12, (what, "offsets")
+
+
+def test_coords_and_scores_are_not_differentiable(gb):
+    """only the seven losses carry a graph; decode outputs and the stored gradients are plain tensors."""
+    from infantposeestimation_gaussianbias_b200 import FusionPoseLoss
+    cfg, batch, g = goldens.load("w32_256x192")
+    o = {k: dev(batch[k]).requires_grad_(True) for k in ("heatmaps", "offsets", "variances")}
+    out = FusionPoseLoss(target_sigma=cfg.sigma)(o, None, dev(batch["vis"][..., None]), dev(batch["kps"]), input_size=cfg.input_size,
+                                                 decode={"alpha_param": torch.tensor(0.5).cuda(), "fusion_weight": torch.tensor(0.62).cuda()})
+    assert out["total_loss"].requires_grad and not out["coords"].requires_grad and not out["scores"].requires_grad
+    out["coords"].cpu().numpy()          # would raise on a tensor that requires grad
+
+
 def test_identical_tiles_tie_rule(gb):
     """All channels equal (a zero-initialised last layer): every min() ties, ATen splits the
     gradient evenly; the kernel must reproduce that."""
@@ -415,8 +485,9 @@ def test_fp16_head_outputs_under_autocast(gb, name):
         scale = torch.tensor(1024.0).cuda()                   # a GradScaler-style loss scale
         (out16["total_loss"] * scale).backward()
     o32 = {k: v.float().requires_grad_(True) for k, v in half.items()}
-    out32 = loss_fn(o32, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size)
-    (out32["total_loss"] * 1024.0).backward()
+    with tile_kernel():
+        out32 = loss_fn(o32, dev(batch["target"]), dev(batch["weight"]), dev(batch["kps"]), input_size=cfg.input_size)
+        (out32["total_loss"] * 1024.0).backward()
     # the same with targets built in the kernel, the decode fused in and per-term upstream gradients
     dec = {"alpha_param": torch.tensor(0.5).cuda(), "fusion_weight": torch.tensor(0.62).cuda()}
     mix = lambda o: 2048.0 * o["total_loss"] + 512.0 * o["heatmap_loss"] - 256.0 * o["shape_loss"]
@@ -424,8 +495,9 @@ def test_fp16_head_outputs_under_autocast(gb, name):
     q16 = loss_fn(p16, None, dev(batch["vis"]), dev(batch["kps"]), input_size=cfg.input_size, decode=dec)
     mix(q16).backward()
     p32 = {k: v.float().requires_grad_(True) for k, v in half.items()}
-    q32 = loss_fn(p32, None, dev(batch["vis"]), dev(batch["kps"]), input_size=cfg.input_size, decode=dec)
-    mix(q32).backward()
+    with tile_kernel():
+        q32 = loss_fn(p32, None, dev(batch["vis"]), dev(batch["kps"]), input_size=cfg.input_size, decode=dec)
+        mix(q32).backward()
     assert torch.equal(q16["coords"], q32["coords"]) and torch.equal(q16["scores"], q32["scores"])
     for k in oc.LOSS_KEYS:
         assert float(q16[k]) == float(q32[k])
@@ -464,7 +536,8 @@ def test_step_with_variance_means(gb, name):
     a, f = torch.tensor(0.5).cuda(), torch.tensor(0.6224593312018546).cuda()
     common = (float(cfg.input_size[0]), float(cfg.input_size[1]), list(oc.DEFAULT_LAMBDAS), cfg.sigma, cfg.sigma, True, pairs, True, True, a, f, 2, 3)
     hm, off, var = dev(batch["heatmaps"]), dev(batch["offsets"]), dev(batch["variances"])
-    full = gb.fusion_loss(hm, off, var, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common)
+    with tile_kernel():
+        full = gb.fusion_loss(hm, off, var, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common)
     vm = var.double().mean(dim=(2, 3)).float()
     res = gb.fusion_step_vmean(hm, off, vm, None, dev(batch["vis"]), dev(batch["kps"]), None, None, *common)
     np.testing.assert_allclose(res[0].cpu().numpy(), full[0].cpu().numpy(), rtol=2e-6, atol=1e-9)

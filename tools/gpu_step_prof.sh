@@ -1,17 +1,12 @@
 #!/usr/bin/env bash
-# sanity + timing + one ncu full capture of the persistent step kernel (one gpurun call)
+# ncu captures of the persistent step kernel (one gpurun call): a quick section list first, then --set full
 set -u
 out=gpurun_out; mkdir -p $out
-for b in 2 64; do
-  timeout 60 tools/bench_loss $b 17 64 48 2 1 || { echo "step kernel failed/hung at B=$b"; exit 1; }
-  GBCODEC_STEP_KERNEL=tile timeout 60 tools/bench_loss $b 17 64 48 2 1
-done
-for i in 1 2; do
-  timeout 120 tools/bench_loss 1024 17 64 48 50 10 | tee -a $out/step_time.log
-done
-GBCODEC_STEP_KERNEL=tile timeout 120 tools/bench_loss 1024 17 64 48 50 10 | tee -a $out/step_time.log
-if [[ "${1:-}" == ncu ]]; then
-  tools/bench_loss 1024 17 64 48 5 3 > $out/plain_step.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:step_tile_kernel -s 3 -c 1 -f -o $out/prof_step tools/bench_loss 1024 17 64 48 5 3 > $out/ncu_step.log 2>&1
-  tail -2 $out/ncu_step.log
-fi
+tools/bench_loss 1024 17 64 48 5 3 > $out/plain_step.log 2>&1 || { cat $out/plain_step.log; exit 1; }
+cat $out/plain_step.log
+SECS="--section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section SchedulerStats --section Occupancy --section LaunchStats --section InstructionStats --section ComputeWorkloadAnalysis"
+timeout 600 ncu $SECS --clock-control none -k regex:step_tile_kernel -s 3 -c 1 -f -o $out/prof_step_quick tools/bench_loss 1024 17 64 48 5 3 > $out/ncu_step_quick.log 2>&1
+tail -3 $out/ncu_step_quick.log
+timeout ${1:-1500} ncu --set full --clock-control none --import-source on -k regex:step_tile_kernel -s 3 -c 1 -f -o $out/prof_step tools/bench_loss 1024 17 64 48 5 3 > $out/ncu_step.log 2>&1
+tail -3 $out/ncu_step.log
+ls -la $out
