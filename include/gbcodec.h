@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GBCODEC_ABI_VERSION 1
+#define GBCODEC_ABI_VERSION 2
 #define GBCODEC_MAX_K 64            /* keypoint channels per image                  */
 #define GBCODEC_MAX_PAIRS 64        /* limb pairs in the overlap term               */
 #define GBCODEC_MAX_PARTNERS 4      /* limb pairs a single channel may take part in */
@@ -398,6 +398,10 @@ int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,
                             void* d_grad_hm, void* d_grad_off, void* d_grad_var,
                             float* d_held6, int held_valid, int workspace_from_forward,
                             void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Kernels launched by this library in this process so far (every launch site counts itself; memsets and copies are not
+ * kernels).  bench.py reads it around its timed region for the `gpu_launches` it reports. */
+unsigned long long gbcodec_launch_count(void);
 
 /* Measurement hook (bench.py): the next gbcodec_fusion_loss_f32 / _step_f32 calls made
  * by THIS host thread record `start_event` right before and `stop_event` right after

@@ -18,7 +18,7 @@ MAX_PARTNERS = 4
 MAX_TILE = 32768
 PEER_HANDLE_BYTES = 64
 MAX_PEERS = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DECODE_REFINE = 1
 DECODE_APPLY_OFFSET = 2
@@ -29,7 +29,7 @@ CRIT_MSE, CRIT_SMOOTHL1, CRIT_L1, CRIT_MSE_WEIGHTED = 0, 1, 2, 3
 TERM_HEATMAP, TERM_MORPH, TERM_REGRESSION, TERM_REFINED = 1, 2, 4, 8
 
 EXPORTS = (
-    "gbcodec_abi_version", "gbcodec_status_string", "gbcodec_last_error",
+    "gbcodec_abi_version", "gbcodec_status_string", "gbcodec_last_error", "gbcodec_launch_count",
     "gbcodec_encode_f32", "gbcodec_decode_f32", "gbcodec_decode_argmax_f32", "gbcodec_refine_centroid_f32",
     "gbcodec_loss_workspace_bytes", "gbcodec_loss_denominators_f32",
     "gbcodec_fusion_loss_f32", "gbcodec_fusion_step_f32", "gbcodec_fusion_loss_backward_f32",
@@ -103,6 +103,8 @@ _P = C.c_void_p
 def _declare(lib):
     f32p = _P
     lib.gbcodec_abi_version.restype = C.c_int
+    lib.gbcodec_launch_count.restype = C.c_ulonglong
+    lib.gbcodec_launch_count.argtypes = []
     lib.gbcodec_status_string.restype = C.c_char_p
     lib.gbcodec_status_string.argtypes = [C.c_int]
     lib.gbcodec_last_error.restype = C.c_char_p

@@ -1,5 +1,6 @@
 // api.cu — the C ABI declared in include/gbcodec.h: argument checks, status
 // mapping and launches.  No torch types, no allocation, no synchronisation.
+#include <atomic>
 #include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -24,6 +25,10 @@ static bool sync_debug() {
     static const int v = [] { const char* e = getenv("GBCODEC_SYNC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
     return v != 0;
 }
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && sync_debug()) {
@@ -83,6 +88,8 @@ using namespace gbc;
 extern "C" {
 
 int gbcodec_abi_version(void) { return GBCODEC_ABI_VERSION; }
+
+unsigned long long gbcodec_launch_count(void) { return launch_count(); }
 
 const char* gbcodec_status_string(int status) {
     switch (status) {

@@ -16,6 +16,9 @@ constexpr float kEps = 1e-8f;
 // ---- status plumbing (api.cu) ------------------------------------------------
 int fail(int status, const char* fmt, ...);
 int check_launch(const char* what);
+// every kernel launch of the library goes through this counter (gbcodec_launch_count): bench.py reports launches it
+// counted, not launches it assumes
+void note_launch();
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -409,7 +409,7 @@ template <int W4, int ROWS, int NIT, bool FLIP, int MINB>
 static int launch_decode_tile(const float* hm, const float* hmf, const int32_t* perm, const float* off, const float* ap,
                               const float* fw, int tiles, int K, int radius, unsigned flags, float* coords, float* scores,
                               int32_t* centre, cudaStream_t s) {
-    decode_tile_kernel<W4, ROWS, NIT, FLIP, MINB><<<tiles, dim3(W4, ROWS), 0, s>>>(hm, hmf, perm, off, ap, fw, K, radius, flags, coords, scores, centre);
+    note_launch(), decode_tile_kernel<W4, ROWS, NIT, FLIP, MINB><<<tiles, dim3(W4, ROWS), 0, s>>>(hm, hmf, perm, off, ap, fw, K, radius, flags, coords, scores, centre);
     return check_launch("decode_tile_kernel");
 }
 
@@ -431,13 +431,13 @@ static void launch_decode_t(int niter, int grid, int threads, cudaStream_t s,
                             float* coords, float* scores, int32_t* centre) {
     // the 64x48 tile (256 threads x 3 float4): hold the register count down so that 6 CTAs (no flip) fit an SM
     if (niter == 3 && threads == 256) {
-        decode_kernel<3, FLIP, 256, FLIP ? 5 : 6><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre);
+        note_launch(), decode_kernel<3, FLIP, 256, FLIP ? 5 : 6><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre);
         return;
     }
-#define GBC_CASE(NI) case NI: decode_kernel<NI, FLIP><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre); break;
+#define GBC_CASE(NI) case NI: note_launch(), decode_kernel<NI, FLIP><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre); break;
     switch (niter) {
         GBC_CASE(1) GBC_CASE(2) GBC_CASE(3) GBC_CASE(4) GBC_CASE(5) GBC_CASE(6) GBC_CASE(7) GBC_CASE(8)
-        default: decode_kernel<0, FLIP><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre); break;
+        default: note_launch(), decode_kernel<0, FLIP><<<grid, threads, 0, s>>>(hm, hmf, perm, off, ap, fw, K, H, W, radius, flags, coords, scores, centre); break;
     }
 #undef GBC_CASE
 }
@@ -545,10 +545,10 @@ int launch_argmax(const float* hm, int B, int K, int H, int W, int mode,
     int threads = pick_threads((H * W) >> 2, &niter);
     if (!threads) threads = 256;
     const int grid = B * K;
-#define GBC_CASE(NI) case NI: argmax_kernel<NI><<<grid, threads, 0, s>>>(hm, H, W, mode, coords, maxvals, index); break;
+#define GBC_CASE(NI) case NI: note_launch(), argmax_kernel<NI><<<grid, threads, 0, s>>>(hm, H, W, mode, coords, maxvals, index); break;
     switch (niter) {
         GBC_CASE(1) GBC_CASE(2) GBC_CASE(3) GBC_CASE(4) GBC_CASE(5) GBC_CASE(6) GBC_CASE(7) GBC_CASE(8)
-        default: argmax_kernel<0><<<grid, threads, 0, s>>>(hm, H, W, mode, coords, maxvals, index); break;
+        default: note_launch(), argmax_kernel<0><<<grid, threads, 0, s>>>(hm, H, W, mode, coords, maxvals, index); break;
     }
 #undef GBC_CASE
     return check_launch("argmax_kernel");
@@ -571,7 +571,7 @@ centroid_kernel(const float* __restrict__ hm, const float* __restrict__ cin, int
 
 int launch_centroid(const float* hm, const float* cin, int B, int K, int H, int W, int window, float* cout, cudaStream_t s) {
     const int tiles = B * K;
-    centroid_kernel<<<(tiles + 3) / 4, 128, 0, s>>>(hm, cin, tiles, H, W, window, cout);
+    note_launch(), centroid_kernel<<<(tiles + 3) / 4, 128, 0, s>>>(hm, cin, tiles, H, W, window, cout);
     return check_launch("centroid_kernel");
 }
 
@@ -677,16 +677,16 @@ int launch_postprocess(const gbcodec_postprocess_desc* d, const float* hm, const
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         const size_t n = (size_t)d->B * d->K * 2;
         const int grid = (int)((n + 255) / 256 < 148 * 4 ? (n + 255) / 256 : 148 * 4);
-        regression_range_kernel<<<grid, 256, 0, s>>>(reg, n, flag);
+        note_launch(), regression_range_kernel<<<grid, 256, 0, s>>>(reg, n, flag);
     }
     int niter = 0;
     int threads = pick_threads((d->H * d->W) >> 2, &niter);
     if (!threads) threads = 256;
     const int grid = d->B * d->K;
-#define GBC_CASE(NI) case NI: postprocess_kernel<NI><<<grid, threads, 0, s>>>(hm, P, reg, flag, center, scale, preds, maxvals, mask); break;
+#define GBC_CASE(NI) case NI: note_launch(), postprocess_kernel<NI><<<grid, threads, 0, s>>>(hm, P, reg, flag, center, scale, preds, maxvals, mask); break;
     switch (niter) {
         GBC_CASE(1) GBC_CASE(2) GBC_CASE(3) GBC_CASE(4) GBC_CASE(5) GBC_CASE(6) GBC_CASE(7) GBC_CASE(8)
-        default: postprocess_kernel<0><<<grid, threads, 0, s>>>(hm, P, reg, flag, center, scale, preds, maxvals, mask); break;
+        default: note_launch(), postprocess_kernel<0><<<grid, threads, 0, s>>>(hm, P, reg, flag, center, scale, preds, maxvals, mask); break;
     }
 #undef GBC_CASE
     return check_launch("postprocess_kernel");
@@ -713,7 +713,7 @@ int launch_coords_to_image(const float* cin, const float* center, const float* s
                            float in_w, float in_h, float* cout, cudaStream_t s) {
     const int tiles = B * K;
     const float kx = (float)((double)in_w / (double)W), ky = (float)((double)in_h / (double)H);
-    coords_to_image_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(cin, center, scale, tiles, K, kx, ky, in_w, in_h, cout);
+    note_launch(), coords_to_image_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(cin, center, scale, tiles, K, kx, ky, in_w, in_h, cout);
     return check_launch("coords_to_image_kernel");
 }
 

@@ -182,16 +182,16 @@ int launch_encode(const float* kps, const float* vis, float* target, float* weig
         case GBCODEC_ENCODE_PATCH:
             if (H * W <= 8192 && tiles >= 148 * 8) {               // small tiles, enough of them: one warp per tile
                 const int wgrid = (tiles + 7) / 8 < 148 * 8 ? (tiles + 7) / 8 : 148 * 8;
-                encode_warp_kernel<<<wgrid, 256, smem, stream>>>(kps, vis, target, weight, tiles, H, W, in_w, in_h, ec);
+                note_launch(), encode_warp_kernel<<<wgrid, 256, smem, stream>>>(kps, vis, target, weight, tiles, H, W, in_w, in_h, ec);
                 return check_launch("encode_warp_kernel");
             }
-            encode_kernel<<<grid, 256, smem, stream>>>(kps, vis, target, weight, tiles, H, W, in_w, in_h, ec);
+            note_launch(), encode_kernel<<<grid, 256, smem, stream>>>(kps, vis, target, weight, tiles, H, W, in_w, in_h, ec);
             return check_launch("encode_kernel");
         case GBCODEC_ENCODE_PATCH_CLIPPED:
-            encode_genb_kernel<GBCODEC_ENCODE_PATCH_CLIPPED><<<grid, 256, smem, stream>>>(kps, vis, target, weight, tiles, H, W, sx, sy, (float)(sigma * 3.0), ec);
+            note_launch(), encode_genb_kernel<GBCODEC_ENCODE_PATCH_CLIPPED><<<grid, 256, smem, stream>>>(kps, vis, target, weight, tiles, H, W, sx, sy, (float)(sigma * 3.0), ec);
             return check_launch("encode_genb_kernel<clipped>");
         case GBCODEC_ENCODE_DENSE:
-            encode_genb_kernel<GBCODEC_ENCODE_DENSE><<<grid, 256, 0, stream>>>(kps, vis, target, weight, tiles, H, W, sx, sy, 0.f, ec);
+            note_launch(), encode_genb_kernel<GBCODEC_ENCODE_DENSE><<<grid, 256, 0, stream>>>(kps, vis, target, weight, tiles, H, W, sx, sy, 0.f, ec);
             return check_launch("encode_genb_kernel<dense>");
         default:
             return fail(GBCODEC_ERR_BAD_ARGUMENT, "encode: mode=%d", mode);

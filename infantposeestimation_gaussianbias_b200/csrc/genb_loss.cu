@@ -328,7 +328,7 @@ static int check_genb(const GenbParams& P, const GenbArgs& A, const void* ws, si
 static int launch_genb(const GenbParams& P, const GenbArgs& A, cudaStream_t s) {
     const bool tiles = P.terms & (GBCODEC_TERM_HEATMAP | GBCODEC_TERM_MORPH);
     const int nt = P.B * P.K;
-    genb_coords_kernel<<<(nt + 255) / 256, 256, 0, s>>>(P, A, tiles ? 0 : 1);
+    note_launch(), genb_coords_kernel<<<(nt + 255) / 256, 256, 0, s>>>(P, A, tiles ? 0 : 1);
     int st = check_launch("genb_coords_kernel");
     if (st || !tiles) return st;
     // both tiles stay in registers: up to 3 float4 each per thread with CTAs of up to 1024 threads (64 registers:
@@ -340,10 +340,10 @@ static int launch_genb(const GenbParams& P, const GenbArgs& A, cudaStream_t s) {
         if (n4 % t == 0 && n4 / t <= 3) { threads = t; niter = n4 / t; }
     for (int t = 128; t <= 512 && !niter; t += 32)
         if (n4 % t == 0 && n4 / t <= 8) { threads = t; niter = n4 / t; }
-#define GBC_CASE(NI, MT) case NI: genb_tile_kernel<NI, MT><<<nt, threads, 0, s>>>(P, A); break;
+#define GBC_CASE(NI, MT) case NI: note_launch(), genb_tile_kernel<NI, MT><<<nt, threads, 0, s>>>(P, A); break;
     switch (niter) {
         GBC_CASE(1, 1024) GBC_CASE(2, 1024) GBC_CASE(3, 1024) GBC_CASE(4, 512) GBC_CASE(5, 512) GBC_CASE(6, 512) GBC_CASE(7, 512) GBC_CASE(8, 512)
-        default: genb_tile_kernel<0, 1024><<<nt, threads, 0, s>>>(P, A); break;
+        default: note_launch(), genb_tile_kernel<0, 1024><<<nt, threads, 0, s>>>(P, A); break;
     }
 #undef GBC_CASE
     return check_launch("genb_tile_kernel");
@@ -372,7 +372,7 @@ int combined_loss(const gbcodec_combined_desc* d, const float* pred, const float
     if (st) return st;
     const int nt = P.B * P.K;
     const int fin = (nt + 255) / 256 < kGenbFinBlocks ? (nt + 255) / 256 : kGenbFinBlocks;
-    genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, losses5, nullptr);
+    note_launch(), genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, losses5, nullptr);
     return check_launch("genb_finalize_kernel");
 }
 
@@ -391,7 +391,7 @@ int combined_loss_backward(const gbcodec_combined_desc* d, const float* pred, co
     if (st) return st;
     const GenbWs L = genb_carve(ws);
     A.partial = L.partial; A.eff = L.eff; A.plan = L.plan;
-    genb_plan_kernel<<<1, 32, 0, s>>>(P, g5, grad_scale, L.plan, L.eff);
+    note_launch(), genb_plan_kernel<<<1, 32, 0, s>>>(P, g5, grad_scale, L.plan, L.eff);
     st = check_launch("genb_plan_kernel");
     if (st) return st;
     return launch_genb(P, A, s);
@@ -535,14 +535,14 @@ int heatmap_step(const float* hm, const float* target, const float* weight, cons
     for (int t = 128; t <= 512 && !niter; t += 32)
         if (n4 % t == 0 && n4 / t <= 8) { threads = t; niter = n4 / t; }
     if (niter == 3 && threads == 256) {                     // 64x48: cap the registers for 8 resident CTAs
-        heatmap_step_kernel<3, 256, 8><<<nt, threads, smem, s>>>(A);
+        note_launch(), heatmap_step_kernel<3, 256, 8><<<nt, threads, smem, s>>>(A);
         niter = -1;
     }
-#define GBC_CASE(NI, MT) case NI: heatmap_step_kernel<NI, MT><<<nt, threads, smem, s>>>(A); break;
+#define GBC_CASE(NI, MT) case NI: note_launch(), heatmap_step_kernel<NI, MT><<<nt, threads, smem, s>>>(A); break;
     switch (niter) {
         case -1: break;
         GBC_CASE(1, 1024) GBC_CASE(2, 1024) GBC_CASE(3, 1024) GBC_CASE(4, 512) GBC_CASE(5, 512) GBC_CASE(6, 512) GBC_CASE(7, 512) GBC_CASE(8, 512)
-        default: heatmap_step_kernel<0, 1024><<<nt, threads, smem, s>>>(A); break;
+        default: note_launch(), heatmap_step_kernel<0, 1024><<<nt, threads, smem, s>>>(A); break;
     }
 #undef GBC_CASE
     int st = check_launch("heatmap_step_kernel");
@@ -551,7 +551,7 @@ int heatmap_step(const float* hm, const float* target, const float* weight, cons
     memset(&P, 0, sizeof(P));
     P.B = B; P.K = K; P.heat_scale = 1.f; P.inv_heat = A.inv_bkn; P.w[0] = 1.f;
     const int fin = (nt + 255) / 256 < kGenbFinBlocks ? (nt + 255) / 256 : kGenbFinBlocks;
-    genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, nullptr, loss);
+    note_launch(), genb_finalize_kernel<<<fin, 256, 0, s>>>(P, L.partial, L.bpart, L.ticket, nullptr, loss);
     return check_launch("genb_finalize_kernel");
 }
 

@@ -666,7 +666,7 @@ static int launch_loss_t(const LossParams& P, const LossArgs& A, cudaStream_t s)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_kernel): %s", cudaGetErrorString(e));
     if (g_prof_start && !A.plan) cudaEventRecord(g_prof_start, s);
-    kern<<<P.B * P.K, TPB, smem, s>>>(P, A);
+    note_launch(), kern<<<P.B * P.K, TPB, smem, s>>>(P, A);
     if (g_prof_stop && !A.plan) cudaEventRecord(g_prof_stop, s);
     return check_launch("loss_kernel");
 }
@@ -679,8 +679,10 @@ static bool force_generic() {
 
 static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s) {
     if (!force_generic()) {
-        // the persistent step kernel covers float32 maps with the target generated on the fly
-        const int st = launch_step_tile(P, A, s, g_prof_start, g_prof_stop);
+        // the persistent step kernels cover float32 maps with the target generated on the fly
+        int st = launch_step_pipe(P, A, s, g_prof_start, g_prof_stop);
+        if (st != 1) return st;
+        st = launch_step_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st != 1) return st;
     }
     if (!force_generic() || A.half_io) {
@@ -716,13 +718,13 @@ static int prepare_weights(const LossParams& P, const WsLayout& L, const float* 
     const int ipb = 256 / P.K;
     const int grid = (P.B + ipb - 1) / ipb;
     if (denoms) {
-        sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
-        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, nullptr, L.ticket, kNoPeers, nullptr);
+        note_launch(), sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
+        note_launch(), denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, nullptr, L.ticket, kNoPeers, nullptr);
     } else {
         // sums, plan, the finalize ticket and the step kernel's tile counter share the first 32 bytes of the workspace
         cudaError_t e = cudaMemsetAsync(L.sums, 0, 32, s);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-        denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, L.sums, L.ticket, peer, peer.world > 1 ? global_out : nullptr);
+        note_launch(), denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, L.sums, L.ticket, peer, peer.world > 1 ? global_out : nullptr);
     }
     return check_launch("denoms_kernel");
 }
@@ -738,7 +740,7 @@ int loss_denominators(const gbcodec_loss_desc* d, const float* weight, const flo
     const WsLayout L = ws_carve(ws, P.B, P.K);
     st = prepare_weights(P, L, weight, gt, target_given, nullptr, s);
     if (st) return st;
-    sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, out2);
+    note_launch(), sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, out2);
     return check_launch("sums_to_float_kernel");
 }
 
@@ -778,7 +780,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, peer, denoms_out);
     if (st) return st;
     if (denoms_out && peer.world <= 1) {                 // with peers the exchanging CTA has written them already
-        sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, denoms_out);
+        note_launch(), sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, denoms_out);
         st = check_launch("sums_to_float_kernel");
         if (st) return st;
     }
@@ -809,7 +811,9 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const float* partial_c = L.partial; const double* sums_c = L.sums;
+        note_launch();
         cudaError_t e = cudaLaunchKernelEx(&cfg, finalize_kernel, P, partial_c, sums_c, L.bpart, L.ticket, losses7, peer);
+        note_launch();
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(finalize_kernel): %s", cudaGetErrorString(e));
     }
     return check_launch("finalize_kernel");
@@ -833,10 +837,10 @@ int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const floa
         st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s);
         if (st) return st;
     }
-    plan_kernel<<<1, 32, 0, s>>>(P, g7, grad_scale, held, held_valid, L.plan, L.lam_eff);
+    note_launch(), plan_kernel<<<1, 32, 0, s>>>(P, g7, grad_scale, held, held_valid, L.plan, L.lam_eff);
     if (!half_io && have_stash) {
         const size_t n4 = (size_t)P.B * P.K * P.H * P.W / 4;
-        rescale_kernel<<<148 * 8, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4,
+        note_launch(), rescale_kernel<<<148 * 8, 256, 0, s>>>(L.plan, L.lam_eff, reinterpret_cast<float4*>(ghm), n4,
                                                 reinterpret_cast<float4*>(goff), 2 * n4, reinterpret_cast<float4*>(gvar), gvar ? n4 : 0);
     }
     LossArgs A;

@@ -193,5 +193,8 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
 // step_tile.cu: persistent kernel (bulk-copy pipeline, one block reduction per tile) for float32 maps with the target
 // generated on the fly; returns 1 if it does not cover this call (the caller then uses launch_loss_tile).
 int launch_step_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+// step_pipe.cu: the same step as a software pipeline of specialised warps (compute warps run only pixel loops, a scalar
+// warp owns the per-tile chain, a producer lane moves the bytes); same coverage and return convention as launch_step_tile.
+int launch_step_pipe(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t ev_start, cudaEvent_t ev_stop);
 
 }  // namespace gbc

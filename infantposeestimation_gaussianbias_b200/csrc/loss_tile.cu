@@ -937,7 +937,7 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
         }
         const int tiles = P.B * P.K, resident = sms * MINB;
         const int per = (tiles + resident - 1) / resident;            // one wave: balanced when there is work, ~sms*MINB CTAs to dismiss when there is none
-        bk<<<(tiles + per - 1) / per, TPB, smem, s>>>(P, A, per);
+        note_launch(), bk<<<(tiles + per - 1) / per, TPB, smem, s>>>(P, A, per);
         return check_launch("loss_tile_backward_kernel");
     }
     auto kern = loss_tile_kernel<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, TM, MINB, HALF, MG, VSLOT>;
@@ -953,7 +953,9 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
+        note_launch();
         e = cudaLaunchKernelEx(&cfg, kern, P, A);
+        note_launch();
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(loss_tile_kernel): %s", cudaGetErrorString(e));
     }
     if (e1) cudaEventRecord(e1, s);

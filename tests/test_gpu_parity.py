@@ -339,11 +339,12 @@ def test_backward_twice_on_one_graph(gb, half):
             got = o[k].grad.float().cpu().numpy()
             want = np.zeros_like(got) if ref_in[k].grad is None else ref_in[k].grad.numpy()     # a term that does not see this map
             tol = 2e-3 if half else LOSS_RTOL              # half: the gradient is rounded to float16 once
-            assert np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-30) + 1e-12, (what, k)
+            # half: gradients of ~1e-6 (no loss scale here) sit in float16's subnormal range, spacing 6e-8
+            assert np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-30) + (6e-8 if half else 1e-12), (what, k)
         go = o["offsets"].grad.float().cpu().numpy()
         wo = ref_in["offsets"].grad
         wo = np.zeros_like(go) if wo is None else wo.numpy()
-        assert np.abs(go - wo).max() <= (2e-3 if half else 3e-5) * max(np.abs(wo).max(), 1e-30) + 1e-12, (what, "offsets")
+        assert np.abs(go - wo).max() <= (2e-3 if half else 3e-5) * max(np.abs(wo).max(), 1e-30) + (6e-8 if half else 1e-12), (what, "offsets")
 
 
 def test_coords_and_scores_are_not_differentiable(gb):

@@ -71,7 +71,7 @@ def world():
         patch.unpatch_reference()
 
 
-def _train_step(w, model, fp16, scale=1024.0):
+def _train_step(w, model, fp16, scale=64.0):
     """train.py:159-183 for one batch, without the optimizer step (the gradients are what is compared).
     The backbone's BatchNorm layers run on their running statistics (frozen-BN fine-tuning): with batch statistics over
     4 random images the random-init HRNet is chaotic — on the CPU two copies of the stock model, same input, differ by
@@ -167,9 +167,16 @@ def test_train_step_autocast_gradscaler_stock_vs_patched(world):
         w.patch.unpatch_reference()
     worst_l = max(abs(got_l[k] - want_l[k]) / max(abs(want_l[k]), 1e-12) for k in want_l)
     heads = _head_last_convs(want_g)
+    bad_stock = sum(int((~torch.isfinite(g)).sum()) for g in want_g.values())
+    bad_ours = sum(int((~torch.isfinite(g)).sum()) for g in got_g.values())
     worst_h = max(float((got_g[n] - g).abs().max()) / max(float(g.abs().max()), 1e-30) for n, g in heads.items())
-    _report("train step autocast+GradScaler", loss_rel_err=worst_l, head_last_conv_grad_maxnorm_err=worst_h)
+    _report("train step autocast+GradScaler", loss_rel_err=worst_l, head_last_conv_grad_maxnorm_err=worst_h,
+            nonfinite_grad_entries_stock=bad_stock, nonfinite_grad_entries_patched=bad_ours)
     assert all(np.isfinite(v) for v in got_l.values())
+    assert bad_ours <= bad_stock, "the patched step overflowed where the stock step did not"
+    if bad_stock:
+        pytest.skip(f"the stock autocast step itself produced {bad_stock} non-finite gradient entries at this loss scale "
+                    f"(GradScaler would skip the step); losses agree to {worst_l:.2g}")
     assert worst_l <= 2e-3 and worst_h <= 2e-2
 
 
