@@ -17,9 +17,16 @@ all-reduced by NCCL (`--exchange nccl`).
 BASELINE.json (configs[2]: 96x72, B=4096, flip test + offset correction; configs[4]: the
 64x48 sweep) under the same contract; `--config hrformer|preemie` the other fused-step shapes.
 
-`--impl reference` times the reference's CPU implementation of the same step on the
-host cores.  The reference is Python and cannot travel to the GPU box, so this is
-the oracle port (oracle/heatmap_codec.py, pinned to the reference by tests/golden).
+`--impl reference` times the reference's own CPU implementation of the same step on the host cores: the UNMODIFIED
+reference tree (baseline/_ref, a verbatim copy made by tools/install_reference.py; /root/reference in the build
+container) — `COCOPoseDataset._generate_target` per sample, `FusionPoseLoss` forward + backward, `head.decode` — with
+every host thread (`kind: "reference"`).  Only if the tree is absent does it fall back to the oracle port
+(oracle/heatmap_codec.py, pinned to the reference by tests/golden; `kind: "port"`).
+
+The default line also carries: `aten_cuda_baseline` (the reference's stock modules run on the SAME GPU with device
+tensors — what a user of the reference sees today), `api_step` (the patched module's forward + total_loss.backward(),
+float32 and float16-autocast), `other_workloads` (BASELINE configs[2], [3], [4]) and `gpu_launches` as counted by the
+library itself.
 """
 from __future__ import annotations
 
@@ -49,7 +56,7 @@ BYTES_PER_HM = 24 * H * W          # fused step: read P,V (8N); write dP,dV,dO (
 
 WORKLOAD = "BASELINE configs[1]: HRNet-W32 256x192 (64x48 heatmaps, K=17, sigma=2)"
 SYNTH_CONFIG = "w32_256x192"        # tests/synth.py config of the CPU arm
-TILE_KERNEL = "loss_tile_kernel<12,16,4,...>"
+TILE_KERNEL = "step_pipe_kernel<12,16,4,3,grads>"
 
 # The default (and the driver's) workload is BASELINE configs[1].  The other fused-step configurations of BASELINE.json
 # can be selected for a measurement of their own; they change the shapes only.
@@ -141,10 +148,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- inputs
-def synth_device_batch(B, device, seed, ops, with_var=True):
+def synth_device_batch(B, device, seed, ops, with_var=True, spec=None):
     """Synthetic batch created on the device (SURVEY §8d recipe): peaked heatmaps around
-    jittered keypoints + noise, gaussian offsets, softplus variances."""
+    jittered keypoints + noise, gaussian offsets, softplus variances.  `spec` overrides the module-level shape
+    (K, H, W, IN_W, IN_H, SIGMA) for the secondary workloads."""
     import torch
+    K, H, W, IN_W, IN_H, SIGMA = (spec[k] for k in ("K", "H", "W", "IN_W", "IN_H", "SIGMA")) if spec else (
+        globals()[k] for k in ("K", "H", "W", "IN_W", "IN_H", "SIGMA"))
     g = torch.Generator(device=device).manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=g, device=device)
     rn = lambda *s: torch.randn(*s, generator=g, device=device)
@@ -164,28 +174,71 @@ def synth_device_batch(B, device, seed, ops, with_var=True):
 
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_step_rate(sample_B: int, min_seconds: float, max_reps: int):
-    """Oracle port of the reference step (encode -> loss fwd+bwd -> decode) on the host cores."""
-    import numpy as np
+    """The reference step (encode -> loss fwd+bwd -> decode) on the host cores: the unmodified reference when its tree is
+    present, the oracle port otherwise.  -> (heatmaps/s, cores, per-pass times, kind)"""
     import torch
-    from oracle import heatmap_codec as oc
-    from tests import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.CONFIGS[SYNTH_CONFIG]
-    batch = synth.make_batch(cfg, seed=0, B=sample_B)
-    T = lambda k: torch.from_numpy(batch[k])
-    args = (batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"))
+    call, kind = reference_step_callable(sample_B)
 
     def one():
         t0 = time.perf_counter()
-        oc.codec_step(*args, heatmap_size=cfg.heatmap_size, input_size=cfg.input_size, sigma=cfg.sigma, loop_decode=True)
+        call()
         return time.perf_counter() - t0
 
     one()                                   # warm-up
     times, t_start = [], time.perf_counter()
     while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
         times.append(one())
-    return sample_B * K / statistics.median(times), cores, times
+    return sample_B * K / statistics.median(times), cores, times, kind
+
+
+def _reference_tree():
+    """The unmodified reference, if it travelled with the repo (tools/install_reference.py) or is mounted."""
+    from tests import refload
+    return refload.Reference() if refload.find() else None
+
+
+def reference_step_callable(sample_B, device="cpu"):
+    """-> (callable running one reference step on `sample_B` images, kind).  The step is the reference's own code:
+    COCOPoseDataset._generate_target per sample (coco_dataset.py:185-250; on the host, as the DataLoader workers do),
+    FusionPoseLoss forward + total_loss.backward() (fusion_head.py:745-806, train.py:182), HeatmapRegressionHead.decode
+    (fusion_head.py:309-365).  Falls back to the oracle port when the tree is absent."""
+    import numpy as np
+    import torch
+    from tests import synth
+    cfg = synth.CONFIGS[SYNTH_CONFIG]
+    batch = synth.make_batch(cfg, seed=0, B=sample_B)
+    ref = _reference_tree()
+    if ref is None:
+        from oracle import heatmap_codec as oc
+        T = lambda k: torch.from_numpy(batch[k])
+        return (lambda: oc.codec_step(batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"),
+                                      heatmap_size=cfg.heatmap_size, input_size=cfg.input_size, sigma=cfg.sigma, loop_decode=True)), "port"
+    ref.__enter__()                       # stays on sys.path for the life of this process
+    fh = ref.fusion_head
+    ds = object.__new__(ref.coco_dataset.COCOPoseDataset)
+    ds.num_keypoints, ds.sigma = cfg.K, cfg.sigma
+    ds.heatmap_size, ds.input_size = np.array(cfg.heatmap_size), np.array(cfg.input_size)
+    loss_fn = fh.FusionPoseLoss(target_sigma=cfg.sigma).to(device)
+    head = fh.HeatmapRegressionHead(32, num_keypoints=cfg.K).to(device)
+    D = lambda k: torch.from_numpy(batch[k]).to(device)
+    hm, off, var, kps = D("heatmaps"), D("offsets"), D("variances"), D("kps")
+    fw = torch.sigmoid(head.fusion_weight.detach())
+
+    def step():
+        enc = [ds._generate_target(batch["kps"][b], batch["vis"][b]) for b in range(sample_B)]
+        target = torch.from_numpy(np.stack([e[0] for e in enc])).to(device)
+        weight = torch.from_numpy(np.stack([e[1] for e in enc])).to(device)
+        outputs = {"heatmaps": hm.clone().requires_grad_(True), "offsets": off.clone().requires_grad_(True),
+                   "variances": var.clone().requires_grad_(True), "fusion_weight": fw}
+        losses = loss_fn(outputs, target, weight, kps, input_size=cfg.input_size, heatmap_size=(cfg.H, cfg.W))
+        losses["total_loss"].backward()
+        with torch.no_grad():
+            coords, scores = head.decode({k: v.detach() for k, v in outputs.items()}, apply_offset=True)
+        return float(losses["total_loss"]), coords, scores
+
+    return step, "reference"
 
 
 def run_reference(args):
@@ -195,15 +248,9 @@ def run_reference(args):
     sample_B = 64
     # each step = one bounded sample of the workload (B=64 of the 1024-image batch)
     import torch
-    from oracle import heatmap_codec as oc
-    from tests import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.CONFIGS[SYNTH_CONFIG]
-    batch = synth.make_batch(cfg, seed=0, B=sample_B)
-    T = lambda k: torch.from_numpy(batch[k])
-    call = lambda: oc.codec_step(batch["kps"], batch["vis"], T("heatmaps"), T("offsets"), T("variances"),
-                                 heatmap_size=cfg.heatmap_size, input_size=cfg.input_size, sigma=cfg.sigma, loop_decode=True)
+    call, kind = reference_step_callable(sample_B)
     for _ in range(max(1, min(args.warmup, 3))):
         call()
     t0 = time.perf_counter()
@@ -212,12 +259,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = sample_B * K * args.steps / dt
     sample = f"{sample_B} images x {K} heatmaps per step (a bounded sample of the {args.batch}-image batch), {args.steps} steps"
+    how = ("the unmodified reference (_generate_target per sample, FusionPoseLoss fwd + backward, head.decode) on the host cores"
+           if kind == "reference" else "oracle port of the reference step (reference tree absent)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.batch), "sample": sample, "what": how},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -253,6 +302,157 @@ def bind_to_gpu_numa_node(local_rank: int):
     except Exception:
         pass
     return None
+
+
+# ----------------------------------------------------------------------------- secondary measurements of the default line
+def _time_cuda(fn, steps, warm=3):
+    """mean milliseconds per call of `fn` on torch's current stream (CUDA events, synchronised on both sides)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def aten_cuda_baseline(device, sample_B=256, steps=2):
+    """The reference's STOCK modules on this GPU with device tensors — its own execution mode (train.py:159-172 moves
+    everything `.to(device)`): FusionPoseLoss forward + backward (ATen kernels), HeatmapRegressionHead.decode (a Python
+    loop over B*K tiles with `.item()` round trips, fusion_head.py:102-126).  Targets are given (the reference builds
+    them in DataLoader workers).  None when the reference tree is absent."""
+    import torch
+    ref = _reference_tree()
+    if ref is None:
+        return None
+    from tests import synth
+    cfg = synth.CONFIGS[SYNTH_CONFIG]
+    batch = synth.make_batch(cfg, seed=0, B=sample_B)
+    with ref:
+        fh = ref.fusion_head
+        loss_fn = fh.FusionPoseLoss(target_sigma=cfg.sigma).to(device)
+        head = fh.HeatmapRegressionHead(32, num_keypoints=cfg.K).to(device)
+        D = lambda k: torch.from_numpy(batch[k]).to(device)
+        hm, off, var, kps, target, weight = D("heatmaps"), D("offsets"), D("variances"), D("kps"), D("target"), D("weight")
+        fw = torch.sigmoid(head.fusion_weight.detach())
+
+        def loss_step():
+            outputs = {"heatmaps": hm.clone().requires_grad_(True), "offsets": off.clone().requires_grad_(True),
+                       "variances": var.clone().requires_grad_(True), "fusion_weight": fw}
+            loss_fn(outputs, target, weight, kps, input_size=cfg.input_size, heatmap_size=(cfg.H, cfg.W))["total_loss"].backward()
+
+        def decode_step():
+            with torch.no_grad():
+                head.decode({"heatmaps": hm, "offsets": off, "fusion_weight": fw}, apply_offset=True)
+
+        loss_ms = _time_cuda(loss_step, max(steps, 5), warm=2)
+        t0 = time.perf_counter()
+        decode_step()
+        torch.cuda.synchronize()
+        dec_ms = (time.perf_counter() - t0) * 1e3          # one pass: B*K Python iterations with host round trips
+    n = sample_B * K
+    return {"what": "reference's stock FusionPoseLoss fwd+bwd and head.decode on cuda:0 (ATen kernels, device tensors)",
+            "sample": f"{sample_B} images x {K} heatmaps (per-heatmap cost is batch-independent for the decode loop; the loss's "
+                      f"~200 launches amortise better at larger batches: extrapolation to batch 1024 is labelled as such)",
+            "loss_fwd_bwd_ms": loss_ms, "decode_ms": dec_ms, "step_ms": loss_ms + dec_ms,
+            "value": n / ((loss_ms + dec_ms) * 1e-3), "loss_only_value": n / (loss_ms * 1e-3), "unit": UNIT}
+
+
+def api_step_rates(device, data, B, steps):
+    """The step a user of the patched reference runs: FusionPoseLoss(...) (the module patch_reference() binds) forward +
+    total_loss.backward(), gradients landing in .grad of the three head outputs; float32, and float16 maps under
+    autocast with a GradScaler-style upstream factor.  Targets are built in the kernel (encode_on_device)."""
+    import torch
+    from infantposeestimation_gaussianbias_b200 import FusionPoseLoss
+    loss_fn = FusionPoseLoss(target_sigma=SIGMA)
+    out = {}
+    for tag, cast, scale in (("fp32", lambda t: t, 1.0), ("fp16_autocast", lambda t: t.half(), 65536.0)):
+        leaves = {k: cast(data[src]).detach().clone().requires_grad_(True) for k, src in (("heatmaps", "hm"), ("offsets", "off"), ("variances", "var"))}
+        sc = torch.tensor(scale, device=device)
+
+        def step():
+            for v in leaves.values():
+                v.grad = None
+            with torch.autocast("cuda", enabled=tag != "fp32"):
+                l = loss_fn(leaves, None, data["vis"], data["kps"], input_size=(IN_W, IN_H))["total_loss"]
+            (l * sc).backward()
+
+        ms = _time_cuda(step, steps, warm=4)
+        out[tag] = {"ms_per_step": ms, "value": B * K / (ms * 1e-3), "unit": UNIT, "upstream_scale": scale}
+        del leaves
+        torch.cuda.empty_cache()
+    out["what"] = "FusionPoseLoss.forward (patched module, targets built in the kernel) + (scale * total_loss).backward(), CUDA events"
+    return out
+
+
+def other_workloads(device, ops, N, world, steps=20):
+    """BASELINE configs[2], [3], [4] beside the headline: short resident measurements (no host-buffer leg, no CPU leg),
+    same timing rules (CUDA events, inputs larger than L2 or rotated).  N > 1: the fused preemie step only (configs[3] is
+    the batch-sharded one); the decode workloads do not couple ranks and are N = 1 lines."""
+    import torch
+    from infantposeestimation_gaussianbias_b200.pose_estimator import flip_permutation
+    peak = _peak()[0]
+    res = {}
+    dflags = N.DECODE_REFINE | N.DECODE_APPLY_OFFSET
+    alpha, fw = torch.tensor([0.5], device=device), torch.tensor([0.6224593312018546], device=device)
+
+    def fused(name, B):
+        sp = WORKLOADS[name]
+        data = synth_device_batch(B, device, 99, ops, spec=sp)
+        pairs = ops.pairs_flat([(i, j) for (i, j) in SKELETON if i < sp["K"] and j < sp["K"]])
+        fn = lambda: ops.fusion_loss(data["hm"], data["off"], data["var"], None, data["vis"], data["kps"], None, None, float(sp["IN_W"]),
+                                     float(sp["IN_H"]), LAMBDAS, sp["SIGMA"], sp["SIGMA"], True, pairs, True, True, alpha, fw, 2, dflags)
+        ms = _time_cuda(fn, steps, warm=3)
+        by = 24 * sp["H"] * sp["W"] * B * sp["K"]
+        del data
+        torch.cuda.empty_cache()
+        return {"workload": sp["WORKLOAD"], "batch_per_gpu": B, "ms_per_step": ms, "value": B * sp["K"] / (ms * 1e-3), "unit": UNIT,
+                "algorithmic_GBps": by / (ms * 1e-3) / 1e9, "frac_of_measured_peak": by / (ms * 1e-3) / 1e9 / peak}
+
+    def decode(name, B):
+        sp = WORKLOADS[name]
+        flip = sp["DECODE"] == "flip"
+        in_bytes = (8 if flip else 4) * sp["H"] * sp["W"] * B * sp["K"]
+        n_rot = max(1, min(8, -(-512_000_000 // in_bytes)))
+        perm = flip_permutation(sp["K"], ((1, 2), (3, 4), (5, 6), (7, 8), (9, 10), (11, 12), (13, 14), (15, 16)), device) if flip else None
+        sets = []
+        for r in range(n_rot):
+            d = synth_device_batch(B, device, 7 + 13 * r, ops, with_var=False, spec=sp)
+            if r > 0:
+                d["off"] = sets[0]["off"]
+            if flip:
+                d["flip"] = torch.flip(d["hm"][:, perm.long()], dims=[-1]).contiguous()
+            sets.append(d)
+        it = [0]
+
+        def fn():
+            d = sets[it[0] % n_rot]
+            it[0] += 1
+            ops.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
+
+        ms = _time_cuda(fn, max(steps, 2 * n_rot), warm=max(3, n_rot))
+        del sets
+        torch.cuda.empty_cache()
+        return {"workload": sp["WORKLOAD"], "batch_per_gpu": B, "ms_per_step": ms, "value": B * sp["K"] / (ms * 1e-3), "unit": UNIT,
+                "algorithmic_GBps": in_bytes / (ms * 1e-3) / 1e9, "frac_of_measured_peak": in_bytes / (ms * 1e-3) / 1e9 / peak,
+                "input_sets_rotated": n_rot}
+
+    res["configs[3] preemie fused step"] = fused("preemie", 1024)
+    if world == 1:
+        res["configs[2] decode_flip"] = decode("decode_flip", 4096)
+        res["configs[4] decode sweep"] = [decode("decode", b) for b in (256, 1024, 4096, 16384)]
+    return res
+
+
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -347,6 +547,7 @@ def run_b200(args):
         res = step()
     t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launched0 = N.lib().gbcodec_launch_count()
     t_a.record()
     for i in range(args.steps):
         if i % 4 == 0:
@@ -355,6 +556,7 @@ def run_b200(args):
             N.lib().gbcodec_profile_loss_kernel(None, None)
         res = step()
     t_b.record()
+    launched = int(N.lib().gbcodec_launch_count() - launched0)      # this library's kernels, counted at their launch sites
     barrier()
     N.lib().gbcodec_profile_loss_kernel(None, None)
     ms = torch.tensor([t_a.elapsed_time(t_b)], device=device, dtype=torch.float64)
@@ -402,17 +604,28 @@ def run_b200(args):
         nt = peer.timeouts()
         if nt:
             raise SystemExit(f"bench.py: rank {rank} gave up waiting for a peer mailbox {nt} time(s)")
+    # ---- the other BASELINE configurations, the API-level step, the reference's own GPU mode ---------------------
+    others = api = aten = None
+    if args.config == "w32" and not args.no_extras:
+        others = other_workloads(device, ops, N, world)
+        if world > 1:
+            # every rank measured its shard; report the slowest rank's time and the job's aggregate rate
+            for k, v in others.items():
+                t = torch.tensor([v["ms_per_step"]], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                v["ms_per_step"] = float(t.item())
+                v["value"] = world * v["batch_per_gpu"] * WORKLOADS["preemie"]["K"] / (v["ms_per_step"] * 1e-3)
+                v["note"] = f"{world} ranks, one shard of {v['batch_per_gpu']} images each, no exchange inside this measurement (normalisers local)"
+        if world == 1:
+            api = api_step_rates(device, data, B, max(10, min(args.steps, 30)))
+            aten = aten_cuda_baseline(device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = _peak()
     achieved = B * K * BYTES_PER_HM / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": f"{TILE_KERNEL} (fused step: on-the-fly target + six-term loss fwd/bwd + decode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_launches_timed": len(sampled),
@@ -426,8 +639,8 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu and world == 1:                 # the CPU baseline is an N=1 figure (all host cores, nothing else running)
-        v, cores, times = cpu_step_rate(sample_B=32, min_seconds=10.0, max_reps=400)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        v, cores, times, kind = cpu_step_rate(sample_B=32, min_seconds=10.0, max_reps=400)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"32 images x {K} heatmaps of the same workload, median of {len(times)} passes ({sum(times):.1f} s of CPU work)"}
 
     line = {
@@ -437,8 +650,9 @@ def run_b200(args):
         "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": exchange, "numa_node_rank0": numa,
                    "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "gpu_launches": launched, "gpu_launches_per_step": launched / args.steps, "clocks": clocks,
         "total_loss": float(res[0][6].item()),
+        "aten_cuda_baseline": aten, "api_step": api, "other_workloads": others,
     }
     print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
@@ -451,29 +665,56 @@ def decode_workload_name(B):
     return f"{WORKLOAD}, batch {B} per GPU"
 
 
-def cpu_decode_rate(sample_B: int, min_seconds: float, max_reps: int):
-    """Oracle port of the reference decode (per-tile window loop of LocalGaussianRefinement, fusion_head.py:84-128,
-    after the flip-test average when the workload has one) on the host cores."""
+def reference_decode_callable(sample_B):
+    """-> (callable, kind): the reference's decode of `sample_B` images on the host — head.decode (fusion_head.py:309-365)
+    after the flip-test average written as PoseEstimator.inference writes it (pose_estimator.py:303-319: flip back, swap
+    the left/right channels pair by pair, average) when the workload has one; the oracle port if the tree is absent."""
     import torch
-    from oracle import heatmap_codec as oc
     from tests import synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = synth.CONFIGS[SYNTH_CONFIG]
     batch = synth.make_batch(cfg, seed=0, B=sample_B)
     hm, off = torch.from_numpy(batch["heatmaps"]), torch.from_numpy(batch["offsets"])
     flipped = torch.from_numpy(batch["heatmaps_flip"]) if DECODE == "flip" else None
+    ref = _reference_tree()
+    if ref is None:
+        from oracle import heatmap_codec as oc
+        return (lambda: oc.fusion_decode(hm, off, 0.5, 0.6224593312018546, True, True, 2, heatmaps_of_flipped_input=flipped, loop=True)), "port"
+    ref.__enter__()
+    head = ref.fusion_head.HeatmapRegressionHead(32, num_keypoints=cfg.K)
+    fw = torch.sigmoid(head.fusion_weight.detach())
+    flip_pairs = ref.config.get_config().data.flip_pairs
+
+    def step():
+        with torch.no_grad():
+            h = hm
+            if flipped is not None:
+                back = torch.flip(flipped, dims=[-1])
+                new = back.clone()
+                for a, b in flip_pairs:
+                    new[:, a] = back[:, b]
+                    new[:, b] = back[:, a]
+                h = (hm + new) / 2
+            return head.decode({"heatmaps": h, "offsets": off, "fusion_weight": fw}, apply_offset=True)
+
+    return step, "reference"
+
+
+def cpu_decode_rate(sample_B: int, min_seconds: float, max_reps: int):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    call, kind = reference_decode_callable(sample_B)
 
     def one():
         t0 = time.perf_counter()
-        oc.fusion_decode(hm, off, 0.5, 0.6224593312018546, True, True, 2, heatmaps_of_flipped_input=flipped, loop=True)
+        call()
         return time.perf_counter() - t0
 
     one()
     times, t_start = [], time.perf_counter()
     while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
         times.append(one())
-    return sample_B * K / statistics.median(times), cores, times
+    return sample_B * K / statistics.median(times), cores, times, kind
 
 
 def run_reference_decode(args):
@@ -481,15 +722,9 @@ def run_reference_decode(args):
         return 0
     sample_B = 64
     import torch
-    from oracle import heatmap_codec as oc
-    from tests import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.CONFIGS[SYNTH_CONFIG]
-    batch = synth.make_batch(cfg, seed=0, B=sample_B)
-    hm, off = torch.from_numpy(batch["heatmaps"]), torch.from_numpy(batch["offsets"])
-    flipped = torch.from_numpy(batch["heatmaps_flip"]) if DECODE == "flip" else None
-    call = lambda: oc.fusion_decode(hm, off, 0.5, 0.6224593312018546, True, True, 2, heatmaps_of_flipped_input=flipped, loop=True)
+    call, kind = reference_decode_callable(sample_B)
     for _ in range(max(1, min(args.warmup, 3))):
         call()
     t0 = time.perf_counter()
@@ -503,7 +738,7 @@ def run_reference_decode(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": decode_workload_name(args.batch), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -573,10 +808,12 @@ def run_decode_b200(args):
         res = step(i)
     t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launched0 = N.lib().gbcodec_launch_count()
     t_a.record()
     for i in range(args.steps):
         res = step(i)
     t_b.record()
+    launched = int(N.lib().gbcodec_launch_count() - launched0)
     barrier()
     ms = torch.tensor([t_a.elapsed_time(t_b)], device=device, dtype=torch.float64)
     if world > 1:
@@ -620,11 +857,8 @@ def run_decode_b200(args):
             dist.destroy_process_group()
         return 0
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy: a 1:1 read:write mix; read-only streams run above it)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = _peak()
+    peak_src += " — a 1:1 read:write mix; read-only streams run above it"
     achieved = in_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": f"{TILE_KERNEL} (soft-argmax + window refinement + offset taps{', flip average in the load' if flip else ''})",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -632,8 +866,8 @@ def run_decode_b200(args):
                 "frac_of_nominal_8TBps": achieved / 8000.0}
     cpu = None
     if not args.no_cpu and world == 1:
-        v, cores, times = cpu_decode_rate(sample_B=32, min_seconds=10.0, max_reps=400)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        v, cores, times, kind = cpu_decode_rate(sample_B=32, min_seconds=10.0, max_reps=400)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"32 images x {K} heatmaps of the same workload, median of {len(times)} passes ({sum(times):.1f} s of CPU work)"}
     l2 = (f"heatmaps {in_bytes / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed" if n_rot == 1 else
           f"heatmaps {in_bytes / 1e6:.0f} MB per step: {n_rot} input sets ({n_rot * in_bytes / 1e6:.0f} MB) visited in rotation, so a launch never finds its heatmaps in the 126 MB L2")
@@ -644,7 +878,7 @@ def run_decode_b200(args):
         "config": {"workload": decode_workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "exchange": "none (shards are independent)", "numa_node_rank0": numa, "l2": l2},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": args.steps, "clocks": clocks,
+        "gpu_launches": launched, "clocks": clocks,
     }
     print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
@@ -675,6 +909,7 @@ def main():
     ap.add_argument("--config", default="w32", choices=sorted(WORKLOADS), help="fused-step workload (default: BASELINE configs[1])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_workloads / api_step / aten_cuda_baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     select_workload(args.config)

@@ -44,7 +44,8 @@ typedef enum gbcodec_status {
     GBCODEC_ERR_UNALIGNED = -3,      /* a tensor pointer is not 16-byte aligned              */
     GBCODEC_ERR_BAD_ARGUMENT = -4,   /* bad mode / flags / skeleton / sigma                  */
     GBCODEC_ERR_WORKSPACE = -5,      /* workspace missing or too small                       */
-    GBCODEC_ERR_CUDA = -6            /* a CUDA runtime call failed (see gbcodec_last_error)  */
+    GBCODEC_ERR_CUDA = -6,           /* a CUDA runtime call failed (see gbcodec_last_error)  */
+    GBCODEC_ERR_PEER_TIMEOUT = -7    /* an earlier sharded call gave up waiting for a peer: its results were NaN */
 } gbcodec_status;
 
 int gbcodec_abi_version(void);
@@ -221,14 +222,19 @@ int gbcodec_fusion_loss_backward_f32(const gbcodec_loss_desc* desc,
  *   gbcodec_peer_connect  maps the peers' mailboxes; all_handles = world x 64 bytes in rank order
  *                         (gathered by the host program, e.g. torch.distributed.all_gather)
  *   gbcodec_peer_destroy
- * Every rank must make the same sequence of sharded calls.  A rank that waits for a dead peer
- * gives up after a few seconds (bounded spin) and counts it: gbcodec_peer_status (synchronises).
+ * Every rank must make the same sequence of sharded calls.  A rank that waits for a peer longer than the
+ * time-out (gbcodec_peer_set_timeout, default 120 s — a peer that saves a checkpoint or evaluates is late, not
+ * dead) gives up: the kernel writes NaN into the normalisers / losses it could not complete (nothing is ever
+ * computed from a stale mailbox slot), raises a sticky flag in mapped host memory, and the NEXT sharded call of
+ * that rank returns GBCODEC_ERR_PEER_TIMEOUT without launching anything.  gbcodec_peer_status reads the count
+ * (synchronises).  A call that fails its argument checks does not advance the exchange's sequence number.
  */
 #define GBCODEC_PEER_HANDLE_BYTES 64
 #define GBCODEC_MAX_PEERS 16
 int gbcodec_peer_create(int rank, int world, void** ctx_out, unsigned char* handle_out);
 int gbcodec_peer_connect(void* ctx, const unsigned char* all_handles);
 int gbcodec_peer_status(void* ctx, int* h_timeouts);
+int gbcodec_peer_set_timeout(void* ctx, double seconds);
 int gbcodec_peer_destroy(void* ctx);
 
 /* gbcodec_fusion_step_f32 for a rank of a sharded job.  d_coords/d_scores may both be NULL (loss

@@ -36,7 +36,7 @@ EXPORTS = (
     "gbcodec_profile_loss_kernel",
     "gbcodec_encode_mode_f32", "gbcodec_postprocess_f32", "gbcodec_coords_to_image_f32",
     "gbcodec_combined_workspace_bytes", "gbcodec_combined_loss_f32", "gbcodec_combined_loss_backward_f32",
-    "gbcodec_peer_create", "gbcodec_peer_connect", "gbcodec_peer_status", "gbcodec_peer_destroy",
+    "gbcodec_peer_create", "gbcodec_peer_connect", "gbcodec_peer_status", "gbcodec_peer_destroy", "gbcodec_peer_set_timeout",
     "gbcodec_fusion_step_sharded_f32", "gbcodec_heatmap_step_f32",
     "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16", "gbcodec_fusion_step_vmean_f32",
 )
@@ -135,6 +135,7 @@ def _declare(lib):
     lib.gbcodec_peer_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
     lib.gbcodec_peer_connect.argtypes = [_P, C.c_char_p]
     lib.gbcodec_peer_status.argtypes = [_P, C.POINTER(C.c_int)]
+    lib.gbcodec_peer_set_timeout.argtypes = [_P, C.c_double]
     lib.gbcodec_peer_destroy.argtypes = [_P]
     lib.gbcodec_fusion_step_sharded_f32.argtypes = [C.POINTER(LossDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                                     f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_uint,

@@ -54,6 +54,7 @@ int peer_create(int, int, void**, unsigned char*);
 int peer_connect(void*, const unsigned char*);
 int peer_status(void*, int*);
 int peer_destroy(void*);
+int peer_set_timeout(void*, double);
 int fusion_loss_backward(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*,
                          const float*, const float*, const float*, const float*, float*, float*, float*, void*, size_t,
                          cudaStream_t, int, int, float*, int, int);
@@ -100,6 +101,7 @@ const char* gbcodec_status_string(int status) {
         case GBCODEC_ERR_BAD_ARGUMENT: return "bad argument";
         case GBCODEC_ERR_WORKSPACE: return "workspace missing or too small";
         case GBCODEC_ERR_CUDA: return "CUDA error";
+        case GBCODEC_ERR_PEER_TIMEOUT: return "peer exchange timed out";
         default: return "unknown status";
     }
 }
@@ -279,6 +281,7 @@ int gbcodec_peer_create(int rank, int world, void** ctx_out, unsigned char* hand
 int gbcodec_peer_connect(void* ctx, const unsigned char* all_handles) { return peer_connect(ctx, all_handles); }
 int gbcodec_peer_status(void* ctx, int* h_timeouts) { return peer_status(ctx, h_timeouts); }
 int gbcodec_peer_destroy(void* ctx) { return peer_destroy(ctx); }
+int gbcodec_peer_set_timeout(void* ctx, double seconds) { return peer_set_timeout(ctx, seconds); }
 
 int gbcodec_fusion_step_vmean_f32(const gbcodec_loss_desc* desc,
                             const float* d_hm, const float* d_off, const float* d_var_mean, const float* d_target,

@@ -117,9 +117,9 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
         __threadfence_system();
         st_release_sys(&dst->den_seq[q][peer.rank], peer.seq);
         PeerMail* mine = peer.mail[peer.rank];
-        wait_seq(&mine->den_seq[q][r], peer.seq, &mine->timeouts);
-        gath[r][0] = mine->den[q][r][0];
-        gath[r][1] = mine->den[q][r][1];
+        const bool ok = wait_seq(&mine->den_seq[q][r], peer.seq, peer, &mine->timeouts);
+        gath[r][0] = ok ? mine->den[q][r][0] : (double)NAN;
+        gath[r][1] = ok ? mine->den[q][r][1] : (double)NAN;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -558,8 +558,8 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
         __threadfence_system();
         st_release_sys(&dst->loss_seq[pq][peer.rank], peer.seq);
         PeerMail* mine = peer.mail[peer.rank];
-        wait_seq(&mine->loss_seq[pq][r], peer.seq, &mine->timeouts);
-        for (int q = 0; q < 6; ++q) gl[r][q] = mine->loss[pq][r][q];
+        const bool ok = wait_seq(&mine->loss_seq[pq][r], peer.seq, peer, &mine->timeouts);
+        for (int q = 0; q < 6; ++q) gl[r][q] = ok ? mine->loss[pq][r][q] : NAN;
     }
     __syncthreads();
     if (threadIdx.x < 6) {
@@ -759,8 +759,9 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
         PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
         if (!pc->connected) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: the peer context is not connected");
         if (denoms) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: d_denoms and a peer context exclude each other");
-        pc->view.seq += 1;
-        peer = pc->view;
+        if (pc->h_failed && *reinterpret_cast<volatile unsigned int*>(pc->h_failed))
+            return fail(GBCODEC_ERR_PEER_TIMEOUT, "sharded step: an earlier call of rank %d gave up waiting for a peer (its normalisers / losses were NaN); "
+                                                  "the exchange is out of step — tear the job down", pc->view.rank);
     }
     if (!losses7) return fail(GBCODEC_ERR_NULL_POINTER, "loss: d_losses7 is NULL");
     const bool grads = ghm || goff || gvar;
@@ -776,6 +777,13 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     LossParams P;
     st = make_params(d, &P);
     if (st) return st;
+    if (peer_ctx) {
+        // every check has passed: only now does this call take its place in the exchange's sequence (a call that
+        // fails validation on one rank must not put that rank one step ahead of the others for the rest of the job)
+        PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
+        pc->view.seq += 1;
+        peer = pc->view;
+    }
     const WsLayout L = ws_carve(ws, P.B, P.K);
     st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, peer, denoms_out);
     if (st) return st;

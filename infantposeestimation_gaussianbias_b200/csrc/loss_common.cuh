@@ -121,12 +121,15 @@ struct PeerView {
     PeerMail* mail[GBCODEC_MAX_PEERS];                   // mail[rank] is the local one
     int rank, world;
     unsigned long long seq;
+    unsigned long long timeout_ns;                       // how long a kernel waits for a peer before it gives up
+    unsigned int* failed;                                // sticky flag in mapped host memory (device alias)
 };
 struct PeerCtx {
     PeerView view;
     cudaIpcMemHandle_t handle;
     int connected;
     int device;
+    unsigned int* h_failed;                              // the same flag, host side: read at the entry of every sharded call
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -136,13 +139,23 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Wait until a peer has published `seq`.  Bounded (a few seconds): a dead peer must not hang the GPU.
-__device__ __forceinline__ bool wait_seq(const unsigned long long* flag, unsigned long long seq, unsigned int* timeouts) {
-    for (unsigned it = 0; it < (1u << 22); ++it) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until a peer has published `seq`.  Bounded by the context's time-out (a dead peer must not hang the GPU); on
+// expiry the sticky flag is raised and the caller poisons what it could not complete with NaN — a mailbox slot that
+// was not published for this call holds the values of two calls ago and must never be used.
+__device__ __forceinline__ bool wait_seq(const unsigned long long* flag, unsigned long long seq, const PeerView& peer, unsigned int* timeouts) {
+    const unsigned long long t0 = global_ns();
+    for (unsigned it = 0;; ++it) {
         if (ld_acquire_sys(flag) == seq) return true;
         __nanosleep(200);
+        if ((it & 63u) == 63u && global_ns() - t0 > peer.timeout_ns) break;
     }
     atomicAdd(timeouts, 1u);
+    if (peer.failed) { *reinterpret_cast<volatile unsigned int*>(peer.failed) = 1u; __threadfence_system(); }
     return false;
 }
 

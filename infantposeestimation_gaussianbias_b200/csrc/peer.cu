@@ -22,11 +22,15 @@ int peer_create(int rank, int world, void** ctx_out, unsigned char* handle_out) 
     pc->view.rank = rank; pc->view.world = world;
     cudaError_t e = cudaGetDevice(&pc->device);
     PeerMail* mail = nullptr;
+    pc->view.timeout_ns = 120ull * 1000000000ull;
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pc->h_failed), sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *pc->h_failed = 0u; e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&pc->view.failed), pc->h_failed, 0); }
     if (e == cudaSuccess) e = cudaMalloc(&mail, sizeof(PeerMail));
     if (e == cudaSuccess) e = cudaMemset(mail, 0, sizeof(PeerMail));
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&pc->handle, mail);
     if (e != cudaSuccess) {
         if (mail) cudaFree(mail);
+        if (pc->h_failed) cudaFreeHost(pc->h_failed);
         delete pc;
         return fail(GBCODEC_ERR_CUDA, "peer_create: %s", cudaGetErrorString(e));
     }
@@ -64,9 +68,17 @@ int peer_status(void* ctx, int* timeouts) {
     return GBCODEC_OK;
 }
 
+int peer_set_timeout(void* ctx, double seconds) {
+    if (!ctx) return fail(GBCODEC_ERR_NULL_POINTER, "peer_set_timeout: NULL context");
+    if (!(seconds > 0.0) || seconds > 86400.0) return fail(GBCODEC_ERR_BAD_ARGUMENT, "peer_set_timeout: %g s", seconds);
+    reinterpret_cast<PeerCtx*>(ctx)->view.timeout_ns = (unsigned long long)(seconds * 1e9);
+    return GBCODEC_OK;
+}
+
 int peer_destroy(void* ctx) {
     if (!ctx) return GBCODEC_OK;
     PeerCtx* pc = reinterpret_cast<PeerCtx*>(ctx);
+    if (pc->h_failed) cudaFreeHost(pc->h_failed);
     for (int r = 0; r < pc->view.world; ++r) {
         if (!pc->view.mail[r]) continue;
         if (r == pc->view.rank) cudaFree(pc->view.mail[r]);

@@ -57,6 +57,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
                  "DONE_%=:\n"
                  "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// waits that are long by design (the scalar warp between tiles, the producer for a free tile buffer): give the issue
+// slots to the compute warps — polling took 15 % of the kernel's instructions
+#ifndef PIPE_SLEEP
+#define PIPE_SLEEP 1
+#endif
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, unsigned parity) {
+#if PIPE_SLEEP == 1
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(400);
+    }
+#elif PIPE_SLEEP == 2
+    asm volatile("{\n"
+                 " .reg .pred p;\n"
+                 "WAITI_%=:\n"
+                 " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+                 " @p bra DONEI_%=;\n"
+                 " bra WAITI_%=;\n"
+                 "DONEI_%=:\n"
+                 "}" :: "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -234,7 +261,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
             // tile j + 1 into the buffer tile j - 2 has left
             const unsigned s1 = (j + 1) % 3u;
-            if (j >= 2) { mbar_wait(hempty + s1, (ph_empty >> s1) & 1u); ph_empty ^= 1u << s1; }
+            if (j >= 2) { mbar_wait_idle(hempty + s1, (ph_empty >> s1) & 1u); ph_empty ^= 1u << s1; }
             cur = nxt; nxt = nxt2;
             w_c = w_n; pk_c = pk_n; pj_c = pj_n;
             if (cur >= (unsigned)tiles) {
@@ -281,7 +308,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         unsigned ph_full = 0, np2 = 0;
         for (unsigned i = 0;; ++i) {
             const unsigned s = i % 3u, b = i & 1u;
-            mbar_wait(hfull + s, (ph_full >> s) & 1u); ph_full ^= 1u << s;
+            mbar_wait_idle(hfull + s, (ph_full >> s) & 1u); ph_full ^= 1u << s;
             const int tile = tids[s];
             if (tile < 0) break;
             const TileDesc* dsc = Db + s;
@@ -298,7 +325,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             if (heavy) tapv = __ldg(off_tile + (lane >> 4) * N + (wy0 + ((lane >> 2) & 3)) * W + wx0 + (lane & 3));
 
             // ---- the warps' partial sums of tile i --------------------------------------------------------------
-            mbar_wait(sfull + b, (i >> 1) & 1u);
+            mbar_wait_idle(sfull + b, (i >> 1) & 1u);
             const float* redb = red + b * (NW * 16);
             const float* red2b = red2 + b * (NW * 4);
             const float* redMb = redM + b * (NW * 2);

@@ -10,7 +10,8 @@ Chunks are shards in the sense of sharded.py: the two batch-global normalisers
 are computed first from the (tiny) keypoint/visibility arrays of the whole
 batch, every chunk is then normalised by them, and the per-chunk loss vectors
 simply add up — so the result equals one pass over the whole batch.
-Gradients stay on the device (their consumer, the backbone backward, is there).
+Gradients stay on the device (their consumer, the backbone backward, is there): every chunk writes its slice of three
+persistent (B, ...) gradient tensors (`grad_hm`, `grad_off`, `grad_var`).
 """
 from __future__ import annotations
 
@@ -49,13 +50,23 @@ class HostCodecStep:
         self.scores_d = torch.empty((B, K), dtype=f, device=d)
         self.alpha = torch.tensor([0.5], dtype=f, device=d)
         self.fw = torch.tensor([0.6224593312018546], dtype=f, device=d)
-        self.grads = None      # last chunk's gradient tensors (device)
+        # gradients of the WHOLE batch, written chunk by chunk (with_grads=False: the loss / decode only, nothing stored)
+        self.grad_hm = torch.empty((B, K, H, W), dtype=f, device=d) if with_grads else None
+        self.grad_off = torch.empty((B, K, 2, H, W), dtype=f, device=d) if with_grads else None
+        self.grad_var = torch.empty((B, K, H, W), dtype=f, device=d) if with_grads else None
+        self.chunk_losses = torch.empty((2, 7), dtype=f, device=d)
+        self.ws = [torch.empty(N.lib().gbcodec_loss_workspace_bytes(C, K, H, W), dtype=torch.uint8, device=d) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=d)
         self.staged = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         self.out_h = dict(losses=torch.empty(7, dtype=f).pin_memory(), coords=torch.empty((B, K, 2), dtype=f).pin_memory(),
                           scores=torch.empty((B, K), dtype=f).pin_memory())
         self.launches = 0
+
+    @property
+    def grads(self):
+        """(grad_hm, grad_off, grad_var) of the whole batch on the device, or None with with_grads=False."""
+        return (self.grad_hm, self.grad_off, self.grad_var) if self.with_grads else None
 
     @property
     def h2d_bytes(self) -> int:
@@ -75,11 +86,11 @@ class HostCodecStep:
         {losses (7,), coords (B,K,2), scores (B,K)}; synchronises before returning."""
         B, K, H, W, C = self.B, self.K, self.H, self.W, self.chunk
         main = torch.cuda.current_stream(self.device)
+        launched0 = N.lib().gbcodec_launch_count()
         self.kps_d.copy_(kps_h, non_blocking=True)
         self.vis_d.copy_(vis_h.reshape(B, K), non_blocking=True)
         den = ops.loss_denominators(self.vis_d, self.kps_d, False, H, W, self.in_w, self.in_h, self.sigma, self.pairs)
         self.losses_d.zero_()
-        self.launches = 2
         self.copy_stream.wait_stream(main)
         nchunk = (B + C - 1) // C
         for c in range(nchunk):
@@ -96,19 +107,18 @@ class HostCodecStep:
                 self.staged[c & 1].record(self.copy_stream)
             main.wait_event(self.staged[c & 1])
             off_c = s["off"][:n] if self.stage_offsets else off_h[lo:hi]
-            res = ops.fusion_loss(s["hm"][:n], off_c, s["var"][:n], None, self.vis_d[lo:hi], self.kps_d[lo:hi],
-                                  den, None, self.in_w, self.in_h, self.lambdas, self.sigma, self.sigma, True, self.pairs,
-                                  self.with_grads, True, self.alpha, self.fw, 2, N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)
+            grads = (self.grad_hm[lo:hi], self.grad_off[lo:hi], self.grad_var[lo:hi]) if self.with_grads else None
+            ops.fusion_step_into(s["hm"][:n], off_c, s["var"][:n], self.vis_d[lo:hi], self.kps_d[lo:hi], den,
+                                 self.in_w, self.in_h, self.lambdas, self.sigma, self.sigma, True, self.pairs, self.alpha, self.fw, 2,
+                                 N.DECODE_REFINE | N.DECODE_APPLY_OFFSET, self.chunk_losses[c & 1], grads,
+                                 self.coords_d[lo:hi], self.scores_d[lo:hi], self.ws[c & 1])
             self.consumed[c & 1].record(main)
-            self.losses_d += res[0]
-            self.coords_d[lo:hi] = res[4]
-            self.scores_d[lo:hi] = res[5]
-            self.grads = res[1:4]
-            self.launches += 3
+            self.losses_d += self.chunk_losses[c & 1]
         self.out_h["losses"].copy_(self.losses_d, non_blocking=True)
         self.out_h["coords"].copy_(self.coords_d, non_blocking=True)
         self.out_h["scores"].copy_(self.scores_d, non_blocking=True)
         main.synchronize()
+        self.launches = int(N.lib().gbcodec_launch_count() - launched0)      # kernels of this library, counted where they are launched
         return self.out_h
 
 
@@ -167,7 +177,7 @@ class HostDecode:
             raise RuntimeError("gbcodec: HostDecode(apply_offset=True) needs the offset maps")
         main = torch.cuda.current_stream(self.device)
         self.copy_stream.wait_stream(main)
-        self.launches = 0
+        launched0 = N.lib().gbcodec_launch_count()
         for c in range((B + C - 1) // C):
             lo, hi = c * C, min(B, (c + 1) * C)
             n = hi - lo
@@ -187,8 +197,8 @@ class HostDecode:
             self.consumed[c & 1].record(main)
             self.coords_d[lo:hi] = coords
             self.scores_d[lo:hi] = scores
-            self.launches += 1
         self.out_h["coords"].copy_(self.coords_d, non_blocking=True)
         self.out_h["scores"].copy_(self.scores_d, non_blocking=True)
         main.synchronize()
+        self.launches = int(N.lib().gbcodec_launch_count() - launched0)
         return self.out_h

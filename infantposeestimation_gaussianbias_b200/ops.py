@@ -242,6 +242,39 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
     return losses, ghm, goff, gvar, coords, scores, den_out, ws
 
 
+def fusion_step_into(hm: Tensor, off: Tensor, var: Optional[Tensor], weight: Tensor, gt_kps: Tensor, denoms: Optional[Tensor],
+                     in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
+                     use_target_weight: bool, pairs: List[int], alpha_param: Tensor, fusion_weight: Tensor, radius: int,
+                     decode_flags: int, losses_out: Tensor, grads_out: Optional[Tuple[Tensor, Tensor, Optional[Tensor]]],
+                     coords_out: Tensor, scores_out: Tensor, workspace: Tensor) -> None:
+    """gbcodec_fusion_step_f32 writing into buffers the caller owns (no allocation, no autograd): the chunked host-buffer
+    pipeline (host_step.HostCodecStep) hands in slices of its persistent (B, ...) result and gradient tensors, so every
+    chunk's gradients stay on the device for the consumer.  Targets are generated on the fly; all outputs must be
+    contiguous float32 CUDA tensors of the shapes gbcodec_fusion_step_f32 documents."""
+    B, K, H, W = hm.shape
+    hm = _cuda_f32("heatmaps", hm)
+    off = _device_readable_f32("offsets", off, (B, K, 2, H, W))
+    if var is not None:
+        var = _cuda_f32("variances", var, (B, K, H, W))
+    for name, t, shape in (("losses_out", losses_out, (7,)), ("coords_out", coords_out, (B, K, 2)), ("scores_out", scores_out, (B, K))):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape):
+            raise RuntimeError(f"gbcodec: `{name}` must be a contiguous float32 CUDA tensor of shape {shape}")
+    ghm = goff = gvar = None
+    if grads_out is not None:
+        ghm, goff, gvar = grads_out
+        for name, t, shape in (("grad_hm", ghm, (B, K, H, W)), ("grad_off", goff, (B, K, 2, H, W)), ("grad_var", gvar, (B, K, H, W))):
+            if t is None and name == "grad_var" and var is None:
+                continue
+            if t is None or not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape):
+                raise RuntimeError(f"gbcodec: `{name}` must be a contiguous float32 CUDA tensor of shape {shape}")
+    desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().gbcodec_fusion_step_f32(
+            desc, _ptr(hm), _ptr(off), _ptr(var), None, _ptr(weight.reshape(B, K)), _ptr(gt_kps), _ptr(denoms), None,
+            _ptr(losses_out), _ptr(ghm), _ptr(goff), _ptr(gvar), _ptr(alpha_param), _ptr(fusion_weight), radius, decode_flags,
+            _ptr(coords_out), _ptr(scores_out), _ptr(workspace), workspace.numel(), _stream(hm)), "fusion_step")
+
+
 @fusion_loss.register_fake
 def _(hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
       use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx=0):

@@ -42,7 +42,10 @@ class PeerExchange:
     every other rank of `group` through CUDA IPC.  Needs one process per GPU on one NVLink / NVSwitch
     domain and an initialised process group (any backend) for the handle exchange."""
 
-    def __init__(self, group=None, device: Optional[torch.device] = None):
+    def __init__(self, group=None, device: Optional[torch.device] = None, timeout_s: Optional[float] = None):
+        """timeout_s: how long a kernel waits for a peer's scalars before it gives up (default 120 s: a rank that saves
+        a checkpoint or runs a rank-local evaluation is late, not dead).  On expiry the step's normalisers / losses are
+        NaN and the next sharded call on this rank raises GbcodecError (GBCODEC_ERR_PEER_TIMEOUT)."""
         import ctypes as C
         from . import _native as N
         if not (dist.is_available() and dist.is_initialized()):
@@ -77,6 +80,12 @@ class PeerExchange:
             self.close()
             raise RuntimeError(f"PeerExchange: peer-memory set-up failed on at least one rank"
                                f"{' (here: ' + str(error) + ')' if error is not None else ''}")
+        if timeout_s is not None:
+            self.set_timeout(timeout_s)
+
+    def set_timeout(self, seconds: float) -> None:
+        from . import _native as N
+        N.check(self._lib.gbcodec_peer_set_timeout(self._ctx, float(seconds)), "peer_set_timeout")
 
     @property
     def address(self) -> int:

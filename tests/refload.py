@@ -20,6 +20,8 @@ _TOP = ("models", "utils", "datasets", "data", "configs")
 
 
 def find() -> Optional[str]:
+    if os.environ.get("GBCODEC_NO_REFERENCE"):          # tests of the fall-back paths
+        return None
     for cand in (os.environ.get("GBCODEC_REF"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
         if cand and os.path.isdir(os.path.join(cand, "models")) and os.path.isfile(os.path.join(cand, "models", "fusion_head.py")):
             return cand

@@ -109,6 +109,61 @@ def test_two_ranks_exchange_through_peer_mailboxes():
         assert got[0][1][step][0] == got[1][1][step][0]
 
 
+def _late_peer_worker(rank, world, port, q):
+    """rank 1 connects and then never calls: rank 0's kernels must give up after the time-out, poison the results and
+    make the next call fail loudly (a late peer used to mean stale normalisers, silently)."""
+    import time
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import infantposeestimation_gaussianbias_b200 as pkg
+        pkg.load()
+        from infantposeestimation_gaussianbias_b200 import _native as N
+        from infantposeestimation_gaussianbias_b200.sharded import PeerExchange, ShardedFusionPoseLoss
+        cfg = synth.CONFIGS["w32_256x192"]
+        peer = PeerExchange(device=dev, timeout_s=1.0)
+        if rank == 0:
+            loss_fn = ShardedFusionPoseLoss(target_sigma=cfg.sigma, peer=peer)
+            batch = synth.make_batch(cfg, seed=7, B=2)
+            D = lambda k: torch.from_numpy(batch[k].copy()).to(dev)
+            outputs = {"heatmaps": D("heatmaps"), "offsets": D("offsets"), "variances": D("variances")}
+            t0 = time.time()
+            out = loss_fn(outputs, None, D("vis"), D("kps"), input_size=cfg.input_size)
+            total = float(out["total_loss"])                 # synchronises
+            waited = time.time() - t0
+            second = "no error"
+            try:
+                loss_fn(outputs, None, D("vis"), D("kps"), input_size=cfg.input_size)
+            except N.GbcodecError as e:
+                second = f"status {e.status}"
+            q.put((total, waited, peer.timeouts(), second, N.lib().gbcodec_status_string(-7).decode()))
+        dist.barrier()
+        peer.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_a_late_peer_poisons_the_step_and_fails_the_next_call():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_late_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    total, waited, timeouts, second, name = q.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert np.isnan(total), "a step whose peers never answered must not return numbers"
+    assert 0.9 <= waited < 60.0 and timeouts >= 1
+    assert second == "status -7" and "peer" in name
+
+
 def test_world_of_one_is_the_plain_step():
     """A peer context of a 1-rank job changes nothing."""
     import ctypes as C
