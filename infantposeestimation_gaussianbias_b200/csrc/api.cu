@@ -49,7 +49,9 @@ size_t loss_workspace_bytes(int B, int K);
 int loss_denominators(const gbcodec_loss_desc*, const float*, const float*, int, float*, void*, size_t, cudaStream_t);
 int fusion_loss(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
                 const float*, const float*, float*, float*, float*, float*,
-                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*, int, const float*, float*);
+                const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*, int, const float*, float*, int = 0);
+int peer_denominators(const gbcodec_loss_desc*, const float*, const float*, int, float*, void*, size_t, void*, cudaStream_t);
+int peer_collect_losses(void*, int, float*, cudaStream_t);
 int peer_create(int, int, void**, unsigned char*);
 int peer_connect(void*, const unsigned char*);
 int peer_status(void*, int*);
@@ -268,13 +270,23 @@ int gbcodec_fusion_step_sharded_f32(const gbcodec_loss_desc* desc,
                             float* d_losses7, float* d_grad_hm, float* d_grad_off, float* d_grad_var,
                             const float* d_alpha_param, const float* d_fusion_weight, int local_radius, unsigned decode_flags,
                             float* d_coords, float* d_scores, float* d_denoms_out,
+                            const float* d_denoms_global, int defer_losses,
                             void* d_workspace, size_t workspace_bytes, void* peer_ctx, void* stream) {
     if (!peer_ctx) return fail(GBCODEC_ERR_NULL_POINTER, "sharded step: peer_ctx is NULL");
     if ((d_coords == nullptr) != (d_scores == nullptr)) return fail(GBCODEC_ERR_NULL_POINTER, "sharded step: give d_coords and d_scores or neither");
-    return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, nullptr, d_grad_scale,
+    return fusion_loss(desc, d_hm, d_off, d_var, d_target, d_weight, d_gt_kps, d_denoms_global, d_grad_scale,
                        d_losses7, d_grad_hm, d_grad_off, d_grad_var,
                        d_alpha_param, d_fusion_weight, local_radius, decode_flags, d_coords, d_scores,
-                       d_workspace, workspace_bytes, (cudaStream_t)stream, peer_ctx, d_denoms_out, 0, nullptr, nullptr);
+                       d_workspace, workspace_bytes, (cudaStream_t)stream, peer_ctx, d_denoms_out, 0, nullptr, nullptr, defer_losses ? 1 : 0);
+}
+
+int gbcodec_peer_denominators_f32(const gbcodec_loss_desc* desc, const float* d_weight, const float* d_gt_kps, int target_given,
+                                  float* d_out2_global_sums, void* d_workspace, size_t workspace_bytes, void* peer_ctx, void* stream) {
+    return peer_denominators(desc, d_weight, d_gt_kps, target_given, d_out2_global_sums, d_workspace, workspace_bytes, peer_ctx, (cudaStream_t)stream);
+}
+
+int gbcodec_peer_collect_losses_f32(void* peer_ctx, int steps_back, float* d_losses7, void* stream) {
+    return peer_collect_losses(peer_ctx, steps_back, d_losses7, (cudaStream_t)stream);
 }
 
 int gbcodec_peer_create(int rank, int world, void** ctx_out, unsigned char* handle_out) { return peer_create(rank, world, ctx_out, handle_out); }

@@ -108,16 +108,16 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
     __syncthreads();
     if (!last) return;
     __threadfence();
-    const int q = (int)(peer.seq & 1ull), r = threadIdx.x;
+    const int q = (int)(peer.den_seq & 1ull), r = threadIdx.x;
     if (r < peer.world) {
         const double sw = __ldcg(sums), sp = __ldcg(sums + 1);
         PeerMail* dst = peer.mail[r];
         dst->den[q][peer.rank][0] = sw;
         dst->den[q][peer.rank][1] = sp;
         __threadfence_system();
-        st_release_sys(&dst->den_seq[q][peer.rank], peer.seq);
+        st_release_sys(&dst->den_seq[q][peer.rank], peer.den_seq);
         PeerMail* mine = peer.mail[peer.rank];
-        const bool ok = wait_seq(&mine->den_seq[q][r], peer.seq, peer, &mine->timeouts);
+        const bool ok = wait_seq(&mine->den_seq[q][r], peer.den_seq, peer, &mine->timeouts);
         gath[r][0] = ok ? mine->den[q][r][0] : (double)NAN;
         gath[r][1] = ok ? mine->den[q][r][1] : (double)NAN;
     }
@@ -551,12 +551,26 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
     // ---- batch-sharded job: every rank's terms are already divided by the GLOBAL normalisers, so the global
     // losses are their sums over the ranks.  Same mailbox protocol as denoms_kernel; fixed rank order.
     __shared__ float gl[GBCODEC_MAX_PEERS][8];
-    const int pq = (int)(peer.seq & 1ull), r = threadIdx.x;
+    const int pq = (int)(peer.seq & 3ull), r = threadIdx.x;
     if (r < peer.world) {
         PeerMail* dst = peer.mail[r];
         for (int q = 0; q < 6; ++q) dst->loss[pq][peer.rank][q] = term[q];
         __threadfence_system();
         st_release_sys(&dst->loss_seq[pq][peer.rank], peer.seq);
+    }
+    if (peer.defer) {
+        // deferred mode: the terms are on their way to every peer; nobody waits inside the step.  d_losses7 holds THIS
+        // rank's share (already divided by the global normalisers); gbcodec_peer_collect_losses_f32 adds the shares up
+        // whenever the caller wants the numbers (they are logging-only: fusion_head.py:795-806 feeds nothing back).
+        if (threadIdx.x == 0) {
+            float total = 0.f;
+            for (int q = 0; q < 6; ++q) total += term[q];
+            losses7[6] = total;
+            *ticket = 0u;
+        }
+        return;
+    }
+    if (r < peer.world) {
         PeerMail* mine = peer.mail[peer.rank];
         const bool ok = wait_seq(&mine->loss_seq[pq][r], peer.seq, peer, &mine->timeouts);
         for (int q = 0; q < 6; ++q) gl[r][q] = ok ? mine->loss[pq][r][q] : NAN;
@@ -575,6 +589,26 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
         losses7[6] = total;
         *ticket = 0u;
     }
+}
+
+// Sum of every rank's loss terms of step `seq`, in rank order (every rank gets the same bits).  One warp.
+__global__ void collect_losses_kernel(const __grid_constant__ PeerView peer, unsigned long long seq, float* __restrict__ losses7) {
+    __shared__ float gl[GBCODEC_MAX_PEERS][8];
+    const int pq = (int)(seq & 3ull), r = threadIdx.x;
+    if (r < peer.world) {
+        PeerMail* mine = peer.mail[peer.rank];
+        const bool ok = wait_seq(&mine->loss_seq[pq][r], seq, peer, &mine->timeouts);
+        for (int q = 0; q < 6; ++q) gl[r][q] = ok ? mine->loss[pq][r][q] : NAN;
+    }
+    __syncthreads();
+    float v = 0.f;
+    if (threadIdx.x < 6) {
+        for (int i = 0; i < peer.world; ++i) v += gl[i][threadIdx.x];
+        losses7[threadIdx.x] = v;
+    }
+    float total = 0.f;
+    for (int q = 0; q < 6; ++q) total += __shfl_sync(0xffffffffu, v, q);
+    if (threadIdx.x == 0) losses7[6] = total;
 }
 
 // ---- backward for an arbitrary upstream gradient --------------------------------------------
@@ -749,7 +783,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
                 float* losses7, float* ghm, float* goff, float* gvar,
                 const float* alpha_param, const float* fusion_weight, int radius, unsigned dflags, float* coords, float* scores,
                 void* ws, size_t ws_size, cudaStream_t s, void* peer_ctx, float* denoms_out, int half_io,
-                const float* var_mean, float* grad_var_mean) {
+                const float* var_mean, float* grad_var_mean, int defer_losses) {
     int st = check_common(d, hm, off, weight, gt, ws, ws_size);
     if (var_mean && var) return fail(GBCODEC_ERR_BAD_ARGUMENT, "loss: give the variance maps or their per-tile means, not both");
     if (var_mean && (ghm != nullptr) != (grad_var_mean != nullptr)) return fail(GBCODEC_ERR_NULL_POINTER, "loss: d_grad_var_mean goes with the other gradients");
@@ -758,7 +792,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     if (peer_ctx) {
         PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
         if (!pc->connected) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: the peer context is not connected");
-        if (denoms) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: d_denoms and a peer context exclude each other");
+        if (defer_losses && !denoms) return fail(GBCODEC_ERR_BAD_ARGUMENT, "sharded step: deferred losses go with prefetched normalisers (d_denoms_global)");
         if (pc->h_failed && *reinterpret_cast<volatile unsigned int*>(pc->h_failed))
             return fail(GBCODEC_ERR_PEER_TIMEOUT, "sharded step: an earlier call of rank %d gave up waiting for a peer (its normalisers / losses were NaN); "
                                                   "the exchange is out of step — tear the job down", pc->view.rank);
@@ -782,10 +816,13 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
         // fails validation on one rank must not put that rank one step ahead of the others for the rest of the job)
         PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
         pc->view.seq += 1;
+        if (!denoms) pc->view.den_seq += 1;              // the normalisers are exchanged inside this call
         peer = pc->view;
+        peer.defer = defer_losses;
     }
     const WsLayout L = ws_carve(ws, P.B, P.K);
-    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, peer, denoms_out);
+    // normalisers given (prefetched with gbcodec_peer_denominators_f32, or all-reduced by the caller): no exchange in front
+    st = prepare_weights(P, L, weight, gt, target != nullptr, denoms, s, denoms ? kNoPeers : peer, denoms_out);
     if (st) return st;
     if (denoms_out && peer.world <= 1) {                 // with peers the exchanging CTA has written them already
         note_launch(), sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, denoms_out);
@@ -821,10 +858,44 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
         const float* partial_c = L.partial; const double* sums_c = L.sums;
         note_launch();
         cudaError_t e = cudaLaunchKernelEx(&cfg, finalize_kernel, P, partial_c, sums_c, L.bpart, L.ticket, losses7, peer);
-        note_launch();
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(finalize_kernel): %s", cudaGetErrorString(e));
     }
     return check_launch("finalize_kernel");
+}
+
+// The normaliser exchange on its own: this rank's raw sums into every peer's mailbox, the global sums out.  A caller
+// that knows the next batch's visibility flags and keypoints (train.py: as soon as the batch is loaded) issues this on a
+// side stream during the current step; the step itself then starts with the global sums in hand.
+int peer_denominators(const gbcodec_loss_desc* d, const float* weight, const float* gt, int target_given,
+                      float* out2, void* ws, size_t ws_size, void* peer_ctx, cudaStream_t s) {
+    LossParams P;
+    int st = make_params(d, &P);
+    if (st) return st;
+    if (!weight || !out2 || !peer_ctx || (!target_given && !gt)) return fail(GBCODEC_ERR_NULL_POINTER, "peer_denominators: NULL pointer");
+    if (!ws || ws_size < loss_workspace_bytes(d->B, d->K) || !aligned16(ws))
+        return fail(GBCODEC_ERR_WORKSPACE, "peer_denominators: workspace of %zu bytes needed", loss_workspace_bytes(d->B, d->K));
+    PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
+    if (!pc->connected) return fail(GBCODEC_ERR_BAD_ARGUMENT, "peer_denominators: the peer context is not connected");
+    if (pc->h_failed && *reinterpret_cast<volatile unsigned int*>(pc->h_failed))
+        return fail(GBCODEC_ERR_PEER_TIMEOUT, "peer_denominators: an earlier call of rank %d gave up waiting for a peer", pc->view.rank);
+    pc->view.den_seq += 1;
+    const WsLayout L = ws_carve(ws, P.B, P.K);
+    st = prepare_weights(P, L, weight, gt, target_given, nullptr, s, pc->view, out2);
+    if (st) return st;
+    if (pc->view.world <= 1) {
+        note_launch(), sums_to_float_kernel<<<1, 32, 0, s>>>(L.sums, out2);
+        return check_launch("sums_to_float_kernel");
+    }
+    return GBCODEC_OK;
+}
+
+int peer_collect_losses(void* peer_ctx, int steps_back, float* losses7, cudaStream_t s) {
+    if (!peer_ctx || !losses7) return fail(GBCODEC_ERR_NULL_POINTER, "peer_collect_losses: NULL pointer");
+    PeerCtx* pc = reinterpret_cast<PeerCtx*>(peer_ctx);
+    if (steps_back < 0 || steps_back > 2 || (unsigned long long)steps_back >= pc->view.seq)
+        return fail(GBCODEC_ERR_BAD_ARGUMENT, "peer_collect_losses: steps_back=%d (0..2, and a step that has been made)", steps_back);
+    note_launch(), collect_losses_kernel<<<1, 32, 0, s>>>(pc->view, pc->view.seq - (unsigned long long)steps_back, losses7);
+    return check_launch("collect_losses_kernel");
 }
 
 int fusion_loss_backward(const gbcodec_loss_desc* d, const float* hm, const float* off, const float* var, const float* target,

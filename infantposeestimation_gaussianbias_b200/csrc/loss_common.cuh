@@ -113,14 +113,16 @@ __device__ __forceinline__ PatchGeom unpack_geom(const int4& v, float weight) {
 struct PeerMail {
     double den[2][GBCODEC_MAX_PEERS][2];                 // [parity][source rank]{sum w, sum w_i w_j}
     unsigned long long den_seq[2][GBCODEC_MAX_PEERS];
-    float loss[2][GBCODEC_MAX_PEERS][8];                 // [parity][source rank] seven loss scalars
-    unsigned long long loss_seq[2][GBCODEC_MAX_PEERS];
+    float loss[4][GBCODEC_MAX_PEERS][8];                 // [seq & 3][source rank] six loss terms; four slots: a deferred reader
+    unsigned long long loss_seq[4][GBCODEC_MAX_PEERS];   // (gbcodec_peer_collect_losses_f32) may be two steps behind the writers
     unsigned int timeouts;                               // bounded spins that gave up (a peer died)
 };
 struct PeerView {
     PeerMail* mail[GBCODEC_MAX_PEERS];                   // mail[rank] is the local one
     int rank, world;
-    unsigned long long seq;
+    unsigned long long seq;                              // sequence number of the step (loss exchange)
+    unsigned long long den_seq;                          // ... of the normaliser exchange (it may run one step ahead of the steps)
+    int defer;                                           // the step publishes its loss terms and does not wait for the peers'
     unsigned long long timeout_ns;                       // how long a kernel waits for a peer before it gives up
     unsigned int* failed;                                // sticky flag in mapped host memory (device alias)
 };

@@ -1020,7 +1020,6 @@ int launch_pipe_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEv
     cfg.attrs = at; cfg.numAttrs = 1;
     note_launch();
     e = cudaLaunchKernelEx(&cfg, kern, P, A);
-    note_launch();
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(step_pipe_kernel): %s", cudaGetErrorString(e));
     if (e1) cudaEventRecord(e1, s);
     return check_launch("step_pipe_kernel");

@@ -895,7 +895,6 @@ static int launch_step_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
     cfg.attrs = at; cfg.numAttrs = 1;
     note_launch();
     e = cudaLaunchKernelEx(&cfg, kern, P, A);
-    note_launch();
     if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(step_tile_kernel): %s", cudaGetErrorString(e));
     if (e1) cudaEventRecord(e1, s);
     return check_launch("step_tile_kernel");

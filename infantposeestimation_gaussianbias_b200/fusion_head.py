@@ -44,6 +44,9 @@ class FusionPoseLoss(nn.Module):
           so that backward() has nothing left to do;
       peer         -> sharded.PeerExchange of a batch-sharded job: normalisers and losses are exchanged
           with the other ranks inside the kernels (NVLink peer memory); the returned losses are global.
+          With `denominators` = the global sums prefetched by `peer.denominators(...)` nothing is exchanged in front of
+          the tile kernel, and with `defer_losses=True` the step only publishes its terms: the returned losses are this
+          rank's share, `peer.collect_losses()` adds the shares up when the numbers are wanted.
     """
 
     def __init__(self, heatmap_weight: float = 1.0, offset_weight: float = 1.0, peak_weight: float = 0.5,
@@ -73,7 +76,8 @@ class FusionPoseLoss(nn.Module):
     def forward(self, outputs: Dict[str, Tensor], target_heatmaps: Optional[Tensor], target_weight: Tensor,
                 gt_keypoints: Tensor, input_size: Tuple[int, int] = (192, 256),
                 heatmap_size: Tuple[int, int] = (48, 64), *, denominators: Optional[Tensor] = None,
-                grad_scale: Optional[Tensor] = None, decode: Optional[dict] = None, peer=None) -> Dict[str, Tensor]:
+                grad_scale: Optional[Tensor] = None, decode: Optional[dict] = None, peer=None,
+                defer_losses: bool = False) -> Dict[str, Tensor]:
         # heatmap_size is accepted and ignored, as in the reference (it uses heatmaps.shape, :771)
         if self._half_maps(outputs) and denominators is None and grad_scale is None and peer is None:
             return self._forward_f16(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, decode)
@@ -92,7 +96,8 @@ class FusionPoseLoss(nn.Module):
             float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
             bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads,
             bool(dec), dec.get("alpha_param"), dec.get("fusion_weight"), int(dec.get("radius", 2)),
-            int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)), int(peer.address) if peer is not None else 0)
+            int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)), int(peer.address) if peer is not None else 0,
+            bool(defer_losses))
         losses7 = res[0]
         out = {k: losses7[i] for i, k in enumerate(LOSS_KEYS)}
         if dec:

@@ -185,11 +185,15 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
                 in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
                 use_target_weight: bool, pairs: List[int], with_grads: bool,
                 with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
-                decode_flags: int, peer_ctx: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                decode_flags: int, peer_ctx: int = 0, peer_defer: bool = False
+                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> losses7, grad_hm, grad_off, grad_var, coords, scores, global_denoms, workspace (empty tensors for what was
     not asked; the workspace holds the pass's per-tile weights / patch geometry / normalisers and is what the backward
     reuses).  peer_ctx: address of a connected gbcodec peer context (sharded.PeerExchange) — the normalisers and
-    the losses are then exchanged with the other ranks inside the kernels, over NVLink peer memory."""
+    the losses are then exchanged with the other ranks inside the kernels, over NVLink peer memory.  With `denoms`
+    given as well (the GLOBAL sums, prefetched with `peer_denominators`) nothing is exchanged in front of the tile
+    kernel, and with `peer_defer` the step only publishes its loss terms (losses7 = this rank's share; add the shares up
+    later with `peer_collect_losses`)."""
     B, K, H, W = hm.shape
     hm = _cuda_f32("heatmaps", hm)
     off = _device_readable_f32("offsets", off, (B, K, 2, H, W))
@@ -226,13 +230,14 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
         else:
             coords, scores = empty(), empty()
         if peer_ctx:
-            if denoms is not None:
-                raise RuntimeError("gbcodec: `denominators` and a peer exchange exclude each other")
-            den_out = torch.empty(2, dtype=torch.float32, device=dev)
+            if peer_defer and denoms is None:
+                raise RuntimeError("gbcodec: deferred losses need the prefetched global `denominators`")
+            den_out = torch.empty(2, dtype=torch.float32, device=dev) if denoms is None else denoms
             N.check(L.gbcodec_fusion_step_sharded_f32(
                 desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(grad_scale), *common[9:],
                 _ptr(alpha_param) if with_decode else None, _ptr(fusion_weight) if with_decode else None, radius, decode_flags,
-                _ptr(coords) if with_decode else None, _ptr(scores) if with_decode else None, _ptr(den_out),
+                _ptr(coords) if with_decode else None, _ptr(scores) if with_decode else None,
+                _ptr(den_out) if denoms is None else None, _ptr(denoms), int(peer_defer),
                 _ptr(ws), ws.numel(), N._P(peer_ctx), _stream(hm)), "fusion_step_sharded")
         elif with_decode:
             N.check(L.gbcodec_fusion_step_f32(*common, _ptr(alpha_param), _ptr(fusion_weight), radius, decode_flags,
@@ -277,7 +282,7 @@ def fusion_step_into(hm: Tensor, off: Tensor, var: Optional[Tensor], weight: Ten
 
 @fusion_loss.register_fake
 def _(hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
-      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx=0):
+      use_target_weight, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx=0, peer_defer=False):
     B, K = hm.shape[0], hm.shape[1]
     e = lambda: hm.new_empty(0)
     return (hm.new_empty(7),
@@ -329,9 +334,9 @@ def fusion_loss_backward(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor,
 
 def _loss_setup_context(ctx, inputs, output):
     (hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma,
-     utw, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx) = inputs
+     utw, pairs, with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags, peer_ctx, peer_defer) = inputs
     losses, ghm, goff, gvar, coords, scores, den_out, ws = output
-    if peer_ctx:
+    if peer_ctx and denoms is None:
         denoms = den_out          # the backward re-uses the global normalisers the forward exchanged
     ctx.with_grads = with_grads
     ctx.has_var = var is not None
@@ -350,7 +355,7 @@ def _loss_setup_context(ctx, inputs, output):
 
 
 def _loss_backward(ctx, g_losses, *_unused):
-    n_in = 22
+    n_in = 23
     none = [None] * n_in
     if g_losses is None:
         return tuple(none)
@@ -372,6 +377,34 @@ def _loss_backward(ctx, g_losses, *_unused):
 
 
 fusion_loss.register_autograd(_loss_backward, setup_context=_loss_setup_context)
+
+
+def peer_denominators(weight: Tensor, gt_kps: Tensor, target_given: bool, H: int, W: int, in_w: float, in_h: float,
+                      encode_sigma: float, pairs: List[int], peer_ctx: int, out: Optional[Tensor] = None) -> Tensor:
+    """gbcodec_peer_denominators_f32: this rank's normaliser sums into every peer's mailbox, the GLOBAL sums out (2 floats
+    on the device).  Issue it for the NEXT batch on a side stream while the current step runs (the sums depend on the
+    visibility flags and keypoints only); every rank must call it once per step, in step order."""
+    B, K = gt_kps.shape[0], gt_kps.shape[1]
+    weight = _cuda_f32("target_weight", weight.reshape(B, K))
+    gt_kps = _cuda_f32("gt_keypoints", gt_kps, (B, K, 2))
+    prs = [(int(pairs[i]), int(pairs[i + 1])) for i in range(0, len(pairs), 2)]
+    desc = N.make_loss_desc(B, K, H, W, in_w, in_h, [0.0] * 6, encode_sigma, encode_sigma, True, prs)
+    out = torch.empty(2, dtype=torch.float32, device=weight.device) if out is None else out
+    nbytes = N.lib().gbcodec_loss_workspace_bytes(B, K, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        N.check(N.lib().gbcodec_peer_denominators_f32(desc, _ptr(weight), _ptr(gt_kps), int(target_given), _ptr(out), _ptr(ws), nbytes,
+                                                      N._P(peer_ctx), _stream(weight)), "peer_denominators")
+    return out
+
+
+def peer_collect_losses(peer_ctx: int, device, steps_back: int = 0, out: Optional[Tensor] = None) -> Tensor:
+    """gbcodec_peer_collect_losses_f32: the ranks' loss terms of the sharded step made `steps_back` calls ago, added in
+    rank order -> the 7 global losses (on the device; read them when you log)."""
+    out = torch.empty(7, dtype=torch.float32, device=device) if out is None else out
+    with torch.cuda.device(out.device):
+        N.check(N.lib().gbcodec_peer_collect_losses_f32(N._P(peer_ctx), int(steps_back), _ptr(out), _stream(out)), "peer_collect_losses")
+    return out
 
 
 def pairs_flat(pairs: Sequence[Tuple[int, int]]) -> List[int]:

@@ -91,6 +91,26 @@ class PeerExchange:
     def address(self) -> int:
         return int(self._ctx.value or 0)
 
+    def denominators(self, loss: FusionPoseLoss, target_weight: Tensor, gt_keypoints: Tensor, heatmap_hw, input_size,
+                     target_given: bool = False, out: Optional[Tensor] = None) -> Tensor:
+        """Global normaliser sums of a batch whose images are spread over the ranks (2 floats on the device), exchanged
+        through the mailboxes on the CURRENT stream.  The sums depend on the visibility flags and the keypoints only, so
+        a training loop calls this for batch t+1 on a side stream as soon as that batch is loaded, while step t runs,
+        and hands the result to the loss as `denominators=`: the step then starts without waiting for anybody."""
+        from . import ops
+        H, W = heatmap_hw
+        K = gt_keypoints.shape[1]
+        sigma_enc = float(loss.encode_sigma if loss.encode_sigma is not None else loss.target_sigma)
+        return ops.peer_denominators(target_weight.float(), gt_keypoints.float(), bool(target_given), int(H), int(W),
+                                     float(input_size[0]), float(input_size[1]), sigma_enc, ops.pairs_flat(loss.pairs_for(K)),
+                                     self.address, out)
+
+    def collect_losses(self, device=None, steps_back: int = 0, out: Optional[Tensor] = None) -> Tensor:
+        """The 7 global losses of the deferred step made `steps_back` (0..2) sharded calls ago, on the device."""
+        from . import ops
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return ops.peer_collect_losses(self.address, dev, steps_back, out)
+
     def timeouts(self) -> int:
         """Bounded spins that gave up so far on this rank (0 in a healthy job).  Synchronises the device."""
         import ctypes as C

@@ -55,8 +55,29 @@ def _worker(rank, world, port, B, q):
             out["total_loss"].backward()
             results.append(({k: float(out[k]) for k in oc.LOSS_KEYS}, outputs["heatmaps"].grad.cpu().numpy(),
                             outputs["variances"].grad.cpu().numpy()))
+        # the same steps again with both exchanges off the critical path: normalisers prefetched (here simply ahead of the
+        # step, on a side stream), loss terms published and collected afterwards
+        side = torch.cuda.Stream(device=dev)
+        deferred = []
+        for step in range(STEPS):
+            batch = synth.make_batch(cfg, seed=50 + step, B=B)
+            lo, hi = shard_bounds(B, rank, world)
+            D = lambda k: torch.from_numpy(batch[k][lo:hi].copy()).to(dev)
+            outputs = {"heatmaps": D("heatmaps").requires_grad_(True), "offsets": D("offsets").requires_grad_(True),
+                       "variances": D("variances").requires_grad_(True)}
+            target = None if step % 2 == 0 else D("target")
+            weight = D("vis") if step % 2 == 0 else D("weight")
+            kps = D("kps")
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                den = peer.denominators(loss_fn, weight, kps, (cfg.H, cfg.W), cfg.input_size, target_given=target is not None)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            out = loss_fn(outputs, target, weight, kps, input_size=cfg.input_size, denominators=den, defer_losses=True)
+            out["total_loss"].backward()
+            glob = peer.collect_losses(dev)
+            deferred.append((glob.cpu().numpy().copy(), outputs["heatmaps"].grad.cpu().numpy(), float(out["total_loss"])))
         torch.cuda.synchronize()
-        q.put((rank, peer.timeouts(), results))
+        q.put((rank, peer.timeouts(), results, deferred))
         dist.barrier()
         peer.close()
     finally:
@@ -78,8 +99,8 @@ def test_two_ranks_exchange_through_peer_mailboxes():
         p.start()
     got = {}
     for _ in range(world):
-        rank, timeouts, results = q.get(timeout=480)
-        got[rank] = (timeouts, results)
+        rank, timeouts, results, deferred = q.get(timeout=480)
+        got[rank] = (timeouts, results, deferred)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -95,9 +116,16 @@ def test_two_ranks_exchange_through_peer_mailboxes():
         out["total_loss"].backward()
         gh, gv = outputs["heatmaps"].grad.cpu().numpy(), outputs["variances"].grad.cpu().numpy()
         for rank in range(world):
-            timeouts, results = got[rank]
+            timeouts, results, deferred = got[rank]
             assert timeouts == 0, f"rank {rank}: {timeouts} mailbox waits timed out"
             losses, rgh, rgv = results[step]
+            # deferred mode: the collected losses are the global ones, the gradients the same bits, the value returned by the
+            # step itself this rank's share only
+            dl, dgh, share = deferred[step]
+            np.testing.assert_allclose(dl, [float(out[k]) for k in oc.LOSS_KEYS], rtol=2e-6, atol=1e-9, err_msg=f"deferred step {step} rank {rank}")
+            lo_, hi_ = shard_bounds(B, rank, world)
+            assert np.array_equal(dgh, gh[lo_:hi_]), f"deferred step {step} rank {rank}: gradient differs"
+            assert share < float(out["total_loss"]) * (1 + 1e-6)
             for k in oc.LOSS_KEYS:
                 # the same per-tile numerators, added per rank first: last-bit differences only
                 np.testing.assert_allclose(losses[k], float(out[k]), rtol=2e-6, atol=1e-9, err_msg=f"step {step} rank {rank} {k}")
