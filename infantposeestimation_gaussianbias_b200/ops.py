@@ -232,7 +232,7 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
         if peer_ctx:
             if peer_defer and denoms is None:
                 raise RuntimeError("gbcodec: deferred losses need the prefetched global `denominators`")
-            den_out = torch.empty(2, dtype=torch.float32, device=dev) if denoms is None else denoms
+            den_out = torch.empty(2, dtype=torch.float32, device=dev) if denoms is None else empty()      # an output must not alias an input
             N.check(L.gbcodec_fusion_step_sharded_f32(
                 desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(grad_scale), *common[9:],
                 _ptr(alpha_param) if with_decode else None, _ptr(fusion_weight) if with_decode else None, radius, decode_flags,
@@ -289,7 +289,7 @@ def _(hm, off, var, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lamb
             torch.empty_like(hm) if with_grads else e(), torch.empty_like(off) if with_grads else e(),
             torch.empty_like(var) if (with_grads and var is not None) else e(),
             hm.new_empty((B, K, 2)) if with_decode else e(), hm.new_empty((B, K)) if with_decode else e(),
-            hm.new_empty(2) if peer_ctx else e(), hm.new_empty(0, dtype=torch.uint8))
+            hm.new_empty(2) if (peer_ctx and denoms is None) else e(), hm.new_empty(0, dtype=torch.uint8))
 
 
 def _backward_call(half: bool, g7: Tensor, ghm: Tensor, goff: Tensor, gvar: Optional[Tensor], stored: bool,
