@@ -29,7 +29,7 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
               const float* __restrict__ gt, int target_given, float* __restrict__ weff, int4* __restrict__ geom,
               TileDesc* __restrict__ desc,
               double* __restrict__ sums, unsigned* __restrict__ ticket, const __grid_constant__ PeerView peer,
-              float* __restrict__ global_out) {
+              float* __restrict__ global_out, const float* __restrict__ denoms_in = nullptr, double* __restrict__ sums_dst = nullptr) {
     __shared__ float wsm[256];
     __shared__ double red[2][8];
     pdl_launch_dependents();                           // the tile kernel may start its bulk loads; it waits before it reads weff / geom / sums
@@ -78,6 +78,12 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
         d.pj = pj;
         d.pad[0] = d.pad[1] = d.pad[2] = 0u;
         desc[t] = d;
+    }
+    if (denoms_in && blockIdx.x == 0) {
+        // normalisers given by the caller (a shard of a global batch): into the workspace as the tile kernel reads them,
+        // and the finalize ticket / tile counter (adjacent words) cleared — what a memset + a one-warp kernel used to do
+        if (threadIdx.x < 2) sums_dst[threadIdx.x] = (double)denoms_in[threadIdx.x];
+        if (threadIdx.x == 2) { ticket[0] = 0u; ticket[1] = 0u; }
     }
     if (!sums) return;
     for (int q = local; q < nimg * P.n_pairs; q += 256) {
@@ -133,10 +139,6 @@ denoms_kernel(const __grid_constant__ LossParams P, const float* __restrict__ we
 
 __global__ void sums_to_float_kernel(const double* __restrict__ sums, float* __restrict__ out2) {
     if (threadIdx.x < 2) out2[threadIdx.x] = (float)sums[threadIdx.x];
-}
-__global__ void sums_from_float_kernel(const float* __restrict__ in2, double* __restrict__ sums, unsigned* __restrict__ ticket) {
-    if (threadIdx.x < 2) sums[threadIdx.x] = (double)in2[threadIdx.x];
-    if (threadIdx.x == 2) { ticket[0] = 0u; ticket[1] = 0u; }      // ticket and the step kernel's tile counter (adjacent words)
 }
 template <int TPB, int NITER, int CACHE>
 __global__ void __launch_bounds__(TPB)
@@ -752,8 +754,7 @@ static int prepare_weights(const LossParams& P, const WsLayout& L, const float* 
     const int ipb = 256 / P.K;
     const int grid = (P.B + ipb - 1) / ipb;
     if (denoms) {
-        note_launch(), sums_from_float_kernel<<<1, 32, 0, s>>>(denoms, L.sums, L.ticket);
-        note_launch(), denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, nullptr, L.ticket, kNoPeers, nullptr);
+        note_launch(), denoms_kernel<<<grid, 256, 0, s>>>(P, weight, gt, target_given, L.weff, L.geom, L.desc, nullptr, L.ticket, kNoPeers, nullptr, denoms, L.sums);
     } else {
         // sums, plan, the finalize ticket and the step kernel's tile counter share the first 32 bytes of the workspace
         cudaError_t e = cudaMemsetAsync(L.sums, 0, 32, s);
