@@ -88,7 +88,22 @@ def sparse(a: np.ndarray):
     return nz.astype(np.int64), flat[nz]
 
 
-def main():
+# Second set, at BASELINE.json configs[0] size (B = 32 at 64x48) and B = 8 for the two larger tile shapes.  The full
+# heatmap gradient would be 6.7 MB per file, so it is stored as (a) every 7th element and (b) six float64 moments per
+# tile (sum g, sum |g|, sum g^2, max |g|, sum g x, sum g y): every tile and every pixel takes part in the comparison.
+LARGE = {"w32_256x192": 32, "hrformer_384x288": 8, "preemie_256": 8}
+LARGE_SEED, LARGE_STRIDE = 1, 7
+
+
+def tile_moments(g: np.ndarray) -> np.ndarray:
+    g = g.astype(np.float64)
+    H, W = g.shape[-2:]
+    xs, ys = np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64)
+    return np.stack([g.sum((2, 3)), np.abs(g).sum((2, 3)), (g * g).sum((2, 3)), np.abs(g).max((2, 3)),
+                     (g * xs[None, None, None, :]).sum((2, 3)), (g * ys[None, None, :, None]).sum((2, 3))], axis=-1)
+
+
+def main(large: bool = False):
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     fh, pe, dsm = import_reference()
@@ -96,7 +111,12 @@ def main():
 
     for name, cfg in synth.CONFIGS.items():
         out = {}
-        batch = synth.make_batch(cfg, seed=0)
+        if large:
+            import dataclasses
+            cfg = dataclasses.replace(cfg, B=LARGE[name])
+            batch = synth.make_batch(cfg, seed=LARGE_SEED, B=cfg.B)
+        else:
+            batch = synth.make_batch(cfg, seed=0)
         out["digest"] = np.array(synth.digest(batch))
         out["kps"], out["vis"] = batch["kps"], batch["vis"]
 
@@ -123,7 +143,12 @@ def main():
                              T("kps").to(dt), input_size=cfg.input_size, heatmap_size=(cfg.H, cfg.W))
             losses["total_loss"].backward()
             out[f"loss_{tag}"] = np.array([float(losses[k].detach()) for k in oc.LOSS_KEYS], np.float64)
-            if tag == "f32":
+            if tag == "f32" and large:
+                out["grad_hm_sub"] = h.grad.numpy().reshape(-1)[::LARGE_STRIDE].copy()
+                out["grad_hm_moments"] = tile_moments(h.grad.numpy())
+                out["grad_off_idx"], out["grad_off_val"] = sparse(o.grad.numpy())
+                out["grad_var_tile"] = v.grad.numpy()[:, :, 0, 0].copy()
+            elif tag == "f32":
                 out["grad_hm"] = h.grad.numpy()
                 out["grad_off_idx"], out["grad_off_val"] = sparse(o.grad.numpy())
                 out["grad_var_tile"] = v.grad.numpy()[:, :, 0, 0].copy()
@@ -162,10 +187,10 @@ def main():
         out["alpha_param"] = np.float32(head.subpixel_refine.alpha.item())
         out["fusion_weight"] = np.float32(fw.item())
 
-        path = os.path.join(HERE, f"{name}.npz")
+        path = os.path.join(HERE, f"{name}_large.npz" if large else f"{name}.npz")
         np.savez_compressed(path, **out)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)  total_loss={out['loss_f32'][-1]:.6f}")
 
 
 if __name__ == "__main__":
-    main()
+    main(large="--large" in sys.argv)

@@ -131,3 +131,27 @@ def test_sharded_denominators_reproduce_global_batch():
         acc = part if acc is None else {k: acc[k] + part[k] for k in acc}
     for k in oc.LOSS_KEYS:
         assert abs(float(acc[k]) - float(full[k])) <= 2e-6 * abs(float(full[k])) + 1e-9
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_against_large_goldens(name):
+    """The second golden set (BASELINE configs[0] size: B = 32 at 64x48, B = 8 for the larger shapes), produced by the
+    reference itself: the oracle must reproduce it too — encode bit for bit, losses / gradients / decode tightly."""
+    from tests.golden.make_golden import LARGE_STRIDE, tile_moments
+    cfg, batch, g = goldens.load_large(name)
+    target, weight = oc.encode_targets(batch["kps"], batch["vis"], cfg.heatmap_size, cfg.input_size, cfg.sigma)
+    assert np.array_equal(target, g["target"]) and np.array_equal(weight, g["enc_weight"])
+    losses, grads = oc.fusion_loss_and_grads(t(batch["heatmaps"]), t(batch["offsets"]), t(batch["variances"]), t(target), t(weight),
+                                             t(batch["kps"]), input_size=cfg.input_size, target_sigma=cfg.sigma)
+    np.testing.assert_allclose([float(losses[k]) for k in oc.LOSS_KEYS], g["loss_f32"], rtol=2e-6, atol=1e-9)
+    gh = grads["heatmaps"].numpy()
+    scale = np.abs(g["grad_hm_sub"]).max()
+    assert np.abs(gh.reshape(-1)[::LARGE_STRIDE] - g["grad_hm_sub"]).max() <= 2e-6 * scale
+    mom, wm = tile_moments(gh), g["grad_hm_moments"]
+    assert (np.abs(mom[..., 1] - wm[..., 1]) / (wm[..., 1] + 1e-30)).max() <= 1e-5
+    assert np.array_equal(grads["offsets"].numpy() != 0, g["grad_off"] != 0)
+    c, s = oc.fusion_decode(t(batch["heatmaps"]), t(batch["offsets"]), float(g["alpha_param"]), float(g["fusion_weight"]))
+    ok = (np.abs(g["dec_softargmax"] - np.floor(g["dec_softargmax"]) - 0.5) > 1e-3).all(-1)
+    assert np.array_equal(s.numpy(), g["dec_scores"]) and np.abs(c.numpy() - g["dec_coords"])[ok].max() <= 2e-5
+    kp, mv, idx = oc.decode_heatmaps(t(batch["heatmaps"]))
+    assert np.array_equal(kp.numpy(), g["argmax_coords"]) and np.array_equal(mv.numpy(), g["argmax_vals"])
