@@ -184,6 +184,15 @@ int gbcodec_fusion_step_vmean_f32(const gbcodec_loss_desc* desc,
                             float* d_coords, float* d_scores,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The caller's half of the per-tile-mean path: the variance branch's last convolution hands over its RAW output (the
+ * Softplus module of models/fusion_head.py:245-251 dropped) and gets mean_N(softplus(raw)) per tile — what
+ * gbcodec_fusion_step_vmean_f32 takes as d_var_mean; the step's d_grad_var_mean goes back through the second call as the
+ * gradient of the raw map, d raw_i = g_tile / N * sigmoid(raw_i) (torch.nn.Softplus, beta 1, threshold 20).  The
+ * (B,K,H,W) variance map and its gradient map never exist.  d_raw (B,K,H,W) 16-byte aligned, d_mean / d_grad_mean (B,K). */
+int gbcodec_softplus_mean_f32(const float* d_raw, float* d_mean, int B, int K, int H, int W, void* stream);
+int gbcodec_softplus_mean_backward_f32(const float* d_raw, const float* d_grad_mean, float* d_grad_raw,
+                                       int B, int K, int H, int W, void* stream);
+
 /* Backward for an arbitrary upstream gradient on the seven outputs (the autograd backward of train.py:182 for
  * whatever reaches the loss dict of fusion_head.py:795-806).  The gradients written by the forward assume
  * d(total)=*d_grad_scale and nothing on the six terms.  This call reads the actual upstream vector on the device and

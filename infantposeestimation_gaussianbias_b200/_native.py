@@ -38,6 +38,7 @@ EXPORTS = (
     "gbcodec_combined_workspace_bytes", "gbcodec_combined_loss_f32", "gbcodec_combined_loss_backward_f32",
     "gbcodec_peer_create", "gbcodec_peer_connect", "gbcodec_peer_status", "gbcodec_peer_destroy", "gbcodec_peer_set_timeout",
     "gbcodec_peer_denominators_f32", "gbcodec_peer_collect_losses_f32",
+    "gbcodec_softplus_mean_f32", "gbcodec_softplus_mean_backward_f32",
     "gbcodec_fusion_step_sharded_f32", "gbcodec_heatmap_step_f32",
     "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16", "gbcodec_fusion_step_vmean_f32",
 )
@@ -143,6 +144,8 @@ def _declare(lib):
                                                     f32p, f32p, f32p, f32p, C.c_int, _P, C.c_size_t, _P, _P]
     lib.gbcodec_peer_denominators_f32.argtypes = [C.POINTER(LossDesc), f32p, f32p, C.c_int, f32p, _P, C.c_size_t, _P, _P]
     lib.gbcodec_peer_collect_losses_f32.argtypes = [_P, C.c_int, f32p, _P]
+    lib.gbcodec_softplus_mean_f32.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, _P]
+    lib.gbcodec_softplus_mean_backward_f32.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, _P]
     lib.gbcodec_encode_mode_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_float, C.c_double, C.c_int, _P]
     lib.gbcodec_postprocess_f32.argtypes = [C.POINTER(PostprocessDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p, _P, _P]

@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libgbcodec.so")
-SOURCES = ("api.cu", "encode.cu", "decode.cu", "loss.cu", "loss_tile.cu", "step_tile.cu", "step_pipe.cu", "genb_loss.cu", "peer.cu")
+SOURCES = ("api.cu", "encode.cu", "decode.cu", "loss.cu", "loss_tile.cu", "step_tile.cu", "step_pipe.cu", "genb_loss.cu", "peer.cu", "head_epilogue.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

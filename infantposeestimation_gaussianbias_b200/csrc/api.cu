@@ -50,6 +50,8 @@ int loss_denominators(const gbcodec_loss_desc*, const float*, const float*, int,
 int fusion_loss(const gbcodec_loss_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
                 const float*, const float*, float*, float*, float*, float*,
                 const float*, const float*, int, unsigned, float*, float*, void*, size_t, cudaStream_t, void*, float*, int, const float*, float*, int = 0);
+int launch_softplus_mean(const float*, float*, int, int, int, int, cudaStream_t);
+int launch_softplus_mean_backward(const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int peer_denominators(const gbcodec_loss_desc*, const float*, const float*, int, float*, void*, size_t, void*, cudaStream_t);
 int peer_collect_losses(void*, int, float*, cudaStream_t);
 int peer_create(int, int, void**, unsigned char*);
@@ -347,6 +349,22 @@ int gbcodec_fusion_loss_backward_f16(const gbcodec_loss_desc* desc,
                                 d_grad_scale, d_grad_losses7, (float*)d_grad_hm, (float*)d_grad_off, (float*)d_grad_var,
                                 d_workspace, workspace_bytes, (cudaStream_t)stream, 1, gradients_stored ? 1 : 0,
                                 d_held6, held_valid, workspace_from_forward);
+}
+
+int gbcodec_softplus_mean_f32(const float* d_raw, float* d_mean, int B, int K, int H, int W, void* stream) {
+    int st = check_tile_shape("softplus_mean", B, K, H, W);
+    if (st) return st;
+    if (!d_raw || !d_mean) return fail(GBCODEC_ERR_NULL_POINTER, "softplus_mean: NULL pointer");
+    if (!aligned16(d_raw)) return fail(GBCODEC_ERR_UNALIGNED, "softplus_mean: d_raw must be 16-byte aligned");
+    return launch_softplus_mean(d_raw, d_mean, B, K, H, W, (cudaStream_t)stream);
+}
+
+int gbcodec_softplus_mean_backward_f32(const float* d_raw, const float* d_grad_mean, float* d_grad_raw, int B, int K, int H, int W, void* stream) {
+    int st = check_tile_shape("softplus_mean_backward", B, K, H, W);
+    if (st) return st;
+    if (!d_raw || !d_grad_mean || !d_grad_raw) return fail(GBCODEC_ERR_NULL_POINTER, "softplus_mean_backward: NULL pointer");
+    if (!aligned16(d_raw) || !aligned16(d_grad_raw)) return fail(GBCODEC_ERR_UNALIGNED, "softplus_mean_backward: maps must be 16-byte aligned");
+    return launch_softplus_mean_backward(d_raw, d_grad_mean, d_grad_raw, B, K, H, W, (cudaStream_t)stream);
 }
 
 int gbcodec_profile_loss_kernel(void* start_event, void* stop_event) {

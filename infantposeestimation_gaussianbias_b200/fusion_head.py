@@ -81,6 +81,26 @@ class FusionPoseLoss(nn.Module):
         # heatmap_size is accepted and ignored, as in the reference (it uses heatmaps.shape, :771)
         if self._half_maps(outputs) and denominators is None and grad_scale is None and peer is None:
             return self._forward_f16(outputs, target_heatmaps, target_weight, gt_keypoints, input_size, decode)
+        v_in = outputs.get("variances")
+        if v_in is not None and v_in.dim() == 2 and peer is None:
+            # a head that reduces its variance branch to mean_N(V) itself (ops.softplus_mean; patch_reference(
+            # variance_means=True)): the (B,K,H,W) variance map and its gradient map never exist
+            hm, off = _f32(outputs["heatmaps"]), _f32(outputs["offsets"])
+            K = hm.shape[1]
+            if target_heatmaps is not None and target_heatmaps.numel() == 0:
+                target_heatmaps = None
+            with_grads = torch.is_grad_enabled() and any(t.requires_grad for t in (hm, off, v_in))
+            sigma_enc = float(self.encode_sigma if self.encode_sigma is not None else self.target_sigma)
+            dec = decode or {}
+            res = ops.fusion_step_vmean(
+                hm, off, _f32(v_in), _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), denominators, grad_scale,
+                float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc, bool(self.use_target_weight),
+                ops.pairs_flat(self.pairs_for(K)), with_grads, bool(dec), dec.get("alpha_param"), dec.get("fusion_weight"),
+                int(dec.get("radius", 2)), int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)))
+            out = {k: res[0][i] for i, k in enumerate(LOSS_KEYS)}
+            if dec:
+                out["coords"], out["scores"] = res[4], res[5]
+            return out
         hm = _f32(outputs["heatmaps"])
         off = _f32(outputs["offsets"])
         var = _f32(outputs.get("variances"))

@@ -316,20 +316,19 @@ def _backward_call(half: bool, g7: Tensor, ghm: Tensor, goff: Tensor, gvar: Opti
                 _ptr(ws), ws.numel(), _stream(hm)), "fusion_loss_backward")
 
 
-@torch.library.custom_op(f"{_NS}::fusion_loss_backward", mutates_args=("grad_hm", "grad_off", "grad_var", "held"))
+@torch.library.custom_op(f"{_NS}::fusion_loss_backward", mutates_args=("grad_hm", "grad_off", "grad_var"))
 def fusion_loss_backward(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor, grad_var: Optional[Tensor],
                          hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor], weight: Tensor,
                          gt_kps: Tensor, denoms: Optional[Tensor], grad_scale: Optional[Tensor],
                          in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
-                         use_target_weight: bool, pairs: List[int], held: Optional[Tensor] = None,
-                         held_valid: bool = False) -> None:
+                         use_target_weight: bool, pairs: List[int]) -> None:
     """The stored gradients (written by fusion_loss for d(total) = grad_scale) brought to the upstream vector
-    `grad_losses` (7): nothing / an in-place rescale / a recompute, decided on the device.  `held` (6 floats, optional)
-    carries across calls what the stored gradients hold, see include/gbcodec.h."""
+    `grad_losses` (7): nothing / an in-place rescale / a recompute, decided on the device.  One call per forward: the
+    autograd rule of fusion_loss (which may be walked several times) keeps the `held` state of include/gbcodec.h itself."""
     B, K = hm.shape[0], hm.shape[1]
     g7 = _cuda_f32("grad_losses", grad_losses.reshape(7), (7,))
     _backward_call(False, g7, grad_hm, grad_off, grad_var, True, hm, off, var, target, weight.reshape(B, K), gt_kps, denoms,
-                   grad_scale, (in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs), held, held_valid, None)
+                   grad_scale, (in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs), None, False, None)
 
 
 def _loss_setup_context(ctx, inputs, output):
@@ -405,6 +404,45 @@ def peer_collect_losses(peer_ctx: int, device, steps_back: int = 0, out: Optiona
     with torch.cuda.device(out.device):
         N.check(N.lib().gbcodec_peer_collect_losses_f32(N._P(peer_ctx), int(steps_back), _ptr(out), _stream(out)), "peer_collect_losses")
     return out
+
+
+# --------------------------------------------------------------------------- variance branch tail: Softplus -> mean_N
+@torch.library.custom_op(f"{_NS}::softplus_mean", mutates_args=())
+def softplus_mean(raw: Tensor) -> Tensor:
+    """mean over each (H,W) tile of softplus(raw): (B,K,H,W) -> (B,K).  The variance branch of the fusion head ends in
+    Softplus (fusion_head.py:245-251) and the loss reads only this mean (:467-478)."""
+    B, K, H, W = raw.shape
+    raw = _cuda_f32("raw_variances", raw)
+    out = torch.empty((B, K), dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        N.check(N.lib().gbcodec_softplus_mean_f32(_ptr(raw), _ptr(out), B, K, H, W, _stream(raw)), "softplus_mean")
+    return out
+
+
+@softplus_mean.register_fake
+def _(raw):
+    return raw.new_empty(raw.shape[:2])
+
+
+@torch.library.custom_op(f"{_NS}::softplus_mean_backward", mutates_args=())
+def softplus_mean_backward(raw: Tensor, grad_mean: Tensor) -> Tensor:
+    B, K, H, W = raw.shape
+    raw = _cuda_f32("raw_variances", raw)
+    grad_mean = _cuda_f32("grad_mean", grad_mean.reshape(B, K), (B, K))
+    out = torch.empty_like(raw)
+    with torch.cuda.device(raw.device):
+        N.check(N.lib().gbcodec_softplus_mean_backward_f32(_ptr(raw), _ptr(grad_mean), _ptr(out), B, K, H, W, _stream(raw)),
+                "softplus_mean_backward")
+    return out
+
+
+@softplus_mean_backward.register_fake
+def _(raw, grad_mean):
+    return torch.empty_like(raw)
+
+
+softplus_mean.register_autograd(lambda ctx, g: softplus_mean_backward(ctx.saved_tensors[0], g),
+                                setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
 
 
 def pairs_flat(pairs: Sequence[Tuple[int, int]]) -> List[int]:
@@ -748,17 +786,16 @@ def _(hm, off, var, target, weight, gt_kps, denoms, expected_upstream, in_w, in_
             torch.empty_like(var) if (with_grads and var is not None) else e(torch.float16), hm.new_empty(0, dtype=torch.uint8))
 
 
-@torch.library.custom_op(f"{_NS}::fusion_loss_backward_f16", mutates_args=("grad_hm", "grad_off", "grad_var", "held"))
+@torch.library.custom_op(f"{_NS}::fusion_loss_backward_f16", mutates_args=("grad_hm", "grad_off", "grad_var"))
 def fusion_loss_backward_f16(grad_losses: Tensor, grad_hm: Tensor, grad_off: Tensor, grad_var: Optional[Tensor], stored: bool,
                              hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional[Tensor],
                              weight: Tensor, gt_kps: Tensor, denoms: Optional[Tensor], expected_upstream: Optional[Tensor],
                              in_w: float, in_h: float, lambdas: List[float], target_sigma: float, encode_sigma: float,
-                             use_target_weight: bool, pairs: List[int], held: Optional[Tensor] = None,
-                             held_valid: bool = False) -> None:
+                             use_target_weight: bool, pairs: List[int]) -> None:
     B, K = hm.shape[0], hm.shape[1]
     g7 = _cuda_f32("grad_losses", grad_losses.reshape(7), (7,))
     _backward_call(True, g7, grad_hm, grad_off, grad_var, stored, hm, off, var, target, weight.reshape(B, K), gt_kps, denoms,
-                   expected_upstream, (in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs), held, held_valid, None)
+                   expected_upstream, (in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs), None, False, None)
 
 
 def _loss_f16_setup(ctx, inputs, output):
@@ -810,10 +847,10 @@ def fusion_step_vmean(hm: Tensor, off: Tensor, var_mean: Tensor, target: Optiona
                       denoms: Optional[Tensor], grad_scale: Optional[Tensor], in_w: float, in_h: float, lambdas: List[float],
                       target_sigma: float, encode_sigma: float, use_target_weight: bool, pairs: List[int], with_grads: bool,
                       with_decode: bool, alpha_param: Optional[Tensor], fusion_weight: Optional[Tensor], radius: int,
-                      decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                      decode_flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """The fused step for a head that hands over mean_N(V) per tile instead of the variance map (16N instead of 24N bytes
-    per tile) -> losses7, grad_hm, grad_off, grad_var_mean (B,K) = d(total)/d(mean_N(V)) times grad_scale, coords, scores.
-    No autograd rule: the caller owns the head and wires the three gradients into its own backward."""
+    per tile) -> losses7, grad_hm, grad_off, grad_var_mean (B,K) = d(total)/d(mean_N(V)) times grad_scale, coords, scores,
+    workspace.  Differentiable w.r.t. hm, off and var_mean (autograd rule below; `softplus_mean` is the other half)."""
     B, K, H, W = hm.shape
     hm = _cuda_f32("heatmaps", hm)
     off = _cuda_f32("offsets", off, (B, K, 2, H, W))
@@ -845,7 +882,7 @@ def fusion_step_vmean(hm: Tensor, off: Tensor, var_mean: Tensor, target: Optiona
             _ptr(losses), opt(ghm, with_grads), opt(goff, with_grads), opt(gvm, with_grads),
             opt(alpha_param, with_decode), opt(fusion_weight, with_decode), radius, decode_flags,
             opt(coords, with_decode), opt(scores, with_decode), _ptr(ws), ws.numel(), _stream(hm)), "fusion_step_vmean")
-    return losses, ghm, goff, gvm, coords, scores
+    return losses, ghm, goff, gvm, coords, scores, ws
 
 
 @fusion_step_vmean.register_fake
@@ -855,4 +892,44 @@ def _(hm, off, var_mean, target, weight, gt_kps, denoms, grad_scale, in_w, in_h,
     e = lambda: hm.new_empty(0)
     return (hm.new_empty(7), torch.empty_like(hm) if with_grads else e(), torch.empty_like(off) if with_grads else e(),
             hm.new_empty((B, K)) if with_grads else e(), hm.new_empty((B, K, 2)) if with_decode else e(),
-            hm.new_empty((B, K)) if with_decode else e())
+            hm.new_empty((B, K)) if with_decode else e(), hm.new_empty(0, dtype=torch.uint8))
+
+
+def _vmean_setup(ctx, inputs, output):
+    (hm, off, var_mean, target, weight, gt_kps, denoms, grad_scale, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs,
+     with_grads, with_decode, alpha_param, fusion_weight, radius, decode_flags) = inputs
+    losses, ghm, goff, gvm, coords, scores, ws = output
+    ctx.with_grads = with_grads
+    ctx.stash, ctx.gvm0, ctx.ws, ctx.held = (ghm, goff), gvm, ws, None
+    B, K = hm.shape[0], hm.shape[1]
+    contig = lambda t: None if t is None else t.detach().contiguous()
+    ctx.tensors = (contig(hm), contig(off), contig(target), weight.detach().reshape(B, K).contiguous(), contig(gt_kps), contig(denoms),
+                   _scalar("grad_scale", grad_scale, hm))
+    ctx.scalars = (in_w, in_h, list(lambdas), target_sigma, encode_sigma, utw, list(pairs))
+    ctx.mark_non_differentiable(ghm, goff, gvm, coords, scores, ws)
+    ctx.set_materialize_grads(False)
+
+
+def _vmean_backward(ctx, g_losses, *_unused):
+    none = [None] * 21
+    if g_losses is None:
+        return tuple(none)
+    if not ctx.with_grads:
+        raise RuntimeError("gbcodec::fusion_step_vmean was run with with_grads=False; its output is not differentiable")
+    ghm, goff = ctx.stash
+    hm, off, target, weight, gt_kps, denoms, grad_scale = ctx.tensors
+    held_valid = ctx.held is not None
+    if not held_valid:
+        ctx.held = torch.empty(6, dtype=torch.float32, device=hm.device)
+    g7 = g_losses.detach().reshape(7).to(torch.float32).contiguous()
+    # the heatmap / offset gradients do not see the variance branch: the map-less backward brings them to the upstream
+    # vector (nothing / rescale / recompute, decided on the device); the (B,K) gradient of the means is linear in the
+    # variance term's upstream factor
+    _backward_call(False, g7, ghm, goff, None, True, hm, off, None, target, weight, gt_kps, denoms, grad_scale, ctx.scalars,
+                   ctx.held, held_valid, ctx.ws)
+    assumed = grad_scale.reshape(()) if grad_scale is not None else 1.0
+    none[0], none[1], none[2] = ghm, goff, ctx.gvm0 * ((g7[6] + g7[3]) / assumed)
+    return tuple(none)
+
+
+fusion_step_vmean.register_autograd(_vmean_backward, setup_context=_vmean_setup)

@@ -66,8 +66,26 @@ def _encode_placeholder(self, keypoints: np.ndarray, keypoints_visible: np.ndarr
     return np.zeros((K, 0, 0), dtype=np.float32), weight
 
 
+def _head_forward_variance_means(self, x):
+    """HeatmapRegressionHead.forward (fusion_head.py:275-307) with the variance branch's tail — Softplus, then the mean
+    over the tile that is all the loss reads of it (:467-478) — done by one kernel on the last convolution's raw output:
+    outputs['variances'] is the (B,K) tensor of per-tile means and the patched loss takes the map-less step."""
+    from . import ops
+    shared_feat = self.shared_layers(x)
+    heatmaps = self.heatmap_branch(shared_feat)
+    offsets = self.offset_branch(shared_feat)
+    B, _, H, W = offsets.shape
+    offsets = offsets.view(B, self.num_keypoints, 2, H, W)
+    raw = shared_feat
+    for layer in list(self.variance_branch)[:-1]:           # everything but the trailing nn.Softplus
+        raw = layer(raw)
+    return {"heatmaps": heatmaps, "offsets": offsets, "variances": ops.softplus_mean(raw.float()),
+            "fusion_weight": torch.sigmoid(self.fusion_weight)}
+
+
 def patch_reference(fusion_head: Optional[ModuleType] = None, pose_estimator: Optional[ModuleType] = None,
-                    coco_dataset: Optional[ModuleType] = None, encode_on_device: bool = False) -> Dict[str, object]:
+                    coco_dataset: Optional[ModuleType] = None, encode_on_device: bool = False,
+                    variance_means: bool = False) -> Dict[str, object]:
     """Rebind the reference's entry points.  Modules default to `models.fusion_head`,
     `models.pose_estimator` (and `datasets.coco_dataset` when `encode_on_device`) imported by name.
     Returns the original callables (also kept for `unpatch_reference`)."""
@@ -83,6 +101,12 @@ def patch_reference(fusion_head: Optional[ModuleType] = None, pose_estimator: Op
     fusion_head.HeatmapRegressionHead.decode = lambda self, outputs, apply_offset=True: fh.head_decode(self, outputs, apply_offset)
     pose_estimator.PoseEstimator.inference = lambda self, x, flip=True, flip_pairs=None: pe.inference(self, x, flip, flip_pairs)
     pose_estimator.PoseEstimator.decode_heatmaps = staticmethod(pe.decode_heatmaps)
+    if variance_means:
+        # opt-in (it changes what outputs['variances'] is): the head hands the loss mean_N(softplus(.)) per tile
+        if type(list(fusion_head.HeatmapRegressionHead(8).variance_branch)[-1]).__name__ != "Softplus":
+            raise RuntimeError("patch_reference(variance_means=True): the variance branch does not end in Softplus")
+        saved["HeatmapRegressionHead.forward"] = fusion_head.HeatmapRegressionHead.forward
+        fusion_head.HeatmapRegressionHead.forward = _head_forward_variance_means
     if encode_on_device:
         coco_dataset = coco_dataset or importlib.import_module("datasets.coco_dataset")
         saved["COCOPoseDataset._generate_target"] = coco_dataset.COCOPoseDataset._generate_target

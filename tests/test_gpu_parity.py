@@ -609,6 +609,24 @@ def test_fp16_head_outputs_under_autocast(gb, name):
     assert torch.equal(c16, c32) and torch.equal(s16, s32) and c16.dtype == torch.float32
 
 
+def test_softplus_mean_matches_torch(gb):
+    """The head-side half of the per-tile-mean path: mean_N(softplus(raw)) and its backward against torch
+    (nn.Softplus beta 1 threshold 20, then .mean(dim=(2, 3)) — fusion_head.py:245-251, :467-478)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    raw = (torch.randn(5, 17, 64, 48, generator=g, device="cuda") * 4.0)
+    raw[0, 0, 0, :4] = torch.tensor([25.0, 20.0, -30.0, 19.999], device="cuda")        # both sides of the threshold
+    a = raw.clone().requires_grad_(True)
+    m = gb.softplus_mean(a)
+    up = torch.randn(5, 17, generator=g, device="cuda")
+    (m * up).sum().backward()
+    b = raw.clone().double().requires_grad_(True)
+    mt = torch.nn.functional.softplus(b, beta=1.0, threshold=20.0).mean(dim=(2, 3))
+    (mt * up.double()).sum().backward()
+    np.testing.assert_allclose(m.detach().cpu().numpy(), mt.detach().cpu().numpy(), rtol=2e-6)
+    gw = b.grad.cpu().numpy()
+    assert np.abs(a.grad.cpu().numpy() - gw).max() <= 2e-6 * np.abs(gw).max()
+
+
 # ---------------------------------------------------------------------- variance branch handed over as per-tile means
 @pytest.mark.parametrize("name", NAMES)
 def test_step_with_variance_means(gb, name):

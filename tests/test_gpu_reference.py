@@ -150,6 +150,37 @@ def test_train_step_encode_on_device_placeholder(world):
     _report("train step, encode on device", head_last_conv_grad_maxnorm_err=worst)
 
 
+def test_train_step_variance_means_stock_vs_patched(world):
+    """patch_reference(variance_means=True) — the head's variance branch ends in one kernel (Softplus ->
+    mean over the tile) instead of the Softplus module, outputs['variances'] is (B,K), the loss takes the map-less step
+    (16N instead of 24N bytes per tile) and neither the variance map nor its gradient map exists.  Same losses, same
+    gradients — including the variance branch's own convolution weights, which the gradient reaches through
+    gbcodec_softplus_mean_backward_f32."""
+    w = world
+    w.patch.unpatch_reference()
+    want_l, want_g = _train_step(w, copy.deepcopy(w.model), fp16=False)
+    w.patch.patch_reference(w.ref.fusion_head, w.ref.pose_estimator, variance_means=True)
+    try:
+        model = copy.deepcopy(w.model)
+        with torch.no_grad():
+            model.train(); model.backbone.eval()
+            assert model(w.imgs)["variances"].shape == (B, CFG.K)
+        got_l, got_g = _train_step(w, copy.deepcopy(w.model), fp16=False)
+    finally:
+        w.patch.unpatch_reference()
+    worst_l = max(abs(got_l[k] - want_l[k]) / max(abs(want_l[k]), 1e-12) for k in want_l)
+    for k in want_l:
+        np.testing.assert_allclose(got_l[k], want_l[k], rtol=1e-5, atol=1e-9, err_msg=k)
+    heads = _head_last_convs(want_g)
+    worst_h = max(float((got_g[n] - g).abs().max()) / max(float(g.abs().max()), 1e-30) for n, g in heads.items())
+    var_w = [n for n in heads if "variance_branch" in n]
+    assert var_w and worst_h <= 1e-4
+    worst_all = max(float((got_g[n] - g).abs().max()) / max(float(g.abs().max()), 1e-30) for n, g in want_g.items())
+    assert worst_all <= 1e-3
+    _report("train step, variance branch as per-tile means", loss_rel_err=worst_l, head_last_conv_grad_maxnorm_err=worst_h,
+            all_params_grad_maxnorm_err=worst_all)
+
+
 def test_train_step_autocast_gradscaler_stock_vs_patched(world):
     """train.py:171-183 with cfg.train.fp16 (the reference's default).  The stock loss runs on the float16 maps under
     autocast (elementwise work in half, softmax / mse / smooth_l1 in float); the codec reads the same float16 maps and

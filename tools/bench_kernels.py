@@ -19,9 +19,14 @@ PEAK = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 66
 SK = ops.pairs_flat(((0, 1), (0, 2), (1, 3), (2, 4), (5, 6), (5, 7), (7, 9), (6, 8), (8, 10), (5, 11), (6, 12), (11, 12), (11, 13), (13, 15), (12, 14), (14, 16)))
 LAM = [1.0, 1.0, 0.5, 0.1, 0.05, 0.05]
 quick = "--quick" in sys.argv
+once = "--once" in sys.argv          # one launch per case, untimed: the workload of the ncu captures (tools/gpu_ncu_all.sh)
 
 
 def timeit(fn, n=20):
+    if once:
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         r = fn()
     torch.cuda.synchronize()
