@@ -382,7 +382,14 @@ def api_step_rates(device, data, B, steps):
             (l * sc).backward()
 
         ms = _time_cuda(step, steps, warm=4)
-        out[tag] = {"ms_per_step": ms, "value": B * K / (ms * 1e-3), "unit": UNIT, "upstream_scale": scale}
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        host_ms = (time.perf_counter() - h0) * 1e3 / steps          # host time to enqueue one API step (nothing synchronises inside)
+        torch.cuda.synchronize()
+        out[tag] = {"ms_per_step": ms, "value": B * K / (ms * 1e-3), "unit": UNIT, "upstream_scale": scale,
+                    "host_enqueue_ms_per_step": host_ms}
         del leaves
         torch.cuda.empty_cache()
     out["what"] = "FusionPoseLoss.forward (patched module, targets built in the kernel) + (scale * total_loss).backward(), CUDA events"
@@ -581,6 +588,7 @@ def run_b200(args):
     t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launched0 = N.lib().gbcodec_launch_count()
+    host_t0 = time.perf_counter()
     t_a.record()
     for i in range(args.steps):
         if i % 4 == 0:
@@ -589,6 +597,7 @@ def run_b200(args):
             N.lib().gbcodec_profile_loss_kernel(None, None)
         res = step()
     t_b.record()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps    # host time to ENQUEUE a step (no sync inside the loop)
     launched = int(N.lib().gbcodec_launch_count() - launched0)      # this library's kernels, counted at their launch sites
     barrier()
     N.lib().gbcodec_profile_loss_kernel(None, None)
@@ -687,7 +696,8 @@ def run_b200(args):
         "config": {"workload": workload_name(B), "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "exchange": exchange, "numa_node_rank0": numa,
                    "l2": f"inputs+outputs {B * K * BYTES_PER_HM / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": launched, "gpu_launches_per_step": launched / args.steps, "clocks": clocks,
+        "gpu_launches": launched, "gpu_launches_per_step": launched / args.steps, "host_enqueue_ms_per_step": host_enqueue_ms,
+        "clocks": clocks,
         "total_loss": float((global_losses if global_losses is not None else res[0])[6].item()),
         "aten_cuda_baseline": aten, "api_step": api, "other_workloads": others,
     }

@@ -111,7 +111,7 @@ class FusionPoseLoss(nn.Module):
             t is not None and t.requires_grad for t in (hm, off, var))
         sigma_enc = float(self.encode_sigma if self.encode_sigma is not None else self.target_sigma)
         dec = decode or {}
-        res = ops.fusion_loss(
+        res = ops.fusion_loss_eager(
             hm, off, var, _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), denominators, grad_scale,
             float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
             bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads,
@@ -146,7 +146,7 @@ def _fusion_loss_half_methods():
             object.__setattr__(self, "_amp_upstream", state)
         sigma_enc = float(self.encode_sigma if self.encode_sigma is not None else self.target_sigma)
         dec = decode or {}
-        losses7, coords, scores, _, _, _, _ = ops.fusion_loss_f16(
+        losses7, coords, scores, _, _, _, _ = ops.fusion_loss_f16_eager(
             hm, off, var, _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), None, state if with_grads else None,
             float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
             bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads, bool(dec), dec.get("alpha_param"),

@@ -390,6 +390,48 @@ def _loss_backward(ctx, g_losses, *_unused):
 fusion_loss.register_autograd(_loss_backward, setup_context=_loss_setup_context)
 
 
+# --------------------------------------------------------------------------- eager fast path
+# torch.library's dispatch of a 23-argument custom op costs ~0.25 ms of host time per call (schema normalisation,
+# fill_defaults, the dynamo-disable wrappers) — as much as the whole step takes on the GPU.  The modules therefore call
+# the same implementation and the same autograd rule through a plain autograd.Function when nothing is being traced;
+# the registered ops stay what torch.compile / export see.
+class _FusionLossDirect(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *args):
+        out = fusion_loss._init_fn(*args)
+        _loss_setup_context(ctx, args, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return _loss_backward(ctx, *grads)
+
+
+class _FusionLossF16Direct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *args):
+        out = fusion_loss_f16._init_fn(*args)
+        _loss_f16_setup(ctx, args, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return _loss_f16_backward(ctx, *grads)
+
+
+def fusion_loss_eager(*args):
+    """`fusion_loss` with every argument given positionally (23 of them), without the dispatcher."""
+    if torch.compiler.is_compiling():
+        return fusion_loss(*args)
+    return _FusionLossDirect.apply(*args)
+
+
+def fusion_loss_f16_eager(*args):
+    if torch.compiler.is_compiling():
+        return fusion_loss_f16(*args)
+    return _FusionLossF16Direct.apply(*args)
+
+
 def peer_denominators(weight: Tensor, gt_kps: Tensor, target_given: bool, H: int, W: int, in_w: float, in_h: float,
                       encode_sigma: float, pairs: List[int], peer_ctx: int, out: Optional[Tensor] = None) -> Tensor:
     """gbcodec_peer_denominators_f32: this rank's normaliser sums into every peer's mailbox, the GLOBAL sums out (2 floats
