@@ -111,6 +111,12 @@ __device__ __forceinline__ float4 lds4(const void* p) {
 #define PIPE_UNROLL 1
 #endif
 constexpr int kPU = PIPE_UNROLL;
+// PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
+// instructions per warp and tile); every lane stores its sums into its own four slots of the sigmoid tile — free once the
+// partner visits are over — and the scalar warp adds up the 6 x 32 lanes (off the critical path, a rolled loop).
+#ifndef PIPE_LANESUMS
+#define PIPE_LANESUMS 1
+#endif
 
 constexpr float kFlatRmax = 1e-3f;              // largest eps / p for which the entropy shortcut holds to 1e-7
 constexpr float kShiftCond = 4.f;               // largest sum |terms| / |result| accepted for the shifted relu moments
@@ -326,12 +332,42 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 
             // ---- the warps' partial sums of tile i --------------------------------------------------------------
             mbar_wait_idle(sfull + b, (i >> 1) & 1u);
+#if !PIPE_LANESUMS
             const float* redb = red + b * (NW * 16);
+#endif
             const float* red2b = red2 + b * (NW * 4);
             const float* redMb = redM + b * (NW * 2);
             float m = redMb[0], hmin = redMb[1];
 #pragma unroll
             for (int ww = 1; ww < NW; ++ww) { m = fmaxf(m, redMb[2 * ww]); hmin = fminf(hmin, redMb[2 * ww + 1]); }
+#if PIPE_LANESUMS
+            // value k = 4 * row + c of warp ww, lane l sits in component c of Sb[row * TPB + ww * 32 + l].  This lane takes
+            // row = lane >> 3 and the source lanes g, g + 8, g + 16, g + 24 (g = lane & 7: conflict-free 128-bit reads),
+            // then the eight lanes of a row add up.  Row 0 carries the softmax sums, relative to each warp's own maximum.
+            float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                const int row = lane >> 3, g = lane & 7;
+#pragma unroll 1
+                for (int ww = 0; ww < NW; ++ww) {
+                    const float4* src = Sb + row * TPB + ww * 32 + g;
+                    const float4 a = src[0], b4 = src[8], c = src[16], d = src[24];
+                    float x0 = (a.x + b4.x) + (c.x + d.x), x1 = (a.y + b4.y) + (c.y + d.y);
+                    float x2 = (a.z + b4.z) + (c.z + d.z), x3 = (a.w + b4.w) + (c.w + d.w);
+                    if (row == 0) {
+                        const float dl = (redMb[2 * ww] - m) * kLog2e;            // (m_w - m) log2 e <= 0
+                        const float sc = ex2(dl);
+                        x3 = fmaf(dl, x0, x3);                                    // sum e t: t is relative to the warp's maximum too
+                        x0 *= sc; x1 *= sc; x2 *= sc; x3 *= sc;
+                    }
+                    acc4[0] += x0; acc4[1] += x1; acc4[2] += x2; acc4[3] += x3;
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc4[c] += __shfl_xor_sync(0xffffffffu, acc4[c], o);
+                }
+            }
+#else
             float acc = 0.f;
             {
                 const int idx = lane >> 1, q = lane & 1;
@@ -348,6 +384,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             }
+#endif
             float a4s = 0.f;
             if (nact > 2) {
                 const int idx = lane >> 3, q = lane & 7;
@@ -362,7 +399,11 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(sempty + b);          // the sums are in registers
+#if PIPE_LANESUMS
+            auto val = [&](int k) -> float { return __shfl_sync(0xffffffffu, acc4[k & 3], (k >> 2) << 3); };
+#else
             auto val = [&](int k) -> float { return __shfl_sync(0xffffffffu, acc, k << 1); };
+#endif
             const float Zs = val(0);
             const float iZ = rcp(Zs);
             const float cx = val(1) * iZ, cy = val(2) * iZ;
@@ -639,6 +680,10 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
             for (int q = 0; q < 16; ++q) r16[q] = 0.f;
             const bool sig = heavy && nact > 0;
+#if PIPE_LANESUMS
+            // the sigmoid slots still hold the lanes' sums of tile i - 1 until the scalar warp has taken them
+            if (i >= 1) mbar_wait(sempty + ((i - 1) & 1u), ((i - 1) >> 1) & 1u);
+#endif
             {
                 const f2 kNML = splat2(nml_w);
                 f2 E01 = splat2(0.f), E23 = splat2(0.f), T01 = splat2(0.f), T23 = splat2(0.f);
@@ -785,12 +830,17 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             tie_now = GRADS && mind == 0.f;
 
             // ---- publish this warp's sums --------------------------------------------------------------------------
-            if (i >= 2) mbar_wait(sempty + b, ((i - 2) >> 1) & 1u);
-            float* const redb = red + b * (NW * 16);
             float* const red2b = red2 + b * (NW * 4);
             float* const redMb = redM + b * (NW * 2);
+#if PIPE_LANESUMS
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Sb[q * TPB + tid] = make_float4(r16[4 * q], r16[4 * q + 1], r16[4 * q + 2], r16[4 * q + 3]);
+#else
+            if (i >= 2) mbar_wait(sempty + b, ((i - 2) >> 1) & 1u);
+            float* const redb = red + b * (NW * 16);
             warp_scatter_sum<16>(r16, lane);
             if ((lane & 1) == 0) redb[warp * 16 + (lane >> 1)] = r16[0];
+#endif
             if (nact > 2) {
                 warp_scatter_sum<4>(r4, lane);
                 if ((lane & 7) == 0) red2b[warp * 4 + (lane >> 3)] = r4[0];
@@ -1007,6 +1057,9 @@ int launch_pipe_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEv
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, L::TPB + 64, smem);
     if (e != cudaSuccess || per_sm <= 0) return fail(GBCODEC_ERR_CUDA, "step_pipe_kernel does not fit an SM (%zu bytes of shared memory)", smem);
     const int tiles = P.B * P.K;
+    // GBCODEC_PIPE_CTAS=<n>: fewer resident CTAs per SM than fit (measurement only: how the kernel scales with the
+    // number of tile pipelines in flight)
+    if (const char* lim = getenv("GBCODEC_PIPE_CTAS")) { const int n = atoi(lim); if (n >= 1 && n < per_sm) per_sm = n; }
     const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
     if (e0) cudaEventRecord(e0, s);
     cudaLaunchConfig_t cfg = {};
