@@ -47,7 +47,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // try_wait suspends the thread in hardware until the phase completes or a time limit passes: a wait costs a few issue
 // slots however long it lasts
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+#ifndef PIPE_OUTLINE
+#define PIPE_OUTLINE 0
+#endif
+#if PIPE_OUTLINE
+#define PIPE_INLINE __noinline__
+#else
+#define PIPE_INLINE __forceinline__
+#endif
+__device__ PIPE_INLINE void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile("{\n"
                  " .reg .pred p;\n"
                  "WAIT_%=:\n"
@@ -62,7 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 #ifndef PIPE_SLEEP
 #define PIPE_SLEEP 1
 #endif
-__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, unsigned parity) {
+__device__ PIPE_INLINE void mbar_wait_idle(uint64_t* bar, unsigned parity) {
 #if PIPE_SLEEP == 1
     for (;;) {
         unsigned ok;
@@ -152,7 +160,7 @@ struct PipePlan {
 
 // the one row (if any) in which this thread meets the on-the-fly target patch
 template <int ROWS, int NIT>
-__device__ __forceinline__ int target_row(const int4& gq, float w, int x0, int ty, const EncodeConst& ec, const float* lut, float4& thit) {
+__device__ PIPE_INLINE int target_row(const int4& gq, float w, int x0, int ty, const EncodeConst& ec, const float* lut, float4& thit) {
     thit = make_float4(0.f, 0.f, 0.f, 0.f);
     const PatchGeom geom = unpack_geom(gq, w);
     if (!(geom.active && x0 + 3 >= geom.x_from && x0 < geom.x_to)) return -1;
