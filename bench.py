@@ -439,7 +439,7 @@ def other_workloads(device, ops, N, world, steps=20):
         def fn():
             d = sets[it[0] % n_rot]
             it[0] += 1
-            ops.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
+            ops.fast.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
 
         ms = _time_cuda(fn, max(steps, 2 * n_rot), warm=max(3, n_rot))
         del sets
@@ -838,7 +838,7 @@ def run_decode_b200(args):
 
     def step(i):
         d = sets[i % n_rot]
-        return ops.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
+        return ops.fast.decode(d["hm"], d.get("flip"), perm, d["off"], alpha, fw, 2, dflags)
 
     def barrier():
         if world > 1:

@@ -169,7 +169,7 @@ _fusion_loss_half_methods()
 
 def soft_argmax(heatmaps: Tensor) -> Tuple[Tensor, Tensor]:
     """SoftArgmax2D.forward (beta = 1): expected pixel and raw maximum per tile."""
-    c, s, _ = ops.decode(_f32(heatmaps), None, None, None, None, None, 0, 0)
+    c, s, _ = ops.fast.decode(_f32(heatmaps), None, None, None, None, None, 0, 0)
     return c, s
 
 
@@ -188,7 +188,7 @@ def decode_outputs(outputs: Dict[str, Tensor], alpha_param: Optional[Tensor], ap
         flags |= N.DECODE_APPLY_OFFSET
         off = _f32(outputs["offsets"])
         fw = outputs["fusion_weight"]
-    coords, scores, centre = ops.decode(hm, _f32(heatmaps_of_flipped_input), flip_perm, off,
+    coords, scores, centre = ops.fast.decode(hm, _f32(heatmaps_of_flipped_input), flip_perm, off,
                                         alpha_param if use_subpixel_refinement else None, fw, local_radius, flags)
     return (coords, scores, centre) if return_centre else (coords, scores)
 

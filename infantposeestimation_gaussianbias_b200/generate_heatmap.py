@@ -24,7 +24,7 @@ def generate_heatmaps(keypoints: Tensor, keypoints_visible: Tensor,
     if squeeze:
         keypoints, keypoints_visible = keypoints[None], keypoints_visible[None]
     W, H = int(heatmap_size[0]), int(heatmap_size[1])
-    target, weight = ops.encode(keypoints.float(), keypoints_visible.float(), H, W,
+    target, weight = ops.fast.encode(keypoints.float(), keypoints_visible.float(), H, W,
                                 float(input_size[0]), float(input_size[1]), float(sigma))
     if squeeze:
         target, weight = target[0], weight[0]
@@ -57,7 +57,7 @@ def generate_heatmaps_clipped(joints: Tensor, joints_vis: Tensor, heatmap_size: 
     B, K = joints.shape[0], joints.shape[1]
     H, W = int(heatmap_size[0]), int(heatmap_size[1])
     from . import _native as N
-    return ops.encode_mode(joints.float(), joints_vis.float().reshape(B, K), H, W, float(image_size[0]), float(image_size[1]),
+    return ops.fast.encode_mode(joints.float(), joints_vis.float().reshape(B, K), H, W, float(image_size[0]), float(image_size[1]),
                            float(sigma), N.ENCODE_PATCH_CLIPPED)
 
 
@@ -85,7 +85,7 @@ class GenerateTarget:
         vis = torch.ones(kps.shape[:2], dtype=torch.float32, device=kps.device) if vis is None else vis.reshape(kps.shape[:2])
         h, w = int(self.heatmap_size[0]), int(self.heatmap_size[1])
         ih, iw = self.input_size
-        heat, weight = ops.encode_mode(kps[..., :2].float().contiguous(), vis.float(), h, w, float(iw), float(ih),
+        heat, weight = ops.fast.encode_mode(kps[..., :2].float().contiguous(), vis.float(), h, w, float(iw), float(ih),
                                        float(self.sigma), N.ENCODE_DENSE)
         weight = weight[..., 0]
         results["heatmaps"] = heat[0] if squeeze else heat

@@ -89,7 +89,7 @@ class HostCodecStep:
         launched0 = N.lib().gbcodec_launch_count()
         self.kps_d.copy_(kps_h, non_blocking=True)
         self.vis_d.copy_(vis_h.reshape(B, K), non_blocking=True)
-        den = ops.loss_denominators(self.vis_d, self.kps_d, False, H, W, self.in_w, self.in_h, self.sigma, self.pairs)
+        den = ops.fast.loss_denominators(self.vis_d, self.kps_d, False, H, W, self.in_w, self.in_h, self.sigma, self.pairs)
         self.losses_d.zero_()
         self.copy_stream.wait_stream(main)
         nchunk = (B + C - 1) // C
@@ -190,7 +190,7 @@ class HostDecode:
                     s["flip"][:n].copy_(hm_flip_h[lo:hi], non_blocking=True)
                 self.staged[c & 1].record(self.copy_stream)
             main.wait_event(self.staged[c & 1])
-            coords, scores, _ = ops.decode(s["hm"][:n], s["flip"][:n] if self.flip else None, self.perm,
+            coords, scores, _ = ops.fast.decode(s["hm"][:n], s["flip"][:n] if self.flip else None, self.perm,
                                            off_h[lo:hi] if self.apply_offset else None,
                                            self.alpha if self.refine else None, self.fw if self.apply_offset else None,
                                            self.radius, self.flags)

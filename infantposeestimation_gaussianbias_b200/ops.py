@@ -999,3 +999,26 @@ def _vmean_backward(ctx, g_losses, *_unused):
 
 
 fusion_step_vmean.register_autograd(_vmean_backward, setup_context=_vmean_setup)
+
+
+# --------------------------------------------------------------------------- eager callers of the ops without autograd
+class _Fast:
+    """`ops.fast.decode(...)` etc.: the op's implementation without torch.library's dispatch (20-40 us of host time per call —
+    more than a B = 256 decode takes on the GPU); the registered op while something is being traced.  For the ops that have
+    no autograd rule (encode*, decode*, refine_centroid, postprocess, coords_to_image, loss_denominators)."""
+    _NAMES = ("encode", "encode_mode", "decode", "decode_argmax", "refine_centroid", "postprocess", "coords_to_image", "loss_denominators")
+
+    def __getattr__(self, name):
+        if name not in self._NAMES:
+            raise AttributeError(name)
+        op = globals()[name]
+        impl = op._init_fn
+
+        def call(*a, **k):
+            return op(*a, **k) if torch.compiler.is_compiling() else impl(*a, **k)
+
+        setattr(self, name, call)
+        return call
+
+
+fast = _Fast()

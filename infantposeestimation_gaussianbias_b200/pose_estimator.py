@@ -24,7 +24,7 @@ def flip_permutation(K: int, flip_pairs: Optional[Sequence[Tuple[int, int]]], de
 
 def decode_heatmaps(heatmaps: Tensor, shift: bool = True) -> Tuple[Tensor, Tensor]:
     """First-maximum pixel (+ quarter-pixel nudge): (keypoints (B,K,2), max_vals (B,K))."""
-    c, v, _ = ops.decode_argmax(_f32(heatmaps), N.ARGMAX_QUARTER if shift else N.ARGMAX_PLAIN)
+    c, v, _ = ops.fast.decode_argmax(_f32(heatmaps), N.ARGMAX_QUARTER if shift else N.ARGMAX_PLAIN)
     return c, v
 
 

@@ -20,17 +20,17 @@ from .fusion_head import _f32
 
 
 def get_max_preds(batch_heatmaps: Tensor):
-    c, v, _ = ops.decode_argmax(_f32(batch_heatmaps), N.ARGMAX_PLAIN)
+    c, v, _ = ops.fast.decode_argmax(_f32(batch_heatmaps), N.ARGMAX_PLAIN)
     return c, v.unsqueeze(-1)
 
 
 def get_max_preds_with_subpixel(batch_heatmaps: Tensor):
-    c, v, _ = ops.decode_argmax(_f32(batch_heatmaps), N.ARGMAX_TAYLOR)
+    c, v, _ = ops.fast.decode_argmax(_f32(batch_heatmaps), N.ARGMAX_TAYLOR)
     return c, v.unsqueeze(-1)
 
 
 def coordinate_refinement(heatmaps: Tensor, initial_coords: Tensor, window_size: int = 5) -> Tensor:
-    return ops.refine_centroid(_f32(heatmaps), _f32(initial_coords), int(window_size))
+    return ops.fast.refine_centroid(_f32(heatmaps), _f32(initial_coords), int(window_size))
 
 
 def fused_decode(heatmaps: Tensor, regression_coords=None, centers=None, scales=None, alpha: float = 0.5):
@@ -38,7 +38,7 @@ def fused_decode(heatmaps: Tensor, regression_coords=None, centers=None, scales=
     confidence-adaptive blend overrides the fixed alpha (postprocess.py:105-131).  The reference
     decides whether to rescale `regression_coords` from a host read of its maximum (:119); here
     that test runs on the device inside the same launch sequence, no sync."""
-    p, v, _ = ops.postprocess(_f32(heatmaps), _f32(regression_coords), None, None, N.ARGMAX_TAYLOR,
+    p, v, _ = ops.fast.postprocess(_f32(heatmaps), _f32(regression_coords), None, None, N.ARGMAX_TAYLOR,
                               centers is not None and scales is not None, 256.0, 0, False, 0.0, False, 256.0, 256.0)
     return p, v.unsqueeze(-1)
 
@@ -63,7 +63,7 @@ def postprocess_predictions(outputs, batch_meta, config):
     both = center is not None and scale is not None
     dev = heatmaps.device
     to = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32, device=dev)
-    p, v, m = ops.postprocess(_f32(heatmaps), _f32(outputs.get("coords", None)), to(center) if both else None,
+    p, v, m = ops.fast.postprocess(_f32(heatmaps), _f32(outputs.get("coords", None)), to(center) if both else None,
                               to(scale) if both else None, N.ARGMAX_TAYLOR, both, 256.0, 5, True, 0.3,
                               "center" in batch_meta and "scale" in batch_meta, 256.0, 256.0)
     return {"preds": p, "maxvals": v.unsqueeze(-1), "mask": m.unsqueeze(-1)}
@@ -72,5 +72,5 @@ def postprocess_predictions(outputs, batch_meta, config):
 def heatmap_to_image(coords: Tensor, center: Tensor, scale: Tensor, heatmap_size, input_size) -> Tensor:
     """validate.py:102-119 / inference.py:143-175 on the device: heatmap px -> input px -> original
     image, in the reference's order of float32 operations.  heatmap_size, input_size are (W, H)."""
-    return ops.coords_to_image(_f32(coords), _f32(center), _f32(scale), int(heatmap_size[1]), int(heatmap_size[0]),
+    return ops.fast.coords_to_image(_f32(coords), _f32(center), _f32(scale), int(heatmap_size[1]), int(heatmap_size[0]),
                                float(input_size[0]), float(input_size[1]))
