@@ -118,7 +118,21 @@ __device__ __forceinline__ float4 lds4(const void* p) {
 #ifndef PIPE_UNROLL
 #define PIPE_UNROLL 1
 #endif
-constexpr int kPU = PIPE_UNROLL;
+// per-loop overrides (A/B measurements): the small loops (zero fill, maximum, variance sum) cost a few instructions per
+// iteration and can be unrolled without growing the hot path much; the three big bodies are what the caches feel
+#ifndef PIPE_UNROLL_SMALL
+#define PIPE_UNROLL_SMALL PIPE_UNROLL
+#endif
+#ifndef PIPE_UNROLL_B
+#define PIPE_UNROLL_B PIPE_UNROLL
+#endif
+#ifndef PIPE_UNROLL_P
+#define PIPE_UNROLL_P PIPE_UNROLL
+#endif
+#ifndef PIPE_UNROLL_D
+#define PIPE_UNROLL_D PIPE_UNROLL
+#endif
+constexpr int kPUs = PIPE_UNROLL_SMALL, kPUb = PIPE_UNROLL_B, kPUp = PIPE_UNROLL_P, kPUd = PIPE_UNROLL_D;
 // PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
 // instructions per warp and tile); every lane stores its sums into its own four slots of the sigmoid tile — free once the
 // partner visits are over — and the scalar warp adds up the 6 x 32 lanes (off the critical path, a rolled loop).
@@ -338,6 +352,20 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             float tapv = 0.f;
             if (heavy) tapv = __ldg(off_tile + (lane >> 4) * N + (wy0 + ((lane >> 2) & 3)) * W + wx0 + (lane & 3));
 
+#ifdef PIPE_JUNK
+            // measurement only: PIPE_JUNK x 16 straight-line instructions of once-per-tile code in the scalar warp (does the
+            // kernel's time follow the instruction-cache footprint of the per-tile code?)
+            {
+                unsigned jk = lane;
+#pragma unroll
+                for (int q = 0; q < PIPE_JUNK; ++q)
+                    asm volatile("add.u32 %0, %0, 1;\n xor.b32 %0, %0, 3;\n add.u32 %0, %0, 5;\n xor.b32 %0, %0, 7;\n"
+                                 "add.u32 %0, %0, 9;\n xor.b32 %0, %0, 11;\n add.u32 %0, %0, 13;\n xor.b32 %0, %0, 15;\n"
+                                 "add.u32 %0, %0, 17;\n xor.b32 %0, %0, 19;\n add.u32 %0, %0, 21;\n xor.b32 %0, %0, 23;\n"
+                                 "add.u32 %0, %0, 25;\n xor.b32 %0, %0, 27;\n add.u32 %0, %0, 29;\n xor.b32 %0, %0, 31;" : "+r"(jk));
+                if (jk == 0xdeadbeefu) tids[3] = (int)jk;
+            }
+#endif
             // ---- the warps' partial sums of tile i --------------------------------------------------------------
             mbar_wait_idle(sfull + b, (i >> 1) & 1u);
 #if !PIPE_LANESUMS
@@ -662,12 +690,12 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
             if (GRADS) {
                 float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
-#pragma unroll kPU
+#pragma unroll (2 * kPUs)
                 for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
             }
             // ---- maximum (and minimum) of the tile: per warp ------------------------------------------------------
             float mw = -INFINITY, mnw = INFINITY;
-#pragma unroll kPU
+#pragma unroll kPUs
             for (int it = 0; it < NIT; ++it) {
                 const float4 o = Hs[it * TPB + tid];
                 mw = max3f(mw, o.x, o.y); mw = max3f(mw, o.z, o.w);
@@ -703,7 +731,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 const f2 kCw = splat2(ex2(nml_w));                // exp(-m_w)
                 auto body = [&](auto mode_c) {
                     constexpr int MODE = decltype(mode_c)::value;     // 0 light, 1 heavy, 2 heavy + sigmoid from e, 3 heavy + plain sigmoid
-                    constexpr int kUnroll = MODE == 2 ? kPU : 1;
+                    constexpr int kUnroll = MODE == 2 ? kPUb : 1;
 #pragma unroll kUnroll
                     for (int it = 0; it < NIT; ++it) {
                         const float4 o = Hs[it * TPB + tid];
@@ -776,7 +804,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     mbar_wait(rfull + q, (rq >> 1) & 1u);
                     const float4* Qs = Rb + q * N4;
                     f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
-#pragma unroll kPU
+#pragma unroll kPUp
                     for (int it = 0; it < NIT; ++it) {
                         const float4 q4 = Qs[it * TPB + tid];
                         const float4 o = Hs[it * TPB + tid];
@@ -824,7 +852,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     mbar_wait(rfull + q, (rq >> 1) & 1u);
                     const float4* Vs = Rb + q * N4;
                     f2 V2 = splat2(0.f);
-#pragma unroll kPU
+#pragma unroll kPUs
                     for (int it = 0; it < NIT; ++it) {
                         const f4 v = as_f4(Vs[it * TPB + tid]);
                         V2 = add2(V2, add2(v.a, v.b));
@@ -949,7 +977,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                         constexpr bool FLAT = decltype(flat_c)::value;
                         const f2 kNKE = splat2(-ke), kEps2 = splat2(kEps), kLn2v = splat2(kLn2);
                         const f2 base01 = pack2(fmaf(dxj[0], fxx, addc), fmaf(dxj[1], fxx, addc)), base23 = pack2(fmaf(dxj[2], fxx, addc), fmaf(dxj[3], fxx, addc));
-                        constexpr int kUnrollD = FLAT ? kPU : 1;
+                        constexpr int kUnrollD = FLAT ? kPUd : 1;
 #pragma unroll kUnrollD
                         for (int it = 0; it < NIT; ++it) {
                             const float4 o = Hs[it * TPB + tid];

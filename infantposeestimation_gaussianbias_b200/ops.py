@@ -694,13 +694,28 @@ def _combined_backward(ctx, g_losses, g_gp, g_gc, g_gr):
         return tuple(none)
     if not ctx.with_grads:
         raise RuntimeError("gbcodec::combined_loss was run with with_grads=False; its output is not differentiable")
-    gp, gc, gr = ctx.stash
-    contig = lambda t: None if t is None else t.contiguous()
-    torch.ops.gbcodec.combined_loss_backward(g_losses.contiguous(), gp, gc, gr, *[contig(t) for t in ctx.tensors], *ctx.scalars)
     pred, target, weight, coords, refined, target_coords, grad_scale = ctx.tensors
+    contig = lambda t: None if t is None else t.contiguous()
+    if ctx.stash is not None:
+        gp, gc, gr = ctx.stash
+        assumed = grad_scale
+    else:
+        # The stored gradients left with an earlier backward through this graph (and that backward may have recomputed
+        # them for another upstream vector): fresh buffers, and an "assumed" scale of NaN, which no upstream matches, so
+        # that the device-side plan is "recompute" — never stale gradients.
+        some = pred if pred is not None else (coords if coords is not None else refined)
+        e = lambda: torch.empty(0, dtype=torch.float32, device=some.device)
+        gp = torch.empty_like(pred) if pred is not None else e()
+        gc = torch.empty_like(coords) if coords is not None else e()
+        gr = torch.empty_like(refined) if refined is not None else e()
+        assumed = torch.full((1,), float("nan"), dtype=torch.float32, device=some.device)
+    combined_loss_backward._init_fn(g_losses.detach().contiguous(), gp, gc, gr, contig(pred), contig(target), contig(weight), contig(coords),
+                                    contig(refined), contig(target_coords), assumed, *ctx.scalars)
+    ctx.stash = None                    # ownership passes to autograd (AccumulateGrad adopts the tensors instead of copying them)
     none[0] = gp if pred is not None else None
     none[3] = gc if coords is not None else None
     none[4] = gr if refined is not None else None
+    del gp, gc, gr
     return tuple(none)
 
 
