@@ -413,6 +413,149 @@ static int launch_decode_tile(const float* hm, const float* hmf, const int32_t* 
     return check_launch("decode_tile_kernel");
 }
 
+// ---------------------------------------------------------------------------------
+// One WARP per tile (tiles of at most 16 KB: 64x48, 64x64; no flip average).  The CTA-per-tile kernel above spends ~2 400
+// warp instructions on a 12 KB tile, most of them on what six warps of 16 pixels per thread owe each other (two block
+// barriers, the cross-warp sums, 16 window tests per thread for the scatter) and runs at 72 % issue utilisation: it is
+// instruction-bound at 5.2 TB/s where a read-only stream reaches 7 TB/s.  Here a warp owns the whole tile: lane l holds the
+// float4 32 j + l (j < N4/32: 24 x 128-bit loads in flight per lane, 512 coalesced bytes per instruction), takes the maximum
+// and the softmax moments from registers, and five shuffles per sum finish the tile — no shared memory, no barrier, ~700
+// instructions.  A warp's tail (window + offset taps: two dependent L2 / HBM round trips) stalls nobody else: the other warps
+// of the SM are independent tiles in other phases.  The window pixels are re-read through L2 (the tile has just come
+// through it); their sums run in decode_tile_kernel's order.
+// Walking 32 float4 ahead moves a lane A = 32 / W4 rows down and Bc = 32 % W4 column groups right (wrapping into the next
+// row), so the pixel coordinates are two running floats per lane.
+// ---------------------------------------------------------------------------------
+constexpr int kDecodeWarpThreads = 128;
+template <int W4, int HH, int MINB>
+__global__ void __launch_bounds__(kDecodeWarpThreads, MINB)
+decode_warp_kernel(const float* __restrict__ hm, const float* __restrict__ off, const float* __restrict__ alpha_param,
+                   const float* __restrict__ fusion_weight, int tiles, int radius, unsigned flags,
+                   float* __restrict__ coords, float* __restrict__ scores, int32_t* __restrict__ centre) {
+    constexpr int W = 4 * W4, H = HH, N4 = W4 * HH, N = 4 * N4, NJ = N4 / 32;
+    constexpr int A = 32 / W4, Bc = 32 % W4;
+    static_assert(N4 % 32 == 0 && NJ <= 32, "a lane holds at most 32 float4 of the tile");
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (kDecodeWarpThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= tiles) return;
+    const bool refine = (flags & GBCODEC_DECODE_REFINE) != 0, want_off = (flags & GBCODEC_DECODE_APPLY_OFFSET) != 0;
+    const float* hm_tile = hm + (size_t)tile * N;
+    const float4* src = reinterpret_cast<const float4*>(hm_tile) + lane;
+    float4 v[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) v[j] = ldg_stream(src + 32 * j);
+    // the two learnable scalars and their sigmoids: in the shadow of the tile loads
+    float a = 0.f, fw = 0.f;
+    if (refine) a = sigmoid_acc(__ldg(alpha_param));
+    if (want_off) {
+        fw = __ldg(fusion_weight);
+        if (flags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw = sigmoid_acc(fw);
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) m = fmaxf(m, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+    m = warp_max(m);
+    const float ml = m * kLog2e;
+    float fc = (float)((lane % W4) << 2), fr = (float)(lane / W4);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};                          // Z, sum e x, sum e y
+    float E1 = 0.f, E2 = 0.f, E3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float e0 = ex2(fmaf(v[j].x, kLog2e, -ml)), e1 = ex2(fmaf(v[j].y, kLog2e, -ml));
+        const float e2 = ex2(fmaf(v[j].z, kLog2e, -ml)), e3 = ex2(fmaf(v[j].w, kLog2e, -ml));
+        const float sr = (e0 + e1) + (e2 + e3);
+        acc[0] += sr;
+        acc[1] = fmaf(fc, sr, acc[1]);
+        acc[2] = fmaf(fr, sr, acc[2]);
+        E1 += e1; E2 += e2; E3 += e3;
+        fc += (float)(4 * Bc); fr += (float)A;
+        if (Bc != 0 && fc >= (float)W) { fc -= (float)W; fr += 1.f; }
+    }
+    acc[1] += fmaf(3.f, E3, fmaf(2.f, E2, E1));
+    warp_scatter_sum<4>(acc, lane);                               // lane l: total of value l >> 3
+    const float iZ = 1.0f / __shfl_sync(0xffffffffu, acc[0], 0);
+    float cx = __shfl_sync(0xffffffffu, acc[0], 8) * iZ, cy = __shfl_sync(0xffffffffu, acc[0], 16) * iZ;
+
+    // torch.round is round-half-to-even == rintf in the default rounding mode
+    const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
+    const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
+    const int S = 2 * radius + 1;
+    int bx = 0, by = 0;
+    float pre = 0.f;
+    const float* off_tile = off + (size_t)tile * 2 * N;
+    if (want_off) {
+        // the 4x4x2 block of offset taps around floor(cx, cy): in flight before the refined coordinate is final
+        bx = (int)floorf(fminf(fmaxf(cx, 0.f), (float)(W - 1))) - 1;
+        by = (int)floorf(fminf(fmaxf(cy, 0.f), (float)(H - 1))) - 1;
+        const int t = lane & 15;
+        const int qx = min(max(bx + (t & 3), 0), W - 1), qy = min(max(by + (t >> 2), 0), H - 1);
+        pre = __ldg(off_tile + (lane >> 4) * N + qy * W + qx);
+    }
+    if (refine) {
+        // window cells outside the map do not exist: validity comes from the coordinates
+        float first = -INFINITY;                                  // this lane's first window pixel stays in a register
+        {
+            const int x = px - radius + lane % S, y = py - radius + lane / S;
+            if (lane < S * S && x >= 0 && x < W && y >= 0 && y < H) first = __ldg(hm_tile + y * W + x);
+        }
+        float vmax = first;
+        for (int c = lane + 32; c < S * S; c += 32) {
+            const int x = px - radius + c % S, y = py - radius + c / S;
+            if (x >= 0 && x < W && y >= 0 && y < H) vmax = fmaxf(vmax, __ldg(hm_tile + y * W + x));
+        }
+        vmax = warp_max(vmax);
+        float sw[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = lane; c < S * S; c += 32) {
+            const int x = px - radius + c % S, y = py - radius + c / S;
+            if (x >= 0 && x < W && y >= 0 && y < H) {
+                const float e = expf((c == lane ? first : __ldg(hm_tile + y * W + x)) - vmax);
+                sw[0] += e; sw[1] += e * (float)x; sw[2] += e * (float)y;
+            }
+        }
+        warp_scatter_sum<4>(sw, lane);
+        const float se = __shfl_sync(0xffffffffu, sw[0], 0), sx = __shfl_sync(0xffffffffu, sw[0], 8), sy = __shfl_sync(0xffffffffu, sw[0], 16);
+        cx = a * cx + (1.f - a) * (sx / se);
+        cy = a * cy + (1.f - a) * (sy / se);
+    }
+    if (want_off) {
+        const Bilinear bl = bilinear_setup(cx, cy, H, W);
+        float ox, oy;
+        const bool covered = bl.x0 >= bx && bl.x1 <= bx + 3 && bl.y0 >= by && bl.y1 <= by + 3;   // warp-uniform
+        if (covered) {
+            const int i00 = (bl.y0 - by) * 4 + (bl.x0 - bx), i01 = (bl.y0 - by) * 4 + (bl.x1 - bx);
+            const int i10 = (bl.y1 - by) * 4 + (bl.x0 - bx), i11 = (bl.y1 - by) * 4 + (bl.x1 - bx);
+            float t[2][4];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                t[c][0] = __shfl_sync(0xffffffffu, pre, c * 16 + i00);
+                t[c][1] = __shfl_sync(0xffffffffu, pre, c * 16 + i01) * bl.okx;
+                t[c][2] = __shfl_sync(0xffffffffu, pre, c * 16 + i10) * bl.oky;
+                t[c][3] = __shfl_sync(0xffffffffu, pre, c * 16 + i11) * (bl.okx * bl.oky);
+            }
+            ox = bl.w00 * t[0][0] + bl.w01 * t[0][1] + bl.w10 * t[0][2] + bl.w11 * t[0][3];
+            oy = bl.w00 * t[1][0] + bl.w01 * t[1][1] + bl.w10 * t[1][2] + bl.w11 * t[1][3];
+        } else {
+            ox = bilinear_read(off_tile, bl, W);
+            oy = bilinear_read(off_tile + N, bl, W);
+        }
+        cx += fw * ox;
+        cy += fw * oy;
+    }
+    if (lane == 0) {
+        coords[2 * tile] = cx; coords[2 * tile + 1] = cy;
+        scores[tile] = m;
+        if (centre) { centre[2 * tile] = px; centre[2 * tile + 1] = py; }
+    }
+}
+
+template <int W4, int HH, int MINB>
+static int launch_decode_warp(const float* hm, const float* off, const float* ap, const float* fw, int tiles, int radius,
+                              unsigned flags, float* coords, float* scores, int32_t* centre, cudaStream_t s) {
+    const int per_cta = kDecodeWarpThreads / 32;
+    note_launch(), decode_warp_kernel<W4, HH, MINB><<<(tiles + per_cta - 1) / per_cta, kDecodeWarpThreads, 0, s>>>(hm, off, ap, fw, tiles, radius, flags, coords, scores, centre);
+    return check_launch("decode_warp_kernel");
+}
+
 // Thread count T (multiple of 32) with n4 == T*NITER, NITER <= 8; 0 if none.
 int pick_threads(int n4, int* niter) {
     for (int pass = 0; pass < 2; ++pass) {
@@ -453,6 +596,13 @@ int launch_decode(const float* hm, const float* hmf, const int32_t* perm, const 
         if (hmf) return launch_decode_tile<W4, ROWS, NIT, true, MB_FLIP>(hm, hmf, perm, off, alpha_param, fusion_weight, grid_t, K, radius, flags, coords, scores, centre, stream); \
         return launch_decode_tile<W4, ROWS, NIT, false, MB_PLAIN>(hm, hmf, perm, off, alpha_param, fusion_weight, grid_t, K, radius, flags, coords, scores, centre, stream); \
     } while (0)
+    // GBCODEC_DECODE_KERNEL=tile: the CTA-per-tile kernel where the warp-per-tile one is the default (A/B measurements)
+    const char* const sel = getenv("GBCODEC_DECODE_KERNEL");                 // read on every call: tests compare the two kernels in one process
+    const bool cta_tile = sel && !strcmp(sel, "tile");
+    if (!generic && !cta_tile && !hmf) {
+        if (H == 64 && W == 48) return launch_decode_warp<12, 64, 4>(hm, off, alpha_param, fusion_weight, grid_t, radius, flags, coords, scores, centre, stream);
+        if (H == 64 && W == 64) return launch_decode_warp<16, 64, 3>(hm, off, alpha_param, fusion_weight, grid_t, radius, flags, coords, scores, centre, stream);
+    }
     if (!generic) {
         if (H == 64 && W == 48) GBC_TILE(12, 16, 4, 10, 8);     // 192 threads, 16 px each
         if (H == 64 && W == 64) GBC_TILE(16, 16, 4, 8, 6);      // 256 threads, 16 px each
@@ -539,8 +689,61 @@ argmax_kernel(const float* __restrict__ hm, int H, int W, int mode,
     }
 }
 
+// One WARP per tile for tiles of whole 512-byte rows of lanes (n4 % 32 == 0: every shape of the reference's configs): lane l
+// visits the float4 32 j + l in ascending j, eight 128-bit loads in flight at a time; strict '>' inside the lane and the
+// smaller index on equal values across lanes keep torch.max's first maximum.  No shared memory, no barrier: ~350
+// instructions per 12 KB tile against ~900 for the CTA-per-tile kernel above, and a tile's tail (the sub-pixel taps, through
+// L2) stalls one warp, not a CTA.
+constexpr int kArgmaxWarpThreads = 256;
+__global__ void __launch_bounds__(kArgmaxWarpThreads)
+argmax_warp_kernel(const float* __restrict__ hm, int tiles, int H, int W, int mode,
+                   float* __restrict__ coords, float* __restrict__ maxvals, int32_t* __restrict__ index) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (kArgmaxWarpThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= tiles) return;
+    const int n = H * W, nj = n >> 7;
+    const float* t = hm + (size_t)tile * n;
+    const float4* src = reinterpret_cast<const float4*>(t) + lane;
+    float best = -INFINITY;
+    int at = 0x7ffffffe;
+    auto visit = [&](const float4& q, int i) {
+        const int base = i << 2;
+        if (q.x > best) { best = q.x; at = base; }
+        if (q.y > best) { best = q.y; at = base + 1; }
+        if (q.z > best) { best = q.z; at = base + 2; }
+        if (q.w > best) { best = q.w; at = base + 3; }
+    };
+    int j = 0;
+    for (; j + 8 <= nj; j += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = ldg_stream(src + 32 * (j + q));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) visit(v[q], 32 * (j + q) + lane);
+    }
+    for (; j < nj; ++j) visit(ldg_stream(src + 32 * j), 32 * j + lane);
+    // NaN-free tiles always find a finite maximum; an all -inf/NaN tile reports index 0 like torch.max on -inf
+    warp_argmax(best, at);
+    if (lane == 0) {
+        if (at >= n) { at = 0; best = t[0]; }
+        float fx, fy;
+        subpixel_step(t, at, H, W, mode, fx, fy);
+        coords[2 * tile] = fx; coords[2 * tile + 1] = fy;
+        maxvals[tile] = best;
+        if (index) index[tile] = at;
+    }
+}
+
 int launch_argmax(const float* hm, int B, int K, int H, int W, int mode,
                   float* coords, float* maxvals, int32_t* index, cudaStream_t s) {
+    // GBCODEC_ARGMAX_KERNEL=tile: the CTA-per-tile kernel for every shape (A/B measurements)
+    const char* const sel = getenv("GBCODEC_ARGMAX_KERNEL");                 // read on every call
+    const bool cta_tile = sel && !strcmp(sel, "tile");
+    if (!cta_tile && (H * W) % 128 == 0 && (reinterpret_cast<uintptr_t>(hm) & 15u) == 0) {
+        const int per_cta = kArgmaxWarpThreads / 32, tiles = B * K;
+        note_launch(), argmax_warp_kernel<<<(tiles + per_cta - 1) / per_cta, kArgmaxWarpThreads, 0, s>>>(hm, tiles, H, W, mode, coords, maxvals, index);
+        return check_launch("argmax_warp_kernel");
+    }
     int niter = 0;
     int threads = pick_threads((H * W) >> 2, &niter);
     if (!threads) threads = 256;

@@ -837,7 +837,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.alpha_param = alpha_param; A.fusion_weight = fusion_weight; A.coords = coords; A.scores = scores;
     A.radius = radius; A.dflags = dflags;
     A.sums = L.sums; A.weff = L.weff; A.geom = L.geom; A.partial = L.partial;
-    A.desc = L.desc; A.tile_counter = L.tile_counter;
+    A.desc = L.desc; A.tile_counter = L.tile_counter; A.sm_slots = L.sm_slots;
     A.half_io = half_io;
     A.var_mean = var_mean; A.grad_var_mean = grad_var_mean;
     if (var_mean) {

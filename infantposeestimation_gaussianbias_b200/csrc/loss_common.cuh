@@ -48,6 +48,7 @@ struct LossArgs {
     // persistent step kernel (step_tile.cu): per-tile descriptors written by denoms_kernel, dynamic tile counter
     const struct TileDesc* desc;
     unsigned* tile_counter;
+    unsigned* sm_slots;                 // [kSmSlots] running count of step CTAs started per SM (never reset: only its value mod 3 is used)
 };
 
 // Everything the persistent step kernel needs to know about one tile besides its pixels, in one 64-byte record
@@ -64,10 +65,12 @@ struct __align__(16) TileDesc {
 static_assert(sizeof(TileDesc) == 64, "one 64-byte bulk copy per tile");
 
 constexpr int kFinBlocks = 32;          // CTAs of the second-stage reduction
-constexpr int kWsHeaderFloats = 512;    // sums (2 doubles), plan, ticket, lam_eff, second-stage partials; 2 KB
+constexpr int kSmSlots = 512;           // per-SM counters of the step kernel (step_pipe.cu: which CTA of its SM a CTA is)
+constexpr int kWsHeaderFloats = 1024;   // sums (2 doubles), plan, ticket, lam_eff, second-stage partials (2 KB); per-SM counters (2 KB)
 struct WsLayout {
     double* sums; int* plan; unsigned* ticket; unsigned* tile_counter; float* lam_eff; double* bpart; float* weff; int4* geom; float* partial;
     TileDesc* desc;
+    unsigned* sm_slots;
 };
 static inline size_t ws_bytes(int B, int K) {
     return (size_t)(kWsHeaderFloats + (size_t)B * K * (13 + 16) + 8 + 16) * sizeof(float);
@@ -81,6 +84,7 @@ static inline WsLayout ws_carve(void* ws, int B, int K) {
     l.tile_counter = reinterpret_cast<unsigned*>(f + 6);   // f[6]: inside the 32 bytes every call clears
     l.lam_eff = f + 8;                              // f[8..15]
     l.bpart = reinterpret_cast<double*>(f + 64);    // kFinBlocks * 6 doubles
+    l.sm_slots = reinterpret_cast<unsigned*>(f + 512);   // kSmSlots words
     // geom rows are 16 bytes and partial rows 32 bytes: keep both aligned
     const size_t tiles = (size_t)B * K, tiles8 = (tiles + 7) & ~(size_t)7;
     l.geom = reinterpret_cast<int4*>(f + kWsHeaderFloats);

@@ -70,6 +70,9 @@ __device__ PIPE_INLINE void mbar_wait(uint64_t* bar, unsigned parity) {
 #ifndef PIPE_SLEEP
 #define PIPE_SLEEP 1
 #endif
+#ifndef PIPE_SLEEP_NS
+#define PIPE_SLEEP_NS 400
+#endif
 __device__ PIPE_INLINE void mbar_wait_idle(uint64_t* bar, unsigned parity) {
 #if PIPE_SLEEP == 1
     for (;;) {
@@ -77,7 +80,7 @@ __device__ PIPE_INLINE void mbar_wait_idle(uint64_t* bar, unsigned parity) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) return;
-        __nanosleep(400);
+        __nanosleep(PIPE_SLEEP_NS);
     }
 #elif PIPE_SLEEP == 2
     asm volatile("{\n"
@@ -121,16 +124,30 @@ __device__ __forceinline__ float4 lds4(const void* p) {
 // per-loop overrides (A/B measurements): the small loops (zero fill, maximum, variance sum) cost a few instructions per
 // iteration and can be unrolled without growing the hot path much; the three big bodies are what the caches feel
 #ifndef PIPE_UNROLL_SMALL
-#define PIPE_UNROLL_SMALL PIPE_UNROLL
+#define PIPE_UNROLL_SMALL 4
 #endif
 #ifndef PIPE_UNROLL_B
 #define PIPE_UNROLL_B PIPE_UNROLL
 #endif
 #ifndef PIPE_UNROLL_P
-#define PIPE_UNROLL_P PIPE_UNROLL
+#define PIPE_UNROLL_P 4
 #endif
 #ifndef PIPE_UNROLL_D
 #define PIPE_UNROLL_D PIPE_UNROLL
+#endif
+#ifndef PIPE_SRED_UNROLL
+#define PIPE_SRED_UNROLL 1
+#endif
+// PIPE_EARLY_DECODE: the scalar warp requests the decode's window pixels and the block of offset taps as soon as the
+// soft-argmax is known and consumes them after the constants of the gradient pass are out: two L2 round trips less on
+// the per-tile chain — and 3 % SLOWER (0.2600 against 0.2520 ms): what the ~100 extra once-per-tile instructions cost in
+// instruction fetch outweighs the latency they hide.  Kept as a measurement switch.
+#ifndef PIPE_EARLY_DECODE
+#define PIPE_EARLY_DECODE 0
+#endif
+constexpr int kSredU = PIPE_SRED_UNROLL;
+#ifndef PIPE_BALANCE
+#define PIPE_BALANCE 1
 #endif
 constexpr int kPUs = PIPE_UNROLL_SMALL, kPUb = PIPE_UNROLL_B, kPUp = PIPE_UNROLL_P, kPUd = PIPE_UNROLL_D;
 // PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
@@ -227,14 +244,22 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     uint64_t* const p2full = bars + 18;      // general second pass: sums published                (compute -> scalar)
     uint64_t* const p2done = bars + 19;      // ... final constants written                        (scalar -> compute)
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
     const int tiles = P.B * P.K;
     const bool has_var = A.var != nullptr;
     const bool decode = A.coords != nullptr;
     const float* const hm = A.hm;
 
     // ---- once per CTA -------------------------------------------------------------------------------
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
+#if PIPE_BALANCE
+        // which of its SM's (three) step CTAs this one is: the roles below are laid out per rank
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tids[3] = A.sm_slots ? (int)(atomicAdd(A.sm_slots + (smid & (kSmSlots - 1)), 1u) % 3u) : 0;
+#else
+        tids[3] = 0;
+#endif
 #pragma unroll
         for (int q = 0; q < 3; ++q) { mbar_init(hfull + q, 1); mbar_init(hempty + q, NW); }
 #pragma unroll
@@ -246,8 +271,29 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         mbar_init(p2full, NW); mbar_init(p2done, 1);
         fence_mbar_init();
     }
-    for (int q = tid; q < P.ec.lut_size; q += TPB + 64) lut[q] = expf(-(float)q / P.ec.two_sigma_sq);
+    for (int q = threadIdx.x; q < P.ec.lut_size; q += TPB + 64) lut[q] = expf(-(float)q / P.ec.two_sigma_sq);
     __syncthreads();
+
+    // ---- roles --------------------------------------------------------------------------------------
+    // A warp's scheduler (SM sub-partition) is its slot in the SM modulo 4, and the CTA's eight warps take consecutive
+    // slots.  With the producer and the scalar warp as warps 6 and 7 of every CTA, the three CTAs of an SM put 6 compute
+    // warps on each of the sub-partitions 0 and 1 and 3 on each of 2 and 3 — and the compute warps of a tile move in lock
+    // step (ring buffers and sums are handed over when ALL of them are done), so the kernel ran at the pace of the two
+    // crowded schedulers.  Laid out per CTA rank, the six light warps of an SM sit 2 / 2 / 1 / 1 on the sub-partitions
+    // and the compute warps 4 / 4 / 5 / 5 (scalar warps, the heavier of the light ones, where only 4 compute warps are):
+    //   rank 0: scalar = warp 4 (sub-partition 0), producer = warp 5 (1)
+    //   rank 1: scalar = warp 4 (0),               producer = warp 6 (2)
+    //   rank 2: scalar = warp 5 (1),               producer = warp 7 (3)
+    // The logical warp index used below: compute warps 0 .. NW-1 in slot order, producer = NW, scalar = NW + 1.
+#if PIPE_BALANCE
+    const int rank = tids[3];
+    const int pw = threadIdx.x >> 5;
+    const int s_pos = rank == 2 ? NW - 1 : NW - 2, p_pos = NW - 1 + rank;
+    const int warp = pw == p_pos ? NW : (pw == s_pos ? NW + 1 : pw - (pw > s_pos ? 1 : 0) - (pw > p_pos ? 1 : 0));
+#else
+    const int warp = threadIdx.x >> 5;
+#endif
+    const int tid = warp * 32 + lane;
 
     // ======================================================================================================
     // producer warp: one lane
@@ -383,7 +429,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             float acc4[4] = {0.f, 0.f, 0.f, 0.f};
             {
                 const int row = lane >> 3, g = lane & 7;
-#pragma unroll 1
+#pragma unroll kSredU
                 for (int ww = 0; ww < NW; ++ww) {
                     const float4* src = Sb + row * TPB + ww * 32 + g;
                     const float4 a = src[0], b4 = src[8], c = src[16], d = src[24];
@@ -445,6 +491,26 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const float cx = val(1) * iZ, cy = val(2) * iZ;
             const float ml = m * kLog2e;
             float* const cb = cons + b * kConsFloats;
+#if PIPE_EARLY_DECODE
+            // decode: this lane's window pixel and the 4x4x2 block of offset taps around floor(cx, cy), requested now
+            float vpx = -INFINITY, pre = 0.f;
+            int wx_ = 0, wy_ = 0, pbx = 0, pby = 0;
+            bool okw = false;
+            if (win_small) {
+                const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
+                const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
+                wx_ = px + wdx; wy_ = py + wdy;
+                okw = in_win && wx_ >= 0 && wx_ < W && wy_ >= 0 && wy_ < H;
+                if (okw) vpx = __ldg(hm + (size_t)tile * N + wy_ * W + wx_);
+                if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
+                    pbx = (int)floorf(fminf(fmaxf(cx, 0.f), (float)(W - 1))) - 1;
+                    pby = (int)floorf(fminf(fmaxf(cy, 0.f), (float)(H - 1))) - 1;
+                    const int tq = lane & 15;
+                    const int qx = min(max(pbx + (tq & 3), 0), W - 1), qy = min(max(pby + (tq >> 2), 0), H - 1);
+                    pre = __ldg(off_tile + (lane >> 4) * N + qy * W + qx);
+                }
+            }
+#endif
 
             if (!heavy) {
                 // weight 0: every term carries a factor w -> zero loss and gradient; decode only
@@ -624,11 +690,16 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             if (decode) {
                 float dx_ = cx, dy_ = cy;
                 if (win_small) {
+#if PIPE_EARLY_DECODE
+                    const int x = wx_, y = wy_;
+                    const bool ok = okw;
+#else
                     const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
                     const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
                     const int x = px + wdx, y = py + wdy;
                     const bool ok = in_win && x >= 0 && x < W && y >= 0 && y < H;
                     const float vpx = ok ? __ldg(hm + (size_t)tile * N + y * W + x) : -INFINITY;
+#endif
                     const float vmax = warp_max(vpx);
                     const float e = ok ? expf(vpx - vmax) : 0.f;
                     const float se = warp_sum(e), sx = warp_sum(e * (float)x), sy = warp_sum(e * (float)y);
@@ -636,8 +707,28 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     dy_ = a_blend * cy + (1.f - a_blend) * (sy / se);
                     if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
                         const Bilinear bl = bilinear_setup(dx_, dy_, H, W);
-                        const float ox = bilinear_read(off_tile, bl, W);
-                        const float oy = bilinear_read(off_tile + N, bl, W);
+                        float ox, oy;
+#if PIPE_EARLY_DECODE
+                        // the refined coordinate stays within a pixel or so of the soft-argmax: the block covers it (warp-uniform test)
+                        if (bl.x0 >= pbx && bl.x1 <= pbx + 3 && bl.y0 >= pby && bl.y1 <= pby + 3) {
+                            const int i00 = (bl.y0 - pby) * 4 + (bl.x0 - pbx), i01 = (bl.y0 - pby) * 4 + (bl.x1 - pbx);
+                            const int i10 = (bl.y1 - pby) * 4 + (bl.x0 - pbx), i11 = (bl.y1 - pby) * 4 + (bl.x1 - pbx);
+                            float tq[2][4];
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                tq[c][0] = __shfl_sync(0xffffffffu, pre, c * 16 + i00);
+                                tq[c][1] = __shfl_sync(0xffffffffu, pre, c * 16 + i01) * bl.okx;
+                                tq[c][2] = __shfl_sync(0xffffffffu, pre, c * 16 + i10) * bl.oky;
+                                tq[c][3] = __shfl_sync(0xffffffffu, pre, c * 16 + i11) * (bl.okx * bl.oky);
+                            }
+                            ox = bl.w00 * tq[0][0] + bl.w01 * tq[0][1] + bl.w10 * tq[0][2] + bl.w11 * tq[0][3];
+                            oy = bl.w00 * tq[1][0] + bl.w01 * tq[1][1] + bl.w10 * tq[1][2] + bl.w11 * tq[1][3];
+                        } else
+#endif
+                        {
+                            ox = bilinear_read(off_tile, bl, W);
+                            oy = bilinear_read(off_tile + N, bl, W);
+                        }
                         dx_ += fw_dec * ox;
                         dy_ += fw_dec * oy;
                     }

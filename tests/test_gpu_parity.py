@@ -193,6 +193,32 @@ def test_decode_larger_batch_vs_oracle(gb):
     assert np.abs(c.cpu().numpy() - alt_c.numpy()).max() <= COORD_ATOL
 
 
+@pytest.mark.parametrize("name,radius", [("w32_256x192", 2), ("w32_256x192", 4), ("w32_256x192", 0)])
+def test_warp_per_tile_kernels_equal_the_cta_per_tile_kernels(gb, name, radius, monkeypatch):
+    """The warp-per-tile decode / arg-max kernels (the default for tiles of at most 16 KB) against the CTA-per-tile ones on
+    the same tiles: arg-max family bit for bit; decode scores and window centres equal, coordinates to 2e-5 px (the
+    softmax sums run in a different order)."""
+    cfg = synth.CONFIGS[name]
+    batch = synth.make_batch(cfg, seed=21, B=37)                      # 629 tiles: not a multiple of the warps per CTA
+    hm, off = dev(batch["heatmaps"]), dev(batch["offsets"])
+    alpha, fw = torch.tensor(0.3).cuda(), torch.tensor(0.7).cuda()
+    flags = (1 if radius > 0 else 0) | 2
+    got = [x.cpu().numpy() for x in gb.decode(hm, None, None, off, alpha, fw, radius, flags)]
+    got_a = [[x.cpu().numpy() for x in gb.decode_argmax(hm, mode)] for mode in (0, 1, 2)]
+    monkeypatch.setenv("GBCODEC_DECODE_KERNEL", "tile")
+    monkeypatch.setenv("GBCODEC_ARGMAX_KERNEL", "tile")
+    want = [x.cpu().numpy() for x in gb.decode(hm, None, None, off, alpha, fw, radius, flags)]
+    want_a = [[x.cpu().numpy() for x in gb.decode_argmax(hm, mode)] for mode in (0, 1, 2)]
+    for g3, w3 in zip(got_a, want_a):
+        for g, w in zip(g3, w3):
+            assert np.array_equal(g, w)
+    assert np.array_equal(got[1], want[1])
+    same = (got[2] == want[2]).all(axis=-1)
+    print(f"[parity] warp-per-tile decode r={radius}: {int((~same).sum())} of {same.size} window centres differ (rounding boundary)")
+    assert same.mean() >= 0.99
+    assert np.abs(got[0] - want[0])[same].max() <= 2e-5
+
+
 # ------------------------------------------------------------------ loss
 def run_loss(gb, cfg, batch, *, on_the_fly, with_grads=True, utw=True, denoms=None, grad_scale=None, decode=False,
              lambdas=oc.DEFAULT_LAMBDAS):
