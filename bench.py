@@ -71,7 +71,7 @@ WORKLOADS = {
                         TILE_KERNEL="decode_tile_kernel<18,16,6,flip>",
                         WORKLOAD="BASELINE configs[2]: HRFormer-base 384x288 (96x72 heatmaps, K=17) decode with flip test + offset correction"),
     "decode": dict(K=17, H=64, W=48, IN_W=192, IN_H=256, SIGMA=2.0, SYNTH_CONFIG="w32_256x192", DECODE="plain", DEFAULT_BATCH=16384,
-                   TILE_KERNEL="decode_tile_kernel<12,16,4>",
+                   TILE_KERNEL="decode_warp_kernel<12,64> (one warp per tile)",
                    WORKLOAD="BASELINE configs[4]: decode-only sweep point (64x48 heatmaps, K=17), sub-pixel refinement + offset correction"),
 }
 PRELOAD_STEPS = 256                 # untimed steps between the warm-up and the timed region while the clock sampler comes up

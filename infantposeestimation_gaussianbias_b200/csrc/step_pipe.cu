@@ -36,13 +36,21 @@ namespace {
 
 // ---- bulk copies and mbarriers (PTX) -----------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+// an mbarrier by its 32-bit shared-memory address: the generic-to-shared conversion happens once per kernel, not at every
+// one of the ~40 arrive / wait sites (it was 135 instructions of the once-per-tile path)
+struct Bar {
+    unsigned a;
+    __device__ __forceinline__ Bar operator+(unsigned k) const { return Bar{a + 8u * k}; }
+    __device__ __forceinline__ Bar operator+(int k) const { return Bar{a + 8u * (unsigned)k}; }
+};
+__device__ __forceinline__ unsigned smem_u32(Bar b) { return b.a; }
+__device__ __forceinline__ void mbar_init(Bar bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+__device__ __forceinline__ void mbar_arrive_expect_tx(Bar bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+__device__ __forceinline__ void mbar_arrive(Bar bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 // try_wait suspends the thread in hardware until the phase completes or a time limit passes: a wait costs a few issue
@@ -55,7 +63,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #else
 #define PIPE_INLINE __forceinline__
 #endif
-__device__ PIPE_INLINE void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ PIPE_INLINE void mbar_wait(Bar bar, unsigned parity) {
     asm volatile("{\n"
                  " .reg .pred p;\n"
                  "WAIT_%=:\n"
@@ -73,7 +81,7 @@ __device__ PIPE_INLINE void mbar_wait(uint64_t* bar, unsigned parity) {
 #ifndef PIPE_SLEEP_NS
 #define PIPE_SLEEP_NS 400
 #endif
-__device__ PIPE_INLINE void mbar_wait_idle(uint64_t* bar, unsigned parity) {
+__device__ PIPE_INLINE void mbar_wait_idle(Bar bar, unsigned parity) {
 #if PIPE_SLEEP == 1
     for (;;) {
         unsigned ok;
@@ -95,7 +103,7 @@ __device__ PIPE_INLINE void mbar_wait_idle(uint64_t* bar, unsigned parity) {
     mbar_wait(bar, parity);
 #endif
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, Bar bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
@@ -146,8 +154,27 @@ __device__ __forceinline__ float4 lds4(const void* p) {
 #define PIPE_EARLY_DECODE 0
 #endif
 constexpr int kSredU = PIPE_SRED_UNROLL;
+// the producer's loop over the ring items of a tile, rolled: the compiler's unrolled version was 175 instructions longer,
+// all of them on the once-per-tile path
+#ifndef PIPE_PROD_UNROLL
+#define PIPE_PROD_UNROLL 1
+#endif
+constexpr int kProdU = PIPE_PROD_UNROLL;
+// target_row out of line: one copy for the front and the back half instead of two inlined ones
+#ifndef PIPE_TROW_OUTLINE
+#define PIPE_TROW_OUTLINE 0
+#endif
+#if PIPE_TROW_OUTLINE
+#define PIPE_TROW_INLINE __noinline__
+#else
+#define PIPE_TROW_INLINE PIPE_INLINE
+#endif
+// the decode's window sums through one 4-value butterfly (6 shuffles) instead of three 5-shuffle sums
+#ifndef PIPE_COMPACT_DECODE
+#define PIPE_COMPACT_DECODE 1
+#endif
 #ifndef PIPE_BALANCE
-#define PIPE_BALANCE 1
+#define PIPE_BALANCE 0
 #endif
 constexpr int kPUs = PIPE_UNROLL_SMALL, kPUb = PIPE_UNROLL_B, kPUp = PIPE_UNROLL_P, kPUd = PIPE_UNROLL_D;
 // PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
@@ -191,7 +218,7 @@ struct PipePlan {
 
 // the one row (if any) in which this thread meets the on-the-fly target patch
 template <int ROWS, int NIT>
-__device__ PIPE_INLINE int target_row(const int4& gq, float w, int x0, int ty, const EncodeConst& ec, const float* lut, float4& thit) {
+__device__ PIPE_TROW_INLINE int target_row(const int4& gq, float w, int x0, int ty, const EncodeConst& ec, const float* lut, float4& thit) {
     thit = make_float4(0.f, 0.f, 0.f, 0.f);
     const PatchGeom geom = unpack_geom(gq, w);
     if (!(geom.active && x0 + 3 >= geom.x_from && x0 < geom.x_to)) return -1;
@@ -233,16 +260,17 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     int* const tids = reinterpret_cast<int*>(smraw + L::oTid);
     float4* const ctas = reinterpret_cast<float4*>(smraw + L::oCta);
     float* const lut = reinterpret_cast<float*>(smraw + L::oLut);
-    uint64_t* const hfull = bars;            // [3] tile + descriptor landed                       (producer -> all)
-    uint64_t* const hempty = bars + 3;       // [3] every compute warp is done with the tile       (compute -> producer)
-    uint64_t* const rfull = bars + 6;        // [2] ring item landed                               (producer -> compute)
-    uint64_t* const rempty = bars + 8;       // [2] every compute warp has consumed it             (compute -> producer)
-    uint64_t* const sfull = bars + 10;       // [2] every compute warp has published its sums      (compute -> scalar)
-    uint64_t* const sempty = bars + 12;      // [2] the scalar warp has read them                  (scalar -> compute)
-    uint64_t* const cfull = bars + 14;       // [2] constants of the gradient pass written         (scalar -> compute)
-    uint64_t* const cempty = bars + 16;      // [2] every compute warp is done with them           (compute -> scalar)
-    uint64_t* const p2full = bars + 18;      // general second pass: sums published                (compute -> scalar)
-    uint64_t* const p2done = bars + 19;      // ... final constants written                        (scalar -> compute)
+    const Bar bar0{smem_u32(static_cast<const void*>(bars))};
+    const Bar hfull = bar0;                  // [3] tile + descriptor landed                       (producer -> all)
+    const Bar hempty = bar0 + 3;             // [3] every compute warp is done with the tile       (compute -> producer)
+    const Bar rfull = bar0 + 6;              // [2] ring item landed                               (producer -> compute)
+    const Bar rempty = bar0 + 8;             // [2] every compute warp has consumed it             (compute -> producer)
+    const Bar sfull = bar0 + 10;             // [2] every compute warp has published its sums      (compute -> scalar)
+    const Bar sempty = bar0 + 12;            // [2] the scalar warp has read them                  (scalar -> compute)
+    const Bar cfull = bar0 + 14;             // [2] constants of the gradient pass written         (scalar -> compute)
+    const Bar cempty = bar0 + 16;            // [2] every compute warp is done with them           (compute -> scalar)
+    const Bar p2full = bar0 + 18;            // general second pass: sums published                (compute -> scalar)
+    const Bar p2done = bar0 + 19;            // ... final constants written                        (scalar -> compute)
 
     const int lane = threadIdx.x & 31;
     const int tiles = P.B * P.K;
@@ -324,6 +352,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             if (heavy) {
                 const int nn = (int)(pk_c & 7u);
                 const size_t b = cur / (unsigned)P.K;
+#pragma unroll kProdU
                 for (int n = 0; n < nn + (has_var ? 1 : 0); ++n) {
                     const unsigned q = rq & 1u;
                     if (rq >= 2) mbar_wait(rempty + q, ((rq - 2) >> 1) & 1u);
@@ -702,7 +731,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #endif
                     const float vmax = warp_max(vpx);
                     const float e = ok ? expf(vpx - vmax) : 0.f;
+#if PIPE_COMPACT_DECODE
+                    float sw4[4] = {e, e * (float)x, e * (float)y, 0.f};
+                    warp_scatter_sum<4>(sw4, lane);
+                    const float se = __shfl_sync(0xffffffffu, sw4[0], 0), sx = __shfl_sync(0xffffffffu, sw4[0], 8), sy = __shfl_sync(0xffffffffu, sw4[0], 16);
+#else
                     const float se = warp_sum(e), sx = warp_sum(e * (float)x), sy = warp_sum(e * (float)y);
+#endif
                     dx_ = a_blend * cx + (1.f - a_blend) * (sx / se);
                     dy_ = a_blend * cy + (1.f - a_blend) * (sy / se);
                     if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {

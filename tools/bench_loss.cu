@@ -79,9 +79,11 @@ int main(int argc, char** argv) {
     std::vector<cudaEvent_t> e0(steps), e1(steps);
     for (int i = 0; i < steps; ++i) { CK(cudaEventCreate(&e0[i])); CK(cudaEventCreate(&e1[i])); }
     cudaEvent_t ta, tb; CK(cudaEventCreate(&ta)); CK(cudaEventCreate(&tb));
+    // BENCH_NODECODE=1: the step without its decode (measurement: what the decode costs inside the step kernel)
+    const bool nodecode = getenv("BENCH_NODECODE") != nullptr;
     auto step = [&]() {
         GB(gbcodec_fusion_step_f32(&d, hm, off, var, nullptr, vis, kps, nullptr, nullptr, losses, ghm, goff, gvar,
-                                   alpha, alpha + 1, 2, GBCODEC_DECODE_REFINE | GBCODEC_DECODE_APPLY_OFFSET, coords, scores, ws, wsb, s));
+                                   alpha, alpha + 1, 2, GBCODEC_DECODE_REFINE | GBCODEC_DECODE_APPLY_OFFSET, nodecode ? nullptr : coords, nodecode ? nullptr : scores, ws, wsb, s));
     };
     for (int i = 0; i < warm; ++i) step();
     CK(cudaStreamSynchronize(s));

@@ -4,7 +4,7 @@
 set -u
 out=gpurun_out; mkdir -p $out
 timeout 300 python tools/bench_kernels.py --once --quick > $out/once_plain.log 2>&1 || { tail -5 $out/once_plain.log; exit 1; }
-K='regex:step_pipe_kernel|loss_tile_kernel|decode_tile_kernel|encode_warp_kernel|encode_kernel|genb_tile_kernel|heatmap_step_kernel|postprocess_kernel|argmax_kernel|loss_tile_backward_kernel'
+K='regex:step_pipe_kernel|loss_tile_kernel|decode_tile_kernel|decode_warp_kernel|argmax_warp_kernel|encode_warp_kernel|encode_kernel|genb_tile_kernel|heatmap_step_kernel|postprocess_kernel|argmax_kernel|loss_tile_backward_kernel'
 timeout 1500 ncu --set full --clock-control none -k "$K" -f -o /tmp/prof_all python tools/bench_kernels.py --once --quick > $out/ncu_all.log 2>&1
 tail -2 $out/ncu_all.log
 python tools/ncu_summary.py /tmp/prof_all.ncu-rep > $out/kernels_ncu_summary.txt 2>&1
