@@ -495,15 +495,148 @@ loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossAr
 // Up to kFinBlocks CTAs each sum a contiguous slice of the tiles in double and publish six
 // partials; the CTA that draws the last ticket adds the partials in slice order and writes the
 // seven losses.  The order of every addition is fixed by the launch shape: bit-reproducible.
-__global__ void __launch_bounds__(256)
+// The tail of a decoding step whose step kernel (step_pipe.cu) left it here: CTAs beyond the `fin_blocks` summing ones,
+// one warp per tile.  The soft-argmax (cx, cy) is in d_coords, the two offset-gradient factors lambda2 ka/2 * SmoothL1'
+// in words 6 and 7 of the tile's numerator row.  Same operations in the same order as the in-kernel versions
+// (step_tile.cu, loss_tile.cu): the taps of the bilinear sample around (cx, cy) into the zero-filled d_grad_off
+// (fusion_head.py:353-359, 686-700), then local refinement + offset correction (fusion_head.py:309-365).
+struct TailArgs {
+    const float* hm; const float* off; float* grad_off; float* coords;
+    const float* alpha_param; const float* fusion_weight;
+    int radius; unsigned dflags; int fin_blocks; int enabled;
+};
+
+// tiles per warp (every load of a warp's tiles is requested before the first is consumed).  Measured on the default
+// workload: 1 tile per warp (6 CTAs per SM, 2.4 waves) 0.2541 ms per step, 2 tiles 0.2568, 3 tiles 0.2571, 4 tiles (one
+// wave) 0.2586 — the tail is not bound by its waves; one tile per warp it stays
+#ifndef FIN_TPW
+#define FIN_TPW 1
+#endif
+constexpr int kTailTPW = FIN_TPW;
+__device__ __forceinline__ void step_tail(const LossParams& P, const TailArgs& T, const float* __restrict__ partial) {
+    const int H = P.H, W = P.W, N = H * W, tiles = P.B * P.K;
+    const int lane = threadIdx.x & 31;
+    const int tile0 = ((blockIdx.x - T.fin_blocks) * 8 + (threadIdx.x >> 5)) * kTailTPW;
+    if (tile0 >= tiles) return;
+    const int wside = 2 * T.radius + 1;
+    const bool win_small = (T.dflags & GBCODEC_DECODE_REFINE) && wside * wside <= 32;
+    const bool want_off = (T.dflags & GBCODEC_DECODE_APPLY_OFFSET) != 0;
+    const int wdx = lane % wside - T.radius, wdy = lane / wside - T.radius;
+    const bool in_win = lane < wside * wside;
+    float cx[kTailTPW], cy[kTailTPW], g0[kTailTPW], g1[kTailTPW], vpx[kTailTPW], pre[kTailTPW];
+#pragma unroll
+    for (int u = 0; u < kTailTPW; ++u) {
+        const int tile = min(tile0 + u, tiles - 1);
+        cx[u] = __ldcg(T.coords + 2 * tile); cy[u] = __ldcg(T.coords + 2 * tile + 1);
+        g0[u] = 0.f; g1[u] = 0.f;
+        if (T.grad_off && lane == 0) { g0[u] = __ldcg(partial + (size_t)tile * 8 + 6); g1[u] = __ldcg(partial + (size_t)tile * 8 + 7); }
+    }
+    // the decode's loads (one window pixel per lane; the 4x4x2 block of offset taps around floor(cx, cy), which covers the
+    // refined coordinate unless it moves by more than a pixel): one round trip for all of them
+#pragma unroll
+    for (int u = 0; u < kTailTPW; ++u) {
+        const int tile = min(tile0 + u, tiles - 1);
+        const int px = (int)fminf(fmaxf(rintf(cx[u]), 0.f), (float)(W - 1));
+        const int py = (int)fminf(fmaxf(rintf(cy[u]), 0.f), (float)(H - 1));
+        const int wx = px + wdx, wy = py + wdy;
+        const bool okw = win_small && in_win && wx >= 0 && wx < W && wy >= 0 && wy < H;
+        vpx[u] = okw ? __ldg(T.hm + (size_t)tile * N + wy * W + wx) : -INFINITY;
+        pre[u] = 0.f;
+        if (win_small && want_off) {
+            const int pbx = (int)floorf(fminf(fmaxf(cx[u], 0.f), (float)(W - 1))) - 1;
+            const int pby = (int)floorf(fminf(fmaxf(cy[u], 0.f), (float)(H - 1))) - 1;
+            const int tq = lane & 15;
+            const int qx = min(max(pbx + (tq & 3), 0), W - 1), qy = min(max(pby + (tq >> 2), 0), H - 1);
+            pre[u] = __ldg(T.off + (size_t)tile * 2 * N + (lane >> 4) * N + qy * W + qx);
+        }
+    }
+    float a_blend = 1.f, fw_dec = 0.f;
+    if (win_small) {
+        a_blend = sigmoid_acc(__ldg(T.alpha_param));
+        if (want_off) {
+            fw_dec = __ldg(T.fusion_weight);
+            if (T.dflags & GBCODEC_DECODE_FUSION_WEIGHT_RAW) fw_dec = sigmoid_acc(fw_dec);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kTailTPW; ++u) {
+        const int tile = tile0 + u;
+        if (tile >= tiles) break;
+        const float* off_tile = T.off + (size_t)tile * 2 * N;
+        if (lane == 0 && (g0[u] != 0.f || g1[u] != 0.f)) {
+            const Taps tp = taps_setup(cx[u], cy[u], H, W);
+            float* go = T.grad_off + (size_t)tile * 2 * N;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float* o = go + ch * N;
+                const float gc = ch == 0 ? g0[u] : g1[u];
+                o[tp.i00] = gc * tp.w00;
+                if (tp.okx != 0.f) o[tp.i01] = gc * tp.w01;
+                if (tp.oky != 0.f) o[tp.i10] = gc * tp.w10;
+                if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = gc * tp.w11;
+            }
+        }
+        float dx_ = cx[u], dy_ = cy[u];
+        if (win_small) {
+            const int px = (int)fminf(fmaxf(rintf(cx[u]), 0.f), (float)(W - 1));
+            const int py = (int)fminf(fmaxf(rintf(cy[u]), 0.f), (float)(H - 1));
+            const int x = px + wdx, y = py + wdy;
+            const bool ok = in_win && x >= 0 && x < W && y >= 0 && y < H;
+            const float vmax = warp_max(vpx[u]);
+            const float e = ok ? expf(vpx[u] - vmax) : 0.f;
+            float sw4[4] = {e, e * (float)x, e * (float)y, 0.f};
+            warp_scatter_sum<4>(sw4, lane);
+            const float se = __shfl_sync(0xffffffffu, sw4[0], 0), sx = __shfl_sync(0xffffffffu, sw4[0], 8), sy = __shfl_sync(0xffffffffu, sw4[0], 16);
+            dx_ = a_blend * cx[u] + (1.f - a_blend) * (sx / se);
+            dy_ = a_blend * cy[u] + (1.f - a_blend) * (sy / se);
+            if (want_off) {
+                const int pbx = (int)floorf(fminf(fmaxf(cx[u], 0.f), (float)(W - 1))) - 1;
+                const int pby = (int)floorf(fminf(fmaxf(cy[u], 0.f), (float)(H - 1))) - 1;
+                const Bilinear bl = bilinear_setup(dx_, dy_, H, W);
+                float ox, oy;
+                if (bl.x0 >= pbx && bl.x1 <= pbx + 3 && bl.y0 >= pby && bl.y1 <= pby + 3) {          // warp-uniform
+                    // the same four values times the same factors in bilinear_read's order
+                    const int i00 = (bl.y0 - pby) * 4 + (bl.x0 - pbx), i01 = (bl.y0 - pby) * 4 + (bl.x1 - pbx);
+                    const int i10 = (bl.y1 - pby) * 4 + (bl.x0 - pbx), i11 = (bl.y1 - pby) * 4 + (bl.x1 - pbx);
+                    float tq[2][4];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        tq[c][0] = __shfl_sync(0xffffffffu, pre[u], c * 16 + i00);
+                        tq[c][1] = __shfl_sync(0xffffffffu, pre[u], c * 16 + i01) * bl.okx;
+                        tq[c][2] = __shfl_sync(0xffffffffu, pre[u], c * 16 + i10) * bl.oky;
+                        tq[c][3] = __shfl_sync(0xffffffffu, pre[u], c * 16 + i11) * (bl.okx * bl.oky);
+                    }
+                    ox = bl.w00 * tq[0][0] + bl.w01 * tq[0][1] + bl.w10 * tq[0][2] + bl.w11 * tq[0][3];
+                    oy = bl.w00 * tq[1][0] + bl.w01 * tq[1][1] + bl.w10 * tq[1][2] + bl.w11 * tq[1][3];
+                } else {
+                    ox = bilinear_read(off_tile, bl, W);
+                    oy = bilinear_read(off_tile + N, bl, W);
+                }
+                dx_ += fw_dec * ox;
+                dy_ += fw_dec * oy;
+            }
+        } else {
+            int qx_, qy_;
+            refine_and_correct<float>(T.hm + (size_t)tile * N, nullptr, off_tile, T.alpha_param, T.fusion_weight, H, W, T.radius, T.dflags, dx_, dy_, qx_, qy_);
+        }
+        if (lane == 0) { T.coords[2 * tile] = dx_; T.coords[2 * tile + 1] = dy_; }
+    }
+}
+
+#ifndef FIN_MINB
+#define FIN_MINB 6
+#endif
+__global__ void __launch_bounds__(256, FIN_MINB)
 finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ partial, const double* __restrict__ sums,
                 double* __restrict__ bpart, unsigned* __restrict__ ticket, float* __restrict__ losses7,
-                const __grid_constant__ PeerView peer) {
+                const __grid_constant__ PeerView peer, const __grid_constant__ TailArgs tail) {
     __shared__ double red[6][8];
     __shared__ bool last;
     pdl_wait();                                        // launched while the tile kernel's last wave is still running
+    const int nblk = tail.enabled ? tail.fin_blocks : (int)gridDim.x;      // the summing CTAs
+    if ((int)blockIdx.x >= nblk) { step_tail(P, tail, partial); return; }
     const int tiles = P.B * P.K;
-    const int per = (tiles + gridDim.x - 1) / gridDim.x;
+    const int per = (tiles + nblk - 1) / nblk;
     const int lo = blockIdx.x * per, hi = min(tiles, lo + per);
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
@@ -525,7 +658,7 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
         __threadfence();
     }
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == (unsigned)nblk - 1u;
     __syncthreads();
     if (!last) return;
     __threadfence();
@@ -533,7 +666,7 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
     if (threadIdx.x < 6) {
         const int q = threadIdx.x;
         double s = 0.0;
-        for (int g = 0; g < (int)gridDim.x; ++g) s += __ldcg(bpart + g * 6 + q);
+        for (int g = 0; g < nblk; ++g) s += __ldcg(bpart + g * 6 + q);
         const float D = (float)sums[0] + kEps, D5 = (float)sums[1] + kEps;
         const float Da = P.use_target_weight ? D : (float)tiles;
         const float den = q < 3 ? Da : (q == 4 ? D5 : D);
@@ -713,11 +846,11 @@ static bool force_generic() {
     return v != 0;
 }
 
-static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s) {
+static int launch_loss_kernel(const LossParams& P, const LossArgs& A, cudaStream_t s, bool* pipe_used = nullptr) {
     if (!force_generic()) {
         // the persistent step kernels cover float32 maps with the target generated on the fly
         int st = launch_step_pipe(P, A, s, g_prof_start, g_prof_stop);
-        if (st != 1) return st;
+        if (st != 1) { if (pipe_used) *pipe_used = (st == 0); return st; }
         st = launch_step_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st != 1) return st;
     }
@@ -830,6 +963,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
         st = check_launch("sums_to_float_kernel");
         if (st) return st;
     }
+    bool pipe_used = false;
     LossArgs A;
     memset(&A, 0, sizeof(A));
     A.hm = hm; A.off = off; A.var = var; A.target = target; A.weight = weight; A.gt = gt; A.grad_scale = grad_scale;
@@ -845,20 +979,30 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
         st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st == 1) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: per-tile variance means are supported for 64x48, 64x64, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
     } else
-    st = launch_loss_kernel(P, A, s);
+    st = launch_loss_kernel(P, A, s, &pipe_used);
     if (st) return st;
     const int tiles = P.B * P.K;
     const int fin_blocks = (tiles + 255) / 256 < kFinBlocks ? (tiles + 255) / 256 : kFinBlocks;
     {
+        // a decoding step through step_pipe_kernel leaves its tail (offset-gradient taps, refinement of the decode) to
+        // extra CTAs of this launch, one warp per tile
+        TailArgs tail;
+        memset(&tail, 0, sizeof(tail));
+        tail.fin_blocks = fin_blocks;
+        if (pipe_used && coords && step_pipe_tail_outside()) {
+            tail.enabled = 1;
+            tail.hm = hm; tail.off = off; tail.grad_off = goff; tail.coords = coords;
+            tail.alpha_param = alpha_param; tail.fusion_weight = fusion_weight; tail.radius = radius; tail.dflags = dflags;
+        }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(fin_blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cfg.gridDim = dim3(fin_blocks + (tail.enabled ? (tiles + 8 * kTailTPW - 1) / (8 * kTailTPW) : 0)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const float* partial_c = L.partial; const double* sums_c = L.sums;
         note_launch();
-        cudaError_t e = cudaLaunchKernelEx(&cfg, finalize_kernel, P, partial_c, sums_c, L.bpart, L.ticket, losses7, peer);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, finalize_kernel, P, partial_c, sums_c, L.bpart, L.ticket, losses7, peer, tail);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaLaunchKernelEx(finalize_kernel): %s", cudaGetErrorString(e));
     }
     return check_launch("finalize_kernel");

@@ -215,5 +215,8 @@ int launch_step_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
 // step_pipe.cu: the same step as a software pipeline of specialised warps (compute warps run only pixel loops, a scalar
 // warp owns the per-tile chain, a producer lane moves the bytes); same coverage and return convention as launch_step_tile.
 int launch_step_pipe(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+// true if launch_step_pipe's kernel leaves the offset-gradient taps and the decode's refinement of a decoding call to
+// finalize_kernel's tail CTAs (d_coords then holds the soft-argmax, words 6 and 7 of a tile's numerator row the two factors)
+bool step_pipe_tail_outside();
 
 }  // namespace gbc

@@ -169,6 +169,13 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #else
 #define PIPE_TROW_INLINE PIPE_INLINE
 #endif
+// PIPE_TAIL_OUTSIDE: when the call decodes, the scalar warp leaves the soft-argmax in d_coords and the two offset-gradient
+// factors in the spare words of the tile's numerator row; finalize_kernel's tail CTAs (loss.cu: one warp per tile, same
+// operations in the same order) place the offset-gradient taps and finish the decode.  ~270 instructions less on the
+// once-per-tile path of this kernel, whose time follows that path's footprint.
+#ifndef PIPE_TAIL_OUTSIDE
+#define PIPE_TAIL_OUTSIDE 1
+#endif
 // the decode's window sums through one 4-value butterfly (6 shuffles) instead of three 5-shuffle sums
 #ifndef PIPE_COMPACT_DECODE
 #define PIPE_COMPACT_DECODE 1
@@ -695,8 +702,14 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     const float shape_t = (Ent - P.e_star) * (Ent - P.e_star);
                     float4* p = reinterpret_cast<float4*>(A.partial + (size_t)tile * 8);
                     p[0] = make_float4(wa * (mse_sum * P.inv_n), wa * (0.5f * sl1), wa * peak_t, w * var_t);
+#if PIPE_TAIL_OUTSIDE
+                    const bool taps_here = !decode;
+                    p[1] = make_float4(pair_loss, w * shape_t, (GRADS && decode) ? h2c * sl1p[0] : 0.f, (GRADS && decode) ? h2c * sl1p[1] : 0.f);
+#else
+                    const bool taps_here = true;
                     p[1] = make_float4(pair_loss, w * shape_t, 0.f, 0.f);
-                    if (GRADS) {
+#endif
+                    if (GRADS && taps_here) {
                         // the zero fill of these addresses was issued by the compute warps before they published their
                         // sums (release) and this warp has waited for that (acquire): these stores come after
                         float* go = A.grad_off + (size_t)tile * 2 * N;
@@ -716,7 +729,14 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // (steps 3-6 of decode_device.cuh's refine_and_correct with the per-call constants hoisted and, for windows of
             // at most 32 pixels, one window pixel per lane: the same operations in the same order, a sixth of the code —
             // this warp's instruction footprint competes with the compute warps' loops for the 32 KB L1.5 I-cache)
+#if PIPE_TAIL_OUTSIDE
             if (decode) {
+                if (lane == 0) { A.coords[2 * tile] = cx; A.coords[2 * tile + 1] = cy; A.scores[tile] = m; }
+            }
+            if (false) {
+#else
+            if (decode) {
+#endif
                 float dx_ = cx, dy_ = cy;
                 if (win_small) {
 #if PIPE_EARLY_DECODE
@@ -1244,6 +1264,8 @@ int launch_pipe_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEv
 
 // GBCODEC_STEP_KERNEL=tile | persist selects the one-CTA-per-tile kernel of loss_tile.cu / the persistent kernel of
 // step_tile.cu instead (A/B measurements, and tests that compare entry points bit for bit).  Read on every call.
+bool step_pipe_tail_outside() { return PIPE_TAIL_OUTSIDE != 0; }
+
 int launch_step_pipe(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     const char* env = getenv("GBCODEC_STEP_KERNEL");
     if (env && (!strcmp(env, "tile") || !strcmp(env, "persist"))) return 1;

@@ -82,8 +82,9 @@ int main(int argc, char** argv) {
     // BENCH_NODECODE=1: the step without its decode (measurement: what the decode costs inside the step kernel)
     const bool nodecode = getenv("BENCH_NODECODE") != nullptr;
     auto step = [&]() {
-        GB(gbcodec_fusion_step_f32(&d, hm, off, var, nullptr, vis, kps, nullptr, nullptr, losses, ghm, goff, gvar,
-                                   alpha, alpha + 1, 2, GBCODEC_DECODE_REFINE | GBCODEC_DECODE_APPLY_OFFSET, nodecode ? nullptr : coords, nodecode ? nullptr : scores, ws, wsb, s));
+        if (nodecode) GB(gbcodec_fusion_loss_f32(&d, hm, off, var, nullptr, vis, kps, nullptr, nullptr, losses, ghm, goff, gvar, ws, wsb, s));
+        else GB(gbcodec_fusion_step_f32(&d, hm, off, var, nullptr, vis, kps, nullptr, nullptr, losses, ghm, goff, gvar,
+                                        alpha, alpha + 1, 2, GBCODEC_DECODE_REFINE | GBCODEC_DECODE_APPLY_OFFSET, coords, scores, ws, wsb, s));
     };
     for (int i = 0; i < warm; ++i) step();
     CK(cudaStreamSynchronize(s));
