@@ -383,6 +383,26 @@ int gbcodec_combined_loss_backward_f32(const gbcodec_combined_desc* desc,
                               float* d_grad_pred, float* d_grad_coords, float* d_grad_refined,
                               void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same two calls for float16 predictions (training under autocast: the head's heatmaps are half, the data
+ * loader's targets float32 — torch's autocast runs mse_loss / smooth_l1_loss on inputs cast to float32 and casts the
+ * gradient back, models/losses.py:10-47 under train.py's autocast).  d_pred_f16 and d_grad_pred_f16 are (B,K,H,W)
+ * float16, every other tensor is float32 as above; the values are up-cast where they are read and the gradient is
+ * rounded to half once, AFTER it has met the upstream factor (*d_grad_scale in the forward, the actual upstream in
+ * the backward, which recomputes only if the two differ).  The call must contain the heatmap term.
+ * Algorithmic HBM bytes per tile: read pred (2N) + target (4N), write d_pred (2N). */
+int gbcodec_combined_loss_f16(const gbcodec_combined_desc* desc,
+                              const void* d_pred_f16, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, float* d_losses5,
+                              void* d_grad_pred_f16, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+int gbcodec_combined_loss_backward_f16(const gbcodec_combined_desc* desc,
+                              const void* d_pred_f16, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, const float* d_grad_losses5,
+                              void* d_grad_pred_f16, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* The plain heatmap head (PoseEstimator with head_type='heatmap') in ONE pass over the heatmaps:
  * KeypointMSELoss forward + backward (models/pose_estimator.py:102-143: mean((p w - t w)^2) over B*K*H*W),
  * the target tiles generated on the fly as COCOPoseDataset._generate_target builds them

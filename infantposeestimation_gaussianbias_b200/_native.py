@@ -41,6 +41,7 @@ EXPORTS = (
     "gbcodec_softplus_mean_f32", "gbcodec_softplus_mean_backward_f32",
     "gbcodec_fusion_step_sharded_f32", "gbcodec_heatmap_step_f32",
     "gbcodec_fusion_step_f16", "gbcodec_fusion_loss_backward_f16", "gbcodec_fusion_step_vmean_f32",
+    "gbcodec_combined_loss_f16", "gbcodec_combined_loss_backward_f16",
 )
 
 
@@ -156,6 +157,10 @@ def _declare(lib):
     comb = [C.POINTER(CombinedDesc), f32p, f32p, f32p, f32p, f32p, f32p, f32p]
     lib.gbcodec_combined_loss_f32.argtypes = comb + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
     lib.gbcodec_combined_loss_backward_f32.argtypes = comb + [f32p, f32p, f32p, f32p, _P, C.c_size_t, _P]
+    # float16 predictions: d_pred_f16 and d_grad_pred_f16 are void*
+    comb16 = [C.POINTER(CombinedDesc), _P, f32p, f32p, f32p, f32p, f32p, f32p]
+    lib.gbcodec_combined_loss_f16.argtypes = comb16 + [f32p, _P, f32p, f32p, _P, C.c_size_t, _P]
+    lib.gbcodec_combined_loss_backward_f16.argtypes = comb16 + [f32p, _P, f32p, f32p, _P, C.c_size_t, _P]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = the library does not export what the header declares
 

@@ -68,9 +68,9 @@ int launch_postprocess(const gbcodec_postprocess_desc*, const float*, const floa
 int launch_coords_to_image(const float*, const float*, const float*, int, int, int, int, float, float, float*, cudaStream_t);
 size_t combined_workspace_bytes(int B, int K);
 int combined_loss(const gbcodec_combined_desc*, const float*, const float*, const float*, const float*, const float*, const float*,
-                  const float*, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+                  const float*, float*, float*, float*, float*, void*, size_t, cudaStream_t, int half_io = 0);
 int combined_loss_backward(const gbcodec_combined_desc*, const float*, const float*, const float*, const float*, const float*,
-                           const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t);
+                           const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t, int half_io = 0);
 
 int heatmap_step(const float*, const float*, const float*, const float*, int, int, int, int, float, float, double, int, int,
                  const float*, float*, float*, int, float*, float*, int32_t*, void*, size_t, cudaStream_t);
@@ -200,6 +200,28 @@ int gbcodec_combined_loss_f32(const gbcodec_combined_desc* desc,
                               void* d_workspace, size_t workspace_bytes, void* stream) {
     return combined_loss(desc, d_pred, d_target, d_weight, d_coords, d_refined, d_target_coords, d_grad_scale, d_losses5,
                          d_grad_pred, d_grad_coords, d_grad_refined, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gbcodec_combined_loss_f16(const gbcodec_combined_desc* desc,
+                              const void* d_pred_f16, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, float* d_losses5,
+                              void* d_grad_pred_f16, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream) {
+    return combined_loss(desc, reinterpret_cast<const float*>(d_pred_f16), d_target, d_weight, d_coords, d_refined, d_target_coords,
+                         d_grad_scale, d_losses5, reinterpret_cast<float*>(d_grad_pred_f16), d_grad_coords, d_grad_refined,
+                         d_workspace, workspace_bytes, (cudaStream_t)stream, 1);
+}
+
+int gbcodec_combined_loss_backward_f16(const gbcodec_combined_desc* desc,
+                              const void* d_pred_f16, const float* d_target, const float* d_weight,
+                              const float* d_coords, const float* d_refined, const float* d_target_coords,
+                              const float* d_grad_scale, const float* d_grad_losses5,
+                              void* d_grad_pred_f16, float* d_grad_coords, float* d_grad_refined,
+                              void* d_workspace, size_t workspace_bytes, void* stream) {
+    return combined_loss_backward(desc, reinterpret_cast<const float*>(d_pred_f16), d_target, d_weight, d_coords, d_refined,
+                                  d_target_coords, d_grad_scale, d_grad_losses5, reinterpret_cast<float*>(d_grad_pred_f16),
+                                  d_grad_coords, d_grad_refined, d_workspace, workspace_bytes, (cudaStream_t)stream, 1);
 }
 
 int gbcodec_combined_loss_backward_f32(const gbcodec_combined_desc* desc,

@@ -13,6 +13,11 @@
 //   with S = sum(p) + 1e-8, m_c = sum(p c)/S, v_c = sum(p (c - m_c)^2)/S  (c = x, y)
 //   d m_c / d p_i = (c_i - m_c)/S         d v_c / d p_i = ((c_i - m_c)^2 - v_c)/S
 // (the cross term 2 (d m_c/d p_i) sum q (c - m_c) = 2 (d m_c/d p_i) m_c eps/S is below fp32 resolution).
+//
+// float16 predictions (autocast: the head's heatmaps arrive in half, the data loader's targets stay float32): the
+// HALF instantiations read pred as 8-byte vectors of four halves, up-cast where they land in registers, and round the
+// gradient to half once where it leaves — what torch's autocast does with mse_loss (inputs cast to float32, the
+// gradient cast back), without the two conversion passes: 2N + 4N bytes read, 2N written per tile.
 #include "common.cuh"
 #include "decode_device.cuh"
 #include <string.h>
@@ -37,6 +42,33 @@ struct GenbArgs {
     float* partial;          // [B*K][4] un-normalised per-tile numerators
     const float* eff;        // backward: device [4] effective upstream gradient per term
     const int* plan;         // backward: run only if *plan != 0
+    int half_io;             // pred and grad_pred are float16 (the pointers are then __half*); everything else float32
+};
+
+// four pixels of pred / grad_pred: 16 bytes of float, 8 bytes of half
+template <bool HALF> struct PredIO;
+template <> struct PredIO<false> {
+    using Vec = float4;
+    static __device__ __forceinline__ float4 load_stream(const Vec* p) { return ldg_stream(p); }
+    static __device__ __forceinline__ float4 load_keep(const Vec* p) { return ldg_keep(p); }
+    static __device__ __forceinline__ void store_stream(Vec* p, const float4& v) { stg_stream(p, v); }
+};
+template <> struct PredIO<true> {
+    using Vec = uint2;
+    static __device__ __forceinline__ float4 up(const uint2& r) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ float4 load_stream(const Vec* p) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return up(r);
+    }
+    static __device__ __forceinline__ float4 load_keep(const Vec* p) { return up(__ldg(p)); }
+    static __device__ __forceinline__ void store_stream(Vec* p, const float4& v) {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(*reinterpret_cast<const unsigned*>(&a)), "r"(*reinterpret_cast<const unsigned*>(&b)) : "memory");
+    }
 };
 
 constexpr int kGenbFinBlocks = 32;
@@ -66,22 +98,24 @@ __device__ __forceinline__ float crit_slope(int crit, float d) {
 }
 
 // ---- per-tile heatmap + morphology terms ------------------------------------------------------
-template <int NITER, int MAXT, int MINB = 1>
+template <int NITER, int MAXT, int MINB = 1, bool HALF = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ GenbArgs A) {
+    using IO = PredIO<HALF>;
+    using PVec = typename IO::Vec;
     __shared__ float red_a[8 * 32], red_b[4 * 32];
     if (A.plan && *A.plan == 0) return;               // stored gradients already right
     const int tile = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n4 = (P.H * P.W) >> 2, w4 = P.W >> 2;
-    const float4* p4 = reinterpret_cast<const float4*>(A.pred) + (size_t)tile * n4;
+    const PVec* p4 = reinterpret_cast<const PVec*>(A.pred) + (size_t)tile * n4;
     const float4* t4 = reinterpret_cast<const float4*>(A.target) + (size_t)tile * n4;
     constexpr int R = NITER > 0 ? NITER : 1;
     float4 pv[R], tv[R];
     if (NITER > 0) {
 #pragma unroll
         for (int it = 0; it < R; ++it) {
-            pv[it] = ldg_stream(p4 + it * blockDim.x + threadIdx.x);
+            pv[it] = IO::load_stream(p4 + it * blockDim.x + threadIdx.x);
             tv[it] = ldg_stream(t4 + it * blockDim.x + threadIdx.x);
         }
     }
@@ -121,7 +155,7 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
 #pragma unroll
         for (int it = 0; it < R; ++it) pass1(pv[it], tv[it], yx[it]);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass1(ldg_stream(p4 + i), ldg_stream(t4 + i), (y << 16) | ((i - y * w4) << 2)); }
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass1(IO::load_stream(p4 + i), ldg_stream(t4 + i), (y << 16) | ((i - y * w4) << 2)); }
     }
     block_sum_1bar<8>(acc, red_a, nw, lane, warp);
     const float Sp = acc[0] + kEps, St = acc[3] + kEps;
@@ -148,7 +182,7 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
 #pragma unroll
         for (int it = 0; it < R; ++it) pass2(pv[it], tv[it], yx[it]);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass2(ldg_keep(p4 + i), ldg_keep(t4 + i), (y << 16) | ((i - y * w4) << 2)); }
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass2(IO::load_keep(p4 + i), ldg_keep(t4 + i), (y << 16) | ((i - y * w4) << 2)); }
     }
     block_sum_1bar<4>(c2, red_b, nw, lane, warp);
     const float pvx = c2[0] * iSp, pvy = c2[1] * iSp, tvx = c2[2] * iSt, tvy = c2[3] * iSt;
@@ -167,7 +201,7 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
     const float Ax = cm * 2.f * P.lam_var * dvx, Ay = cm * 2.f * P.lam_var * dvy;
     const float Bx = cm * 2.f * P.lam_mean * dmx, By = cm * 2.f * P.lam_mean * dmy;
     const float C0 = -(Ax * pvx + Ay * pvy);
-    float4* g4 = reinterpret_cast<float4*>(A.grad_pred) + (size_t)tile * n4;
+    PVec* g4 = reinterpret_cast<PVec*>(A.grad_pred) + (size_t)tile * n4;
     auto pass3 = [&](const float4& p, const float4& t, int c, int i) {
         const int x = c & 0xffff;
         const float dy = (float)(c >> 16) - pmy;
@@ -179,13 +213,13 @@ genb_tile_kernel(const __grid_constant__ GenbParams P, const __grid_constant__ G
             const float dx = ((float)x + (float)j) - pmx;
             g[j] = fmaf(ch, crit_slope(crit, pe[j] - te[j]), fmaf(dx, fmaf(Ax, dx, Bx), rowc));
         }
-        stg_stream(g4 + i, make_float4(g[0], g[1], g[2], g[3]));
+        IO::store_stream(g4 + i, make_float4(g[0], g[1], g[2], g[3]));
     };
     if (NITER > 0) {
 #pragma unroll
         for (int it = 0; it < R; ++it) pass3(pv[it], tv[it], yx[it], it * blockDim.x + threadIdx.x);
     } else {
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass3(ldg_keep(p4 + i), ldg_keep(t4 + i), (y << 16) | ((i - y * w4) << 2), i); }
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) { const int y = i / w4; pass3(IO::load_keep(p4 + i), ldg_keep(t4 + i), (y << 16) | ((i - y * w4) << 2), i); }
     }
 }
 
@@ -321,6 +355,7 @@ static int check_genb(const GenbParams& P, const GenbArgs& A, const void* ws, si
     if (!ws || ws_size < genb_ws_bytes(P.B, P.K)) return fail(GBCODEC_ERR_WORKSPACE, "combined_loss: workspace of %zu bytes needed", genb_ws_bytes(P.B, P.K));
     if (!aligned16(ws) || (tiles && (!aligned16(A.pred) || !aligned16(A.target))) || (A.grad_pred && !aligned16(A.grad_pred)))
         return fail(GBCODEC_ERR_UNALIGNED, "combined_loss: tensors must be 16-byte aligned");
+    if (A.half_io && !tiles) return fail(GBCODEC_ERR_BAD_ARGUMENT, "combined_loss (float16): the call has no heatmap term; use the float32 entry point");
     if (backward && tiles && !A.grad_pred) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss backward: d_grad_pred is NULL");
     return GBCODEC_OK;
 }
@@ -340,10 +375,11 @@ static int launch_genb(const GenbParams& P, const GenbArgs& A, cudaStream_t s) {
         if (n4 % t == 0 && n4 / t <= 3) { threads = t; niter = n4 / t; }
     for (int t = 128; t <= 512 && !niter; t += 32)
         if (n4 % t == 0 && n4 / t <= 8) { threads = t; niter = n4 / t; }
-#define GBC_CASE(NI, MT) case NI: note_launch(), genb_tile_kernel<NI, MT><<<nt, threads, 0, s>>>(P, A); break;
+#define GBC_CASE(NI, MT) case NI: note_launch(); if (A.half_io) genb_tile_kernel<NI, MT, 1, true><<<nt, threads, 0, s>>>(P, A); \
+                                                  else genb_tile_kernel<NI, MT><<<nt, threads, 0, s>>>(P, A); break;
     switch (niter) {
         GBC_CASE(1, 1024) GBC_CASE(2, 1024) GBC_CASE(3, 1024) GBC_CASE(4, 512) GBC_CASE(5, 512) GBC_CASE(6, 512) GBC_CASE(7, 512) GBC_CASE(8, 512)
-        default: note_launch(), genb_tile_kernel<0, 1024><<<nt, threads, 0, s>>>(P, A); break;
+        default: GBC_CASE(0, 1024)
     }
 #undef GBC_CASE
     return check_launch("genb_tile_kernel");
@@ -353,7 +389,8 @@ size_t combined_workspace_bytes(int B, int K) { return genb_ws_bytes(B, K); }
 
 int combined_loss(const gbcodec_combined_desc* d, const float* pred, const float* target, const float* weight,
                   const float* coords, const float* refined, const float* target_coords, const float* grad_scale,
-                  float* losses5, float* gpred, float* gcoords, float* grefined, void* ws, size_t ws_size, cudaStream_t s) {
+                  float* losses5, float* gpred, float* gcoords, float* grefined, void* ws, size_t ws_size, cudaStream_t s,
+                  int half_io) {
     GenbParams P;
     int st = make_genb_params(d, &P);
     if (st) return st;
@@ -362,6 +399,7 @@ int combined_loss(const gbcodec_combined_desc* d, const float* pred, const float
     memset(&A, 0, sizeof(A));
     A.pred = pred; A.target = target; A.weight = weight; A.coords = coords; A.refined = refined; A.target_coords = target_coords;
     A.grad_scale = grad_scale; A.grad_pred = gpred; A.grad_coords = gcoords; A.grad_refined = grefined;
+    A.half_io = half_io;
     st = check_genb(P, A, ws, ws_size, false);
     if (st) return st;
     const GenbWs L = genb_carve(ws);
@@ -378,7 +416,8 @@ int combined_loss(const gbcodec_combined_desc* d, const float* pred, const float
 
 int combined_loss_backward(const gbcodec_combined_desc* d, const float* pred, const float* target, const float* weight,
                            const float* coords, const float* refined, const float* target_coords, const float* grad_scale,
-                           const float* g5, float* gpred, float* gcoords, float* grefined, void* ws, size_t ws_size, cudaStream_t s) {
+                           const float* g5, float* gpred, float* gcoords, float* grefined, void* ws, size_t ws_size, cudaStream_t s,
+                           int half_io) {
     GenbParams P;
     int st = make_genb_params(d, &P);
     if (st) return st;
@@ -387,6 +426,7 @@ int combined_loss_backward(const gbcodec_combined_desc* d, const float* pred, co
     memset(&A, 0, sizeof(A));
     A.pred = pred; A.target = target; A.weight = weight; A.coords = coords; A.refined = refined; A.target_coords = target_coords;
     A.grad_pred = gpred; A.grad_coords = gcoords; A.grad_refined = grefined;
+    A.half_io = half_io;
     st = check_genb(P, A, ws, ws_size, true);
     if (st) return st;
     const GenbWs L = genb_carve(ws);

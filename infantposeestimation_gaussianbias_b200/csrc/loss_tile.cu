@@ -929,12 +929,9 @@ static int launch_tile_t(const LossParams& P, const LossArgs& A, cudaStream_t s,
         cudaError_t e = cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return fail(GBCODEC_ERR_CUDA, "cudaFuncSetAttribute(loss_tile_backward_kernel): %s", cudaGetErrorString(e));
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        }
+        int sms = 0, dev = 0;                           // per call: the process may drive devices of different sizes
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         const int tiles = P.B * P.K, resident = sms * MINB;
         const int per = (tiles + resident - 1) / resident;            // one wave: balanced when there is work, ~sms*MINB CTAs to dismiss when there is none
         note_launch(), bk<<<(tiles + per - 1) / per, TPB, smem, s>>>(P, A, per);

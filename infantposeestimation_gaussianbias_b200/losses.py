@@ -37,7 +37,10 @@ def _needs_grad(*ts) -> bool:
 def _run(pred=None, target=None, weight=None, coords=None, refined=None, target_coords=None, *, heat_crit=N.CRIT_MSE,
          coord_crit=N.CRIT_SMOOTHL1, use_target_weight=True, heat_scale=1.0, lam_var=1.0, lam_mean=0.5,
          weights=(1.0, 0.0, 0.0), morph=False, norm_batch=0, grad_scale=None):
-    res = ops.combined_loss(_f32(pred), _f32(target), _f32(weight), _f32(coords), _f32(refined), _f32(target_coords),
+    # float16 heatmaps (autocast) go to the kernel as they are: it up-casts them where it reads them and returns a float16
+    # gradient rounded once (gbcodec_combined_loss_f16); everything else is float32
+    keep_half = pred is not None and pred.dtype == torch.float16 and pred.is_cuda
+    res = ops.combined_loss(pred if keep_half else _f32(pred), _f32(target), _f32(weight), _f32(coords), _f32(refined), _f32(target_coords),
                             grad_scale, int(norm_batch), int(heat_crit), int(coord_crit), bool(use_target_weight),
                             float(heat_scale), float(lam_var), float(lam_mean), [float(w) for w in weights], bool(morph),
                             _needs_grad(pred, coords, refined))

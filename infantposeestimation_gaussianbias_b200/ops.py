@@ -600,13 +600,16 @@ def combined_loss(pred: Optional[Tensor], target: Optional[Tensor], weight: Opti
                   use_target_weight: bool, heat_scale: float, lam_var: float, lam_mean: float, weights: List[float],
                   morph: bool, with_grads: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """models/losses.py:205-290 -> losses5 (heatmap, morph, regression, refined, total), grad_pred, grad_coords,
-    grad_refined (empty tensors for what was not asked / not present)."""
+    grad_refined (empty tensors for what was not asked / not present).  `pred` may be float16 (the head's heatmaps
+    under autocast; every other tensor float32): gbcodec_combined_loss_f16 up-casts it where it is read and leaves
+    grad_pred in float16, rounded once after the upstream factor `grad_scale`."""
     B, K, H, W = _combined_shapes(pred, coords, refined, target_coords)
     some = pred if pred is not None else (coords if coords is not None else refined)
     dev = some.device
     terms = 0
+    half = pred is not None and pred.dtype == torch.float16
     if pred is not None:
-        pred = _cuda_f32("pred_heatmaps", pred, (B, K, H, W))
+        pred = _cuda_f16_or_f32("pred_heatmaps", pred, (B, K, H, W))
         target = _cuda_f32("target_heatmaps", target, (B, K, H, W))
         terms |= N.TERM_HEATMAP | (N.TERM_MORPH if morph else 0)
     if coords is not None:
@@ -624,16 +627,16 @@ def combined_loss(pred: Optional[Tensor], target: Optional[Tensor], weight: Opti
                           lam_mean, weights)
     losses = torch.empty(5, dtype=torch.float32, device=dev)
     empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
-    gp = torch.empty_like(pred) if (with_grads and pred is not None) else empty()
+    gp = torch.empty_like(pred) if (with_grads and pred is not None) else torch.empty(0, dtype=torch.float16 if half else torch.float32, device=dev)
     gc = torch.empty_like(coords) if (with_grads and coords is not None) else empty()
     gr = torch.empty_like(refined) if (with_grads and refined is not None) else empty()
     nbytes = N.lib().gbcodec_combined_workspace_bytes(B, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     opt = lambda t: _ptr(t) if t.numel() else None
+    entry = N.lib().gbcodec_combined_loss_f16 if half else N.lib().gbcodec_combined_loss_f32
     with torch.cuda.device(dev):
-        N.check(N.lib().gbcodec_combined_loss_f32(desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined),
-                                                  _ptr(target_coords), _ptr(grad_scale), _ptr(losses), opt(gp), opt(gc), opt(gr),
-                                                  _ptr(ws), nbytes, _stream(some)), "combined_loss")
+        N.check(entry(desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined), _ptr(target_coords),
+                      _ptr(grad_scale), _ptr(losses), opt(gp), opt(gc), opt(gr), _ptr(ws), nbytes, _stream(some)), "combined_loss")
     return losses, gp, gc, gr
 
 
@@ -641,9 +644,10 @@ def combined_loss(pred: Optional[Tensor], target: Optional[Tensor], weight: Opti
 def _(pred, target, weight, coords, refined, target_coords, grad_scale, norm_batch, heat_crit, coord_crit,
       use_target_weight, heat_scale, lam_var, lam_mean, weights, morph, with_grads):
     some = pred if pred is not None else (coords if coords is not None else refined)
-    e = lambda: some.new_empty(0)
+    e = lambda: some.new_empty(0, dtype=torch.float32)
     g = lambda t: torch.empty_like(t) if (with_grads and t is not None) else e()
-    return some.new_empty(5), g(pred), g(coords), g(refined)
+    gp = torch.empty_like(pred) if (with_grads and pred is not None) else some.new_empty(0)
+    return some.new_empty(5, dtype=torch.float32), gp, g(coords), g(refined)
 
 
 @torch.library.custom_op(f"{_NS}::combined_loss_backward", mutates_args=("grad_pred", "grad_coords", "grad_refined"))
@@ -670,8 +674,12 @@ def combined_loss_backward(grad_losses: Tensor, grad_pred: Tensor, grad_coords: 
     nbytes = N.lib().gbcodec_combined_workspace_bytes(B, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=some.device)
     opt = lambda t: _ptr(t) if t.numel() else None
+    half = pred is not None and pred.dtype == torch.float16
+    if half and grad_pred.dtype != torch.float16:
+        raise RuntimeError("gbcodec: float16 predictions take a float16 grad_pred")
+    entry = N.lib().gbcodec_combined_loss_backward_f16 if half else N.lib().gbcodec_combined_loss_backward_f32
     with torch.cuda.device(some.device):
-        N.check(N.lib().gbcodec_combined_loss_backward_f32(
+        N.check(entry(
             desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined), _ptr(target_coords), _ptr(grad_scale),
             _ptr(g5), opt(grad_pred), opt(grad_coords), opt(grad_refined), _ptr(ws), nbytes, _stream(some)),
             "combined_loss_backward")
@@ -789,6 +797,10 @@ heatmap_step.register_autograd(_heatmap_step_backward, setup_context=_heatmap_st
 
 # --------------------------------------------------------------------------- float16 maps (autocast)
 HALF_TILE_SHAPES = ((64, 48), (64, 64), (96, 72), (128, 128))
+
+
+def _cuda_f16_or_f32(name: str, t: Tensor, shape: Sequence[int]) -> Tensor:
+    return _cuda_f16(name, t, shape) if t.dtype == torch.float16 else _cuda_f32(name, t, shape)
 
 
 def _cuda_f16(name: str, t: Tensor, shape: Sequence[int]) -> Tensor:

@@ -231,6 +231,72 @@ def test_combined_loss_larger_batch_vs_oracle(pkg):
     maxnorm_close(p.grad.cpu().numpy(), pc.grad.numpy(), what="d total / d pred (B=24, 96x72)")
 
 
+@pytest.mark.parametrize("name", NAMES + ["odd_56x40"])
+def test_combined_loss_float16_predictions(pkg, name):
+    """autocast: the head's heatmaps arrive in float16 (targets and coordinates stay float32).  The float16 entry points
+    up-cast where they read and round the gradient once where they write, so against the float32 path on the up-cast
+    maps the five losses are BIT-equal and the gradient is the float32 gradient rounded to half, bit for bit — with the
+    loss scaler's factor as the assumed upstream (stored gradients used as they are), with an upstream that differs from
+    the assumed one (recompute in the backward) and for the single-term modules.  Shapes: the three register-resident
+    instantiations and one that takes the kernel's strided loop (56x40)."""
+    L = pkg.losses
+    if name == "odd_56x40":
+        rng = np.random.default_rng(5)
+        B, K, H, W = 3, 5, 56, 40
+        pred32 = rng.normal(0.2, 0.5, (B, K, H, W)).astype(np.float32)
+        target = np.clip(rng.normal(0.1, 0.3, (B, K, H, W)), 0, 1).astype(np.float32)
+        weight = rng.integers(0, 3, (B, K)).astype(np.float32)
+        coords = rng.uniform(0, 40, (B, K, 2)).astype(np.float32)
+        tcoords = rng.uniform(0, 40, (B, K, 2)).astype(np.float32)
+    else:
+        cfg, batch, ex, g = goldens_genb.load(name)
+        pred32, target, weight, coords, tcoords = ex["pred"], batch["target"], batch["weight"], ex["coords"], ex["target_coords"]
+    config = types.SimpleNamespace(LOSS=types.SimpleNamespace(MORPH_LAMBDA=1.2, MORPH_WEIGHT=0.15, REG_WEIGHT=0.6))
+    crit = L.build_loss(config)
+    ph = dev(pred32).half()
+    tg = {"heatmaps": dev(target), "coords": dev(tcoords), "weights": dev(weight)}
+
+    def run(pred, scale_assumed, scale_actual):
+        p = pred.clone().requires_grad_(True)
+        c = dev(coords).requires_grad_(True)
+        gs = None if scale_assumed is None else torch.tensor(float(scale_assumed)).cuda()
+        total, parts = crit({"heatmaps": p, "coords": c}, tg, grad_scale=gs)
+        (total * scale_actual).backward()
+        return [float(parts[k].detach()) for k in ("heatmap", "morph", "regression", "total")], p.grad, c.grad
+
+    for assumed, actual in ((None, 1.0), (65536.0, 65536.0), (None, 1024.0), (65536.0, 32768.0)):
+        lh, gh, ch = run(ph, assumed, actual)
+        lf, gf, cf = run(ph.float(), assumed, actual)
+        assert gh.dtype == torch.float16 and gf.dtype == torch.float32
+        assert lh == lf, f"{name} {assumed}/{actual}: losses differ {lh} vs {lf}"
+        same(gh.cpu().numpy().view(np.uint16), gf.half().cpu().numpy().view(np.uint16), f"{name} {assumed}/{actual}: d/d pred (float16)")
+        same(ch.cpu().numpy(), cf.cpu().numpy(), f"{name} {assumed}/{actual}: d/d coords")
+        assert torch.isfinite(gh.float()).all()
+    # without the scale the small gradients flush to zero in half — the reason the scale must be met BEFORE rounding
+    _, g1, _ = run(ph, None, 1.0)
+    _, g2, _ = run(ph, 65536.0, 65536.0)
+    assert (g2 != 0).float().mean() >= (g1 != 0).float().mean()
+    # single-term modules, the criterion variants and a forward under no_grad
+    for mod, args in ((L.FusedPoseLoss(True, "smoothl1"), (tg["heatmaps"], tg["weights"])), (L.MorphologyShapeLoss(1.2, 0.5), (tg["heatmaps"], tg["weights"])),
+                      (L.JointsMSELoss(True), (tg["heatmaps"], tg["weights"])), (L.KeypointMSELoss(True), (tg["heatmaps"], tg["weights"]))):
+        a = ph.clone().requires_grad_(True)
+        b = ph.float().requires_grad_(True)
+        la, lb = mod(a, *args), mod(b, *args)
+        assert float(la) == float(lb), type(mod).__name__
+        (la * 4096.0).backward(); (lb * 4096.0).backward()
+        same(a.grad.cpu().numpy().view(np.uint16), b.grad.half().cpu().numpy().view(np.uint16), type(mod).__name__)
+        with torch.no_grad():
+            assert float(mod(ph, *args)) == float(lb)
+    # torch.autocast hands the same dtype over: the module is called inside the region as train.py does
+    with torch.autocast("cuda", dtype=torch.float16):
+        a = ph.clone().requires_grad_(True)
+        total, _ = crit({"heatmaps": a, "coords": dev(coords)}, tg)
+    total.backward()
+    lf, gf, _ = run(ph.float(), None, 1.0)
+    assert float(total) == lf[3]
+    same(a.grad.cpu().numpy().view(np.uint16), gf.half().cpu().numpy().view(np.uint16), "under torch.autocast")
+
+
 # ------------------------------------------------------------------ encoders
 @pytest.mark.parametrize("name", NAMES)
 def test_encoders_against_golden(pkg, name):
