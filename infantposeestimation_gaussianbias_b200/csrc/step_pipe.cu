@@ -183,6 +183,30 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #ifndef PIPE_BALANCE
 #define PIPE_BALANCE 0
 #endif
+// PIPE_V_FIRST: the variance tile is the FIRST ring item of a tile, not the last.  It is the one ring item that always
+// comes from HBM (the limb partners are other CTAs' tiles of the same image: L2 hits), and as the last item of a
+// two-deep ring it could only be requested once the first partner had been consumed: the compute warps then sat out most
+// of a DRAM round trip per tile in front of it (10 % of the kernel's stall samples, profiles/r02_step_pipe_kernel_lines.txt:
+// step_pipe.cu:998).  As the first item it is requested while the previous tile's partners are still being consumed and
+// has landed long before pass B is over.
+#ifndef PIPE_V_FIRST
+#define PIPE_V_FIRST 1
+#endif
+// PIPE_CARRY_TARGET: the row in which a thread meets the target patch (target_row: ~100 instructions) is worked out in the
+// front half and carried in five registers to the tile's back half one iteration later, instead of being worked out
+// again there: one inlined copy of target_row less on the once-per-tile path.
+#ifndef PIPE_CARRY_TARGET
+#define PIPE_CARRY_TARGET 0
+#endif
+// measurement only (wrong results): PIPE_NO_OFFZERO skips the dense zero fill of d_offsets (what an opt-in sparse offset
+// gradient would save: 8N of the 16N bytes written); PIPE_NO_MSE_FIX skips the squared-error correction on the target
+// patch in the front half (what moving it to the tail CTAs would save)
+#ifndef PIPE_NO_OFFZERO
+#define PIPE_NO_OFFZERO 0
+#endif
+#ifndef PIPE_NO_MSE_FIX
+#define PIPE_NO_MSE_FIX 0
+#endif
 constexpr int kPUs = PIPE_UNROLL_SMALL, kPUb = PIPE_UNROLL_B, kPUp = PIPE_UNROLL_P, kPUd = PIPE_UNROLL_D;
 // PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
 // instructions per warp and tile); every lane stores its sums into its own four slots of the sigmoid tile — free once the
@@ -363,7 +387,12 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 for (int n = 0; n < nn + (has_var ? 1 : 0); ++n) {
                     const unsigned q = rq & 1u;
                     if (rq >= 2) mbar_wait(rempty + q, ((rq - 2) >> 1) & 1u);
+#if PIPE_V_FIRST
+                    const int pn = n - (has_var ? 1 : 0);       // -1: the variance tile
+                    const float* src = pn >= 0 ? hm + (b * P.K + ((pj_c >> (8 * pn)) & 0xFFu)) * N : A.var + (size_t)cur * N;
+#else
                     const float* src = n < nn ? hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N : A.var + (size_t)cur * N;
+#endif
                     mbar_arrive_expect_tx(rfull + q, kTile);
                     bulk_g2s(Rb + q * N4, src, kTile, rfull + q);
                     ++rq;
@@ -815,6 +844,10 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
     for (int q = 0; q < NIT; ++q) wprev[q] = 0u;
     bool tie_prev = false;
+#if PIPE_CARRY_TARGET
+    int hit_prev = -1;
+    float4 thit_prev = z4;
+#endif
 
     for (unsigned i = 0;; ++i) {
         const unsigned s = i % 3u, b = i & 1u;
@@ -822,6 +855,10 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
         for (int q = 0; q < NIT; ++q) words[q] = 0u;
         bool tie_now = false;
+#if PIPE_CARRY_TARGET
+        int hit_now = -1;
+        float4 thit_now = z4;
+#endif
         // ================================================== front(i) ==================================================
         mbar_wait(hfull + s, (ph_full >> s) & 1u); ph_full ^= 1u << s;
         const int tile = tids[s];
@@ -834,7 +871,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const bool heavy = (w != 0.f) || !P.use_target_weight;
 
             // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
-            if (GRADS) {
+            if (GRADS && !PIPE_NO_OFFZERO) {
                 float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
 #pragma unroll (2 * kPUs)
                 for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
@@ -854,7 +891,10 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // ---- on-the-fly target: the one row (if any) in which this thread meets the patch ---------------------
             int hit_it = -1;
             float4 thit = z4;
-            if (heavy) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
+            if (heavy && !PIPE_NO_MSE_FIX) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
+#if PIPE_CARRY_TARGET
+            hit_now = hit_it; thit_now = thit;
+#endif
 
             // ---- pass B: softmax moments (relative to the warp's maximum), entropy sum, sigmoid, relu moments about the
             //      tile centre, sum h^2 -----------------------------------------------------------------------------
@@ -945,6 +985,24 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             float mind = INFINITY;                // smallest |own - partner| logit difference seen (0 = a tie)
             float r4[4] = {0.f, 0.f, 0.f, 0.f};
             if (heavy) {
+#if PIPE_V_FIRST
+                // ---- variance tile: its sum only ---------------------------------------------------------------------
+                if (has_var) {
+                    const unsigned q = rq & 1u;
+                    mbar_wait(rfull + q, (rq >> 1) & 1u);
+                    const float4* Vs = Rb + q * N4;
+                    f2 V2 = splat2(0.f);
+#pragma unroll kPUs
+                    for (int it = 0; it < NIT; ++it) {
+                        const f4 v = as_f4(Vs[it * TPB + tid]);
+                        V2 = add2(V2, add2(v.a, v.b));
+                    }
+                    r16[5] = hsum2(V2);
+                    ++rq;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(rempty + q);
+                }
+#endif
                 for (int n = 0; n < nact; ++n) {
                     const unsigned q = rq & 1u;
                     mbar_wait(rfull + q, (rq >> 1) & 1u);
@@ -992,6 +1050,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty + q);          // this warp has consumed the buffer
                 }
+#if !PIPE_V_FIRST
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
                     const unsigned q = rq & 1u;
@@ -1008,6 +1067,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty + q);
                 }
+#endif
             }
             tie_now = GRADS && mind == 0.f;
 
@@ -1103,8 +1163,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     const float fyy = k2.x, ke = k2.y, addc = k2.z, gvar = k2.w;
                     const bool flat = (flags & kFFlat) != 0u, g_live = (flags & kFLive) != 0u;
                     const TileDesc* dsc = Db + sp;
+#if PIPE_CARRY_TARGET
+                    const float4 thit = thit_prev;
+                    const int hit_it = hit_prev;
+#else
                     float4 thit;
                     const int hit_it = target_row<ROWS, NIT>(dsc->geom, dsc->w, x0, ty, P.ec, lut, thit);
+#endif
                     // ---- pass D: the heatmap gradient ---------------------------------------------------------------------
                     // g = c1 (h - t) + p (c6 (a - pa) + (x - cx) Fx + (y - cy) Fy) + [h > 0] (c4 ((x-cx)^2 + (y-cy)^2) + k4) + overlap
                     // flat tiles: c6 (a - pa) = c6 ln2 (tbar - t_i)
@@ -1218,6 +1283,9 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
         for (int q = 0; q < NIT; ++q) wprev[q] = words[q];
         tie_prev = tie_now;
+#if PIPE_CARRY_TARGET
+        hit_prev = hit_now; thit_prev = thit_now;
+#endif
     }
 }
 

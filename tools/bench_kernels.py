@@ -109,6 +109,12 @@ wts = [1.0, 0.15, 0.6]
 comb = lambda grads: ops.combined_loss(pred, tgt, wgt, d["kps"], None, d["kps"], None, 0, N.CRIT_MSE, N.CRIT_SMOOTHL1, True, 1.0, 1.2, 0.5, wts, True, grads)
 report("genb_tile_kernel CombinedLoss fwd+bwd", "cfg1 64x48 B=1024", B * K, 12 * n, timeit(lambda: comb(True)))
 report("genb_tile_kernel CombinedLoss fwd", "cfg1 64x48 B=1024", B * K, 8 * n, timeit(lambda: comb(False)))
+pred16 = pred.half()
+comb16 = lambda grads: ops.combined_loss(pred16, tgt, wgt, d["kps"], None, d["kps"], scale, 0, N.CRIT_MSE, N.CRIT_SMOOTHL1, True, 1.0, 1.2, 0.5, wts, True, grads)
+report("genb_tile_kernel<HALF> CombinedLoss fwd+bwd, float16 predictions / gradients (2N + 4N read, 2N written)", "cfg1 64x48 B=1024", B * K, 8 * n, timeit(lambda: comb16(True)))
+report("CombinedLoss float16 the up-cast way (pred.float() -> float32 kernel -> grad.half()): what the float16 entry point replaces", "cfg1 64x48 B=1024", B * K, 8 * n,
+       timeit(lambda: ops.combined_loss(pred16.float(), tgt, wgt, d["kps"], None, d["kps"], scale, 0, N.CRIT_MSE, N.CRIT_SMOOTHL1, True, 1.0, 1.2, 0.5, wts, True, True)[1].half()))
+del pred16
 cen = torch.rand(B, 2, device=dev) * 300 + 100
 scl = torch.rand(B, 2, device=dev) * 200 + 150
 report("postprocess_kernel (whole pipeline)", "cfg1 64x48 B=1024", B * K, 4 * n,
