@@ -192,11 +192,27 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #ifndef PIPE_V_FIRST
 #define PIPE_V_FIRST 1
 #endif
+// PIPE_V_SCALAR: the variance tile does not go through the ring at all.  Only its SUM is needed, so the scalar warp — idle
+// most of a tile period — reads it itself with plain 128-bit loads (lane l the float4s l, l + 32, ...: 512 contiguous bytes
+// per instruction), the first half requested when the tile is known and the second while it waits for the compute warps'
+// sums; the ring then carries limb partners only (both slots free for them) and the compute warps lose the pass and its wait.
+#ifndef PIPE_V_SCALAR
+#define PIPE_V_SCALAR 0
+#endif
+#ifndef PIPE_V_BATCHES
+#define PIPE_V_BATCHES 3
+#endif
 // PIPE_CARRY_TARGET: the row in which a thread meets the target patch (target_row: ~100 instructions) is worked out in the
 // front half and carried in five registers to the tile's back half one iteration later, instead of being worked out
 // again there: one inlined copy of target_row less on the once-per-tile path.
 #ifndef PIPE_CARRY_TARGET
-#define PIPE_CARRY_TARGET 0
+#define PIPE_CARRY_TARGET 1
+#endif
+// PIPE_TILE_FIRST: the producer requests tile j + 1 (into the buffer tile j - 2 has left) BEFORE the ring items of tile j.
+// The ring loop blocks until the compute warps have consumed all but two of a tile's items, so behind it the next tile was
+// requested only late in front(j) and the compute warps waited for its bytes at the top of front(j + 1).
+#ifndef PIPE_TILE_FIRST
+#define PIPE_TILE_FIRST 0
 #endif
 // measurement only (wrong results): PIPE_NO_OFFZERO skips the dense zero fill of d_offsets (what an opt-in sparse offset
 // gradient would save: 8N of the 16N bytes written); PIPE_NO_MSE_FIX skips the squared-error correction on the target
@@ -378,16 +394,33 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         unsigned rq = 0;                                     // ring items started so far
         unsigned ph_empty = 0;                               // phase bits per tile buffer
         for (unsigned j = 0;; ++j) {
-            // ring items of tile j: its limb partners, then its variance tile
+            const unsigned s1 = (j + 1) % 3u;
+#if PIPE_TILE_FIRST
+            // tile j + 1 into the buffer tile j - 2 has left
+            if (j >= 2) { mbar_wait_idle(hempty + s1, (ph_empty >> s1) & 1u); ph_empty ^= 1u << s1; }
+            const bool last = nxt >= (unsigned)tiles;
+            if (last) {
+                tids[s1] = -1;
+                mbar_arrive(hfull + s1);                     // the sentinel: everybody leaves at tile j + 1
+            } else {
+                tids[s1] = (int)nxt;
+                mbar_arrive_expect_tx(hfull + s1, kTile + 64);
+                bulk_g2s(Hb + s1 * N4, hm + (size_t)nxt * N, kTile, hfull + s1);
+                bulk_g2s(Db + s1, A.desc + nxt, 64, hfull + s1);
+            }
+#endif
+            // ring items of tile j: its variance tile, then its limb partners
             const bool heavy = (w_c != 0.f) || !P.use_target_weight;
             if (heavy) {
                 const int nn = (int)(pk_c & 7u);
                 const size_t b = cur / (unsigned)P.K;
 #pragma unroll kProdU
-                for (int n = 0; n < nn + (has_var ? 1 : 0); ++n) {
+                for (int n = 0; n < nn + ((has_var && !PIPE_V_SCALAR) ? 1 : 0); ++n) {
                     const unsigned q = rq & 1u;
                     if (rq >= 2) mbar_wait(rempty + q, ((rq - 2) >> 1) & 1u);
-#if PIPE_V_FIRST
+#if PIPE_V_SCALAR
+                    const float* src = hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N;
+#elif PIPE_V_FIRST
                     const int pn = n - (has_var ? 1 : 0);       // -1: the variance tile
                     const float* src = pn >= 0 ? hm + (b * P.K + ((pj_c >> (8 * pn)) & 0xFFu)) * N : A.var + (size_t)cur * N;
 #else
@@ -398,8 +431,14 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     ++rq;
                 }
             }
+#if PIPE_TILE_FIRST
+            if (last) break;
+            cur = nxt; nxt = nxt2;
+            w_c = w_n; pk_c = pk_n; pj_c = pj_n;
+            w_n = desc_w(nxt); pk_n = desc_pk(nxt); pj_n = desc_pj(nxt);
+            if (nxt2 < (unsigned)tiles) nxt2 = atomicAdd(A.tile_counter, 1u) + gridDim.x;
+#else
             // tile j + 1 into the buffer tile j - 2 has left
-            const unsigned s1 = (j + 1) % 3u;
             if (j >= 2) { mbar_wait_idle(hempty + s1, (ph_empty >> s1) & 1u); ph_empty ^= 1u << s1; }
             cur = nxt; nxt = nxt2;
             w_c = w_n; pk_c = pk_n; pj_c = pj_n;
@@ -414,6 +453,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             mbar_arrive_expect_tx(hfull + s1, kTile + 64);
             bulk_g2s(Hb + s1 * N4, hm + (size_t)cur * N, kTile, hfull + s1);
             bulk_g2s(Db + s1, A.desc + cur, 64, hfull + s1);
+#endif
         }
         return;
     }
@@ -477,8 +517,39 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 if (jk == 0xdeadbeefu) tids[3] = (int)jk;
             }
 #endif
+#if PIPE_V_SCALAR
+            // ---- the variance tile's sum, read by this warp: half of it before the wait for the compute warps, half across it
+            constexpr int kVPer = N4 / 32, kVB = PIPE_V_BATCHES, kVN = kVPer / kVB;      // kVB batches of kVN loads per lane
+            static_assert(kVPer % kVB == 0, "equal batches of whole warp rows");
+            f2 vacc = splat2(0.f);
+            float4 vb[kVN];
+            const bool v_here = heavy && has_var;
+            if (v_here) {
+                const float4* vp = reinterpret_cast<const float4*>(A.var) + (size_t)tile * N4 + lane;
+#pragma unroll
+                for (int j = 0; j < kVN; ++j) vb[j] = ldg_stream(vp + j * 32);
+#pragma unroll 1
+                for (int bt = 1; bt < kVB; ++bt) {
+                    vp += kVN * 32;
+#pragma unroll
+                    for (int j = 0; j < kVN; ++j) {
+                        const f4 v = as_f4(vb[j]);
+                        vacc = add2(vacc, add2(v.a, v.b));
+                        vb[j] = ldg_stream(vp + j * 32);
+                    }
+                }
+            }
+#endif
             // ---- the warps' partial sums of tile i --------------------------------------------------------------
             mbar_wait_idle(sfull + b, (i >> 1) & 1u);
+#if PIPE_V_SCALAR
+            float vsum_own = 0.f;
+            if (v_here) {
+#pragma unroll
+                for (int j = 0; j < kVN; ++j) { const f4 v = as_f4(vb[j]); vacc = add2(vacc, add2(v.a, v.b)); }
+                vsum_own = warp_sum(hsum2(vacc));
+            }
+#endif
 #if !PIPE_LANESUMS
             const float* redb = red + b * (NW * 16);
 #endif
@@ -590,7 +661,12 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 if (lane == 0) mbar_arrive(cfull + b);
             } else {
                 // ---- per-tile scalars ------------------------------------------------------------------------------
-                const float ET = val(3), Ssum = val(4), Vsum = val(5), Rm = val(6), Rxa = val(7), Rya = val(8), M2a = val(9), mse_sum = val(10);
+#if PIPE_V_SCALAR
+                const float Vsum = vsum_own;
+#else
+                const float Vsum = val(5);
+#endif
+                const float ET = val(3), Ssum = val(4), Rm = val(6), Rxa = val(7), Rya = val(8), M2a = val(9), mse_sum = val(10);
                 const float mV = has_var ? Vsum * P.inv_n : P.sigma;
                 const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
                 // relu moments shifted from the tile centre to (cx, cy)
@@ -985,7 +1061,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             float mind = INFINITY;                // smallest |own - partner| logit difference seen (0 = a tie)
             float r4[4] = {0.f, 0.f, 0.f, 0.f};
             if (heavy) {
-#if PIPE_V_FIRST
+#if PIPE_V_FIRST && !PIPE_V_SCALAR
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
                     const unsigned q = rq & 1u;
@@ -1050,7 +1126,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty + q);          // this warp has consumed the buffer
                 }
-#if !PIPE_V_FIRST
+#if !PIPE_V_FIRST && !PIPE_V_SCALAR
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
                     const unsigned q = rq & 1u;
