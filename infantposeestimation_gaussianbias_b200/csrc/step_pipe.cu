@@ -192,6 +192,25 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #ifndef PIPE_V_FIRST
 #define PIPE_V_FIRST 1
 #endif
+// PIPE_V_EARLY: with the variance tile as the first ring item, the compute warps take its sum at the very START of the front
+// half (it was requested during the previous tile's front half and has landed) instead of after pass B: its ring slot is
+// free a pass earlier, so a tile's second limb partner is requested while pass B runs, not when the partner visits begin.
+#ifndef PIPE_V_EARLY
+#define PIPE_V_EARLY 0
+#endif
+// PIPE_LATE_TARGET: the target row, the squared-error correction on it and the zero fill of d_offsets come BETWEEN the
+// variance sum and the limb-partner visits instead of in front of pass B: a tile's second partner is requested when the
+// variance tile's ring slot is released, and these ~150 instructions give that copy time to land.  Measured: 9 % SLOWER
+// (0.2336 against 0.2140 ms); kept as a measurement switch, like PIPE_V_EARLY (+2 %), PIPE_V_SCALAR (+35 %: the scalar
+// warp's chain then holds three DRAM round trips per tile and becomes the pipeline's period) and PIPE_TILE_FIRST (+4 %).
+#ifndef PIPE_LATE_TARGET
+#define PIPE_LATE_TARGET 0
+#endif
+// PIPE_MERGE_B1: heavy tiles without an active limb partner (6-8 % of the tiles) run pass B with the sigmoid too (its
+// result unused) instead of a pass-B instantiation of their own: ~1 KB less of warm code.
+#ifndef PIPE_MERGE_B1
+#define PIPE_MERGE_B1 1
+#endif
 // PIPE_V_SCALAR: the variance tile does not go through the ring at all.  Only its SUM is needed, so the scalar warp — idle
 // most of a tile period — reads it itself with plain 128-bit loads (lane l the float4s l, l + 32, ...: 512 contiguous bytes
 // per instruction), the first half requested when the tile is known and the second while it waits for the compute warps'
@@ -946,12 +965,33 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const int nact = (int)(dsc->pk & 7u);
             const bool heavy = (w != 0.f) || !P.use_target_weight;
 
+#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY
+            // ---- variance tile (first ring item, long landed): its sum only; the slot goes back to the producer at once
+            float vsum_early = 0.f;
+            if (heavy && has_var) {
+                const unsigned q = rq & 1u;
+                mbar_wait(rfull + q, (rq >> 1) & 1u);
+                const float4* Vs = Rb + q * N4;
+                f2 V2 = splat2(0.f);
+#pragma unroll kPUs
+                for (int it = 0; it < NIT; ++it) {
+                    const f4 v = as_f4(Vs[it * TPB + tid]);
+                    V2 = add2(V2, add2(v.a, v.b));
+                }
+                vsum_early = hsum2(V2);
+                ++rq;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rempty + q);
+            }
+#endif
+#if !PIPE_LATE_TARGET
             // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
             if (GRADS && !PIPE_NO_OFFZERO) {
                 float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
 #pragma unroll (2 * kPUs)
                 for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
             }
+#endif
             // ---- maximum (and minimum) of the tile: per warp ------------------------------------------------------
             float mw = -INFINITY, mnw = INFINITY;
 #pragma unroll kPUs
@@ -967,9 +1007,11 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // ---- on-the-fly target: the one row (if any) in which this thread meets the patch ---------------------
             int hit_it = -1;
             float4 thit = z4;
+#if !PIPE_LATE_TARGET
             if (heavy && !PIPE_NO_MSE_FIX) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
 #if PIPE_CARRY_TARGET
             hit_now = hit_it; thit_now = thit;
+#endif
 #endif
 
             // ---- pass B: softmax moments (relative to the warp's maximum), entropy sum, sigmoid, relu moments about the
@@ -977,7 +1019,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             float r16[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) r16[q] = 0.f;
-            const bool sig = heavy && nact > 0;
+            const bool sig = heavy && (nact > 0 || PIPE_MERGE_B1);
 #if PIPE_LANESUMS
             // the sigmoid slots still hold the lanes' sums of tile i - 1 until the scalar warp has taken them
             if (i >= 1) mbar_wait(sempty + ((i - 1) & 1u), ((i - 1) >> 1) & 1u);
@@ -1028,7 +1070,9 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     }
                 };
                 if (!heavy) body(std::integral_constant<int, 0>{});
+#if !PIPE_MERGE_B1
                 else if (!sig) body(std::integral_constant<int, 1>{});
+#endif
                 else if (fastsig) body(std::integral_constant<int, 2>{});
                 else body(std::integral_constant<int, 3>{});
                 float Ej[4], Rj[4];
@@ -1048,7 +1092,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     r16[9] = fmaf(xa0 * xa0, Rj[0], fmaf(xa1 * xa1, Rj[1], fmaf(xa2 * xa2, Rj[2], fmaf(xa3 * xa3, Rj[3], Ry2))));
                     // squared error: sum h^2 everywhere, corrected in the one row that meets the target patch
                     float h2 = hsum2(Hq);
-                    if (hit_it >= 0) {
+                    if (!PIPE_LATE_TARGET && hit_it >= 0) {
                         const float4 o = Hs[hit_it * TPB + tid];
                         const float d0 = o.x - thit.x, d1_ = o.y - thit.y, d2 = o.z - thit.z, d3 = o.w - thit.w;
                         h2 += (fmaf(d0, d0, -o.x * o.x) + fmaf(d1_, d1_, -o.y * o.y)) + (fmaf(d2, d2, -o.z * o.z) + fmaf(d3, d3, -o.w * o.w));
@@ -1058,10 +1102,18 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
 
             // ---- limb partners: one visit each; sums for the overlap ratio, one tie bit per pixel and partner ------
+#if PIPE_LATE_TARGET
+            // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
+            if (GRADS && !PIPE_NO_OFFZERO) {
+                float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
+#pragma unroll (2 * kPUs)
+                for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
+            }
+#endif
             float mind = INFINITY;                // smallest |own - partner| logit difference seen (0 = a tie)
             float r4[4] = {0.f, 0.f, 0.f, 0.f};
             if (heavy) {
-#if PIPE_V_FIRST && !PIPE_V_SCALAR
+#if PIPE_V_FIRST && !PIPE_V_SCALAR && !PIPE_V_EARLY
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
                     const unsigned q = rq & 1u;
@@ -1077,6 +1129,17 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     ++rq;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty + q);
+                }
+#endif
+#if PIPE_LATE_TARGET
+                if (!PIPE_NO_MSE_FIX) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
+#if PIPE_CARRY_TARGET
+                hit_now = hit_it; thit_now = thit;
+#endif
+                if (hit_it >= 0) {
+                    const float4 o = Hs[hit_it * TPB + tid];
+                    const float d0 = o.x - thit.x, d1_ = o.y - thit.y, d2 = o.z - thit.z, d3 = o.w - thit.w;
+                    r16[10] += (fmaf(d0, d0, -o.x * o.x) + fmaf(d1_, d1_, -o.y * o.y)) + (fmaf(d2, d2, -o.z * o.z) + fmaf(d3, d3, -o.w * o.w));
                 }
 #endif
                 for (int n = 0; n < nact; ++n) {
@@ -1146,6 +1209,9 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #endif
             }
             tie_now = GRADS && mind == 0.f;
+#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY
+            r16[5] = vsum_early;
+#endif
 
             // ---- publish this warp's sums --------------------------------------------------------------------------
             float* const red2b = red2 + b * (NW * 4);
