@@ -500,10 +500,13 @@ loss_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossAr
 // in words 6 and 7 of the tile's numerator row.  Same operations in the same order as the in-kernel versions
 // (step_tile.cu, loss_tile.cu): the taps of the bilinear sample around (cx, cy) into the zero-filled d_grad_off
 // (fusion_head.py:353-359, 686-700), then local refinement + offset correction (fusion_head.py:309-365).
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
 struct TailArgs {
     const float* hm; const float* off; float* grad_off; float* coords;
     const float* alpha_param; const float* fusion_weight;
     int radius; unsigned dflags; int fin_blocks; int enabled;
+    int half_io;          // hm, off and grad_off are float16 (the pointers are then __half*)
 };
 
 // tiles per warp (every load of a warp's tiles is requested before the first is consumed).  Measured on the default
@@ -513,7 +516,11 @@ struct TailArgs {
 #define FIN_TPW 1
 #endif
 constexpr int kTailTPW = FIN_TPW;
+template <typename E>
 __device__ __forceinline__ void step_tail(const LossParams& P, const TailArgs& T, const float* __restrict__ partial) {
+    const E* const t_hm = reinterpret_cast<const E*>(T.hm);
+    const E* const t_off = reinterpret_cast<const E*>(T.off);
+    E* const t_goff = reinterpret_cast<E*>(T.grad_off);
     const int H = P.H, W = P.W, N = H * W, tiles = P.B * P.K;
     const int lane = threadIdx.x & 31;
     const int tile0 = ((blockIdx.x - T.fin_blocks) * 8 + (threadIdx.x >> 5)) * kTailTPW;
@@ -540,14 +547,14 @@ __device__ __forceinline__ void step_tail(const LossParams& P, const TailArgs& T
         const int py = (int)fminf(fmaxf(rintf(cy[u]), 0.f), (float)(H - 1));
         const int wx = px + wdx, wy = py + wdy;
         const bool okw = win_small && in_win && wx >= 0 && wx < W && wy >= 0 && wy < H;
-        vpx[u] = okw ? __ldg(T.hm + (size_t)tile * N + wy * W + wx) : -INFINITY;
+        vpx[u] = okw ? ld1(t_hm + (size_t)tile * N + wy * W + wx) : -INFINITY;
         pre[u] = 0.f;
         if (win_small && want_off) {
             const int pbx = (int)floorf(fminf(fmaxf(cx[u], 0.f), (float)(W - 1))) - 1;
             const int pby = (int)floorf(fminf(fmaxf(cy[u], 0.f), (float)(H - 1))) - 1;
             const int tq = lane & 15;
             const int qx = min(max(pbx + (tq & 3), 0), W - 1), qy = min(max(pby + (tq >> 2), 0), H - 1);
-            pre[u] = __ldg(T.off + (size_t)tile * 2 * N + (lane >> 4) * N + qy * W + qx);
+            pre[u] = ld1(t_off + (size_t)tile * 2 * N + (lane >> 4) * N + qy * W + qx);
         }
     }
     float a_blend = 1.f, fw_dec = 0.f;
@@ -562,18 +569,18 @@ __device__ __forceinline__ void step_tail(const LossParams& P, const TailArgs& T
     for (int u = 0; u < kTailTPW; ++u) {
         const int tile = tile0 + u;
         if (tile >= tiles) break;
-        const float* off_tile = T.off + (size_t)tile * 2 * N;
+        const E* off_tile = t_off + (size_t)tile * 2 * N;
         if (lane == 0 && (g0[u] != 0.f || g1[u] != 0.f)) {
             const Taps tp = taps_setup(cx[u], cy[u], H, W);
-            float* go = T.grad_off + (size_t)tile * 2 * N;
+            E* go = t_goff + (size_t)tile * 2 * N;
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                float* o = go + ch * N;
+                E* o = go + ch * N;
                 const float gc = ch == 0 ? g0[u] : g1[u];
-                o[tp.i00] = gc * tp.w00;
-                if (tp.okx != 0.f) o[tp.i01] = gc * tp.w01;
-                if (tp.oky != 0.f) o[tp.i10] = gc * tp.w10;
-                if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = gc * tp.w11;
+                st1(o + tp.i00, gc * tp.w00);
+                if (tp.okx != 0.f) st1(o + tp.i01, gc * tp.w01);
+                if (tp.oky != 0.f) st1(o + tp.i10, gc * tp.w10);
+                if (tp.okx != 0.f && tp.oky != 0.f) st1(o + tp.i11, gc * tp.w11);
             }
         }
         float dx_ = cx[u], dy_ = cy[u];
@@ -617,7 +624,7 @@ __device__ __forceinline__ void step_tail(const LossParams& P, const TailArgs& T
             }
         } else {
             int qx_, qy_;
-            refine_and_correct<float>(T.hm + (size_t)tile * N, nullptr, off_tile, T.alpha_param, T.fusion_weight, H, W, T.radius, T.dflags, dx_, dy_, qx_, qy_);
+            refine_and_correct<E>(t_hm + (size_t)tile * N, nullptr, off_tile, T.alpha_param, T.fusion_weight, H, W, T.radius, T.dflags, dx_, dy_, qx_, qy_);
         }
         if (lane == 0) { T.coords[2 * tile] = dx_; T.coords[2 * tile + 1] = dy_; }
     }
@@ -634,7 +641,10 @@ finalize_kernel(const __grid_constant__ LossParams P, const float* __restrict__ 
     __shared__ bool last;
     pdl_wait();                                        // launched while the tile kernel's last wave is still running
     const int nblk = tail.enabled ? tail.fin_blocks : (int)gridDim.x;      // the summing CTAs
-    if ((int)blockIdx.x >= nblk) { step_tail(P, tail, partial); return; }
+    if ((int)blockIdx.x >= nblk) {
+        if (tail.half_io) step_tail<__half>(P, tail, partial); else step_tail<float>(P, tail, partial);
+        return;
+    }
     const int tiles = P.B * P.K;
     const int per = (tiles + nblk - 1) / nblk;
     const int lo = blockIdx.x * per, hi = min(tiles, lo + per);
@@ -993,6 +1003,7 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
             tail.enabled = 1;
             tail.hm = hm; tail.off = off; tail.grad_off = goff; tail.coords = coords;
             tail.alpha_param = alpha_param; tail.fusion_weight = fusion_weight; tail.radius = radius; tail.dflags = dflags;
+            tail.half_io = half_io;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(fin_blocks + (tail.enabled ? (tiles + 8 * kTailTPW - 1) / (8 * kTailTPW) : 0)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;

@@ -27,6 +27,7 @@
 // Algorithmic HBM bytes per tile: read hm, var (8N); write d_hm, d_var, d_off (16N).
 #include "loss_common.cuh"
 #include "f32x2.cuh"
+#include "decode_device.cuh"
 #include <stdlib.h>
 #include <type_traits>
 #include <stdio.h>
@@ -208,6 +209,10 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #endif
 // PIPE_MERGE_B1: heavy tiles without an active limb partner (6-8 % of the tiles) run pass B with the sigmoid too (its
 // result unused) instead of a pass-B instantiation of their own: ~1 KB less of warm code.
+// ring depth of the float16 instantiation (its tiles are 6 KB: four ring buffers and the rest are 55 KB per CTA)
+#ifndef PIPE_HALF_RING
+#define PIPE_HALF_RING 4
+#endif
 #ifndef PIPE_MERGE_B1
 #define PIPE_MERGE_B1 1
 #endif
@@ -261,24 +266,68 @@ constexpr unsigned kFHeavy = 1u, kFFlat = 2u, kFLive = 4u, kFFastSig = 8u;
 // 12 flags  13 eM (= exp(m), for the sigmoid derivative)  14,15 - | 16..31 overlap coefficient per tie pattern | 32..35 cj
 constexpr int kConsFloats = 48;
 
-template <int W4, int ROWS, int NIT>
+// ---- element type of the maps: float32, or float16 under autocast (train.py:171) ---------------------------------------
+// A "vector" is four pixels: 16 bytes of float, 8 bytes of half.  Half maps travel as they are (bulk copies of raw halves:
+// a 64x48 tile is 6 KB) and are up-cast value by value where a warp reads them from shared memory; gradients are rounded
+// once where they leave.  Everything in between is the same code, so losses and decode equal the float32 kernel's on the
+// up-cast maps bit for bit.
+template <bool HALF> struct PX;
+template <> struct PX<false> {
+    using Vec = float4;
+    using Elem = float;
+    static __device__ __forceinline__ float4 lds(const Vec* p) { return *p; }
+    static __device__ __forceinline__ float4 ldg(const Vec* p) { return ldg_keep(p); }
+    static __device__ __forceinline__ float4 ld_plain(const Vec* p) { return *p; }
+    static __device__ __forceinline__ void stg(Vec* p, const float4& v) { stg_stream(p, v); }
+    static __device__ __forceinline__ void st_plain(Vec* p, const float4& v) { *p = v; }
+    static __device__ __forceinline__ void st1(Elem* p, float v) { *p = v; }
+};
+template <> struct PX<true> {
+    using Vec = uint2;
+    using Elem = __half;
+    static __device__ __forceinline__ float4 up(const uint2& r) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ uint2 down(const float4& v) {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned*>(&a); r.y = *reinterpret_cast<const unsigned*>(&b);
+        return r;
+    }
+    static __device__ __forceinline__ float4 lds(const Vec* p) { return up(*p); }
+    static __device__ __forceinline__ float4 ldg(const Vec* p) { return up(__ldg(p)); }
+    static __device__ __forceinline__ float4 ld_plain(const Vec* p) { return up(*p); }
+    static __device__ __forceinline__ void stg(Vec* p, const float4& v) {
+        const uint2 r = down(v);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(r.x), "r"(r.y) : "memory");
+    }
+    static __device__ __forceinline__ void st_plain(Vec* p, const float4& v) { *p = down(v); }
+    static __device__ __forceinline__ void st1(Elem* p, float v) { *p = __float2half_rn(v); }
+};
+
+// RD: depth of the ring that carries the variance tile and the limb partners (a power of two).  Two for float32 tiles
+// (six 12 KB buffers are what fits an SM three times); four for float16 tiles, whose buffers are half the size.
+template <int W4, int ROWS, int NIT, bool HALF = false, int RD = 2>
 struct PipePlan {
     static constexpr int TPB = W4 * ROWS, NW = TPB / 32, N4 = TPB * NIT, N = 4 * N4, W = 4 * W4, H = ROWS * NIT;
-    static constexpr int kTile = N4 * 16;
+    static constexpr int kTile = N4 * (HALF ? 8 : 16);           // bytes of one tile as it travels
     static constexpr int oH = 0;                                 // three tile buffers
-    static constexpr int oS = 3 * kTile;                         // sigmoid of the tile in its front half
-    static constexpr int oR = 4 * kTile;                         // two ring buffers: limb partners, variance tile
-    static constexpr int oDesc = 6 * kTile;                      // three descriptors
+    static constexpr int oS = 3 * kTile;                         // sigmoid of the tile in its front half (float32 either way)
+    static constexpr int oR = oS + N4 * 16;                      // RD ring buffers: variance tile, limb partners
+    static constexpr int oDesc = oR + RD * kTile;                // three descriptors
     static constexpr int oRed = oDesc + 3 * 64;                  // 2 x NW x 16 floats
     static constexpr int oRed2 = oRed + 2 * NW * 16 * 4;         // 2 x NW x 4 floats (partners 3 and 4)
     static constexpr int oRedM = oRed2 + 2 * NW * 4 * 4;         // 2 x NW x 2 floats (per-warp max, min)
     static constexpr int oRedC = oRedM + 2 * NW * 2 * 4;         // NW x 8 floats (general second pass)
     static constexpr int oCons = oRedC + NW * 8 * 4;             // 2 x kConsFloats
-    static constexpr int oBar = oCons + 2 * kConsFloats * 4;     // 20 mbarriers
-    static constexpr int oTid = oBar + 20 * 8;                   // 3 tile indices (+ pad)
+    static constexpr int oBar = oCons + 2 * kConsFloats * 4;     // 20 + 2 RD mbarriers
+    static constexpr int oTid = oBar + (20 + 2 * RD) * 8;        // 3 tile indices (+ pad)
     static constexpr int oCta = oTid + 16;                       // float4: 1/(sum w + eps), 1/(sum w_i w_j + eps), gradient scale
     static constexpr int oLut = oCta + 16;                       // exp table of the target patch
     static_assert(TPB % 32 == 0 && NW >= 2 && NW <= 16, "whole warps");
+    static_assert(RD >= 2 && (RD & (RD - 1)) == 0, "ring depth: a power of two");
+    static_assert((oS % 16) == 0 && (oR % 16) == 0 && (kTile % 16) == 0, "bulk copies land on 16-byte boundaries");
     static_assert((oBar % 8) == 0 && (oDesc % 16) == 0 && (oLut % 16) == 0 && (oCons % 16) == 0 && (oRed % 16) == 0, "alignment");
 };
 
@@ -306,16 +355,20 @@ __device__ PIPE_TROW_INLINE int target_row(const int4& gq, float w, int x0, int 
 // ---- the kernel ------------------------------------------------------------------------------------
 // GRADS = false: forward only (validate.py:90 evaluates the loss under no_grad every batch): no tie words, no gradient
 // pass, no stores besides the per-tile loss numerators and the decode.
-template <int W4, int ROWS, int NIT, int MINB, bool GRADS>
+template <int W4, int ROWS, int NIT, int MINB, bool GRADS, bool HALF = false, int RD = 2>
 __global__ void __launch_bounds__(W4* ROWS + 64, MINB)
 step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ LossArgs A) {
-    using L = PipePlan<W4, ROWS, NIT>;
+    using L = PipePlan<W4, ROWS, NIT, HALF, RD>;
+    using IO = PX<HALF>;
+    using Vec = typename IO::Vec;
+    using Elem = typename IO::Elem;
+    static_assert(!HALF || PIPE_TAIL_OUTSIDE, "the float16 instantiation leaves the decode tail to finalize_kernel");
     constexpr int TPB = L::TPB, NW = L::NW, N4 = L::N4, N = L::N, W = L::W, H = L::H;
     constexpr unsigned kTile = L::kTile;
     extern __shared__ __align__(128) unsigned char smraw[];
-    float4* const Hb = reinterpret_cast<float4*>(smraw + L::oH);
+    Vec* const Hb = reinterpret_cast<Vec*>(smraw + L::oH);
     float4* const Sb = reinterpret_cast<float4*>(smraw + L::oS);
-    float4* const Rb = reinterpret_cast<float4*>(smraw + L::oR);
+    Vec* const Rb = reinterpret_cast<Vec*>(smraw + L::oR);
     TileDesc* const Db = reinterpret_cast<TileDesc*>(smraw + L::oDesc);
     float* const red = reinterpret_cast<float*>(smraw + L::oRed);
     float* const red2 = reinterpret_cast<float*>(smraw + L::oRed2);
@@ -329,8 +382,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const Bar bar0{smem_u32(static_cast<const void*>(bars))};
     const Bar hfull = bar0;                  // [3] tile + descriptor landed                       (producer -> all)
     const Bar hempty = bar0 + 3;             // [3] every compute warp is done with the tile       (compute -> producer)
-    const Bar rfull = bar0 + 6;              // [2] ring item landed                               (producer -> compute)
-    const Bar rempty = bar0 + 8;             // [2] every compute warp has consumed it             (compute -> producer)
+    const Bar rfull = bar0 + 20;             // [RD] ring item landed                              (producer -> compute)
+    const Bar rempty = bar0 + (20 + RD);     // [RD] every compute warp has consumed it            (compute -> producer)
     const Bar sfull = bar0 + 10;             // [2] every compute warp has published its sums      (compute -> scalar)
     const Bar sempty = bar0 + 12;            // [2] the scalar warp has read them                  (scalar -> compute)
     const Bar cfull = bar0 + 14;             // [2] constants of the gradient pass written         (scalar -> compute)
@@ -342,7 +395,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const int tiles = P.B * P.K;
     const bool has_var = A.var != nullptr;
     const bool decode = A.coords != nullptr;
-    const float* const hm = A.hm;
+    const Elem* const hm = reinterpret_cast<const Elem*>(A.hm);
+    const Elem* const var_maps = reinterpret_cast<const Elem*>(A.var);
 
     // ---- once per CTA -------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -357,8 +411,9 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
         for (int q = 0; q < 3; ++q) { mbar_init(hfull + q, 1); mbar_init(hempty + q, NW); }
 #pragma unroll
+        for (int q = 0; q < RD; ++q) { mbar_init(rfull + q, 1); mbar_init(rempty + q, NW); }
+#pragma unroll
         for (int q = 0; q < 2; ++q) {
-            mbar_init(rfull + q, 1); mbar_init(rempty + q, NW);
             mbar_init(sfull + q, NW); mbar_init(sempty + q, 1);
             mbar_init(cfull + q, 1); mbar_init(cempty + q, NW);
         }
@@ -435,15 +490,15 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 const size_t b = cur / (unsigned)P.K;
 #pragma unroll kProdU
                 for (int n = 0; n < nn + ((has_var && !PIPE_V_SCALAR) ? 1 : 0); ++n) {
-                    const unsigned q = rq & 1u;
-                    if (rq >= 2) mbar_wait(rempty + q, ((rq - 2) >> 1) & 1u);
+                    const unsigned q = rq & (unsigned)(RD - 1);
+                    if (rq >= (unsigned)RD) mbar_wait(rempty + q, ((rq - RD) / RD) & 1u);
 #if PIPE_V_SCALAR
-                    const float* src = hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N;
+                    const Elem* src = hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N;
 #elif PIPE_V_FIRST
                     const int pn = n - (has_var ? 1 : 0);       // -1: the variance tile
-                    const float* src = pn >= 0 ? hm + (b * P.K + ((pj_c >> (8 * pn)) & 0xFFu)) * N : A.var + (size_t)cur * N;
+                    const Elem* src = pn >= 0 ? hm + (b * P.K + ((pj_c >> (8 * pn)) & 0xFFu)) * N : var_maps + (size_t)cur * N;
 #else
-                    const float* src = n < nn ? hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N : A.var + (size_t)cur * N;
+                    const Elem* src = n < nn ? hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N : var_maps + (size_t)cur * N;
 #endif
                     mbar_arrive_expect_tx(rfull + q, kTile);
                     bulk_g2s(Rb + q * N4, src, kTile, rfull + q);
@@ -517,10 +572,10 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const int nact = (int)(pk & 7u);
             const float wa = P.use_target_weight ? w : 1.f;
             const bool heavy = (w != 0.f) || !P.use_target_weight;
-            const float* off_tile = A.off + (size_t)tile * 2 * N;
+            const Elem* off_tile = reinterpret_cast<const Elem*>(A.off) + (size_t)tile * 2 * N;
             // the 4x4x2 window of offset taps around the tile centre (consumed after the sums)
             float tapv = 0.f;
-            if (heavy) tapv = __ldg(off_tile + (lane >> 4) * N + (wy0 + ((lane >> 2) & 3)) * W + wx0 + (lane & 3));
+            if (heavy) tapv = ld1(off_tile + (lane >> 4) * N + (wy0 + ((lane >> 2) & 3)) * W + wx0 + (lane & 3));
 
 #ifdef PIPE_JUNK
             // measurement only: PIPE_JUNK x 16 straight-line instructions of once-per-tile code in the scalar warp (does the
@@ -656,13 +711,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
                 wx_ = px + wdx; wy_ = py + wdy;
                 okw = in_win && wx_ >= 0 && wx_ < W && wy_ >= 0 && wy_ < H;
-                if (okw) vpx = __ldg(hm + (size_t)tile * N + wy_ * W + wx_);
+                if (okw) vpx = ld1(hm + (size_t)tile * N + wy_ * W + wx_);
                 if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
                     pbx = (int)floorf(fminf(fmaxf(cx, 0.f), (float)(W - 1))) - 1;
                     pby = (int)floorf(fminf(fmaxf(cy, 0.f), (float)(H - 1))) - 1;
                     const int tq = lane & 15;
                     const int qx = min(max(pbx + (tq & 3), 0), W - 1), qy = min(max(pby + (tq >> 2), 0), H - 1);
-                    pre = __ldg(off_tile + (lane >> 4) * N + qy * W + qx);
+                    pre = ld1(off_tile + (lane >> 4) * N + qy * W + qx);
                 }
             }
 #endif
@@ -751,8 +806,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     } else {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            ov[c][0] = __ldg(off_tile + c * N + tp.i00); ov[c][1] = __ldg(off_tile + c * N + tp.i01);
-                            ov[c][2] = __ldg(off_tile + c * N + tp.i10); ov[c][3] = __ldg(off_tile + c * N + tp.i11);
+                            ov[c][0] = ld1(off_tile + c * N + tp.i00); ov[c][1] = ld1(off_tile + c * N + tp.i01);
+                            ov[c][2] = ld1(off_tile + c * N + tp.i10); ov[c][3] = ld1(off_tile + c * N + tp.i11);
                         }
                     }
                 }
@@ -836,15 +891,15 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     if (GRADS && taps_here) {
                         // the zero fill of these addresses was issued by the compute warps before they published their
                         // sums (release) and this warp has waited for that (acquire): these stores come after
-                        float* go = A.grad_off + (size_t)tile * 2 * N;
+                        Elem* go = reinterpret_cast<Elem*>(A.grad_off) + (size_t)tile * 2 * N;
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
-                            float* o = go + ch * N;
+                            Elem* o = go + ch * N;
                             const float gc = h2c * sl1p[ch];
-                            o[tp.i00] = gc * tp.w00;
-                            if (tp.okx != 0.f) o[tp.i01] = gc * tp.w01;
-                            if (tp.oky != 0.f) o[tp.i10] = gc * tp.w10;
-                            if (tp.okx != 0.f && tp.oky != 0.f) o[tp.i11] = gc * tp.w11;
+                            IO::st1(o + tp.i00, gc * tp.w00);
+                            if (tp.okx != 0.f) IO::st1(o + tp.i01, gc * tp.w01);
+                            if (tp.oky != 0.f) IO::st1(o + tp.i10, gc * tp.w10);
+                            if (tp.okx != 0.f && tp.oky != 0.f) IO::st1(o + tp.i11, gc * tp.w11);
                         }
                     }
                 }
@@ -857,10 +912,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             if (decode) {
                 if (lane == 0) { A.coords[2 * tile] = cx; A.coords[2 * tile + 1] = cy; A.scores[tile] = m; }
             }
-            if (false) {
 #else
             if (decode) {
-#endif
                 float dx_ = cx, dy_ = cy;
                 if (win_small) {
 #if PIPE_EARLY_DECODE
@@ -871,7 +924,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
                     const int x = px + wdx, y = py + wdy;
                     const bool ok = in_win && x >= 0 && x < W && y >= 0 && y < H;
-                    const float vpx = ok ? __ldg(hm + (size_t)tile * N + y * W + x) : -INFINITY;
+                    const float vpx = ok ? ld1(hm + (size_t)tile * N + y * W + x) : -INFINITY;
 #endif
                     const float vmax = warp_max(vpx);
                     const float e = ok ? expf(vpx - vmax) : 0.f;
@@ -913,11 +966,12 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     }
                 } else {
                     int px, py;
-                    refine_and_correct<float>(hm + (size_t)tile * N, nullptr, off_tile, A.alpha_param, A.fusion_weight,
+                    refine_and_correct<Elem>(hm + (size_t)tile * N, nullptr, off_tile, A.alpha_param, A.fusion_weight,
                                               H, W, A.radius, A.dflags, dx_, dy_, px, py);
                 }
                 if (lane == 0) { A.coords[2 * tile] = dx_; A.coords[2 * tile + 1] = dy_; A.scores[tile] = m; }
             }
+#endif
         }
         return;
     }
@@ -933,7 +987,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const f2 kL2E = splat2(kLog2e), kNL2E = splat2(-kLog2e), kOne = splat2(1.f);
 
-    unsigned rq = 0;                        // ring items consumed so far (buffer = rq & 1, parity = (rq >> 1) & 1)
+    unsigned rq = 0;                        // ring items consumed so far (buffer = rq % RD, parity = (rq / RD) & 1)
     unsigned ph_full = 0, np2 = 0;
     unsigned wprev[NIT];                    // tie words of the tile whose back half is due
 #pragma unroll
@@ -958,7 +1012,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         mbar_wait(hfull + s, (ph_full >> s) & 1u); ph_full ^= 1u << s;
         const int tile = tids[s];
         if (tile >= 0) {
-            const float4* const Hs = Hb + s * N4;
+            const Vec* const Hs = Hb + s * N4;
             const TileDesc* dsc = Db + s;
             const int4 gq = dsc->geom;
             const float w = dsc->w;
@@ -966,16 +1020,18 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const bool heavy = (w != 0.f) || !P.use_target_weight;
 
 #if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY
-            // ---- variance tile (first ring item, long landed): its sum only; the slot goes back to the producer at once
             float vsum_early = 0.f;
+#endif
+#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY == 1
+            // ---- variance tile (first ring item, long landed): its sum only; the slot goes back to the producer at once
             if (heavy && has_var) {
-                const unsigned q = rq & 1u;
-                mbar_wait(rfull + q, (rq >> 1) & 1u);
-                const float4* Vs = Rb + q * N4;
+                const unsigned q = rq & (unsigned)(RD - 1);
+                mbar_wait(rfull + q, (rq / RD) & 1u);
+                const Vec* Vs = Rb + q * N4;
                 f2 V2 = splat2(0.f);
 #pragma unroll kPUs
                 for (int it = 0; it < NIT; ++it) {
-                    const f4 v = as_f4(Vs[it * TPB + tid]);
+                    const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
                     V2 = add2(V2, add2(v.a, v.b));
                 }
                 vsum_early = hsum2(V2);
@@ -987,16 +1043,17 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #if !PIPE_LATE_TARGET
             // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
             if (GRADS && !PIPE_NO_OFFZERO) {
-                float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
+                constexpr int kZ = HALF ? NIT : 2 * NIT;                // 16-byte stores per thread: 2N elements per tile
+                float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * (kZ * TPB) + tid;
 #pragma unroll (2 * kPUs)
-                for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
+                for (int it = 0; it < kZ; ++it) stg_stream(go4 + it * TPB, z4);
             }
 #endif
             // ---- maximum (and minimum) of the tile: per warp ------------------------------------------------------
             float mw = -INFINITY, mnw = INFINITY;
 #pragma unroll kPUs
             for (int it = 0; it < NIT; ++it) {
-                const float4 o = Hs[it * TPB + tid];
+                const float4 o = IO::lds(Hs + it * TPB + tid);
                 mw = max3f(mw, o.x, o.y); mw = max3f(mw, o.z, o.w);
                 mnw = min3f(mnw, o.x, o.y); mnw = min3f(mnw, o.z, o.w);
             }
@@ -1020,6 +1077,25 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
             for (int q = 0; q < 16; ++q) r16[q] = 0.f;
             const bool sig = heavy && (nact > 0 || PIPE_MERGE_B1);
+#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY == 2
+            // (2: in front of pass B rather than at the very start — the copy has had the maximum pass and the target row to land)
+            // ---- variance tile (first ring item, long landed): its sum only; the slot goes back to the producer at once
+            if (heavy && has_var) {
+                const unsigned q = rq & (unsigned)(RD - 1);
+                mbar_wait(rfull + q, (rq / RD) & 1u);
+                const Vec* Vs = Rb + q * N4;
+                f2 V2 = splat2(0.f);
+#pragma unroll kPUs
+                for (int it = 0; it < NIT; ++it) {
+                    const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
+                    V2 = add2(V2, add2(v.a, v.b));
+                }
+                vsum_early = hsum2(V2);
+                ++rq;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rempty + q);
+            }
+#endif
 #if PIPE_LANESUMS
             // the sigmoid slots still hold the lanes' sums of tile i - 1 until the scalar warp has taken them
             if (i >= 1) mbar_wait(sempty + ((i - 1) & 1u), ((i - 1) >> 1) & 1u);
@@ -1038,7 +1114,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     constexpr int kUnroll = MODE == 2 ? kPUb : 1;
 #pragma unroll kUnroll
                     for (int it = 0; it < NIT; ++it) {
-                        const float4 o = Hs[it * TPB + tid];
+                        const float4 o = IO::lds(Hs + it * TPB + tid);
                         const f4 hv = as_f4(o);
                         const f2 t01 = fma2(hv.a, kL2E, kNML), t23 = fma2(hv.b, kL2E, kNML);
                         const f2 e01 = pack2(ex2(lo2(t01)), ex2(hi2(t01))), e23 = pack2(ex2(lo2(t23)), ex2(hi2(t23)));
@@ -1093,7 +1169,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     // squared error: sum h^2 everywhere, corrected in the one row that meets the target patch
                     float h2 = hsum2(Hq);
                     if (!PIPE_LATE_TARGET && hit_it >= 0) {
-                        const float4 o = Hs[hit_it * TPB + tid];
+                        const float4 o = IO::lds(Hs + hit_it * TPB + tid);
                         const float d0 = o.x - thit.x, d1_ = o.y - thit.y, d2 = o.z - thit.z, d3 = o.w - thit.w;
                         h2 += (fmaf(d0, d0, -o.x * o.x) + fmaf(d1_, d1_, -o.y * o.y)) + (fmaf(d2, d2, -o.z * o.z) + fmaf(d3, d3, -o.w * o.w));
                     }
@@ -1105,9 +1181,10 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #if PIPE_LATE_TARGET
             // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
             if (GRADS && !PIPE_NO_OFFZERO) {
-                float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * 2 * N4 + tid;
+                constexpr int kZ = HALF ? NIT : 2 * NIT;                // 16-byte stores per thread: 2N elements per tile
+                float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * (kZ * TPB) + tid;
 #pragma unroll (2 * kPUs)
-                for (int it = 0; it < 2 * NIT; ++it) stg_stream(go4 + it * TPB, z4);
+                for (int it = 0; it < kZ; ++it) stg_stream(go4 + it * TPB, z4);
             }
 #endif
             float mind = INFINITY;                // smallest |own - partner| logit difference seen (0 = a tie)
@@ -1116,13 +1193,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #if PIPE_V_FIRST && !PIPE_V_SCALAR && !PIPE_V_EARLY
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
-                    const unsigned q = rq & 1u;
-                    mbar_wait(rfull + q, (rq >> 1) & 1u);
-                    const float4* Vs = Rb + q * N4;
+                    const unsigned q = rq & (unsigned)(RD - 1);
+                    mbar_wait(rfull + q, (rq / RD) & 1u);
+                    const Vec* Vs = Rb + q * N4;
                     f2 V2 = splat2(0.f);
 #pragma unroll kPUs
                     for (int it = 0; it < NIT; ++it) {
-                        const f4 v = as_f4(Vs[it * TPB + tid]);
+                        const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
                         V2 = add2(V2, add2(v.a, v.b));
                     }
                     r16[5] = hsum2(V2);
@@ -1137,20 +1214,20 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 hit_now = hit_it; thit_now = thit;
 #endif
                 if (hit_it >= 0) {
-                    const float4 o = Hs[hit_it * TPB + tid];
+                    const float4 o = IO::lds(Hs + hit_it * TPB + tid);
                     const float d0 = o.x - thit.x, d1_ = o.y - thit.y, d2 = o.z - thit.z, d3 = o.w - thit.w;
                     r16[10] += (fmaf(d0, d0, -o.x * o.x) + fmaf(d1_, d1_, -o.y * o.y)) + (fmaf(d2, d2, -o.z * o.z) + fmaf(d3, d3, -o.w * o.w));
                 }
 #endif
                 for (int n = 0; n < nact; ++n) {
-                    const unsigned q = rq & 1u;
-                    mbar_wait(rfull + q, (rq >> 1) & 1u);
-                    const float4* Qs = Rb + q * N4;
+                    const unsigned q = rq & (unsigned)(RD - 1);
+                    mbar_wait(rfull + q, (rq / RD) & 1u);
+                    const Vec* Qs = Rb + q * N4;
                     f2 Sj2 = splat2(0.f), M2 = splat2(0.f);
 #pragma unroll kPUp
                     for (int it = 0; it < NIT; ++it) {
-                        const float4 q4 = Qs[it * TPB + tid];
-                        const float4 o = Hs[it * TPB + tid];
+                        const float4 q4 = IO::lds(Qs + it * TPB + tid);
+                        const float4 o = IO::lds(Hs + it * TPB + tid);
                         const float4 s4 = Sb[it * TPB + tid];
                         const f4 hv = as_f4(o), qv = as_f4(q4);
                         const f2 u01 = mul2(qv.a, kNL2E), u23 = mul2(qv.b, kNL2E);
@@ -1192,13 +1269,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #if !PIPE_V_FIRST && !PIPE_V_SCALAR
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
-                    const unsigned q = rq & 1u;
-                    mbar_wait(rfull + q, (rq >> 1) & 1u);
-                    const float4* Vs = Rb + q * N4;
+                    const unsigned q = rq & (unsigned)(RD - 1);
+                    mbar_wait(rfull + q, (rq / RD) & 1u);
+                    const Vec* Vs = Rb + q * N4;
                     f2 V2 = splat2(0.f);
 #pragma unroll kPUs
                     for (int it = 0; it < NIT; ++it) {
-                        const f4 v = as_f4(Vs[it * TPB + tid]);
+                        const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
                         V2 = add2(V2, add2(v.a, v.b));
                     }
                     r16[5] = hsum2(V2);
@@ -1237,7 +1314,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         // ================================================== back(i - 1) ===============================================
         if (i >= 1) {
             const unsigned sp = (i - 1) % 3u, bp = (i - 1) & 1u;
-            const float4* const Hs = Hb + sp * N4;
+            const Vec* const Hs = Hb + sp * N4;
             const int tile_p = tids[sp];
             const float* const cb = cons + bp * kConsFloats;
             mbar_wait(cfull + bp, ((i - 1) >> 1) & 1u);
@@ -1254,7 +1331,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     const float dy0 = fty - cy;
 #pragma unroll 1
                     for (int it = 0; it < NIT; ++it) {
-                        const float4 o = Hs[it * TPB + tid];
+                        const float4 o = IO::lds(Hs + it * TPB + tid);
                         const f4 hv = as_f4(o);
                         const f2 t01 = fma2(hv.a, kL2E, kNML), t23 = fma2(hv.b, kL2E, kNML);
                         const f2 p01 = mul2(pack2(ex2(lo2(t01)), ex2(hi2(t01))), kIZ), p23 = mul2(pack2(ex2(lo2(t23)), ex2(hi2(t23))), kIZ);
@@ -1290,13 +1367,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 flags = __float_as_uint(k3.x);
             }
             if (GRADS) {
-                float4* gh4 = reinterpret_cast<float4*>(A.grad_hm) + (size_t)tile_p * N4 + tid;
-                float4* gv4 = has_var ? reinterpret_cast<float4*>(A.grad_var) + (size_t)tile_p * N4 + tid : nullptr;
+                Vec* gh4 = reinterpret_cast<Vec*>(A.grad_hm) + (size_t)tile_p * N4 + tid;
+                Vec* gv4 = has_var ? reinterpret_cast<Vec*>(A.grad_var) + (size_t)tile_p * N4 + tid : nullptr;
                 if (!(flags & kFHeavy)) {
 #pragma unroll
                     for (int it = 0; it < NIT; ++it) {
-                        stg_stream(gh4 + it * TPB, z4);
-                        if (gv4) stg_stream(gv4 + it * TPB, z4);
+                        IO::stg(gh4 + it * TPB, z4);
+                        if (gv4) IO::stg(gv4 + it * TPB, z4);
                     }
                 } else {
                     const float4 k1 = lds4(cb + 4), k2 = lds4(cb + 8);
@@ -1333,7 +1410,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                         constexpr int kUnrollD = FLAT ? kPUd : 1;
 #pragma unroll kUnrollD
                         for (int it = 0; it < NIT; ++it) {
-                            const float4 o = Hs[it * TPB + tid];
+                            const float4 o = IO::lds(Hs + it * TPB + tid);
                             const f4 hv = as_f4(o);
                             const f2 t01 = fma2(hv.a, kL2E, kNML), t23 = fma2(hv.b, kL2E, kNML);
                             const f2 e01 = pack2(ex2(lo2(t01)), ex2(hi2(t01))), e23 = pack2(ex2(lo2(t23)), ex2(hi2(t23)));
@@ -1384,8 +1461,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                                 g01 = fma2(pack2(G[0], G[1]), sd01, g01);
                                 g23 = fma2(pack2(G[2], G[3]), sd23, g23);
                             }
-                            stg_stream(gh4 + it * TPB, as_float4(f4{g01, g23}));
-                            if (gv4) stg_stream(gv4 + it * TPB, gv);
+                            IO::stg(gh4 + it * TPB, as_float4(f4{g01, g23}));
+                            if (gv4) IO::stg(gv4 + it * TPB, gv);
                         }
                     };
                     if (flat) pass_d(std::true_type{}); else pass_d(std::false_type{});
@@ -1401,17 +1478,17 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                         for (int n = 0; n < nact_p; ++n) {
                             const float cjp = cjv[n == 0 ? 0 : (n == 1 ? 1 : (n == 2 ? 2 : 3))];
                             if (cjp == 0.f) continue;
-                            const float4* src = reinterpret_cast<const float4*>(hm) + ((size_t)bimg * P.K + ((pj >> (8 * n)) & 0xFFu)) * N4 + tid;
+                            const Vec* src = reinterpret_cast<const Vec*>(hm) + ((size_t)bimg * P.K + ((pj >> (8 * n)) & 0xFFu)) * N4 + tid;
                             for (int it = 0; it < NIT; ++it) {
-                                const float4 q = ldg_keep(src + it * TPB), o = Hs[it * TPB + tid];
+                                const float4 q = IO::ldg(src + it * TPB), o = IO::lds(Hs + it * TPB + tid);
                                 if (q.x == o.x || q.y == o.y || q.z == o.z || q.w == o.w) {
-                                    float4 g = gh4[it * TPB];
+                                    float4 g = IO::ld_plain(gh4 + it * TPB);
                                     float sg;
                                     if (q.x == o.x) { sg = sigmoid_fast(o.x); g.x = fmaf(0.5f * cjp * sg, 1.f - sg, g.x); }
                                     if (q.y == o.y) { sg = sigmoid_fast(o.y); g.y = fmaf(0.5f * cjp * sg, 1.f - sg, g.y); }
                                     if (q.z == o.z) { sg = sigmoid_fast(o.z); g.z = fmaf(0.5f * cjp * sg, 1.f - sg, g.z); }
                                     if (q.w == o.w) { sg = sigmoid_fast(o.w); g.w = fmaf(0.5f * cjp * sg, 1.f - sg, g.w); }
-                                    gh4[it * TPB] = g;
+                                    IO::st_plain(gh4 + it * TPB, g);
                                 }
                             }
                         }
@@ -1432,11 +1509,11 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 }
 
 // ---- launcher ------------------------------------------------------------------------------------------
-template <int W4, int ROWS, int NIT, int MINB, bool GRADS>
+template <int W4, int ROWS, int NIT, int MINB, bool GRADS, bool HALF = false, int RD = 2>
 int launch_pipe_t(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
-    using L = PipePlan<W4, ROWS, NIT>;
+    using L = PipePlan<W4, ROWS, NIT, HALF, RD>;
     const size_t smem = (size_t)L::oLut + (size_t)((P.ec.lut_size + 3) & ~3) * 4;
-    auto kern = step_pipe_kernel<W4, ROWS, NIT, MINB, GRADS>;
+    auto kern = step_pipe_kernel<W4, ROWS, NIT, MINB, GRADS, HALF, RD>;
     int dev = 0, sms = 0, max_optin = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
@@ -1479,11 +1556,19 @@ bool step_pipe_tail_outside() { return PIPE_TAIL_OUTSIDE != 0; }
 int launch_step_pipe(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     const char* env = getenv("GBCODEC_STEP_KERNEL");
     if (env && (!strcmp(env, "tile") || !strcmp(env, "persist"))) return 1;
-    // float32 maps, target generated on the fly with a patch no taller than the CTA's rows, the ordinary forward (+ backward) call
-    if (A.half_io || A.target || A.lam_eff || A.plan || A.var_mean || A.grad_var_mean || !A.desc || !A.tile_counter) return 1;
+    // target generated on the fly with a patch no taller than the CTA's rows, the ordinary forward (+ backward) call;
+    // float32 maps, or float16 maps (autocast) with a four-deep ring
+    if (A.target || A.lam_eff || A.plan || A.var_mean || A.grad_var_mean || !A.desc || !A.tile_counter) return 1;
     if (A.coords && A.radius > 8) return 1;
     const bool grads = A.grad_hm != nullptr;
     if (P.H == 64 && P.W == 48 && P.ec.ntap <= 16) {
+        if (A.half_io) {
+            // GBCODEC_STEP_F16=tile keeps float16 maps on loss_tile_kernel<..., HALF> (A/B measurements)
+            const char* h = getenv("GBCODEC_STEP_F16");
+            if (h && !strcmp(h, "tile")) return 1;
+            return grads ? launch_pipe_t<12, 16, 4, 3, true, true, PIPE_HALF_RING>(P, A, s, e0, e1)
+                         : launch_pipe_t<12, 16, 4, 3, false, true, PIPE_HALF_RING>(P, A, s, e0, e1);
+        }
         return grads ? launch_pipe_t<12, 16, 4, 3, true>(P, A, s, e0, e1) : launch_pipe_t<12, 16, 4, 3, false>(P, A, s, e0, e1);
     }
     return 1;

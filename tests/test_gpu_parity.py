@@ -605,9 +605,11 @@ def test_fp16_head_outputs_under_autocast(gb, name):
     q16 = loss_fn(p16, None, dev(batch["vis"]), dev(batch["kps"]), input_size=cfg.input_size, decode=dec)
     mix(q16).backward()
     p32 = {k: v.float().requires_grad_(True) for k, v in half.items()}
-    with tile_kernel():
-        q32 = loss_fn(p32, None, dev(batch["vis"]), dev(batch["kps"]), input_size=cfg.input_size, decode=dec)
-        mix(q32).backward()
+    # (no tile_kernel() here: with targets built in the kernel both element types take the same kernel of their shape —
+    # the persistent step kernel for 64x48, the one-CTA-per-tile kernel otherwise — and the per-term upstream sends
+    # both backwards through the recompute of the one-CTA-per-tile kernel)
+    q32 = loss_fn(p32, None, dev(batch["vis"]), dev(batch["kps"]), input_size=cfg.input_size, decode=dec)
+    mix(q32).backward()
     assert torch.equal(q16["coords"], q32["coords"]) and torch.equal(q16["scores"], q32["scores"])
     for k in oc.LOSS_KEYS:
         assert float(q16[k]) == float(q32[k])
@@ -633,6 +635,72 @@ def test_fp16_head_outputs_under_autocast(gb, name):
     c16, s16 = decode_outputs({**half, "fusion_weight": fw}, a)
     c32, s32 = decode_outputs({**{k: v.float() for k, v in half.items()}, "fusion_weight": fw}, a)
     assert torch.equal(c16, c32) and torch.equal(s16, s32) and c16.dtype == torch.float32
+
+
+@contextlib.contextmanager
+def env(name, value):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+def test_fp16_step_kernel_many_tiles_per_cta(gb):
+    """The float16 instantiation of the persistent step kernel (64x48, targets built in the kernel; bulk copies of raw
+    halves, a four-deep partner ring) on a batch that gives every CTA several tiles, weight-0 tiles and tiles with up to
+    four limb partners: against the float32 instantiation on the up-cast maps the seven losses, coordinates and scores are
+    BIT-equal and the gradients are that path's gradients rounded to half (tie pixels: rounded twice); against the
+    one-CTA-per-tile float16 kernel (GBCODEC_STEP_F16=tile) everything agrees to float32 round-off."""
+    cfg = synth.CONFIGS["w32_256x192"]
+    batch = synth.make_batch(cfg, seed=77, B=96)
+    half = {k: dev(batch[k]).half() for k in ("heatmaps", "offsets", "variances")}
+    vis, kps = dev(batch["vis"]), dev(batch["kps"])
+    alpha, fw = torch.tensor(0.5).cuda(), torch.tensor(0.62).cuda()
+    scale = torch.tensor([1024.0]).cuda()
+    from infantposeestimation_gaussianbias_b200 import FusionPoseLoss, ops
+    loss_fn = FusionPoseLoss(target_sigma=cfg.sigma)
+    sk = ops.pairs_flat(loss_fn.pairs_for(cfg.K))
+    DF = 1 | 2
+
+    def f16():
+        return ops.fusion_loss_f16(half["heatmaps"], half["offsets"], half["variances"], None, vis, kps, None, scale,
+                                   float(cfg.input_size[0]), float(cfg.input_size[1]), loss_fn.lambdas, float(cfg.sigma), float(cfg.sigma), True, sk,
+                                   True, True, alpha, fw, 2, DF)
+
+    def f32():
+        return ops.fusion_loss(half["heatmaps"].float(), half["offsets"].float(), half["variances"].float(), None, vis, kps, None, scale,
+                               float(cfg.input_size[0]), float(cfg.input_size[1]), loss_fn.lambdas, float(cfg.sigma), float(cfg.sigma), True, sk,
+                               True, True, alpha, fw, 2, DF, 0, False)
+
+    a = f16()
+    b = f32()
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]), (a[0], b[0])                       # losses7
+    assert torch.equal(a[1], b[4]) and torch.equal(a[2], b[5])          # coords, scores
+    for i, k in ((3, "heatmaps"), (4, "offsets"), (5, "variances")):
+        assert a[i].dtype == torch.float16
+        same_up_to_tie_pixels(a[i], b[i - 2], f"{k} (step kernel, float16 against float32)")
+    with env("GBCODEC_STEP_F16", "tile"):
+        c = f16()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(a[0].cpu().numpy(), c[0].cpu().numpy(), rtol=2e-6)
+    assert torch.equal(a[2], c[2])
+    ok = (np.abs(oc.soft_argmax(torch.from_numpy(batch["heatmaps"]).half().float())[0].numpy() % 1 - 0.5) > 1e-3).all(-1)
+    assert np.abs(a[1].cpu().numpy() - c[1].cpu().numpy())[ok].max() <= 1e-4
+    for i in (3, 4, 5):
+        d = (a[i].float() - c[i].float()).abs()
+        ulp = torch.maximum(c[i].float().abs(), torch.tensor(6.1e-5, device=d.device)) * 2.0 ** -10
+        assert bool((d <= ulp).all()) and (a[i] == c[i]).float().mean().item() > 0.99, i
+    # forward only (no gradients): the same losses and decode
+    e = ops.fusion_loss_f16(half["heatmaps"], half["offsets"], half["variances"], None, vis, kps, None, scale,
+                            float(cfg.input_size[0]), float(cfg.input_size[1]), loss_fn.lambdas, float(cfg.sigma), float(cfg.sigma), True, sk,
+                            False, True, alpha, fw, 2, DF)
+    assert torch.equal(e[0], a[0]) and torch.equal(e[1], a[1]) and torch.equal(e[2], a[2])
 
 
 def test_softplus_mean_matches_torch(gb):
