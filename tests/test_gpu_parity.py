@@ -693,9 +693,12 @@ def test_fp16_step_kernel_many_tiles_per_cta(gb):
     ok = (np.abs(oc.soft_argmax(torch.from_numpy(batch["heatmaps"]).half().float())[0].numpy() % 1 - 0.5) > 1e-3).all(-1)
     assert np.abs(a[1].cpu().numpy() - c[1].cpu().numpy())[ok].max() <= 1e-4
     for i in (3, 4, 5):
+        # two kernels, two orders of float32 summation: an element may differ by one ulp of half, plus float32 round-off
+        # on the scale of its tile's largest gradient where terms cancel (the bound the float32 kernels meet among themselves)
         d = (a[i].float() - c[i].float()).abs()
         ulp = torch.maximum(c[i].float().abs(), torch.tensor(6.1e-5, device=d.device)) * 2.0 ** -10
-        assert bool((d <= ulp).all()) and (a[i] == c[i]).float().mean().item() > 0.99, i
+        tile_max = c[i].float().abs().amax(dim=(-2, -1), keepdim=True)
+        assert bool((d <= ulp + 1e-5 * tile_max).all()) and (a[i] == c[i]).float().mean().item() > 0.99, i
     # forward only (no gradients): the same losses and decode
     e = ops.fusion_loss_f16(half["heatmaps"], half["offsets"], half["variances"], None, vis, kps, None, scale,
                             float(cfg.input_size[0]), float(cfg.input_size[1]), loss_fn.lambdas, float(cfg.sigma), float(cfg.sigma), True, sk,
