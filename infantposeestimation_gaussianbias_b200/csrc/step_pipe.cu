@@ -184,68 +184,32 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #ifndef PIPE_BALANCE
 #define PIPE_BALANCE 0
 #endif
-// PIPE_V_FIRST: the variance tile is the FIRST ring item of a tile, not the last.  It is the one ring item that always
-// comes from HBM (the limb partners are other CTAs' tiles of the same image: L2 hits), and as the last item of a
-// two-deep ring it could only be requested once the first partner had been consumed: the compute warps then sat out most
-// of a DRAM round trip per tile in front of it (10 % of the kernel's stall samples, profiles/r02_step_pipe_kernel_lines.txt:
-// step_pipe.cu:998).  As the first item it is requested while the previous tile's partners are still being consumed and
-// has landed long before pass B is over.
-#ifndef PIPE_V_FIRST
-#define PIPE_V_FIRST 1
-#endif
-// PIPE_V_EARLY: with the variance tile as the first ring item, the compute warps take its sum at the very START of the front
-// half (it was requested during the previous tile's front half and has landed) instead of after pass B: its ring slot is
-// free a pass earlier, so a tile's second limb partner is requested while pass B runs, not when the partner visits begin.
-#ifndef PIPE_V_EARLY
-#define PIPE_V_EARLY 0
-#endif
-// PIPE_LATE_TARGET: the target row, the squared-error correction on it and the zero fill of d_offsets come BETWEEN the
-// variance sum and the limb-partner visits instead of in front of pass B: a tile's second partner is requested when the
-// variance tile's ring slot is released, and these ~150 instructions give that copy time to land.  Measured: 9 % SLOWER
-// (0.2336 against 0.2140 ms); kept as a measurement switch, like PIPE_V_EARLY (+2 %), PIPE_V_SCALAR (+35 %: the scalar
-// warp's chain then holds three DRAM round trips per tile and becomes the pipeline's period) and PIPE_TILE_FIRST (+4 %).
-#ifndef PIPE_LATE_TARGET
-#define PIPE_LATE_TARGET 0
-#endif
+// Ring order: the variance tile is the FIRST ring item of a tile, the limb partners follow.  It is the one ring item that
+// always comes from HBM (the partners are other CTAs' tiles of the same image: L2 hits); as the last item of the two-deep
+// ring it could only be requested once the first partner had been consumed, and the compute warps sat out most of a DRAM
+// round trip per tile in front of it (10 % of the kernel's stall samples).  As the first item it is requested while the
+// previous tile's partners are still being consumed and has landed before pass B is over: 0.2300 -> 0.2220 ms.
+// Measured and NOT kept (profiles/r02_step_variants_s4.jsonl; the switches are in the history of this
+// file): the variance sum at the very start of the front half or right in front of pass B (+2 %, +1.5 %: the copy has not
+// always landed), the scalar warp reading the variance tile itself with plain loads so that the ring carries partners only
+// (+35 %: three DRAM round trips on its chain make it the pipeline's period), the next tile requested before the ring
+// items (+4 %), the target row / squared-error correction / zero fill between the variance sum and the partner visits (+9 %).
+//
 // PIPE_MERGE_B1: heavy tiles without an active limb partner (6-8 % of the tiles) run pass B with the sigmoid too (its
-// result unused) instead of a pass-B instantiation of their own: ~1 KB less of warm code.
-// ring depth of the float16 instantiation (its tiles are 6 KB: four ring buffers and the rest are 55 KB per CTA)
-#ifndef PIPE_HALF_RING
-#define PIPE_HALF_RING 4
-#endif
+// result unused) instead of a pass-B instantiation of their own: ~1 KB less of warm code (0.2140 -> 0.2118 ms).
 #ifndef PIPE_MERGE_B1
 #define PIPE_MERGE_B1 1
 #endif
-// PIPE_V_SCALAR: the variance tile does not go through the ring at all.  Only its SUM is needed, so the scalar warp — idle
-// most of a tile period — reads it itself with plain 128-bit loads (lane l the float4s l, l + 32, ...: 512 contiguous bytes
-// per instruction), the first half requested when the tile is known and the second while it waits for the compute warps'
-// sums; the ring then carries limb partners only (both slots free for them) and the compute warps lose the pass and its wait.
-#ifndef PIPE_V_SCALAR
-#define PIPE_V_SCALAR 0
-#endif
-#ifndef PIPE_V_BATCHES
-#define PIPE_V_BATCHES 3
+// ring depth of the float16 instantiation (its tiles are 6 KB: four ring buffers and the rest are 55 KB per CTA; a
+// two-deep ring measures the same)
+#ifndef PIPE_HALF_RING
+#define PIPE_HALF_RING 4
 #endif
 // PIPE_CARRY_TARGET: the row in which a thread meets the target patch (target_row: ~100 instructions) is worked out in the
 // front half and carried in five registers to the tile's back half one iteration later, instead of being worked out
-// again there: one inlined copy of target_row less on the once-per-tile path.
+// again there: one inlined copy of target_row less on the once-per-tile path (0.2220 -> 0.2140 ms).
 #ifndef PIPE_CARRY_TARGET
 #define PIPE_CARRY_TARGET 1
-#endif
-// PIPE_TILE_FIRST: the producer requests tile j + 1 (into the buffer tile j - 2 has left) BEFORE the ring items of tile j.
-// The ring loop blocks until the compute warps have consumed all but two of a tile's items, so behind it the next tile was
-// requested only late in front(j) and the compute warps waited for its bytes at the top of front(j + 1).
-#ifndef PIPE_TILE_FIRST
-#define PIPE_TILE_FIRST 0
-#endif
-// measurement only (wrong results): PIPE_NO_OFFZERO skips the dense zero fill of d_offsets (what an opt-in sparse offset
-// gradient would save: 8N of the 16N bytes written); PIPE_NO_MSE_FIX skips the squared-error correction on the target
-// patch in the front half (what moving it to the tail CTAs would save)
-#ifndef PIPE_NO_OFFZERO
-#define PIPE_NO_OFFZERO 0
-#endif
-#ifndef PIPE_NO_MSE_FIX
-#define PIPE_NO_MSE_FIX 0
 #endif
 constexpr int kPUs = PIPE_UNROLL_SMALL, kPUb = PIPE_UNROLL_B, kPUp = PIPE_UNROLL_P, kPUd = PIPE_UNROLL_D;
 // PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
@@ -469,49 +433,22 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         unsigned ph_empty = 0;                               // phase bits per tile buffer
         for (unsigned j = 0;; ++j) {
             const unsigned s1 = (j + 1) % 3u;
-#if PIPE_TILE_FIRST
-            // tile j + 1 into the buffer tile j - 2 has left
-            if (j >= 2) { mbar_wait_idle(hempty + s1, (ph_empty >> s1) & 1u); ph_empty ^= 1u << s1; }
-            const bool last = nxt >= (unsigned)tiles;
-            if (last) {
-                tids[s1] = -1;
-                mbar_arrive(hfull + s1);                     // the sentinel: everybody leaves at tile j + 1
-            } else {
-                tids[s1] = (int)nxt;
-                mbar_arrive_expect_tx(hfull + s1, kTile + 64);
-                bulk_g2s(Hb + s1 * N4, hm + (size_t)nxt * N, kTile, hfull + s1);
-                bulk_g2s(Db + s1, A.desc + nxt, 64, hfull + s1);
-            }
-#endif
             // ring items of tile j: its variance tile, then its limb partners
             const bool heavy = (w_c != 0.f) || !P.use_target_weight;
             if (heavy) {
                 const int nn = (int)(pk_c & 7u);
                 const size_t b = cur / (unsigned)P.K;
 #pragma unroll kProdU
-                for (int n = 0; n < nn + ((has_var && !PIPE_V_SCALAR) ? 1 : 0); ++n) {
+                for (int n = 0; n < nn + (has_var ? 1 : 0); ++n) {
                     const unsigned q = rq & (unsigned)(RD - 1);
                     if (rq >= (unsigned)RD) mbar_wait(rempty + q, ((rq - RD) / RD) & 1u);
-#if PIPE_V_SCALAR
-                    const Elem* src = hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N;
-#elif PIPE_V_FIRST
                     const int pn = n - (has_var ? 1 : 0);       // -1: the variance tile
                     const Elem* src = pn >= 0 ? hm + (b * P.K + ((pj_c >> (8 * pn)) & 0xFFu)) * N : var_maps + (size_t)cur * N;
-#else
-                    const Elem* src = n < nn ? hm + (b * P.K + ((pj_c >> (8 * n)) & 0xFFu)) * N : var_maps + (size_t)cur * N;
-#endif
                     mbar_arrive_expect_tx(rfull + q, kTile);
                     bulk_g2s(Rb + q * N4, src, kTile, rfull + q);
                     ++rq;
                 }
             }
-#if PIPE_TILE_FIRST
-            if (last) break;
-            cur = nxt; nxt = nxt2;
-            w_c = w_n; pk_c = pk_n; pj_c = pj_n;
-            w_n = desc_w(nxt); pk_n = desc_pk(nxt); pj_n = desc_pj(nxt);
-            if (nxt2 < (unsigned)tiles) nxt2 = atomicAdd(A.tile_counter, 1u) + gridDim.x;
-#else
             // tile j + 1 into the buffer tile j - 2 has left
             if (j >= 2) { mbar_wait_idle(hempty + s1, (ph_empty >> s1) & 1u); ph_empty ^= 1u << s1; }
             cur = nxt; nxt = nxt2;
@@ -527,7 +464,6 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             mbar_arrive_expect_tx(hfull + s1, kTile + 64);
             bulk_g2s(Hb + s1 * N4, hm + (size_t)cur * N, kTile, hfull + s1);
             bulk_g2s(Db + s1, A.desc + cur, 64, hfull + s1);
-#endif
         }
         return;
     }
@@ -550,6 +486,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
         const bool win_small = decode && (A.dflags & GBCODEC_DECODE_REFINE) && wside * wside <= 32;
         const bool in_win = lane < wside * wside;
         const int wdx = lane % wside - A.radius, wdy = lane / wside - A.radius;
+        (void)in_win; (void)wdx; (void)wdy;             // used by the in-kernel decode only (PIPE_TAIL_OUTSIDE = 0)
         float a_blend = 1.f, fw_dec = 0.f;
         if (win_small) {
             a_blend = sigmoid_acc(__ldg(A.alpha_param));
@@ -591,39 +528,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 if (jk == 0xdeadbeefu) tids[3] = (int)jk;
             }
 #endif
-#if PIPE_V_SCALAR
-            // ---- the variance tile's sum, read by this warp: half of it before the wait for the compute warps, half across it
-            constexpr int kVPer = N4 / 32, kVB = PIPE_V_BATCHES, kVN = kVPer / kVB;      // kVB batches of kVN loads per lane
-            static_assert(kVPer % kVB == 0, "equal batches of whole warp rows");
-            f2 vacc = splat2(0.f);
-            float4 vb[kVN];
-            const bool v_here = heavy && has_var;
-            if (v_here) {
-                const float4* vp = reinterpret_cast<const float4*>(A.var) + (size_t)tile * N4 + lane;
-#pragma unroll
-                for (int j = 0; j < kVN; ++j) vb[j] = ldg_stream(vp + j * 32);
-#pragma unroll 1
-                for (int bt = 1; bt < kVB; ++bt) {
-                    vp += kVN * 32;
-#pragma unroll
-                    for (int j = 0; j < kVN; ++j) {
-                        const f4 v = as_f4(vb[j]);
-                        vacc = add2(vacc, add2(v.a, v.b));
-                        vb[j] = ldg_stream(vp + j * 32);
-                    }
-                }
-            }
-#endif
             // ---- the warps' partial sums of tile i --------------------------------------------------------------
             mbar_wait_idle(sfull + b, (i >> 1) & 1u);
-#if PIPE_V_SCALAR
-            float vsum_own = 0.f;
-            if (v_here) {
-#pragma unroll
-                for (int j = 0; j < kVN; ++j) { const f4 v = as_f4(vb[j]); vacc = add2(vacc, add2(v.a, v.b)); }
-                vsum_own = warp_sum(hsum2(vacc));
-            }
-#endif
 #if !PIPE_LANESUMS
             const float* redb = red + b * (NW * 16);
 #endif
@@ -735,11 +641,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 if (lane == 0) mbar_arrive(cfull + b);
             } else {
                 // ---- per-tile scalars ------------------------------------------------------------------------------
-#if PIPE_V_SCALAR
-                const float Vsum = vsum_own;
-#else
                 const float Vsum = val(5);
-#endif
                 const float ET = val(3), Ssum = val(4), Rm = val(6), Rxa = val(7), Rya = val(8), M2a = val(9), mse_sum = val(10);
                 const float mV = has_var ? Vsum * P.inv_n : P.sigma;
                 const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
@@ -1019,36 +921,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             const int nact = (int)(dsc->pk & 7u);
             const bool heavy = (w != 0.f) || !P.use_target_weight;
 
-#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY
-            float vsum_early = 0.f;
-#endif
-#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY == 1
-            // ---- variance tile (first ring item, long landed): its sum only; the slot goes back to the producer at once
-            if (heavy && has_var) {
-                const unsigned q = rq & (unsigned)(RD - 1);
-                mbar_wait(rfull + q, (rq / RD) & 1u);
-                const Vec* Vs = Rb + q * N4;
-                f2 V2 = splat2(0.f);
-#pragma unroll kPUs
-                for (int it = 0; it < NIT; ++it) {
-                    const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
-                    V2 = add2(V2, add2(v.a, v.b));
-                }
-                vsum_early = hsum2(V2);
-                ++rq;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rempty + q);
-            }
-#endif
-#if !PIPE_LATE_TARGET
             // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
-            if (GRADS && !PIPE_NO_OFFZERO) {
+            if (GRADS) {
                 constexpr int kZ = HALF ? NIT : 2 * NIT;                // 16-byte stores per thread: 2N elements per tile
                 float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * (kZ * TPB) + tid;
 #pragma unroll (2 * kPUs)
                 for (int it = 0; it < kZ; ++it) stg_stream(go4 + it * TPB, z4);
             }
-#endif
             // ---- maximum (and minimum) of the tile: per warp ------------------------------------------------------
             float mw = -INFINITY, mnw = INFINITY;
 #pragma unroll kPUs
@@ -1064,11 +943,9 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // ---- on-the-fly target: the one row (if any) in which this thread meets the patch ---------------------
             int hit_it = -1;
             float4 thit = z4;
-#if !PIPE_LATE_TARGET
-            if (heavy && !PIPE_NO_MSE_FIX) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
+            if (heavy) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
 #if PIPE_CARRY_TARGET
             hit_now = hit_it; thit_now = thit;
-#endif
 #endif
 
             // ---- pass B: softmax moments (relative to the warp's maximum), entropy sum, sigmoid, relu moments about the
@@ -1077,25 +954,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 #pragma unroll
             for (int q = 0; q < 16; ++q) r16[q] = 0.f;
             const bool sig = heavy && (nact > 0 || PIPE_MERGE_B1);
-#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY == 2
-            // (2: in front of pass B rather than at the very start — the copy has had the maximum pass and the target row to land)
-            // ---- variance tile (first ring item, long landed): its sum only; the slot goes back to the producer at once
-            if (heavy && has_var) {
-                const unsigned q = rq & (unsigned)(RD - 1);
-                mbar_wait(rfull + q, (rq / RD) & 1u);
-                const Vec* Vs = Rb + q * N4;
-                f2 V2 = splat2(0.f);
-#pragma unroll kPUs
-                for (int it = 0; it < NIT; ++it) {
-                    const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
-                    V2 = add2(V2, add2(v.a, v.b));
-                }
-                vsum_early = hsum2(V2);
-                ++rq;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rempty + q);
-            }
-#endif
+            (void)sig;
 #if PIPE_LANESUMS
             // the sigmoid slots still hold the lanes' sums of tile i - 1 until the scalar warp has taken them
             if (i >= 1) mbar_wait(sempty + ((i - 1) & 1u), ((i - 1) >> 1) & 1u);
@@ -1168,7 +1027,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     r16[9] = fmaf(xa0 * xa0, Rj[0], fmaf(xa1 * xa1, Rj[1], fmaf(xa2 * xa2, Rj[2], fmaf(xa3 * xa3, Rj[3], Ry2))));
                     // squared error: sum h^2 everywhere, corrected in the one row that meets the target patch
                     float h2 = hsum2(Hq);
-                    if (!PIPE_LATE_TARGET && hit_it >= 0) {
+                    if (hit_it >= 0) {
                         const float4 o = IO::lds(Hs + hit_it * TPB + tid);
                         const float d0 = o.x - thit.x, d1_ = o.y - thit.y, d2 = o.z - thit.z, d3 = o.w - thit.w;
                         h2 += (fmaf(d0, d0, -o.x * o.x) + fmaf(d1_, d1_, -o.y * o.y)) + (fmaf(d2, d2, -o.z * o.z) + fmaf(d3, d3, -o.w * o.w));
@@ -1178,19 +1037,9 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
 
             // ---- limb partners: one visit each; sums for the overlap ratio, one tie bit per pixel and partner ------
-#if PIPE_LATE_TARGET
-            // the offset gradient is zero except on (up to) four taps per channel, patched by the scalar warp
-            if (GRADS && !PIPE_NO_OFFZERO) {
-                constexpr int kZ = HALF ? NIT : 2 * NIT;                // 16-byte stores per thread: 2N elements per tile
-                float4* go4 = reinterpret_cast<float4*>(A.grad_off) + (size_t)tile * (kZ * TPB) + tid;
-#pragma unroll (2 * kPUs)
-                for (int it = 0; it < kZ; ++it) stg_stream(go4 + it * TPB, z4);
-            }
-#endif
             float mind = INFINITY;                // smallest |own - partner| logit difference seen (0 = a tie)
             float r4[4] = {0.f, 0.f, 0.f, 0.f};
             if (heavy) {
-#if PIPE_V_FIRST && !PIPE_V_SCALAR && !PIPE_V_EARLY
                 // ---- variance tile: its sum only ---------------------------------------------------------------------
                 if (has_var) {
                     const unsigned q = rq & (unsigned)(RD - 1);
@@ -1207,18 +1056,6 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty + q);
                 }
-#endif
-#if PIPE_LATE_TARGET
-                if (!PIPE_NO_MSE_FIX) hit_it = target_row<ROWS, NIT>(gq, w, x0, ty, P.ec, lut, thit);
-#if PIPE_CARRY_TARGET
-                hit_now = hit_it; thit_now = thit;
-#endif
-                if (hit_it >= 0) {
-                    const float4 o = IO::lds(Hs + hit_it * TPB + tid);
-                    const float d0 = o.x - thit.x, d1_ = o.y - thit.y, d2 = o.z - thit.z, d3 = o.w - thit.w;
-                    r16[10] += (fmaf(d0, d0, -o.x * o.x) + fmaf(d1_, d1_, -o.y * o.y)) + (fmaf(d2, d2, -o.z * o.z) + fmaf(d3, d3, -o.w * o.w));
-                }
-#endif
                 for (int n = 0; n < nact; ++n) {
                     const unsigned q = rq & (unsigned)(RD - 1);
                     mbar_wait(rfull + q, (rq / RD) & 1u);
@@ -1266,29 +1103,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty + q);          // this warp has consumed the buffer
                 }
-#if !PIPE_V_FIRST && !PIPE_V_SCALAR
-                // ---- variance tile: its sum only ---------------------------------------------------------------------
-                if (has_var) {
-                    const unsigned q = rq & (unsigned)(RD - 1);
-                    mbar_wait(rfull + q, (rq / RD) & 1u);
-                    const Vec* Vs = Rb + q * N4;
-                    f2 V2 = splat2(0.f);
-#pragma unroll kPUs
-                    for (int it = 0; it < NIT; ++it) {
-                        const f4 v = as_f4(IO::lds(Vs + it * TPB + tid));
-                        V2 = add2(V2, add2(v.a, v.b));
-                    }
-                    r16[5] = hsum2(V2);
-                    ++rq;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(rempty + q);
-                }
-#endif
             }
             tie_now = GRADS && mind == 0.f;
-#if PIPE_V_FIRST && !PIPE_V_SCALAR && PIPE_V_EARLY
-            r16[5] = vsum_early;
-#endif
 
             // ---- publish this warp's sums --------------------------------------------------------------------------
             float* const red2b = red2 + b * (NW * 4);
