@@ -73,6 +73,15 @@ class FusionPoseLoss(nn.Module):
     def pairs_for(self, K: int):
         return [(i, j) for (i, j) in self.skeleton if i < K and j < K]
 
+    def _pairs_flat(self, K: int):
+        # the flattened limb pairs of a K-channel head, built once per (skeleton, K) instead of once per call
+        key = (self.skeleton, K)
+        cache = self.__dict__.setdefault("_pairs_flat_cache", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = ops.pairs_flat(self.pairs_for(K))
+        return cache[key]
+
     def forward(self, outputs: Dict[str, Tensor], target_heatmaps: Optional[Tensor], target_weight: Tensor,
                 gt_keypoints: Tensor, input_size: Tuple[int, int] = (192, 256),
                 heatmap_size: Tuple[int, int] = (48, 64), *, denominators: Optional[Tensor] = None,
@@ -95,7 +104,7 @@ class FusionPoseLoss(nn.Module):
             res = ops.fusion_step_vmean(
                 hm, off, _f32(v_in), _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), denominators, grad_scale,
                 float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc, bool(self.use_target_weight),
-                ops.pairs_flat(self.pairs_for(K)), with_grads, bool(dec), dec.get("alpha_param"), dec.get("fusion_weight"),
+                self._pairs_flat(K), with_grads, bool(dec), dec.get("alpha_param"), dec.get("fusion_weight"),
                 int(dec.get("radius", 2)), int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)))
             out = {k: res[0][i] for i, k in enumerate(LOSS_KEYS)}
             if dec:
@@ -114,7 +123,7 @@ class FusionPoseLoss(nn.Module):
         res = ops.fusion_loss_eager(
             hm, off, var, _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), denominators, grad_scale,
             float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
-            bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads,
+            bool(self.use_target_weight), self._pairs_flat(K), with_grads,
             bool(dec), dec.get("alpha_param"), dec.get("fusion_weight"), int(dec.get("radius", 2)),
             int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)), int(peer.address) if peer is not None else 0,
             bool(defer_losses))
@@ -149,7 +158,7 @@ def _fusion_loss_half_methods():
         losses7, coords, scores, _, _, _, _ = ops.fusion_loss_f16_eager(
             hm, off, var, _f32(target_heatmaps), _f32(target_weight), _f32(gt_keypoints), None, state if with_grads else None,
             float(input_size[0]), float(input_size[1]), self.lambdas, float(self.target_sigma), sigma_enc,
-            bool(self.use_target_weight), ops.pairs_flat(self.pairs_for(K)), with_grads, bool(dec), dec.get("alpha_param"),
+            bool(self.use_target_weight), self._pairs_flat(K), with_grads, bool(dec), dec.get("alpha_param"),
             dec.get("fusion_weight"), int(dec.get("radius", 2)), int(dec.get("flags", N.DECODE_REFINE | N.DECODE_APPLY_OFFSET)))
         if with_grads and losses7.requires_grad:
             def remember(g, st=state):          # what total_loss actually received, kept on the device for the next step

@@ -145,10 +145,23 @@ def _(hm, coords, window):
 
 
 # --------------------------------------------------------------------------- loss
+_DESC_CACHE: dict = {}
+
+
 def _desc(hm: Tensor, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs_flat):
+    """struct gbcodec_loss_desc for this call.  Filling the ctypes structure (6 lambdas, up to 32 limb pairs) takes ~22 us
+    of host time and a training loop asks for the same one twice per step (forward, backward): memoised by value.  The
+    library only reads it."""
     B, K, H, W = hm.shape
-    pairs = [(int(pairs_flat[i]), int(pairs_flat[i + 1])) for i in range(0, len(pairs_flat), 2)]
-    return N.make_loss_desc(B, K, H, W, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs)
+    key = (B, K, H, W, in_w, in_h, tuple(lambdas), target_sigma, encode_sigma, bool(utw), tuple(pairs_flat))
+    d = _DESC_CACHE.get(key)
+    if d is None:
+        pairs = [(int(pairs_flat[i]), int(pairs_flat[i + 1])) for i in range(0, len(pairs_flat), 2)]
+        d = N.make_loss_desc(B, K, H, W, in_w, in_h, lambdas, target_sigma, encode_sigma, utw, pairs)
+        if len(_DESC_CACHE) >= 64:
+            _DESC_CACHE.clear()
+        _DESC_CACHE[key] = d
+    return d
 
 
 def _workspace(hm: Tensor) -> Tensor:
