@@ -16,6 +16,27 @@ from . import _native as N
 _NS = "gbcodec"
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` only when `dev` is not the current device already (the context manager costs ~8 us of
+    host time per call; one process per GPU never needs it)."""
+    __slots__ = ("guard",)
+
+    def __init__(self, dev):
+        if dev.type != "cuda":
+            raise RuntimeError("gbcodec: tensors must live on a CUDA device (this library has no CPU path)")
+        cur = torch.cuda.current_device()
+        self.guard = None if (dev.index is None or dev.index == cur) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else N._P(t.data_ptr())
 
@@ -52,6 +73,8 @@ def _scalar(name: str, t: Optional[Tensor], like: Tensor) -> Optional[Tensor]:
         return None
     if t.numel() != 1:
         raise RuntimeError(f"gbcodec: `{name}` must hold one element")
+    if t.dtype is torch.float32 and t.device == like.device and not t.requires_grad:
+        return t if t.dim() == 1 else t.reshape(1)             # (the common case costs 0.5 us instead of 5)
     return t.detach().to(device=like.device, dtype=torch.float32).reshape(1).contiguous()
 
 
@@ -63,7 +86,7 @@ def encode(kps: Tensor, vis: Tensor, H: int, W: int, in_w: float, in_h: float, s
     vis = _cuda_f32("visible", vis.reshape(B, K), (B, K))
     target = torch.empty((B, K, H, W), dtype=torch.float32, device=kps.device)
     weight = torch.empty((B, K, 1), dtype=torch.float32, device=kps.device)
-    with torch.cuda.device(kps.device):
+    with _on_device(kps.device):
         N.check(N.lib().gbcodec_encode_f32(_ptr(kps), _ptr(vis), _ptr(target), _ptr(weight), B, K, H, W,
                                            in_w, in_h, sigma, _stream(kps)), "encode")
     return target, weight
@@ -95,7 +118,7 @@ def decode(hm: Tensor, hm_flipped: Optional[Tensor], flip_perm: Optional[Tensor]
     coords = torch.empty((B, K, 2), dtype=torch.float32, device=hm.device)
     scores = torch.empty((B, K), dtype=torch.float32, device=hm.device)
     centre = torch.empty((B, K, 2), dtype=torch.int32, device=hm.device)
-    with torch.cuda.device(hm.device):
+    with _on_device(hm.device):
         N.check(N.lib().gbcodec_decode_f32(_ptr(hm), _ptr(hm_flipped), _ptr(flip_perm), _ptr(off), _ptr(alpha_param),
                                            _ptr(fusion_weight), B, K, H, W, radius, flags,
                                            _ptr(coords), _ptr(scores), _ptr(centre), _stream(hm)), "decode")
@@ -115,7 +138,7 @@ def decode_argmax(hm: Tensor, mode: int) -> Tuple[Tensor, Tensor, Tensor]:
     coords = torch.empty((B, K, 2), dtype=torch.float32, device=hm.device)
     maxvals = torch.empty((B, K), dtype=torch.float32, device=hm.device)
     index = torch.empty((B, K), dtype=torch.int32, device=hm.device)
-    with torch.cuda.device(hm.device):
+    with _on_device(hm.device):
         N.check(N.lib().gbcodec_decode_argmax_f32(_ptr(hm), B, K, H, W, mode, _ptr(coords), _ptr(maxvals),
                                                   _ptr(index), _stream(hm)), "decode_argmax")
     return coords, maxvals, index
@@ -133,7 +156,7 @@ def refine_centroid(hm: Tensor, coords: Tensor, window: int) -> Tensor:
     hm = _cuda_f32("heatmaps", hm)
     coords = _cuda_f32("coords", coords, (B, K, 2))
     out = torch.empty_like(coords)
-    with torch.cuda.device(hm.device):
+    with _on_device(hm.device):
         N.check(N.lib().gbcodec_refine_centroid_f32(_ptr(hm), _ptr(coords), B, K, H, W, window, _ptr(out), _stream(hm)),
                 "refine_centroid")
     return out
@@ -181,7 +204,7 @@ def loss_denominators(weight: Tensor, gt_kps: Tensor, target_given: bool, H: int
     out = torch.empty(2, dtype=torch.float32, device=weight.device)
     nbytes = N.lib().gbcodec_loss_workspace_bytes(B, K, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    with torch.cuda.device(weight.device):
+    with _on_device(weight.device):
         N.check(N.lib().gbcodec_loss_denominators_f32(desc, _ptr(weight), _ptr(gt_kps), int(target_given), _ptr(out),
                                                       _ptr(ws), nbytes, _stream(weight)), "loss_denominators")
     return out
@@ -234,7 +257,7 @@ def fusion_loss(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Optional
               _ptr(losses), _ptr(ghm) if with_grads else None, _ptr(goff) if with_grads else None,
               _ptr(gvar) if (with_grads and var is not None) else None)
     den_out = empty()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if with_decode:
             coords = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
             scores = torch.empty((B, K), dtype=torch.float32, device=dev)
@@ -286,7 +309,7 @@ def fusion_step_into(hm: Tensor, off: Tensor, var: Optional[Tensor], weight: Ten
             if t is None or not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape):
                 raise RuntimeError(f"gbcodec: `{name}` must be a contiguous float32 CUDA tensor of shape {shape}")
     desc = _desc(hm, in_w, in_h, lambdas, target_sigma, encode_sigma, use_target_weight, pairs)
-    with torch.cuda.device(hm.device):
+    with _on_device(hm.device):
         N.check(N.lib().gbcodec_fusion_step_f32(
             desc, _ptr(hm), _ptr(off), _ptr(var), None, _ptr(weight.reshape(B, K)), _ptr(gt_kps), _ptr(denoms), None,
             _ptr(losses_out), _ptr(ghm), _ptr(goff), _ptr(gvar), _ptr(alpha_param), _ptr(fusion_weight), radius, decode_flags,
@@ -316,7 +339,7 @@ def _backward_call(half: bool, g7: Tensor, ghm: Tensor, goff: Tensor, gvar: Opti
     from_forward = ws is not None and ws.numel() > 0
     if not from_forward:
         ws = _workspace(hm)
-    with torch.cuda.device(hm.device):
+    with _on_device(hm.device):
         if half:
             N.check(N.lib().gbcodec_fusion_loss_backward_f16(
                 desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(assumed),
@@ -458,7 +481,7 @@ def peer_denominators(weight: Tensor, gt_kps: Tensor, target_given: bool, H: int
     out = torch.empty(2, dtype=torch.float32, device=weight.device) if out is None else out
     nbytes = N.lib().gbcodec_loss_workspace_bytes(B, K, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    with torch.cuda.device(weight.device):
+    with _on_device(weight.device):
         N.check(N.lib().gbcodec_peer_denominators_f32(desc, _ptr(weight), _ptr(gt_kps), int(target_given), _ptr(out), _ptr(ws), nbytes,
                                                       N._P(peer_ctx), _stream(weight)), "peer_denominators")
     return out
@@ -468,7 +491,7 @@ def peer_collect_losses(peer_ctx: int, device, steps_back: int = 0, out: Optiona
     """gbcodec_peer_collect_losses_f32: the ranks' loss terms of the sharded step made `steps_back` calls ago, added in
     rank order -> the 7 global losses (on the device; read them when you log)."""
     out = torch.empty(7, dtype=torch.float32, device=device) if out is None else out
-    with torch.cuda.device(out.device):
+    with _on_device(out.device):
         N.check(N.lib().gbcodec_peer_collect_losses_f32(N._P(peer_ctx), int(steps_back), _ptr(out), _stream(out)), "peer_collect_losses")
     return out
 
@@ -481,7 +504,7 @@ def softplus_mean(raw: Tensor) -> Tensor:
     B, K, H, W = raw.shape
     raw = _cuda_f32("raw_variances", raw)
     out = torch.empty((B, K), dtype=torch.float32, device=raw.device)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         N.check(N.lib().gbcodec_softplus_mean_f32(_ptr(raw), _ptr(out), B, K, H, W, _stream(raw)), "softplus_mean")
     return out
 
@@ -497,7 +520,7 @@ def softplus_mean_backward(raw: Tensor, grad_mean: Tensor) -> Tensor:
     raw = _cuda_f32("raw_variances", raw)
     grad_mean = _cuda_f32("grad_mean", grad_mean.reshape(B, K), (B, K))
     out = torch.empty_like(raw)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         N.check(N.lib().gbcodec_softplus_mean_backward_f32(_ptr(raw), _ptr(grad_mean), _ptr(out), B, K, H, W, _stream(raw)),
                 "softplus_mean_backward")
     return out
@@ -529,7 +552,7 @@ def encode_mode(kps: Tensor, vis: Tensor, H: int, W: int, in_w: float, in_h: flo
     vis = _cuda_f32("visible", vis.reshape(B, K), (B, K))
     target = torch.empty((B, K, H, W), dtype=torch.float32, device=kps.device)
     weight = torch.empty((B, K, 1), dtype=torch.float32, device=kps.device)
-    with torch.cuda.device(kps.device):
+    with _on_device(kps.device):
         N.check(N.lib().gbcodec_encode_mode_f32(_ptr(kps), _ptr(vis), _ptr(target), _ptr(weight), B, K, H, W,
                                                 in_w, in_h, sigma, mode, _stream(kps)), "encode_mode")
     return target, weight
@@ -562,7 +585,7 @@ def postprocess(hm: Tensor, regression: Optional[Tensor], center: Optional[Tenso
     maxvals = torch.empty((B, K), dtype=torch.float32, device=dev)
     mask = torch.empty((B, K), dtype=torch.float32, device=dev)
     ws = torch.empty(16, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         N.check(N.lib().gbcodec_postprocess_f32(d, _ptr(hm), _ptr(regression), _ptr(center), _ptr(scale), _ptr(preds),
                                                 _ptr(maxvals), _ptr(mask), _ptr(ws), _stream(hm)), "postprocess")
     return preds, maxvals, mask
@@ -583,7 +606,7 @@ def coords_to_image(coords: Tensor, center: Tensor, scale: Tensor, H: int, W: in
     center = _cuda_f32("center", center, (B, 2))
     scale = _cuda_f32("scale", scale, (B, 2))
     out = torch.empty_like(coords)
-    with torch.cuda.device(coords.device):
+    with _on_device(coords.device):
         N.check(N.lib().gbcodec_coords_to_image_f32(_ptr(coords), _ptr(center), _ptr(scale), B, K, H, W, in_w, in_h,
                                                     _ptr(out), _stream(coords)), "coords_to_image")
     return out
@@ -647,7 +670,7 @@ def combined_loss(pred: Optional[Tensor], target: Optional[Tensor], weight: Opti
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     opt = lambda t: _ptr(t) if t.numel() else None
     entry = N.lib().gbcodec_combined_loss_f16 if half else N.lib().gbcodec_combined_loss_f32
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         N.check(entry(desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined), _ptr(target_coords),
                       _ptr(grad_scale), _ptr(losses), opt(gp), opt(gc), opt(gr), _ptr(ws), nbytes, _stream(some)), "combined_loss")
     return losses, gp, gc, gr
@@ -691,7 +714,7 @@ def combined_loss_backward(grad_losses: Tensor, grad_pred: Tensor, grad_coords: 
     if half and grad_pred.dtype != torch.float16:
         raise RuntimeError("gbcodec: float16 predictions take a float16 grad_pred")
     entry = N.lib().gbcodec_combined_loss_backward_f16 if half else N.lib().gbcodec_combined_loss_backward_f32
-    with torch.cuda.device(some.device):
+    with _on_device(some.device):
         N.check(entry(
             desc, _ptr(pred), _ptr(target), _ptr(weight), _ptr(coords), _ptr(refined), _ptr(target_coords), _ptr(grad_scale),
             _ptr(g5), opt(grad_pred), opt(grad_coords), opt(grad_refined), _ptr(ws), nbytes, _stream(some)),
@@ -768,7 +791,7 @@ def heatmap_step(hm: Tensor, target: Optional[Tensor], weight: Optional[Tensor],
     maxvals = torch.empty((B, K), dtype=torch.float32, device=dev) if with_decode else empty()
     nbytes = N.lib().gbcodec_combined_workspace_bytes(B, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         N.check(N.lib().gbcodec_heatmap_step_f32(
             _ptr(hm), _ptr(target), _ptr(weight), _ptr(gt_kps), B, K, H, W, in_w, in_h, sigma, int(use_target_weight), norm_batch,
             _ptr(grad_scale), _ptr(loss), _ptr(ghm) if with_grads else None, argmax_mode,
@@ -858,7 +881,7 @@ def fusion_loss_f16(hm: Tensor, off: Tensor, var: Optional[Tensor], target: Opti
         alpha_param = _scalar("alpha", alpha_param, hm)
         fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
     ws = _workspace(hm)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         N.check(N.lib().gbcodec_fusion_step_f16(
             desc, _ptr(hm), _ptr(off), _ptr(var), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(expected_upstream),
             _ptr(losses), _ptr(ghm) if with_grads else None, _ptr(goff) if with_grads else None,
@@ -975,7 +998,7 @@ def fusion_step_vmean(hm: Tensor, off: Tensor, var_mean: Tensor, target: Optiona
         fusion_weight = _scalar("fusion_weight", fusion_weight, hm)
     ws = _workspace(hm)
     opt = lambda t, on: _ptr(t) if on else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         N.check(N.lib().gbcodec_fusion_step_vmean_f32(
             desc, _ptr(hm), _ptr(off), _ptr(var_mean), _ptr(target), _ptr(weight), _ptr(gt_kps), _ptr(denoms), _ptr(grad_scale),
             _ptr(losses), opt(ghm, with_grads), opt(goff, with_grads), opt(gvm, with_grads),
