@@ -985,8 +985,10 @@ int fusion_loss(const gbcodec_loss_desc* d, const float* hm, const float* off, c
     A.half_io = half_io;
     A.var_mean = var_mean; A.grad_var_mean = grad_var_mean;
     if (var_mean) {
-        // only the tile kernels take the means
-        st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
+        // the persistent step kernel (64x48, targets built in the kernel) and the tile kernels take the means
+        st = force_generic() ? 1 : launch_step_pipe(P, A, s, g_prof_start, g_prof_stop);
+        if (st == 0) pipe_used = true;
+        if (st == 1) st = launch_loss_tile(P, A, s, g_prof_start, g_prof_stop);
         if (st == 1) return fail(GBCODEC_ERR_BAD_SHAPE, "loss: per-tile variance means are supported for 64x48, 64x64, 96x72 and 128x128 tiles (got %dx%d)", P.H, P.W);
     } else
     st = launch_loss_kernel(P, A, s, &pipe_used);

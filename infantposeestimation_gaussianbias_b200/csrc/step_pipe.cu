@@ -358,6 +358,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     const int lane = threadIdx.x & 31;
     const int tiles = P.B * P.K;
     const bool has_var = A.var != nullptr;
+    const bool has_vmean = A.var_mean != nullptr;            // the variance branch reduced to mean_N(V) by the head: no variance tile
     const bool decode = A.coords != nullptr;
     const Elem* const hm = reinterpret_cast<const Elem*>(A.hm);
     const Elem* const var_maps = reinterpret_cast<const Elem*>(A.var);
@@ -513,6 +514,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // the 4x4x2 window of offset taps around the tile centre (consumed after the sums)
             float tapv = 0.f;
             if (heavy) tapv = ld1(off_tile + (lane >> 4) * N + (wy0 + ((lane >> 2) & 3)) * W + wx0 + (lane & 3));
+            float vmean_in = 0.f;
+            if (has_vmean && heavy) vmean_in = __ldg(A.var_mean + tile);
 
 #ifdef PIPE_JUNK
             // measurement only: PIPE_JUNK x 16 straight-line instructions of once-per-tile code in the scalar warp (does the
@@ -636,6 +639,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     *reinterpret_cast<float4*>(cb + 12) = make_float4(__uint_as_float(0u), 0.f, 0.f, 0.f);
                     float4* p = reinterpret_cast<float4*>(A.partial + (size_t)tile * 8);
                     p[0] = make_float4(0.f, 0.f, 0.f, 0.f); p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (GRADS && has_vmean) A.grad_var_mean[tile] = 0.f;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(cfull + b);
@@ -643,7 +647,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 // ---- per-tile scalars ------------------------------------------------------------------------------
                 const float Vsum = val(5);
                 const float ET = val(3), Ssum = val(4), Rm = val(6), Rxa = val(7), Rya = val(8), M2a = val(9), mse_sum = val(10);
-                const float mV = has_var ? Vsum * P.inv_n : P.sigma;
+                const float mV = has_var ? Vsum * P.inv_n : (has_vmean ? vmean_in : P.sigma);
                 const float ka = P.use_target_weight ? wa * iD : 1.f / (float)(P.B * P.K), kb = w * iD;
                 // relu moments shifted from the tile centre to (cx, cy)
                 const float dcx = cx - ax, dcy = cy - ay;
@@ -779,7 +783,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                 // ---- off the critical path: loss numerators, offset gradient taps ----------------------------------------
                 if (lane == 0) {
                     const float peak_t = (cx - gx) * (cx - gx) + (cy - gy) * (cy - gy);
-                    const float var_t = (sd - P.sigma) * (sd - P.sigma) + (has_var ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
+                    const float var_t = (sd - P.sigma) * (sd - P.sigma) + ((has_var || has_vmean) ? (mV - P.sigma) * (mV - P.sigma) : 0.f);
+                    if (GRADS && has_vmean) A.grad_var_mean[tile] = (P.lam[3] * gscale) * kb * 2.f * (mV - P.sigma);      // d(total) / d(mean_N(V))
                     const float shape_t = (Ent - P.e_star) * (Ent - P.e_star);
                     float4* p = reinterpret_cast<float4*>(A.partial + (size_t)tile * 8);
                     p[0] = make_float4(wa * (mse_sum * P.inv_n), wa * (0.5f * sl1), wa * peak_t, w * var_t);
@@ -1374,7 +1379,8 @@ int launch_step_pipe(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
     if (env && (!strcmp(env, "tile") || !strcmp(env, "persist"))) return 1;
     // target generated on the fly with a patch no taller than the CTA's rows, the ordinary forward (+ backward) call;
     // float32 maps, or float16 maps (autocast) with a four-deep ring
-    if (A.target || A.lam_eff || A.plan || A.var_mean || A.grad_var_mean || !A.desc || !A.tile_counter) return 1;
+    if (A.target || A.lam_eff || A.plan || !A.desc || !A.tile_counter) return 1;
+    if ((A.var_mean || A.grad_var_mean) && (A.half_io || A.var)) return 1;          // per-tile variance means: float32 maps only
     if (A.coords && A.radius > 8) return 1;
     const bool grads = A.grad_hm != nullptr;
     if (P.H == 64 && P.W == 48 && P.ec.ntap <= 16) {
