@@ -353,8 +353,11 @@ static int check_genb(const GenbParams& P, const GenbArgs& A, const void* ws, si
     if ((P.terms & GBCODEC_TERM_REFINED) && !A.refined) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_refined is NULL");
     if (coords && !A.target_coords) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss: d_target_coords is NULL");
     if (!ws || ws_size < genb_ws_bytes(P.B, P.K)) return fail(GBCODEC_ERR_WORKSPACE, "combined_loss: workspace of %zu bytes needed", genb_ws_bytes(P.B, P.K));
-    if (!aligned16(ws) || (tiles && (!aligned16(A.pred) || !aligned16(A.target))) || (A.grad_pred && !aligned16(A.grad_pred)))
-        return fail(GBCODEC_ERR_UNALIGNED, "combined_loss: tensors must be 16-byte aligned");
+    // four pixels per access: 16 bytes of float32, 8 bytes of float16 (a slice of whole images of a float16 batch need
+    // not start on a 16-byte boundary)
+    const auto vec_ok = [&](const void* p) { return A.half_io ? (reinterpret_cast<uintptr_t>(p) & 7u) == 0 : aligned16(p); };
+    if (!aligned16(ws) || (tiles && (!vec_ok(A.pred) || !aligned16(A.target))) || (A.grad_pred && !vec_ok(A.grad_pred)))
+        return fail(GBCODEC_ERR_UNALIGNED, "combined_loss: tensors must be 16-byte aligned (float16 predictions and their gradient: 8-byte)");
     if (A.half_io && !tiles) return fail(GBCODEC_ERR_BAD_ARGUMENT, "combined_loss (float16): the call has no heatmap term; use the float32 entry point");
     if (backward && tiles && !A.grad_pred) return fail(GBCODEC_ERR_NULL_POINTER, "combined_loss backward: d_grad_pred is NULL");
     return GBCODEC_OK;

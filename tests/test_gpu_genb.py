@@ -288,6 +288,21 @@ def test_combined_loss_float16_predictions(pkg, name):
         same(a.grad.cpu().numpy().view(np.uint16), b.grad.half().cpu().numpy().view(np.uint16), type(mod).__name__)
         with torch.no_grad():
             assert float(mod(ph, *args)) == float(lb)
+    # a slice of whole images of a float16 batch starts on an 8-byte boundary, not necessarily a 16-byte one
+    if name == "odd_56x40":
+        small = torch.rand(3, 1, 3, 4, device="cuda").half()
+        tsm = torch.rand(3, 1, 3, 4, device="cuda")
+        view = small[1:]
+        assert view.data_ptr() % 16 == 8 and view.is_contiguous()
+        a = view.clone().requires_grad_(True)          # (a clone is 16-byte aligned again: the reference value)
+        la = L.KeypointMSELoss(False)(a, tsm[1:], None)
+        la.backward()
+        with torch.no_grad():
+            assert float(L.KeypointMSELoss(False)(view, tsm[1:], None)) == float(la)
+        b = view.detach().requires_grad_(True)
+        lb = L.KeypointMSELoss(False)(b, tsm[1:], None)
+        lb.backward()
+        assert float(lb) == float(la) and torch.equal(a.grad, b.grad)
     # torch.autocast hands the same dtype over: the module is called inside the region as train.py does
     with torch.autocast("cuda", dtype=torch.float16):
         a = ph.clone().requires_grad_(True)
