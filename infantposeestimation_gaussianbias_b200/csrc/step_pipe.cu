@@ -56,14 +56,7 @@ __device__ __forceinline__ void mbar_arrive(Bar bar) {
 }
 // try_wait suspends the thread in hardware until the phase completes or a time limit passes: a wait costs a few issue
 // slots however long it lasts
-#ifndef PIPE_OUTLINE
-#define PIPE_OUTLINE 0
-#endif
-#if PIPE_OUTLINE
-#define PIPE_INLINE __noinline__
-#else
 #define PIPE_INLINE __forceinline__
-#endif
 __device__ PIPE_INLINE void mbar_wait(Bar bar, unsigned parity) {
     asm volatile("{\n"
                  " .reg .pred p;\n"
@@ -147,13 +140,6 @@ __device__ __forceinline__ float4 lds4(const void* p) {
 #ifndef PIPE_SRED_UNROLL
 #define PIPE_SRED_UNROLL 1
 #endif
-// PIPE_EARLY_DECODE: the scalar warp requests the decode's window pixels and the block of offset taps as soon as the
-// soft-argmax is known and consumes them after the constants of the gradient pass are out: two L2 round trips less on
-// the per-tile chain — and 3 % SLOWER (0.2600 against 0.2520 ms): what the ~100 extra once-per-tile instructions cost in
-// instruction fetch outweighs the latency they hide.  Kept as a measurement switch.
-#ifndef PIPE_EARLY_DECODE
-#define PIPE_EARLY_DECODE 0
-#endif
 constexpr int kSredU = PIPE_SRED_UNROLL;
 // the producer's loop over the ring items of a tile, rolled: the compiler's unrolled version was 175 instructions longer,
 // all of them on the once-per-tile path
@@ -161,28 +147,13 @@ constexpr int kSredU = PIPE_SRED_UNROLL;
 #define PIPE_PROD_UNROLL 1
 #endif
 constexpr int kProdU = PIPE_PROD_UNROLL;
-// target_row out of line: one copy for the front and the back half instead of two inlined ones
-#ifndef PIPE_TROW_OUTLINE
-#define PIPE_TROW_OUTLINE 0
-#endif
-#if PIPE_TROW_OUTLINE
-#define PIPE_TROW_INLINE __noinline__
-#else
 #define PIPE_TROW_INLINE PIPE_INLINE
-#endif
 // PIPE_TAIL_OUTSIDE: when the call decodes, the scalar warp leaves the soft-argmax in d_coords and the two offset-gradient
 // factors in the spare words of the tile's numerator row; finalize_kernel's tail CTAs (loss.cu: one warp per tile, same
 // operations in the same order) place the offset-gradient taps and finish the decode.  ~270 instructions less on the
 // once-per-tile path of this kernel, whose time follows that path's footprint.
 #ifndef PIPE_TAIL_OUTSIDE
 #define PIPE_TAIL_OUTSIDE 1
-#endif
-// the decode's window sums through one 4-value butterfly (6 shuffles) instead of three 5-shuffle sums
-#ifndef PIPE_COMPACT_DECODE
-#define PIPE_COMPACT_DECODE 1
-#endif
-#ifndef PIPE_BALANCE
-#define PIPE_BALANCE 0
 #endif
 // Ring order: the variance tile is the FIRST ring item of a tile, the limb partners follow.  It is the one ring item that
 // always comes from HBM (the partners are other CTAs' tiles of the same image: L2 hits); as the last item of the two-deep
@@ -212,12 +183,12 @@ constexpr int kProdU = PIPE_PROD_UNROLL;
 #define PIPE_CARRY_TARGET 1
 #endif
 constexpr int kPUs = PIPE_UNROLL_SMALL, kPUb = PIPE_UNROLL_B, kPUp = PIPE_UNROLL_P, kPUd = PIPE_UNROLL_D;
-// PIPE_LANESUMS: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
+// Lane sums: the compute warps do not reduce their 16 running sums across lanes (a 31-shuffle butterfly, ~125
 // instructions per warp and tile); every lane stores its sums into its own four slots of the sigmoid tile — free once the
 // partner visits are over — and the scalar warp adds up the 6 x 32 lanes (off the critical path, a rolled loop).
-#ifndef PIPE_LANESUMS
-#define PIPE_LANESUMS 1
-#endif
+// Also measured and not kept in earlier sessions (profiles/r02_step_variants.jsonl; switches in this file's history):
+// helpers out of line, decode loads requested early in the scalar warp (+3 %: ~100 once-per-tile instructions more),
+// roles laid out per CTA rank for balanced schedulers, a code-size probe (4 KB of hot code more = +5 %).
 
 constexpr float kFlatRmax = 1e-3f;              // largest eps / p for which the entropy shortcut holds to 1e-7
 constexpr float kShiftCond = 4.f;               // largest sum |terms| / |result| accepted for the shifted relu moments
@@ -365,14 +336,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
 
     // ---- once per CTA -------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
-#if PIPE_BALANCE
-        // which of its SM's (three) step CTAs this one is: the roles below are laid out per rank
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        tids[3] = A.sm_slots ? (int)(atomicAdd(A.sm_slots + (smid & (kSmSlots - 1)), 1u) % 3u) : 0;
-#else
         tids[3] = 0;
-#endif
 #pragma unroll
         for (int q = 0; q < 3; ++q) { mbar_init(hfull + q, 1); mbar_init(hempty + q, NW); }
 #pragma unroll
@@ -399,14 +363,7 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
     //   rank 1: scalar = warp 4 (0),               producer = warp 6 (2)
     //   rank 2: scalar = warp 5 (1),               producer = warp 7 (3)
     // The logical warp index used below: compute warps 0 .. NW-1 in slot order, producer = NW, scalar = NW + 1.
-#if PIPE_BALANCE
-    const int rank = tids[3];
-    const int pw = threadIdx.x >> 5;
-    const int s_pos = rank == 2 ? NW - 1 : NW - 2, p_pos = NW - 1 + rank;
-    const int warp = pw == p_pos ? NW : (pw == s_pos ? NW + 1 : pw - (pw > s_pos ? 1 : 0) - (pw > p_pos ? 1 : 0));
-#else
     const int warp = threadIdx.x >> 5;
-#endif
     const int tid = warp * 32 + lane;
 
     // ======================================================================================================
@@ -517,31 +474,13 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             float vmean_in = 0.f;
             if (has_vmean && heavy) vmean_in = __ldg(A.var_mean + tile);
 
-#ifdef PIPE_JUNK
-            // measurement only: PIPE_JUNK x 16 straight-line instructions of once-per-tile code in the scalar warp (does the
-            // kernel's time follow the instruction-cache footprint of the per-tile code?)
-            {
-                unsigned jk = lane;
-#pragma unroll
-                for (int q = 0; q < PIPE_JUNK; ++q)
-                    asm volatile("add.u32 %0, %0, 1;\n xor.b32 %0, %0, 3;\n add.u32 %0, %0, 5;\n xor.b32 %0, %0, 7;\n"
-                                 "add.u32 %0, %0, 9;\n xor.b32 %0, %0, 11;\n add.u32 %0, %0, 13;\n xor.b32 %0, %0, 15;\n"
-                                 "add.u32 %0, %0, 17;\n xor.b32 %0, %0, 19;\n add.u32 %0, %0, 21;\n xor.b32 %0, %0, 23;\n"
-                                 "add.u32 %0, %0, 25;\n xor.b32 %0, %0, 27;\n add.u32 %0, %0, 29;\n xor.b32 %0, %0, 31;" : "+r"(jk));
-                if (jk == 0xdeadbeefu) tids[3] = (int)jk;
-            }
-#endif
             // ---- the warps' partial sums of tile i --------------------------------------------------------------
             mbar_wait_idle(sfull + b, (i >> 1) & 1u);
-#if !PIPE_LANESUMS
-            const float* redb = red + b * (NW * 16);
-#endif
             const float* red2b = red2 + b * (NW * 4);
             const float* redMb = redM + b * (NW * 2);
             float m = redMb[0], hmin = redMb[1];
 #pragma unroll
             for (int ww = 1; ww < NW; ++ww) { m = fmaxf(m, redMb[2 * ww]); hmin = fminf(hmin, redMb[2 * ww + 1]); }
-#if PIPE_LANESUMS
             // value k = 4 * row + c of warp ww, lane l sits in component c of Sb[row * TPB + ww * 32 + l].  This lane takes
             // row = lane >> 3 and the source lanes g, g + 8, g + 16, g + 24 (g = lane & 7: conflict-free 128-bit reads),
             // then the eight lanes of a row add up.  Row 0 carries the softmax sums, relative to each warp's own maximum.
@@ -568,24 +507,6 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
                     for (int c = 0; c < 4; ++c) acc4[c] += __shfl_xor_sync(0xffffffffu, acc4[c], o);
                 }
             }
-#else
-            float acc = 0.f;
-            {
-                const int idx = lane >> 1, q = lane & 1;
-#pragma unroll
-                for (int t = 0; t < (NW + 1) / 2; ++t) {
-                    const int ww = q + 2 * t;
-                    if (ww < NW) {
-                        float x = redb[ww * 16 + idx];
-                        const float dl = (redMb[2 * ww] - m) * kLog2e;            // (m_w - m) log2 e <= 0
-                        if (idx == 3) x = fmaf(dl, redb[ww * 16], x);             // sum e t: t is relative to the warp's maximum too
-                        if (idx < 4) x *= ex2(dl);
-                        acc += x;
-                    }
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            }
-#endif
             float a4s = 0.f;
             if (nact > 2) {
                 const int idx = lane >> 3, q = lane & 7;
@@ -600,36 +521,12 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(sempty + b);          // the sums are in registers
-#if PIPE_LANESUMS
             auto val = [&](int k) -> float { return __shfl_sync(0xffffffffu, acc4[k & 3], (k >> 2) << 3); };
-#else
-            auto val = [&](int k) -> float { return __shfl_sync(0xffffffffu, acc, k << 1); };
-#endif
             const float Zs = val(0);
             const float iZ = rcp(Zs);
             const float cx = val(1) * iZ, cy = val(2) * iZ;
             const float ml = m * kLog2e;
             float* const cb = cons + b * kConsFloats;
-#if PIPE_EARLY_DECODE
-            // decode: this lane's window pixel and the 4x4x2 block of offset taps around floor(cx, cy), requested now
-            float vpx = -INFINITY, pre = 0.f;
-            int wx_ = 0, wy_ = 0, pbx = 0, pby = 0;
-            bool okw = false;
-            if (win_small) {
-                const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
-                const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
-                wx_ = px + wdx; wy_ = py + wdy;
-                okw = in_win && wx_ >= 0 && wx_ < W && wy_ >= 0 && wy_ < H;
-                if (okw) vpx = ld1(hm + (size_t)tile * N + wy_ * W + wx_);
-                if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
-                    pbx = (int)floorf(fminf(fmaxf(cx, 0.f), (float)(W - 1))) - 1;
-                    pby = (int)floorf(fminf(fmaxf(cy, 0.f), (float)(H - 1))) - 1;
-                    const int tq = lane & 15;
-                    const int qx = min(max(pbx + (tq & 3), 0), W - 1), qy = min(max(pby + (tq >> 2), 0), H - 1);
-                    pre = ld1(off_tile + (lane >> 4) * N + qy * W + qx);
-                }
-            }
-#endif
 
             if (!heavy) {
                 // weight 0: every term carries a factor w -> zero loss and gradient; decode only
@@ -823,47 +720,21 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             if (decode) {
                 float dx_ = cx, dy_ = cy;
                 if (win_small) {
-#if PIPE_EARLY_DECODE
-                    const int x = wx_, y = wy_;
-                    const bool ok = okw;
-#else
                     const int px = (int)fminf(fmaxf(rintf(cx), 0.f), (float)(W - 1));
                     const int py = (int)fminf(fmaxf(rintf(cy), 0.f), (float)(H - 1));
                     const int x = px + wdx, y = py + wdy;
                     const bool ok = in_win && x >= 0 && x < W && y >= 0 && y < H;
                     const float vpx = ok ? ld1(hm + (size_t)tile * N + y * W + x) : -INFINITY;
-#endif
                     const float vmax = warp_max(vpx);
                     const float e = ok ? expf(vpx - vmax) : 0.f;
-#if PIPE_COMPACT_DECODE
                     float sw4[4] = {e, e * (float)x, e * (float)y, 0.f};
                     warp_scatter_sum<4>(sw4, lane);
                     const float se = __shfl_sync(0xffffffffu, sw4[0], 0), sx = __shfl_sync(0xffffffffu, sw4[0], 8), sy = __shfl_sync(0xffffffffu, sw4[0], 16);
-#else
-                    const float se = warp_sum(e), sx = warp_sum(e * (float)x), sy = warp_sum(e * (float)y);
-#endif
                     dx_ = a_blend * cx + (1.f - a_blend) * (sx / se);
                     dy_ = a_blend * cy + (1.f - a_blend) * (sy / se);
                     if (A.dflags & GBCODEC_DECODE_APPLY_OFFSET) {
                         const Bilinear bl = bilinear_setup(dx_, dy_, H, W);
                         float ox, oy;
-#if PIPE_EARLY_DECODE
-                        // the refined coordinate stays within a pixel or so of the soft-argmax: the block covers it (warp-uniform test)
-                        if (bl.x0 >= pbx && bl.x1 <= pbx + 3 && bl.y0 >= pby && bl.y1 <= pby + 3) {
-                            const int i00 = (bl.y0 - pby) * 4 + (bl.x0 - pbx), i01 = (bl.y0 - pby) * 4 + (bl.x1 - pbx);
-                            const int i10 = (bl.y1 - pby) * 4 + (bl.x0 - pbx), i11 = (bl.y1 - pby) * 4 + (bl.x1 - pbx);
-                            float tq[2][4];
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                tq[c][0] = __shfl_sync(0xffffffffu, pre, c * 16 + i00);
-                                tq[c][1] = __shfl_sync(0xffffffffu, pre, c * 16 + i01) * bl.okx;
-                                tq[c][2] = __shfl_sync(0xffffffffu, pre, c * 16 + i10) * bl.oky;
-                                tq[c][3] = __shfl_sync(0xffffffffu, pre, c * 16 + i11) * (bl.okx * bl.oky);
-                            }
-                            ox = bl.w00 * tq[0][0] + bl.w01 * tq[0][1] + bl.w10 * tq[0][2] + bl.w11 * tq[0][3];
-                            oy = bl.w00 * tq[1][0] + bl.w01 * tq[1][1] + bl.w10 * tq[1][2] + bl.w11 * tq[1][3];
-                        } else
-#endif
                         {
                             ox = bilinear_read(off_tile, bl, W);
                             oy = bilinear_read(off_tile + N, bl, W);
@@ -960,10 +831,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             for (int q = 0; q < 16; ++q) r16[q] = 0.f;
             const bool sig = heavy && (nact > 0 || PIPE_MERGE_B1);
             (void)sig;
-#if PIPE_LANESUMS
             // the sigmoid slots still hold the lanes' sums of tile i - 1 until the scalar warp has taken them
             if (i >= 1) mbar_wait(sempty + ((i - 1) & 1u), ((i - 1) >> 1) & 1u);
-#endif
             {
                 const f2 kNML = splat2(nml_w);
                 f2 E01 = splat2(0.f), E23 = splat2(0.f), T01 = splat2(0.f), T23 = splat2(0.f);
@@ -1114,15 +983,8 @@ step_pipe_kernel(const __grid_constant__ LossParams P, const __grid_constant__ L
             // ---- publish this warp's sums --------------------------------------------------------------------------
             float* const red2b = red2 + b * (NW * 4);
             float* const redMb = redM + b * (NW * 2);
-#if PIPE_LANESUMS
 #pragma unroll
             for (int q = 0; q < 4; ++q) Sb[q * TPB + tid] = make_float4(r16[4 * q], r16[4 * q + 1], r16[4 * q + 2], r16[4 * q + 3]);
-#else
-            if (i >= 2) mbar_wait(sempty + b, ((i - 2) >> 1) & 1u);
-            float* const redb = red + b * (NW * 16);
-            warp_scatter_sum<16>(r16, lane);
-            if ((lane & 1) == 0) redb[warp * 16 + (lane >> 1)] = r16[0];
-#endif
             if (nact > 2) {
                 warp_scatter_sum<4>(r4, lane);
                 if ((lane & 7) == 0) red2b[warp * 4 + (lane >> 3)] = r4[0];
