@@ -965,12 +965,6 @@ static int launch_tile_tm(const LossParams& P, const LossArgs& A, cudaStream_t s
     return launch_tile_t<W4, ROWS, NIT, CE, CS, CA, CQ, ROLL, kTargetLut, MINB, HALF, MG, VSLOT>(P, A, s, e0, e1);
 }
 
-// GBCODEC_TILE_VARIANT=<n>: alternative CTA shapes for the 64x48 tile (measurement only)
-static int tile_variant() {
-    static const int v = [] { const char* e = getenv("GBCODEC_TILE_VARIANT"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
 int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cudaEvent_t e0, cudaEvent_t e1) {
     // The instantiations with sigmoid slots (CS) take the variance tile through them as an asynchronous copy (VSLOT): no
     // registers held across the first wait for HBM (64x48 0.2755 -> 0.2670 ms, 96x72 0.659 -> 0.616, 64x64 0.360 -> 0.345).
@@ -984,25 +978,18 @@ int launch_loss_tile(const LossParams& P, const LossArgs& A, cudaStream_t s, cud
         if (P.H == 64 && P.W == 64) return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, true, true, true>(P, A, s, e0, e1);
         return 1;
     }
-    // GBCODEC_TILE_VARIANT=<n> selects an alternative CTA shape / shared-memory budget (A/B measurements; DESIGN.md §4
-    // lists what was tried: 96- and 384-thread CTAs, register-resident unrolled loops, 4-8 CTAs per SM — all slower)
-    const int v = tile_variant();
+    // (DESIGN.md §4 lists the CTA shapes that were tried and measured slower — 96- and 384-thread CTAs, register-resident
+    // unrolled loops, 4-8 CTAs per SM, a maximum reduction of its own, the variance tile through registers; their
+    // instantiations are in the history of this file)
     if (P.H == 64 && P.W == 48) {
-        if (v == 1) return launch_tile_tm<12, 16, 4, false, true, true, 5, false, true>(P, A, s, e0, e1);    // rolled; H,S,A in smem, partners through L2
-        if (v == 2) return launch_tile_tm<12, 16, 4, true, true, true, 4>(P, A, s, e0, e1);                  // tile in registers, unrolled; E,S,A,Q
-        if (v == 13) return launch_tile_tm<12, 16, 4, false, true, false, 6, false, true, false, true, true>(P, A, s, e0, e1);  // rolled; H,S; partners one row ahead from L2; 6 CTAs (0.2815 ms; 7 CTAs at 48 registers: 0.3136)
-        if (v == 21) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true>(P, A, s, e0, e1);   // the default with a maximum reduction of its own (one more barrier)
-        if (v == 22) return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, false, true>(P, A, s, e0, e1);   // the default with the variance tile loaded into registers (0.2755 ms against 0.2665)
         return launch_tile_tm<12, 16, 4, false, true, false, 5, true, true, false, true, true>(P, A, s, e0, e1);   // 192 threads, 16 px each; H,S,Q in smem, 5 CTAs
     }
     if (P.H == 96 && P.W == 72) {
-        if (v == 8) return launch_tile_tm<18, 16, 6, false, true, false, 2, true, true>(P, A, s, e0, e1);    // rolled, 288 threads, H,S,Q: 2 CTAs (0.696 ms at B=1024)
         return launch_tile_tm<18, 16, 6, false, true, false, 3, false, true, false, true, true>(P, A, s, e0, e1);  // rolled, 288 threads, 24 px each; H,S in smem, partners through a two-row ring: 3 CTAs (0.581 ms)
     }
     if (P.H == 64 && P.W == 64)          // the reference's other default map (data/pose_transforms.py:391): 256 threads, H,S,Q in smem, 4 CTAs
         return launch_tile_tm<16, 16, 4, false, true, false, 4, true, true, false, true, true>(P, A, s, e0, e1);
     if (P.H == 128 && P.W == 128) {
-        if (v == 8) return launch_tile_tm<32, 16, 8, false, true, false, 1, true, true>(P, A, s, e0, e1);    // rolled, 512 threads, H,S,Q: 1 CTA (1.277 ms at B=1024, K=13)
         return launch_tile_tm<32, 16, 8, false, false, false, 2, false, true, false, true>(P, A, s, e0, e1); // rolled, 512 threads, 32 px each; own tile + a two-row ring for the variance and partner rows in smem: 2 CTAs (1.067 ms)
     }
     return 1;

@@ -101,6 +101,6 @@ int main(int argc, char** argv) {
     printf("{\"B\": %d, \"K\": %d, \"H\": %d, \"W\": %d, \"ms_per_step\": %.4f, \"kernel_ms_mean\": %.4f, \"kernel_ms_min\": %.4f, "
            "\"hm_per_s\": %.4g, \"kernel_GBps\": %.1f, \"total_loss\": %.6f, \"variant\": \"%s\"}\n",
            B, K, H, W, total / steps, kern / steps, kmin, tiles * steps / (total * 1e-3), bytes / (kern / steps * 1e-3) / 1e9, hl[6],
-           getenv("GBCODEC_TILE_VARIANT") ? getenv("GBCODEC_TILE_VARIANT") : (getenv("GBCODEC_LOSS_KERNEL") ? getenv("GBCODEC_LOSS_KERNEL") : "default"));
+           getenv("GBCODEC_LOSS_KERNEL") ? getenv("GBCODEC_LOSS_KERNEL") : "default");
     return 0;
 }
