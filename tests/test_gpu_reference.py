@@ -307,3 +307,51 @@ def test_generate_target_stock_vs_device_encoder(world):
     assert np.array_equal(gt != 0, wt != 0)
     np.testing.assert_allclose(gt, wt, rtol=1e-6, atol=0)
     _report("encode", tiles=B * CFG.K, max_rel_err=float((np.abs(gt - wt) / np.maximum(wt, 1e-30))[wt != 0].max()))
+
+
+def test_genb_combined_loss_under_autocast_stock_vs_float16_kernels(world):
+    """The second generation's CombinedLoss (models/losses.py:205-290) under torch.autocast with float16 heatmaps: the STOCK
+    reference module against this package's, which hands the half maps to gbcodec_combined_loss_f16 as they are.  Under
+    autocast the reference does its elementwise work in half and its reductions / criteria in float; the kernel computes
+    everything in float32 on the up-cast values.  Against the stock autocast step the bound is therefore half-precision
+    round-off (on the CPU, where autocast leaves `sum` in half, the stock losses are 1e-3 from their own float32
+    evaluation; on CUDA `sum` is promoted and the stock step is much closer); against the stock module's FLOAT32 evaluation
+    of the same up-cast maps the bound is the usual one.  The distances are printed."""
+    ref = world.ref
+    RL = ref.module("models.losses")
+    from infantposeestimation_gaussianbias_b200 import losses as L
+    K = CFG.K
+    cfg_l = types.SimpleNamespace(LOSS=types.SimpleNamespace(MORPH_LAMBDA=1.2, MORPH_WEIGHT=0.15, REG_WEIGHT=0.6))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    pred = (world.targets * 0.8 + 0.05 * torch.rand(world.targets.shape, generator=g, device="cuda")).half()
+    coords = torch.rand(B, K, 2, generator=g, device="cuda") * 40.0
+    tcoords = coords + torch.randn(B, K, 2, generator=g, device="cuda")
+    tg = {"heatmaps": world.targets, "coords": tcoords, "weights": world.weights}
+    scale = 256.0
+
+    def run(module, p, autocast):
+        a = p.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            total, parts = module({"heatmaps": a, "coords": coords}, tg)
+        (total * scale).backward()
+        return {k: float(v.detach()) for k, v in parts.items()}, a.grad
+
+    stock16, g_stock16 = run(RL.CombinedLoss(cfg_l), pred, True)
+    stock32, g_stock32 = run(RL.CombinedLoss(cfg_l), pred.float(), False)          # the float32 evaluation of the same maps
+    ours16, g_ours16 = run(L.CombinedLoss(cfg_l), pred, True)
+    assert g_ours16.dtype == torch.float16 and g_stock16.dtype == torch.float16
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-12)
+    worst_vs_stock16 = max(rel(ours16[k], stock16[k]) for k in stock16)
+    worst_vs_f32 = max(rel(ours16[k], stock32[k]) for k in stock32)
+    stock16_vs_f32 = max(rel(stock16[k], stock32[k]) for k in stock32)
+    gmax = float(g_stock32.abs().max())
+    d_ours = float((g_ours16.float() - g_stock32).abs().max()) / gmax
+    d_stock = float((g_stock16.float() - g_stock32).abs().max()) / gmax
+    d_between = float((g_ours16.float() - g_stock16.float()).abs().max()) / gmax
+    _report("Gen-B CombinedLoss autocast", loss_rel_ours_vs_stock16=worst_vs_stock16, loss_rel_ours_vs_float32=worst_vs_f32,
+            loss_rel_stock16_vs_float32=stock16_vs_f32, grad_maxnorm_ours_vs_float32=d_ours, grad_maxnorm_stock16_vs_float32=d_stock,
+            grad_maxnorm_ours_vs_stock16=d_between)
+    assert set(ours16) == set(stock16)
+    assert worst_vs_f32 <= 1e-5                         # float32 arithmetic on the up-cast maps: the float32 reference's losses
+    assert d_ours <= 2.0 ** -10                         # ... and its gradient rounded to half once
+    assert worst_vs_stock16 <= 5e-3 and d_between <= 2e-2          # half-precision round-off of the stock autocast step
